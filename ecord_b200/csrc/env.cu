@@ -1,0 +1,329 @@
+// env.cu -- Max-Cut environment kernels (SURVEY.md 8a rows a2, a3, a4 and seam B3).
+//
+// Replaces the reference's only native component, _tradjectory_step_cy.pyx:9-171, and the NumPy/
+// torch_scatter set-up around it (tradjectories.py:62-148,336-376,387-405).
+// All arithmetic is fp32 in the reference's order of operations, so results are bit-identical
+// (spins are +-1, so every product below is exact and each update is a single rounding).
+//
+// Work decomposition: the reference loops serially over (graph, trajectory) and then over the CSR
+// row of the flipped vertex.  Here ONE WARP owns one (graph, trajectory) unit; its lanes stride over
+// the CSR row (coalesced col/w loads), the neighbour read-modify-writes scatter inside the unit's
+// contiguous row of the trajectory-major plane.  HBM/latency-bound: ~20 B per neighbour.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// a2: initial peeks / scores (tradjectories.py:130-148), sequential per segment like segment_csr.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_env_init_peek(ecord_graph g, ecord_env e, const int8_t *__restrict__ s0) {
+    const int T = e.num_tradj;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)g.num_nodes * T) return;
+    const int v = (int)(idx / T), t = (int)(idx % T);
+    const float si = (float)(2 * s0[idx] - 1);
+    float acc = 0.0f;
+    for (int k = g.row_ptr[v]; k < g.row_ptr[v + 1]; ++k) {
+        const float sj = (float)(2 * s0[(long long)g.col[k] * T + t] - 1);
+        acc += g.w[k] * si * sj;
+    }
+    const int gi = g.node_graph[v];
+    int n;
+    const long long o = unit_base(g.graph_ptr, gi, t, T, n) + (v - g.graph_ptr[gi]);
+    e.peek[o] = acc;
+    e.sp[o] = (int32_t)s0[idx];          // last_flip_step = 0
+    e.best_state[o] = (uint8_t)s0[idx];  // tradjectories.py:116
+}
+
+__global__ void k_env_init_score(ecord_graph g, ecord_env e, const int8_t *__restrict__ s0) {
+    const int T = e.num_tradj;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.num_graphs * T) return;
+    const int gi = m / T, t = m % T;
+    float acc = 0.0f;
+    for (int v = g.graph_ptr[gi]; v < g.graph_ptr[gi + 1]; ++v) {
+        const int sv = s0[(long long)v * T + t];
+        for (int k = g.row_ptr[v]; k < g.row_ptr[v + 1]; ++k) {
+            const int su = s0[(long long)g.col[k] * T + t];
+            acc += g.w[k] * (float)((sv + su) & 1);
+        }
+    }
+    const float sc = 0.5f * acc;
+    e.score[m] = sc;
+    e.best_score[m] = sc;   // tradjectories.py:81
+    e.best_step[m] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a3: one step on the SoA state.  One warp per (g,t).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, const int32_t *step_base, int step_off,
+           float *score_log, int32_t *action_log, int log_stride) {
+    const int T = e.num_tradj;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= g.num_graphs * T) return;
+    const int step_no = (step_base ? *step_base : 0) + step_off;   // steps completed before this one
+    const int gi = m / T, t = m - gi * T;
+    int n;
+    const long long base = unit_base(g.graph_ptr, gi, t, T, n);
+    const int lo = g.graph_ptr[gi];
+    const int a = actions[m];
+    const float pa = e.peek[base + a];
+    const int spa = e.sp[base + a];
+    const int sa = spa & 1;
+    // 5(ii): neighbours gain/lose the connecting edge weight (pyx:119-137), PRE-flip state of a
+    const float fa = (float)(2 * sa - 1);
+    const int k1 = g.row_ptr[lo + a + 1];
+    for (int k = g.row_ptr[lo + a] + lane; k < k1; k += 32) {
+        const int nb = g.col[k] - lo;
+        const float fn = (float)(2 * (e.sp[base + nb] & 1) - 1);
+        const float sw = fa * fn * g.w[k];
+        e.peek[base + nb] = e.peek[base + nb] - 2.0f * sw;
+    }
+    if (lane == 0) {
+        const float sc = e.score[m] + pa;                      // 1. pyx:87
+        e.score[m] = sc;
+        const bool new_best = sc > e.best_score[m];            // 2. pyx:90-93
+        if (new_best) { e.best_score[m] = sc; e.best_step[m] = step_no + 1; }
+        e.peek[base + a] = -1.0f * pa;                         // 5(i). pyx:109
+        e.sp[base + a] = ((step_no + 1) << 1) | (sa ^ 1);      // 7 + 9: flip, static = 0
+        if (new_best) e.best_state[base + a] = (uint8_t)(sa ^ 1);   // 8. pyx:142-146 (quirk D)
+        if (score_log) score_log[(long long)step_no * log_stride + m] = sc;
+        if (action_log) action_log[(long long)step_no * log_stride + m] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4 / parity view: materialise the reference's arrays.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_env_export_nodes(ecord_graph g, ecord_env e, int steps_done, int normalise,
+                                   float *__restrict__ nf, float *__restrict__ bs) {
+    const int T = e.num_tradj;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)g.num_nodes * T) return;
+    const int v = (int)(idx / T), t = (int)(idx % T);
+    const int gi = g.node_graph[v];
+    int n;
+    const long long o = unit_base(g.graph_ptr, gi, t, T, n) + (v - g.graph_ptr[gi]);
+    const int sp = e.sp[o];
+    float peek = e.peek[o];
+    float stat = (float)(steps_done - (sp >> 1));
+    if (normalise) {
+        peek = peek / (float)n;                                            // PEEK_NORM
+        stat = fminf(stat, (float)ECORD_STATIC_CLIP) / (float)ECORD_STATIC_CLIP;   // STEPS_STATIC_CLIP
+    }
+    if (nf) { nf[idx * 3 + 0] = (float)(sp & 1); nf[idx * 3 + 1] = peek; nf[idx * 3 + 2] = stat; }
+    if (bs) bs[idx] = (float)e.best_state[o];
+}
+
+__global__ void k_env_export_glob(ecord_graph g, ecord_env e, int normalise, float *__restrict__ gf) {
+    const int T = e.num_tradj;
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= g.num_graphs * T) return;
+    const int gi = m / T;
+    float d = e.best_score[m] - e.score[m];                               // pyx:96-97
+    if (normalise) d = d / (float)(g.graph_ptr[gi + 1] - g.graph_ptr[gi]); // SCORE_FROM_BEST_NORM
+    gf[m * 2 + 0] = d;
+    gf[m * 2 + 1] = 0.0f;   // quirk C: PEEK_MAX* is never configured (tradjectories.py:294)
+}
+
+// ------------------------------------------------------------------------------------------------
+// B3: step_cy() on the reference's own AoS layout with its full feature-index tables.
+// ------------------------------------------------------------------------------------------------
+struct StepCyIdx { int state, peek, best, stat, degree; int sfb, ssb, ngr, steps, maxp, meanp; };
+
+__global__ void k_stepcy_prologue(float *nf, float *gf, long long NT, int GT, int Fn, int Fg, int d_static, int g_steps) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d_static >= 0 && i < NT) nf[i * Fn + d_static] += 1.0f;            // pyx:160-161
+    if (g_steps >= 0 && i < GT) gf[i * Fg + g_steps] += 1.0f;              // pyx:163-164
+}
+
+__global__ void __launch_bounds__(256)
+k_stepcy(const int64_t *__restrict__ actions, float *scores, float *best_scores, float *best_states,
+         float *nf, float *gf, StepCyIdx ix, const int32_t *__restrict__ e_src, const int32_t *__restrict__ e_dst,
+         const float *__restrict__ ew, const int32_t *__restrict__ eptr, int G, int T, int Fn, int Fg) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= G * T) return;
+    const int t = m % T;
+    const long long a = actions[m];
+#define NFA(v, d) nf[((long long)(v) * T + t) * Fn + (d)]
+    const float pa = NFA(a, ix.peek);
+    // neighbours first (they never touch a's own entries; a simple graph has no self loops)
+    int dgreedy = 0;
+    const int k1 = eptr[a + 1];
+    for (int k = eptr[a] + lane; k < k1; k += 32) {
+        const int u = e_src[k], v = e_dst[k];
+        const float sw = (2.0f * NFA(u, ix.state) - 1.0f) * (2.0f * NFA(v, ix.state) - 1.0f) * ew[k];
+        const float old_peek = NFA(v, ix.peek);
+        const float new_peek = old_peek - 2.0f * sw;
+        if (new_peek > 0.0f && old_peek <= 0.0f) dgreedy += 1;
+        else if (new_peek <= 0.0f && old_peek > 0.0f) dgreedy -= 1;
+        NFA(v, ix.peek) = new_peek;
+    }
+    if (ix.ngr >= 0) dgreedy = warp_sum_int(dgreedy);
+    if (lane == 0) {
+        const float sc = scores[m] + pa;
+        scores[m] = sc;
+        int new_best = 0;
+        if (sc > best_scores[m]) { best_scores[m] = sc; new_best = 1; }
+        float *gfm = gf + (long long)m * Fg;
+        if (ix.sfb >= 0) gfm[ix.sfb] = best_scores[m] - sc;
+        if (ix.ssb >= 0) gfm[ix.ssb] = new_best ? 0.0f : gfm[ix.ssb] + 1.0f;
+        const float npa = -1.0f * pa;
+        NFA(a, ix.peek) = npa;
+        if (ix.ngr >= 0) {
+            // integer-valued float counter: +-1 updates are exact, so their order is immaterial
+            float c = gfm[ix.ngr];
+            if (npa > 0.0f) c += 1.0f;
+            if (npa < 0.0f) c -= 1.0f;
+            gfm[ix.ngr] = c + (float)dgreedy;
+        }
+        const float ns = fmodf(NFA(a, ix.state) + 1.0f, 2.0f);
+        NFA(a, ix.state) = ns;
+        if (new_best) {
+            best_states[a * T + t] = ns;
+            if (ix.best > 0) NFA(a, ix.best) = ns;      // sic: "> 0", pyx:145
+        }
+        if (ix.stat >= 0) NFA(a, ix.stat) = 0.0f;
+    }
+#undef NFA
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int check_graph(const ecord_graph *g) {
+    ECORD_RET_IF(!g, ECORD_E_NULL);
+    ECORD_RET_IF(g->num_graphs <= 0 || g->num_nodes <= 0 || g->num_edges < 0 || g->n_max <= 0, ECORD_E_SIZE);
+    ECORD_RET_IF(!g->graph_ptr || !g->node_graph || !g->row_ptr || (g->num_edges > 0 && (!g->col || !g->w)), ECORD_E_NULL);
+    return 0;
+}
+static int check_env(const ecord_env *e) {
+    ECORD_RET_IF(!e, ECORD_E_NULL);
+    ECORD_RET_IF(e->num_tradj <= 0, ECORD_E_SIZE);
+    ECORD_RET_IF(!e->peek || !e->sp || !e->best_state || !e->score || !e->best_score || !e->best_step, ECORD_E_NULL);
+    return 0;
+}
+
+extern "C" int ecord_env_init(const ecord_graph *g, const ecord_env *env, const int8_t *init_state, void *stream) {
+    int rc;
+    if ((rc = check_graph(g)) || (rc = check_env(env))) return rc;
+    ECORD_RET_IF(!init_state, ECORD_E_NULL);
+    const long long NT = (long long)g->num_nodes * env->num_tradj;
+    const int GT = g->num_graphs * env->num_tradj;
+    k_env_init_peek<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state);
+    ECORD_LAUNCH_CHECK();
+    k_env_init_score<<<ceil_div(GT, 64), 64, 0, as_stream(stream)>>>(*g, *env, init_state);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, const int32_t *step_base,
+                    int step_off, float *score_log, int32_t *action_log, cudaStream_t st) {
+    const int GT = g->num_graphs * env->num_tradj;
+    k_env_step<<<ceil_div((long long)GT * 32, 256), 256, 0, st>>>(*g, *env, actions, step_base, step_off, score_log,
+                                                                  action_log, GT);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ecord_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, int32_t step_no,
+                              float *score_log, void *stream) {
+    int rc;
+    if ((rc = check_graph(g)) || (rc = check_env(env))) return rc;
+    ECORD_RET_IF(!actions, ECORD_E_NULL);
+    ECORD_RET_IF(step_no < 0, ECORD_E_SIZE);
+    // score_log here is a single [G*T] row: bias the pointer so row `step_no` lands on it
+    const int GT = g->num_graphs * env->num_tradj;
+    float *log0 = score_log ? score_log - (long long)step_no * GT : nullptr;
+    return launch_env_step(g, env, actions, nullptr, step_no, log0, nullptr, as_stream(stream));
+}
+
+extern "C" int ecord_env_export(const ecord_graph *g, const ecord_env *env, int32_t steps_done, int32_t normalise,
+                                float *node_features, float *glob_features, float *best_states, void *stream) {
+    int rc;
+    if ((rc = check_graph(g)) || (rc = check_env(env))) return rc;
+    const long long NT = (long long)g->num_nodes * env->num_tradj;
+    const int GT = g->num_graphs * env->num_tradj;
+    if (node_features || best_states) {
+        k_env_export_nodes<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(*g, *env, steps_done, normalise,
+                                                                             node_features, best_states);
+        ECORD_LAUNCH_CHECK();
+    }
+    if (glob_features) {
+        k_env_export_glob<<<ceil_div(GT, 128), 128, 0, as_stream(stream)>>>(*g, *env, normalise, glob_features);
+        ECORD_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int ecord_step_cy_device(const int64_t *actions, float *scores, float *best_scores, float *best_states,
+                                    float *node_features, float *global_features, const int32_t *nidx,
+                                    const int32_t *gidx, const int32_t *edges_by_node, const float *edge_attrs,
+                                    const int32_t *edge_ptr, int32_t N, int32_t G, int32_t T, int32_t Fn, int32_t Fg,
+                                    int32_t E, void *stream) {
+    ECORD_RET_IF(!actions || !scores || !best_scores || !best_states || !node_features || !nidx || !gidx || !edge_ptr,
+                 ECORD_E_NULL);
+    ECORD_RET_IF(E > 0 && (!edges_by_node || !edge_attrs), ECORD_E_NULL);
+    ECORD_RET_IF(N <= 0 || G <= 0 || T <= 0 || Fn <= 0 || Fg < 0 || E < 0, ECORD_E_SIZE);
+    StepCyIdx ix{nidx[0], nidx[1], nidx[2], nidx[3], nidx[4], gidx[0], gidx[1], gidx[2], gidx[3], gidx[4], gidx[5]};
+    // the reference asserts STATE and one PEEK variant are configured (tradjectories.py:226-227)
+    ECORD_RET_IF(ix.state < 0 || ix.peek < 0 || ix.state >= Fn || ix.peek >= Fn, ECORD_E_UNSUPPORTED);
+    ECORD_RET_IF(ix.best >= Fn || ix.stat >= Fn || ix.sfb >= Fg || ix.ssb >= Fg || ix.ngr >= Fg || ix.steps >= Fg,
+                 ECORD_E_SIZE);
+    const bool any_glob = ix.sfb >= 0 || ix.ssb >= 0 || ix.ngr >= 0 || ix.steps >= 0;
+    ECORD_RET_IF(any_glob && !global_features, ECORD_E_NULL);
+    cudaStream_t st = as_stream(stream);
+    const long long NT = (long long)N * T;
+    if (ix.stat >= 0 || ix.steps >= 0) {
+        k_stepcy_prologue<<<ceil_div(NT, 256), 256, 0, st>>>(node_features, global_features, NT, G * T, Fn, Fg, ix.stat,
+                                                             ix.steps);
+        ECORD_LAUNCH_CHECK();
+    }
+    k_stepcy<<<ceil_div((long long)G * T * 32, 256), 256, 0, st>>>(actions, scores, best_scores, best_states,
+                                                                   node_features, global_features, ix, edges_by_node,
+                                                                   edges_by_node + E, edge_attrs, edge_ptr, G, T, Fn, Fg);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ecord_step_cy(const int64_t *actions, float *scores, float *best_scores, float *best_states,
+                             float *node_features, float *global_features, const int32_t *nidx, const int32_t *gidx,
+                             const int32_t *edges_by_node, const float *edge_attrs, const int32_t *edge_ptr, int32_t N,
+                             int32_t G, int32_t T, int32_t Fn, int32_t Fg) {
+    ECORD_RET_IF(!actions || !scores || !best_scores || !best_states || !node_features || !nidx || !gidx || !edge_ptr,
+                 ECORD_E_NULL);
+    ECORD_RET_IF(N <= 0 || G <= 0 || T <= 0 || Fn <= 0 || Fg < 0, ECORD_E_SIZE);
+    const int E = edge_ptr[N];   // host buffer: the CSR pointer's last entry is the edge count
+    ECORD_RET_IF(E < 0, ECORD_E_SIZE);
+    const size_t GT = (size_t)G * T, NT = (size_t)N * T;
+    // one device arena, carved 256-byte aligned
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_act = carve(GT * 8), o_sc = carve(GT * 4), o_bs = carve(GT * 4), o_bst = carve(NT * 4),
+                 o_nf = carve(NT * Fn * 4), o_gf = carve(GT * (Fg > 0 ? Fg : 1) * 4), o_e = carve((size_t)E * 8 + 8),
+                 o_w = carve((size_t)E * 4 + 4), o_p = carve((size_t)(N + 1) * 4);
+    char *d = nullptr;
+    ECORD_CUDA(cudaMalloc(&d, off));
+    cudaStream_t st = nullptr;
+    int rc = 0;
+#define UP(o, src, bytes) if (!rc && (bytes) && (src)) rc = (int)cudaMemcpyAsync(d + (o), (src), (bytes), cudaMemcpyHostToDevice, st)
+    UP(o_act, actions, GT * 8); UP(o_sc, scores, GT * 4); UP(o_bs, best_scores, GT * 4); UP(o_bst, best_states, NT * 4);
+    UP(o_nf, node_features, NT * Fn * 4); UP(o_gf, global_features, GT * Fg * 4);
+    UP(o_e, edges_by_node, (size_t)E * 8); UP(o_w, edge_attrs, (size_t)E * 4); UP(o_p, edge_ptr, (size_t)(N + 1) * 4);
+#undef UP
+    if (!rc)
+        rc = ecord_step_cy_device((const int64_t *)(d + o_act), (float *)(d + o_sc), (float *)(d + o_bs),
+                                  (float *)(d + o_bst), (float *)(d + o_nf),
+                                  global_features ? (float *)(d + o_gf) : nullptr, nidx, gidx,
+                                  (const int32_t *)(d + o_e), (const float *)(d + o_w), (const int32_t *)(d + o_p), N, G, T,
+                                  Fn, Fg, E, st);
+#define DOWN(dst, o, bytes) if (!rc && (bytes) && (dst)) rc = (int)cudaMemcpyAsync((dst), d + (o), (bytes), cudaMemcpyDeviceToHost, st)
+    DOWN(scores, o_sc, GT * 4); DOWN(best_scores, o_bs, GT * 4); DOWN(best_states, o_bst, NT * 4);
+    DOWN(node_features, o_nf, NT * Fn * 4); DOWN(global_features, o_gf, GT * Fg * 4);
+#undef DOWN
+    if (!rc) rc = (int)cudaStreamSynchronize(st);
+    cudaFree(d);
+    return rc;
+}

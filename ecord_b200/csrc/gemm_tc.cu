@@ -1,0 +1,386 @@
+// gemm_tc.cu -- the two dense contractions of the policy step on 5th-gen tensor cores (sm_100a):
+//
+//   GRU  :  [M, 64+1024] x [1088, 3072]  fused with the GRU cell   (models/rnn_decoder.py:369-381 -> nn.GRUCell)
+//   PROJ :  [M, 1024]    x [1024, 512]   + bias                    (models/rnn_decoder.py:84-86, proj_rnn_to_gnn.1)
+//
+// Hand-written tcgen05 pipeline, one output tile per CTA:
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B) -> 4-stage smem ring, mbarrier complete_tx
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//               (bf16 x bf16 -> fp32 accumulate in TMEM), tcgen05.commit releases smem stages / signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> fused math -> global
+//
+// GRU tile = 128 rows x 64 hidden units.  The weight rows of one 64-unit block are packed (ecord_pack_weights)
+// as [r | z | hn | in] so ONE accumulator [128 x 256] holds all four gate pre-activations of the block:
+//   k-chunk 0      : A = u[128 x 64],        B = [W_ir; W_iz; 0; W_in] (256 x 64)   -> N = 256, initialises all columns
+//   k-chunks 1..16 : A = h[128 x 64 chunk],  B = [W_hr; W_hz; W_hn]    (192 x 64)   -> N = 192, accumulates cols 0..191
+// so gi_n and gh_n stay separate (n = tanh(gi_n + r * gh_n)) at no extra MMA work, and the epilogue applies the
+// cell per element:  h' = (h - n) * z + n.  It writes h' (fp32, the recurrent state), h' (bf16, next step's A
+// operand) and tanh(h') (bf16, PROJ's A operand).  h is double-buffered: buffer (s & 1) holds the state after s steps.
+#include "common.cuh"
+#include <math.h>
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched at run time (no link-time libcuda dependency)
+
+namespace {
+constexpr int H = ECORD_DIM_H;
+constexpr int BM = 128;          // rows per tile (UMMA_M)
+constexpr int BK = 64;           // bf16 elements per k-chunk = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kThreads = 192;    // 6 warps
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// K-major, SWIZZLE_128B canonical layout: 8-row groups 1024 B apart (SBO), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct TcParams {
+    // GRU
+    const float *hidden;          // [2][Mp][1024] fp32
+    __nv_bfloat16 *hidden_bf16;   // [2][Mp][1024]
+    __nv_bfloat16 *th_bf16;       // [Mp][1024]
+    const float *bih, *bhh;       // [3072]
+    // PROJ
+    const float *p1_b;            // [512]
+    float *y1;                    // [Mp][512]
+    int rows, rows_pad;
+    const int32_t *step_base;     // device step counter (or NULL)
+    int step_off;
+};
+
+// MODE 0 = GRU (first chunk N=256 from (mapA0=u, mapB0=Wu), then 16 chunks N=192 from (h[cur], Wh)), 256 TMEM cols
+// MODE 1 = PROJ (16 chunks N=64 from (th, W1)), 64 TMEM cols
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
+          const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+          const __grid_constant__ CUtensorMap mapB, TcParams prm) {
+    constexpr int N_FIRST = MODE == 0 ? 256 : 0;
+    constexpr int N_MAIN = MODE == 0 ? 192 : 64;
+    constexpr int B_ROWS = MODE == 0 ? 256 : 64;             // smem rows reserved per stage for B
+    constexpr int TMEM_COLS = MODE == 0 ? 256 : 64;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024-byte alignment
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = blockIdx.x;            // output-column block
+    const int m0 = blockIdx.y * BM;
+    const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
+
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]), accum_bar = smem_u32(&bars[2 * kStages]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const CUtensorMap *mapA = (MODE == 0) ? (cur ? &mapA1 : &mapA0) : &mapA0;
+            tmap_prefetch(mapA); tmap_prefetch(&mapB);
+            if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int s = c % kStages;
+                const uint32_t ph = (uint32_t)(c / kStages) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                if (MODE == 0 && c == 0) {
+                    mbar_expect_tx(full0 + 8 * s, A_BYTES + N_FIRST * BK * 2);
+                    tma_load_2d(a_dst, &mapU, full0 + 8 * s, 0, m0);
+                    tma_load_2d(b_dst, &mapWu, full0 + 8 * s, 0, nb * N_FIRST);
+                } else {
+                    const int kc = (MODE == 0 ? c - 1 : c) * BK;
+                    mbar_expect_tx(full0 + 8 * s, A_BYTES + N_MAIN * BK * 2);
+                    tma_load_2d(a_dst, mapA, full0 + 8 * s, kc, m0);
+                    tma_load_2d(b_dst, &mapB, full0 + 8 * s, kc, nb * N_MAIN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int s = c % kStages;
+                const uint32_t ph = (uint32_t)(c / kStages) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+                const uint32_t idesc = (MODE == 0 && c == 0) ? umma_idesc(BM, 256) : umma_idesc(BM, N_MAIN);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
+                    umma_bf16(tmem_d, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty0 + 8 * s);              // frees the smem stage once these MMAs retire
+            }
+            umma_commit(accum_bar);                       // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16);
+        if (MODE == 0) {
+            const float *hold = prm.hidden + ((size_t)cur * prm.rows_pad + row) * H + nb * 64;
+            float *hnew = const_cast<float *>(prm.hidden) + ((size_t)(1 - cur) * prm.rows_pad + row) * H + nb * 64;
+            __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + nb * 64;
+            __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + nb * 64;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 64; j0 += 16) {
+                float ar[16], az[16], ahn[16], ain[16];
+                tmem_ld16(tbase + j0, ar);
+                tmem_ld16(tbase + 64 + j0, az);
+                tmem_ld16(tbase + 128 + j0, ahn);
+                tmem_ld16(tbase + 192 + j0, ain);
+                tmem_ld_wait();
+                if (row < prm.rows) {
+                    float hv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + j0 + i);
+                    __align__(16) __nv_bfloat16 ob[16], ot[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int j = nb * 64 + j0 + i;
+                        const float r = sigmoidf_acc((ar[i] + prm.bhh[j]) + prm.bih[j]);
+                        const float z = sigmoidf_acc((az[i] + prm.bhh[H + j]) + prm.bih[H + j]);
+                        const float n = tanhf(__fadd_rn(ain[i] + prm.bih[2 * H + j], __fmul_rn(ahn[i] + prm.bhh[2 * H + j], r)));
+                        const float hn = __fadd_rn(__fmul_rn(__fsub_rn(hv[i], n), z), n);
+                        hv[i] = hn;
+                        ob[i] = __float2bfloat16(hn);
+                        ot[i] = __float2bfloat16(tanhf(hn));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(hnew + j0 + i) = *reinterpret_cast<float4 *>(&hv[i]);
+                    *reinterpret_cast<uint4 *>(hb + j0) = *reinterpret_cast<uint4 *>(&ob[0]);
+                    *reinterpret_cast<uint4 *>(hb + j0 + 8) = *reinterpret_cast<uint4 *>(&ob[8]);
+                    *reinterpret_cast<uint4 *>(tb + j0) = *reinterpret_cast<uint4 *>(&ot[0]);
+                    *reinterpret_cast<uint4 *>(tb + j0 + 8) = *reinterpret_cast<uint4 *>(&ot[8]);
+                }
+            }
+        } else {
+            float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + nb * 64;
+#pragma unroll 1
+            for (int j0 = 0; j0 < 64; j0 += 16) {
+                float acc[16];
+                tmem_ld16(tbase + j0, acc);
+                tmem_ld_wait();
+                if (row < prm.rows) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const int j = nb * 64 + j0 + i;
+                        float4 o = make_float4(acc[i] + prm.p1_b[j], acc[i + 1] + prm.p1_b[j + 1], acc[i + 2] + prm.p1_b[j + 2],
+                                               acc[i + 3] + prm.p1_b[j + 3]);
+                        *reinterpret_cast<float4 *>(yrow + j0 + i) = o;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encoder(PFN_encodeTiled *out) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return (int)e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return ECORD_E_DEVICE;
+    *out = reinterpret_cast<PFN_encodeTiled>(fn);
+    return 0;
+}
+
+// 2-D bf16 row-major [rows][cols], box = [box_rows][64 cols], 128-byte swizzle
+int make_map(PFN_encodeTiled enc, CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : ECORD_E_DEVICE;
+}
+
+template <int MODE>
+constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + (MODE == 0 ? 256 : 64) * BK * 2) + 1024; }
+
+// ---------------------------------------------------------------------------------------------
+// weight packing (device): fp32 PyTorch layout -> bf16 tile-permuted, plus the folded encoder constants
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_weights(ecord_weights w) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    __nv_bfloat16 *wh = reinterpret_cast<__nv_bfloat16 *>(w.gru_w_bf16);
+    __nv_bfloat16 *wu = wh + (size_t)3072 * H;
+    const long long n_wh = (long long)3072 * H, n_wu = (long long)4096 * 64, n_p1 = (long long)512 * H;
+    if (i < n_wh) {                               // Wh pack: row = jb*192 + gate*64 + jj  <-  W_hh[gate*1024 + jb*64 + jj]
+        const int row = (int)(i / H), k = (int)(i % H);
+        const int jb = row / 192, gate = (row % 192) / 64, jj = row % 64;
+        wh[i] = __float2bfloat16(w.gru_whh[(size_t)(gate * H + jb * 64 + jj) * H + k]);
+    } else if (i < n_wh + n_wu) {                 // Wu pack: row = jb*256 + slot*64 + jj; slots r, z, (zero), in
+        const long long t = i - n_wh;
+        const int row = (int)(t / 64), k = (int)(t % 64);
+        const int jb = row / 256, slot = (row % 256) / 64, jj = row % 64;
+        float v = 0.0f;
+        if (slot != 2) {
+            const int gate = slot == 3 ? 2 : slot;
+            v = w.gru_wih[(size_t)(gate * H + jb * 64 + jj) * 64 + k];
+        }
+        wu[t] = __float2bfloat16(v);
+    } else if (i < n_wh + n_wu + n_p1) {
+        const long long t = i - n_wh - n_wu;
+        reinterpret_cast<__nv_bfloat16 *>(w.p1_w_bf16)[t] = __float2bfloat16(w.p1_w[t]);
+    }
+}
+
+}  // namespace
+
+extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
+    ECORD_RET_IF(!w || !w->gru_w_bf16 || !w->p1_w_bf16 || !w->gru_whh || !w->gru_wih || !w->p1_w, ECORD_E_NULL);
+    const long long n = (long long)3072 * H + (long long)4096 * 64 + (long long)512 * H;
+    k_pack_weights<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(*w);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+// Host-side fold of the node-feature encoder into mlp_out[0] (all arguments are HOST arrays):
+//   C[c][k] = sum_i Wq[c][48+i] W_enc[i][k]   (64 x 3), stored as three planes C0|C1|C2, then gamma|beta|w_o.
+extern "C" int ecord_fold_q_host(const float *q1_w, const float *enc_w, const float *qln_w, const float *qln_b,
+                                 const float *q2_w, float *out384) {
+    ECORD_RET_IF(!q1_w || !enc_w || !qln_w || !qln_b || !q2_w || !out384, ECORD_E_NULL);
+    for (int c = 0; c < ECORD_DIM_Q; ++c) {
+        for (int k = 0; k < 3; ++k) {
+            float a = 0.0f;
+            for (int i = 0; i < 16; ++i) a = fmaf(q1_w[c * ECORD_DIM_Q + 48 + i], enc_w[i * 3 + k], a);
+            out384[k * ECORD_DIM_Q + c] = a;
+        }
+        out384[3 * ECORD_DIM_Q + c] = qln_w[c];
+        out384[4 * ECORD_DIM_Q + c] = qln_b[c];
+        out384[5 * ECORD_DIM_Q + c] = q2_w[c];
+    }
+    return 0;
+}
+
+int tc_init_attrs() {
+    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<0>()));
+    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
+    return 0;
+}
+
+int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, cudaStream_t st) {
+    PFN_encodeTiled enc;
+    int rc = get_encoder(&enc);
+    if (rc) return rc;
+    const int Mp = p->rows_pad;
+    const __nv_bfloat16 *wh = reinterpret_cast<const __nv_bfloat16 *>(w->gru_w_bf16);
+    const __nv_bfloat16 *wu = wh + (size_t)3072 * H;
+    const __nv_bfloat16 *hb = reinterpret_cast<const __nv_bfloat16 *>(p->hidden_bf16);
+    CUtensorMap mU, mWu, mA0, mA1, mB;
+    if ((rc = make_map(enc, &mU, p->u_bf16, Mp, 64, BM))) return rc;
+    if ((rc = make_map(enc, &mWu, wu, 4096, 64, 256))) return rc;
+    if ((rc = make_map(enc, &mA0, hb, Mp, H, BM))) return rc;
+    if ((rc = make_map(enc, &mA1, hb + (size_t)Mp * H, Mp, H, BM))) return rc;
+    if ((rc = make_map(enc, &mB, wh, 3072, H, 192))) return rc;
+    TcParams prm{};
+    prm.hidden = p->hidden; prm.hidden_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->hidden_bf16);
+    prm.th_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->th_bf16);
+    prm.bih = w->gru_bih; prm.bhh = w->gru_bhh;
+    prm.rows = p->rows; prm.rows_pad = Mp; prm.step_base = step_base; prm.step_off = step_off;
+    k_gemm_tc<0><<<dim3(H / 64, Mp / BM), kThreads, tc_smem_bytes<0>(), st>>>(mU, mWu, mA0, mA1, mB, prm);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st) {
+    PFN_encodeTiled enc;
+    int rc = get_encoder(&enc);
+    if (rc) return rc;
+    const int Mp = p->rows_pad;
+    CUtensorMap mA, mB;
+    if ((rc = make_map(enc, &mA, p->th_bf16, Mp, H, BM))) return rc;
+    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, 64))) return rc;
+    TcParams prm{};
+    prm.p1_b = w->p1_b; prm.y1 = p->y1; prm.rows = p->rows; prm.rows_pad = Mp;
+    k_gemm_tc<1><<<dim3(ECORD_DIM_P1 / 64, Mp / BM), kThreads, tc_smem_bytes<1>(), st>>>(mA, mB, mA, mA, mB, prm);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,236 @@
+// gnn.cu -- t=0 GNN embedding ("Subsystem 3").
+//
+// Replaces GNNEmbedder.forward / NodeModel.forward (models/gnn_embedder.py:133-149,182-199), GNN2RNN
+// (models/gnn_to_rnn.py:16-18) as driven by _ActorBase.initialise_embeddings (actors/_base.py:185-237):
+//   x0 = LN(W_e * 1 + b_e)
+//   4x { y = LReLU(W_s x + b_s);  m_i = mean_{j->i} w_ji * y_j;  x_i = GRUCell(LReLU(W_r [m_i; x_i] + b_r), x_i);  x = LN(x) }
+//   node_emb = W_g x + b_g
+// LN is PyG's LayerNorm(affine=False) called without `batch` (gnn_embedder.py:178,194,199): statistics
+// over ALL vertices of ALL graphs in the batch (quirk B):  (x - mean) / (std_pop + 1e-5).
+//
+// Shape of the work: N x 16 activations, E edge messages of 16 channels; one-off per rollout and tiny
+// next to the S-step loop, so the design goal is exactness of summation order (incoming edges are
+// accumulated sequentially in global edge order, as scatter_add does on the CPU), not peak bandwidth:
+// one thread per vertex gathers its incoming CSR row (16 consecutive floats per neighbour = one
+// 64-byte segment), weights staged once per block in shared memory.  Batch-wide LN sums are
+// block-reduced and accumulated in fp64 atomics.
+#include "common.cuh"
+
+namespace {
+constexpr int D = ECORD_DIM_GNN;   // 16
+
+struct GnnSmem {
+    float snd_w[D * D], snd_b[D];
+    float rec_w[2 * D * 2 * D], rec_b[2 * D];
+    float wih[3 * D * 2 * D], whh[3 * D * D], bih[3 * D], bhh[3 * D];
+};
+
+__device__ __forceinline__ void block_accumulate(double s, double ss, double *acc) {
+    __shared__ double red[2][32];
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = s; red[1][w] = ss; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        s = l < nw ? red[0][l] : 0.0;
+        ss = l < nw ? red[1][l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (l == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], ss); }
+    }
+}
+
+// x0 = W_e * 1 + b_e for every vertex (input feature is the constant 1, data.py:119)
+__global__ void k_gnn_embed0(int N, const float *__restrict__ ew, const float *__restrict__ eb, float *x, double *acc) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0, ss = 0.0;
+    if (v < N) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const float val = ew[c] * 1.0f + eb[c];
+            x[(long long)v * D + c] = val;
+            s += val; ss += (double)val * val;
+        }
+    }
+    block_accumulate(s, ss, acc);
+}
+
+// x <- (x - mean) / (std_pop + eps), batch-wide
+__global__ void k_gnn_ln(int N, float *x, const double *acc) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * D) return;
+    const double cnt = (double)N * D;
+    const double mean = acc[0] / cnt;
+    double var = acc[1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float meanf = (float)mean, stdf = (float)sqrt(var);
+    const float c = x[i] - meanf;
+    x[i] = c / (stdf + kLnEps);
+}
+
+// y = LReLU(W_s x + b_s)
+__global__ void k_gnn_send(int N, const float *__restrict__ x, const float *__restrict__ sw, const float *__restrict__ sb,
+                           float *y) {
+    __shared__ float w[D * D], b[D];
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) w[i] = sw[i];
+    if (threadIdx.x < D) b[threadIdx.x] = sb[threadIdx.x];
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N) return;
+    float xi[D];
+#pragma unroll
+    for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(&xi[c]) = *reinterpret_cast<const float4 *>(&x[(long long)v * D + c]);
+#pragma unroll
+    for (int o = 0; o < D; ++o) {
+        float a = b[o];
+#pragma unroll
+        for (int c = 0; c < D; ++c) a = fmaf(w[o * D + c], xi[c], a);
+        y[(long long)v * D + o] = lrelu(a);
+    }
+}
+
+// aggregate + receive + GRUCell; writes the pre-LN x_new and accumulates the LN sums
+__global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const float *__restrict__ y,
+                             float *xn, double *acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GnnSmem &S = *reinterpret_cast<GnnSmem *>(smem_raw);
+    for (int i = threadIdx.x; i < 2 * D * 2 * D; i += blockDim.x) S.rec_w[i] = wt.gnn_rec_w[i];
+    for (int i = threadIdx.x; i < 3 * D * 2 * D; i += blockDim.x) S.wih[i] = wt.gnn_wih[i];
+    for (int i = threadIdx.x; i < 3 * D * D; i += blockDim.x) S.whh[i] = wt.gnn_whh[i];
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) { S.bih[i] = wt.gnn_bih[i]; S.bhh[i] = wt.gnn_bhh[i]; }
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) S.rec_b[i] = wt.gnn_rec_b[i];
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0, ss = 0.0;
+    if (v < g.num_nodes) {
+        float in[2 * D];   // [msg ; x]
+#pragma unroll
+        for (int c = 0; c < D; ++c) in[c] = 0.0f;
+        const int k0 = g.in_ptr[v], k1 = g.in_ptr[v + 1];
+        for (int k = k0; k < k1; ++k) {             // sequential, global edge order (scatter_add on CPU)
+            const float wk = g.in_w[k];
+            const float *yj = y + (long long)g.in_src[k] * D;
+#pragma unroll
+            for (int c = 0; c < D; c += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(yj + c);
+                // product rounded separately, as the reference's `y[row] * edge_attr` then scatter_add does
+                in[c + 0] = __fadd_rn(in[c + 0], __fmul_rn(t.x, wk)); in[c + 1] = __fadd_rn(in[c + 1], __fmul_rn(t.y, wk));
+                in[c + 2] = __fadd_rn(in[c + 2], __fmul_rn(t.z, wk)); in[c + 3] = __fadd_rn(in[c + 3], __fmul_rn(t.w, wk));
+            }
+        }
+        const float cnt = (float)max(k1 - k0, 1);    // scatter_mean: count clamped to >= 1
+#pragma unroll
+        for (int c = 0; c < D; ++c) in[c] = in[c] / cnt;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(&in[D + c]) = *reinterpret_cast<const float4 *>(&x[(long long)v * D + c]);
+        float r[2 * D];    // LReLU(W_r [msg;x] + b_r)
+#pragma unroll
+        for (int o = 0; o < 2 * D; ++o) {
+            float a = S.rec_b[o];
+#pragma unroll
+            for (int c = 0; c < 2 * D; ++c) a = fmaf(S.rec_w[o * 2 * D + c], in[c], a);
+            r[o] = lrelu(a);
+        }
+        // GRUCell(32 -> 16), PyTorch gate order r, z, n
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            float gi[3], gh[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float a = S.bih[q * D + j], b = S.bhh[q * D + j];
+#pragma unroll
+                for (int c = 0; c < 2 * D; ++c) a = fmaf(S.wih[(q * D + j) * 2 * D + c], r[c], a);
+#pragma unroll
+                for (int c = 0; c < D; ++c) b = fmaf(S.whh[(q * D + j) * D + c], in[D + c], b);
+                gi[q] = a; gh[q] = b;
+            }
+            const float rg = sigmoidf_acc(gi[0] + gh[0]);
+            const float zg = sigmoidf_acc(gi[1] + gh[1]);
+            // ATen's GRU cell: n = tanh(gi_n + r * gh_n); h' = (h - n) * z + n, each op rounded
+            const float ng = tanhf(__fadd_rn(gi[2], __fmul_rn(gh[2], rg)));
+            const float hn = __fadd_rn(__fmul_rn(__fsub_rn(in[D + j], ng), zg), ng);
+            xn[(long long)v * D + j] = hn;
+            s += hn; ss += (double)hn * hn;
+        }
+    }
+    block_accumulate(s, ss, acc);
+}
+
+// node_emb = W_g x + b_g ; node_B = Wq[:,32:48] node_emb + Wq[:,48:64] b_enc
+__global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ x, float *gnn_out, float *node_emb,
+                             float *node_B) {
+    __shared__ float gw[D * D], gb[D], qb[ECORD_DIM_Q * D], qd[ECORD_DIM_Q];
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) gw[i] = wt.g2r_w[i];
+    if (threadIdx.x < D) gb[threadIdx.x] = wt.g2r_b[threadIdx.x];
+    for (int i = threadIdx.x; i < ECORD_DIM_Q * D; i += blockDim.x) qb[i] = wt.q1_w[(i / D) * ECORD_DIM_Q + 32 + (i % D)];
+    for (int c = threadIdx.x; c < ECORD_DIM_Q; c += blockDim.x) {
+        float a = 0.0f;
+        for (int i = 0; i < D; ++i) a = fmaf(wt.q1_w[c * ECORD_DIM_Q + 48 + i], wt.enc_b[i], a);
+        qd[c] = a;
+    }
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N) return;
+    float xi[D], e[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) { xi[c] = x[(long long)v * D + c]; if (gnn_out) gnn_out[(long long)v * D + c] = xi[c]; }
+#pragma unroll
+    for (int o = 0; o < D; ++o) {
+        float a = gb[o];
+#pragma unroll
+        for (int c = 0; c < D; ++c) a = fmaf(gw[o * D + c], xi[c], a);
+        e[o] = a;
+        node_emb[(long long)v * D + o] = a;
+    }
+    for (int c = 0; c < ECORD_DIM_Q; ++c) {
+        float a = qd[c];
+#pragma unroll
+        for (int i = 0; i < D; ++i) a = fmaf(qb[c * D + i], e[i], a);
+        node_B[(long long)v * ECORD_DIM_Q + c] = a;
+    }
+}
+}  // namespace
+
+extern "C" size_t ecord_gnn_workspace_bytes(int32_t N) {
+    if (N <= 0) return 0;
+    return (size_t)3 * N * D * sizeof(float) + 256 + 16 * sizeof(double);
+}
+
+extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
+                               void *workspace, void *stream) {
+    ECORD_RET_IF(!g || !w || !node_emb || !node_B || !workspace, ECORD_E_NULL);
+    ECORD_RET_IF(g->num_nodes <= 0, ECORD_E_SIZE);
+    ECORD_RET_IF(!g->in_ptr || (g->num_edges > 0 && (!g->in_src || !g->in_w)), ECORD_E_NULL);
+    ECORD_RET_IF(((uintptr_t)workspace & 15) != 0, ECORD_E_ALIGN);
+    cudaStream_t st = as_stream(stream);
+    const int N = g->num_nodes;
+    float *x = reinterpret_cast<float *>(workspace);
+    float *y = x + (size_t)N * D;
+    float *xn = y + (size_t)N * D;
+    double *acc = reinterpret_cast<double *>(((uintptr_t)(xn + (size_t)N * D) + 255) & ~(uintptr_t)255);
+    ECORD_CUDA(cudaMemsetAsync(acc, 0, 16 * sizeof(double), st));
+    const int TB = 128, nb = ceil_div(N, TB);
+    k_gnn_embed0<<<nb, TB, 0, st>>>(N, w->gnn_embed_w, w->gnn_embed_b, x, acc);
+    ECORD_LAUNCH_CHECK();
+    k_gnn_ln<<<ceil_div((long long)N * D, 256), 256, 0, st>>>(N, x, acc);
+    ECORD_LAUNCH_CHECK();
+    float *cur = x, *nxt = xn;
+    for (int l = 0; l < 4; ++l) {   // num_layers is hard-coded to 4 by experiments/configs.py:99
+        k_gnn_send<<<nb, TB, 0, st>>>(N, cur, w->gnn_snd_w, w->gnn_snd_b, y);
+        ECORD_LAUNCH_CHECK();
+        k_gnn_update<<<nb, TB, sizeof(GnnSmem), st>>>(*g, *w, cur, y, nxt, acc + 2 * (l + 1));
+        ECORD_LAUNCH_CHECK();
+        k_gnn_ln<<<ceil_div((long long)N * D, 256), 256, 0, st>>>(N, nxt, acc + 2 * (l + 1));
+        ECORD_LAUNCH_CHECK();
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    k_gnn_finish<<<nb, TB, 0, st>>>(N, *w, cur, gnn_out, node_emb, node_B);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,269 @@
+// policy.cu -- per-(graph,trajectory) recurrent unit and state head (SURVEY.md 8a rows a6 and the
+// per-(g,t) half of a8; "Subsystem 2a").
+//
+// Replaces, per step (reference paths relative to the upstream tree):
+//   _ActorBase._update_internal_state            solvers/actors/_base.py:247-269
+//   GRUDecoder.update_embeddings                 models/rnn_decoder.py:369-381
+//       u  = LReLU(W_m [e_{a_{t-1}} (32); glob_t (2)] + b_m)            (34 -> 64)
+//       h' = GRUCell(u, h)                                              (64 -> 1024; gate order r,z,n)
+//   proj_rnn_to_gnn + val_out of _forward_action_value                   models/rnn_decoder.py:84-90,108-113,285-311
+//       P  = LReLU(LN32(W2 LReLU(LN512(W1 tanh(h') + b1)) + b2))
+//       v  = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2
+// and pre-computes the per-(g,t) part of mlp_out[0]:  A = Wq[:, :32] P + b_q   (see qselect.cu).
+//
+// Rows are m = g*T + t (M = G*T of them), padded to a multiple of 128.
+// Two arithmetic paths for the two dense contractions ([M,1088]x[1088,3072] and [M,1024]x[1024,512]):
+//   ECORD_GEMM_FP32: CUDA-core FMA SGEMM below (parity mode),
+//   ECORD_GEMM_BF16: tcgen05/TMA kernels in gemm_tc.cu (throughput mode).
+#include "common.cuh"
+
+// gemm_tc.cu
+int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, cudaStream_t st);
+int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st);
+int tc_init_attrs();
+
+namespace {
+constexpr int H = ECORD_DIM_H;      // 1024
+constexpr int MSG = ECORD_DIM_MSG;  // 64
+constexpr int P1 = ECORD_DIM_P1;    // 512
+constexpr int ND = ECORD_DIM_NODE;  // 32
+
+// ------------------------------------------------------------------------------------------------
+// u = LReLU(msg_in([last_sel ; glob]))   one warp per row
+// glob = ((best - score) / n_g, 0)  (SCORE_FROM_BEST_NORM; 2nd feature dead: quirk C)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_policy_pre(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p) {
+    __shared__ float wt[34 * MSG];   // transposed msg_in weight: wt[i][o]
+    __shared__ float wb[MSG];
+    for (int i = threadIdx.x; i < 34 * MSG; i += blockDim.x) wt[i] = w.msg_w[(i % MSG) * 34 + (i / MSG)];
+    if (threadIdx.x < MSG) wb[threadIdx.x] = w.msg_b[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= p.rows) return;
+    const int T = e.num_tradj, gi = m / T;
+    const float x = p.last_sel[(long long)m * ND + lane];
+    const float glob0 = (e.best_score[m] - e.score[m]) / (float)(g.graph_ptr[gi + 1] - g.graph_ptr[gi]);
+    float a0 = wb[lane], a1 = wb[lane + 32];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+        const float xi = __shfl_sync(0xffffffffu, x, i);
+        a0 = fmaf(wt[i * MSG + lane], xi, a0);
+        a1 = fmaf(wt[i * MSG + lane + 32], xi, a1);
+    }
+    a0 = fmaf(wt[32 * MSG + lane], glob0, a0);
+    a1 = fmaf(wt[32 * MSG + lane + 32], glob0, a1);
+    // + wt[33][.] * 0
+    a0 = lrelu(a0); a1 = lrelu(a1);
+    p.u[(long long)m * MSG + lane] = a0;
+    p.u[(long long)m * MSG + lane + 32] = a1;
+    if (p.u_bf16) {
+        __nv_bfloat16 *ub = reinterpret_cast<__nv_bfloat16 *>(p.u_bf16);
+        ub[(long long)m * MSG + lane] = __float2bfloat16(a0);
+        ub[(long long)m * MSG + lane + 32] = __float2bfloat16(a1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 SGEMM, C[M][ldc] (+col offset) = A[M][K] . B[N][K]^T + bias[N]    (both operands K-contiguous)
+// 64x64x16 tiles, 256 threads, 4x4 register blocking.  M % 64 == 0, N % 64 == 0, K % 16 == 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sgemm_nt_bias(const float *__restrict__ A0, const float *__restrict__ A1, const int32_t *step_base, int step_off,
+                const float *__restrict__ B, const float *__restrict__ bias, float *__restrict__ C, int K, int ldc) {
+    // A = A0 when the step parity is even, A1 when odd (double-buffered hidden state)
+    const float *__restrict__ A = (((step_base ? *step_base : 0) + step_off) & 1) ? A1 : A0;
+    __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int lr = tid >> 2, lk = (tid & 3) * 4;        // loader: row 0..63, k-quad
+    const int ty = tid >> 4, tx = tid & 15;             // compute: 16x16 threads, 4x4 each
+    float acc[4][4] = {};
+    const float *Ap = A + (long long)(m0 + lr) * K + lk;
+    const float *Bp = B + (long long)(n0 + lr) * K + lk;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        const float4 a = *reinterpret_cast<const float4 *>(Ap + k0);
+        const float4 b = *reinterpret_cast<const float4 *>(Bp + k0);
+        As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
+        Bs[lk + 0][lr] = b.x; Bs[lk + 1][lr] = b.y; Bs[lk + 2][lr] = b.z; Bs[lk + 3][lr] = b.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const float4 bb = *reinterpret_cast<const float4 *>(bias + n0 + tx * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 o = make_float4(acc[i][0] + bb.x, acc[i][1] + bb.y, acc[i][2] + bb.z, acc[i][3] + bb.w);
+        *reinterpret_cast<float4 *>(C + (long long)(m0 + ty * 4 + i) * ldc + n0 + tx * 4) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRU gate math (fp32 mode), element-wise over [M][1024].  gates = [gi (3072) | gh (3072)] incl. biases.
+// Follows ATen's cell: r = s(gh_r+gi_r), z = s(gh_z+gi_z), n = tanh(gi_n + gh_n*r), h' = (h-n)*z + n.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gru_gates(ecord_policy p, const int32_t *step_base, int step_off) {
+    const int cur = ((step_base ? *step_base : 0) + step_off) & 1;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.rows * H) return;
+    const long long m = i / H;
+    const int j = (int)(i - m * H);
+    const float *gi = p.gates + m * 6144, *gh = gi + 3072;
+    const float *hold = p.hidden + (long long)cur * p.rows_pad * H;
+    float *hnew = p.hidden + (long long)(1 - cur) * p.rows_pad * H;
+    const float r = sigmoidf_acc(gh[j] + gi[j]);
+    const float z = sigmoidf_acc(gh[H + j] + gi[H + j]);
+    const float n = tanhf(__fadd_rn(gi[2 * H + j], __fmul_rn(gh[2 * H + j], r)));
+    const float h = hold[i];
+    const float hn = __fadd_rn(__fmul_rn(__fsub_rn(h, n), z), n);
+    hnew[i] = hn;
+    p.th[i] = tanhf(hn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tail: y1 [M][512] -> LN512 -> LReLU -> W2 -> LN32 -> LReLU = P ; v ; A.   16 rows per block (8 warps x 2),
+// W2 (64 KB) staged in shared memory once per block.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTailRowsPerWarp = 2;
+constexpr int kTailWarps = 8;
+constexpr int kTailRows = kTailRowsPerWarp * kTailWarps;
+struct TailSmem {
+    float w2[ND * P1];          // [o][i]
+    float v1t[ND * ND];         // transposed val_out.1: [i][o]
+    float qt[ND * ECORD_DIM_Q]; // transposed Wq[:, :32]: [i][c]
+};
+
+__global__ void __launch_bounds__(kTailWarps * 32)
+k_policy_tail(ecord_weights w, ecord_policy p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TailSmem &S = *reinterpret_cast<TailSmem *>(smem_raw);
+    for (int i = threadIdx.x; i < ND * P1 / 4; i += blockDim.x)
+        reinterpret_cast<float4 *>(S.w2)[i] = reinterpret_cast<const float4 *>(w.p2_w)[i];
+    for (int i = threadIdx.x; i < ND * ND; i += blockDim.x) S.v1t[i] = w.v1_w[(i % ND) * ND + (i / ND)];
+    for (int i = threadIdx.x; i < ND * ECORD_DIM_Q; i += blockDim.x)
+        S.qt[i] = w.q1_w[(i % ECORD_DIM_Q) * ECORD_DIM_Q + (i / ECORD_DIM_Q)];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = 0; rr < kTailRowsPerWarp; ++rr) {
+        const int m = blockIdx.x * kTailRows + warp * kTailRowsPerWarp + rr;
+        if (m >= p.rows) break;
+        // ---- LN512 + LReLU (lane holds elements lane + 32 j) ----
+        float x[16];
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = p.y1[(long long)m * P1 + lane + 32 * j]; s += x[j]; }
+        const float mean = warp_sum(s) * (1.0f / P1);
+        float ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float d = x[j] - mean; ss = fmaf(d, d, ss); }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.0f / P1) + kLnEps);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int i = lane + 32 * j;
+            x[j] = lrelu((x[j] - mean) * rstd * w.ln1_w[i] + w.ln1_b[i]);
+        }
+        // ---- W2: 512 -> 32; lane o ends up holding output o ----
+        float mine = 0.0f;
+#pragma unroll 4
+        for (int o = 0; o < ND; ++o) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a = fmaf(S.w2[o * P1 + lane + 32 * j], x[j], a);
+            a = warp_sum(a);
+            if (lane == o) mine = a;
+        }
+        mine += w.p2_b[lane];
+        // ---- LN32 + LReLU ----
+        const float mean2 = warp_sum(mine) * (1.0f / ND);
+        const float d2 = mine - mean2;
+        const float rstd2 = rsqrtf(warp_sum(d2 * d2) * (1.0f / ND) + kLnEps);
+        const float Pv = lrelu(d2 * rstd2 * w.ln2_w[lane] + w.ln2_b[lane]);
+        p.P[(long long)m * ND + lane] = Pv;
+        // ---- state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 ----
+        const float tp = tanhf(Pv);
+        float hv = w.v1_b[lane];
+        float a0 = w.q1_b[lane], a1 = w.q1_b[lane + 32];
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+            const float ti = __shfl_sync(0xffffffffu, tp, i);
+            const float pi = __shfl_sync(0xffffffffu, Pv, i);
+            hv = fmaf(S.v1t[i * ND + lane], ti, hv);
+            a0 = fmaf(S.qt[i * ECORD_DIM_Q + lane], pi, a0);
+            a1 = fmaf(S.qt[i * ECORD_DIM_Q + lane + 32], pi, a1);
+        }
+        const float vv = warp_sum(w.v2_w[lane] * lrelu(hv));
+        if (lane == 0) p.v[m] = vv + w.v2_b[0];
+        p.A[(long long)m * ECORD_DIM_Q + lane] = a0;
+        p.A[(long long)m * ECORD_DIM_Q + lane + 32] = a1;
+    }
+}
+}  // namespace
+
+// the hidden buffer holding the current state is ((*step_base) + step_off) & 1, resolved on the device so that a
+// captured CUDA graph stays valid when replayed at a later step count
+int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                       const int32_t *step_base, int step_off, int gemm_mode, cudaStream_t st) {
+    const int M = p->rows, Mp = p->rows_pad;
+    k_policy_pre<<<ceil_div((long long)M * 32, 256), 256, 0, st>>>(*g, *env, *w, *p);
+    ECORD_LAUNCH_CHECK();
+    if (gemm_mode == ECORD_GEMM_FP32) {
+        const float *h0 = p->hidden, *h1 = p->hidden + (long long)Mp * H;
+        k_sgemm_nt_bias<<<dim3(3072 / 64, Mp / 64), 256, 0, st>>>(p->u, p->u, nullptr, 0, w->gru_wih, w->gru_bih, p->gates,
+                                                                   MSG, 6144);
+        ECORD_LAUNCH_CHECK();
+        k_sgemm_nt_bias<<<dim3(3072 / 64, Mp / 64), 256, 0, st>>>(h0, h1, step_base, step_off, w->gru_whh, w->gru_bhh,
+                                                                   p->gates + 3072, H, 6144);
+        ECORD_LAUNCH_CHECK();
+        k_gru_gates<<<ceil_div((long long)M * H, 256), 256, 0, st>>>(*p, step_base, step_off);
+        ECORD_LAUNCH_CHECK();
+        k_sgemm_nt_bias<<<dim3(P1 / 64, Mp / 64), 256, 0, st>>>(p->th, p->th, nullptr, 0, w->p1_w, w->p1_b, p->y1, H, P1);
+        ECORD_LAUNCH_CHECK();
+    } else {
+        int rc = launch_gru_tc_ex(w, p, step_base, step_off, st);
+        if (rc) return rc;
+        rc = launch_proj1_tc(w, p, st);
+        if (rc) return rc;
+    }
+    k_policy_tail<<<ceil_div(M, kTailRows), kTailWarps * 32, sizeof(TailSmem), st>>>(*w, *p);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+int policy_kernels_per_step(int gemm_mode) { return gemm_mode == ECORD_GEMM_FP32 ? 6 : 4; }
+
+int policy_init_attrs() {
+    ECORD_CUDA(cudaFuncSetAttribute(k_policy_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+    return tc_init_attrs();
+}
+
+int check_policy(const ecord_policy *p, int gemm_mode) {
+    ECORD_RET_IF(!p, ECORD_E_NULL);
+    ECORD_RET_IF(p->rows <= 0 || p->rows_pad < p->rows || (p->rows_pad % 128) != 0, ECORD_E_SIZE);
+    ECORD_RET_IF(!p->hidden || !p->u || !p->y1 || !p->P || !p->A || !p->v || !p->last_sel, ECORD_E_NULL);
+    if (gemm_mode == ECORD_GEMM_FP32) ECORD_RET_IF(!p->gates || !p->th, ECORD_E_NULL);
+    else ECORD_RET_IF(!p->hidden_bf16 || !p->th_bf16 || !p->u_bf16, ECORD_E_NULL);
+    return 0;
+}
+
+extern "C" int ecord_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                                 int32_t cur, int32_t gemm_mode, void *stream) {
+    ECORD_RET_IF(!g || !env || !w, ECORD_E_NULL);
+    ECORD_RET_IF(gemm_mode != ECORD_GEMM_FP32 && gemm_mode != ECORD_GEMM_BF16, ECORD_E_UNSUPPORTED);
+    ECORD_RET_IF(cur != 0 && cur != 1, ECORD_E_SIZE);
+    int rc = check_policy(p, gemm_mode);
+    if (rc) return rc;
+    ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj, ECORD_E_SIZE);
+    if (gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!w->gru_w_bf16 || !w->p1_w_bf16, ECORD_E_NULL);
+    if ((rc = policy_init_attrs())) return rc;
+    return launch_policy_step(g, env, w, p, nullptr, cur, gemm_mode, as_stream(stream));
+}

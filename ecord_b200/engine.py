@@ -1,0 +1,310 @@
+"""Device-side objects of the rollout engine: graph batch, weights, and per-rollout state.
+
+PyTorch is used for device memory, streams and (in dist.py) torch.distributed only; every computation
+on the hot path is a kernel of libecord_b200.so reached through the C ABI (include/ecord_b200.h).
+There is no CPU or eager-PyTorch fallback: without a CUDA device these classes raise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GEMM_BF16, GEMM_FP32, check, ptr
+from .network import check_state_dicts
+
+_GEMM_MODES = {"fp32": GEMM_FP32, "bf16": GEMM_BF16}
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise _lib.EcordError("ecord_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device(device if device is not None else "cuda")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceGraph:
+    """Uploads one batch (data.TgBatch) and fills the C struct `ecord_graph`."""
+
+    def __init__(self, tg, device=None):
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        self.tg = tg
+        N, G, E = tg.num_nodes, tg.num_graphs, tg.num_edges
+        src, dst, w = tg.np_src, tg.np_dst, tg.np_w
+        deg = np.bincount(src, minlength=N)
+        row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+        # incoming lists in GLOBAL EDGE ORDER: stable sort of the edge list by destination
+        order = np.argsort(dst, kind="stable")
+        in_ptr = np.concatenate([[0], np.cumsum(np.bincount(dst, minlength=N))]).astype(np.int32)
+        gep = np.concatenate([[0], np.cumsum(tg.np_edge_counts)]).astype(np.int64)
+        dev = self.device
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        self.graph_ptr = up(tg.np_ptr.astype(np.int32))
+        self.node_graph = up(np.repeat(np.arange(G), tg.num_nodes_list).astype(np.int32))
+        self.row_ptr = up(row_ptr)
+        self.col = up(dst.astype(np.int32))
+        self.w = up(w.astype(np.float32))
+        self.graph_edge_ptr = up(gep)
+        self.in_ptr = up(in_ptr)
+        self.in_src = up(src[order].astype(np.int32))
+        self.in_w = up(w[order].astype(np.float32))
+        self.N, self.G, self.E = N, G, E
+        self.n_max = int(tg.num_nodes_list.max())
+        self.num_nodes_list = tg.num_nodes_list
+        self.c = _lib.Graph(G, N, E, self.n_max, ptr(self.graph_ptr), ptr(self.node_graph), ptr(self.row_ptr),
+                            ptr(self.col), ptr(self.w), ptr(self.graph_edge_ptr), ptr(self.in_ptr),
+                            ptr(self.in_src), ptr(self.in_w))
+
+    def plane_index(self, T):
+        """int64 [N,T]: plane offset of every (vertex, trajectory) -- host-side layout helper for views."""
+        ptrs = torch.from_numpy(self.tg.np_ptr)
+        n_of = torch.from_numpy(self.num_nodes_list)[self.tg.batch]
+        lo = ptrs[:-1][self.tg.batch]
+        v_local = torch.arange(self.N) - lo
+        t = torch.arange(T)
+        return (lo * T).unsqueeze(1) + t.unsqueeze(0) * n_of.unsqueeze(1) + v_local.unsqueeze(1)
+
+
+class DeviceWeights:
+    """fp32 weights on the device under the reference's names + the packed / folded forms."""
+
+    def __init__(self, state_dicts, device=None, pack_bf16=True):
+        self.device = _require_cuda(device)
+        self.lib = _lib.load()
+        sd = check_state_dicts(state_dicts)
+        self.host = sd
+        self.t = {}
+        kw = {}
+        for field, mod, key in _lib.WEIGHT_FIELDS:
+            self.t[field] = sd[mod][key].to(self.device).contiguous()
+            kw[field] = ptr(self.t[field])
+        # folded Q-head constants (host array, passed to the kernel by value)
+        r = sd['rnn']
+        self.q_fold = torch.empty(6 * 64, dtype=torch.float32)
+        check(self.lib.ecord_fold_q_host(ptr(r['mlp_out.0.weight']), ptr(sd['node_encoder']['0.weight']),
+                                         ptr(r['mlp_out.1.weight']), ptr(r['mlp_out.1.bias']),
+                                         ptr(r['mlp_out.3.weight']), ptr(self.q_fold)), "ecord_fold_q_host")
+        self.gru_w_bf16 = self.p1_w_bf16 = None
+        if pack_bf16:
+            self.gru_w_bf16 = torch.empty(_lib.GRU_PACK_ELEMS, dtype=torch.bfloat16, device=self.device)
+            self.p1_w_bf16 = torch.empty(512 * 1024, dtype=torch.bfloat16, device=self.device)
+        self.c = _lib.Weights(gru_w_bf16=ptr(self.gru_w_bf16), p1_w_bf16=ptr(self.p1_w_bf16), q_fold=ptr(self.q_fold), **kw)
+        if pack_bf16:
+            check(self.lib.ecord_pack_weights(C.byref(self.c), _stream()), "ecord_pack_weights")
+
+
+class RolloutState:
+    """Environment + policy state of one rollout batch (G graphs x T trajectories) on one GPU.
+
+    Step-wise methods (`policy_step`, `q_select`, `env_step`) expose the individual kernels for parity
+    tests and `log_stats`; `run()` executes whole steps through the CUDA-graph plan."""
+
+    def __init__(self, dgraph, weights, num_tradj, gemm="bf16", compat=True, tau=0.0, seed=0,
+                 max_steps=0, log_scores=True, log_actions=True, steps_per_graph=16, dump_q=False):
+        self.lib = _lib.load()
+        self.g, self.w = dgraph, weights
+        dev = dgraph.device
+        self.device = dev
+        self.T = T = int(num_tradj)
+        self.gemm = _GEMM_MODES[gemm]
+        if self.gemm == GEMM_BF16 and weights.gru_w_bf16 is None:
+            raise ValueError("weights were created with pack_bf16=False")
+        self.compat, self.tau, self.seed = bool(compat), float(tau), int(seed)
+        N, G = dgraph.N, dgraph.G
+        M = G * T
+        Mp = (M + 127) // 128 * 128
+        self.M, self.Mp = M, Mp
+        f32 = dict(dtype=torch.float32, device=dev)
+        # environment (trajectory-major planes)
+        self.peek = torch.empty(N * T, **f32)
+        self.sp = torch.empty(N * T, dtype=torch.int32, device=dev)
+        self.best_state = torch.empty(N * T, dtype=torch.uint8, device=dev)
+        self.score = torch.empty(M, **f32)
+        self.best_score = torch.empty(M, **f32)
+        self.best_step = torch.empty(M, dtype=torch.int32, device=dev)
+        self.env_c = _lib.Env(T, 0, ptr(self.peek), ptr(self.sp), ptr(self.best_state), ptr(self.score),
+                              ptr(self.best_score), ptr(self.best_step))
+        # policy
+        self.hidden = torch.zeros(2, Mp, 1024, **f32)
+        self.u = torch.zeros(Mp, 64, **f32)
+        self.y1 = torch.zeros(Mp, 512, **f32)
+        self.P = torch.zeros(Mp, 32, **f32)
+        self.A = torch.zeros(Mp, 64, **f32)
+        self.v = torch.zeros(Mp, **f32)
+        self.last_sel = torch.zeros(Mp, 32, **f32)
+        self.actions = torch.zeros(M, dtype=torch.int32, device=dev)
+        self.hidden_bf16 = self.th_bf16 = self.u_bf16 = self.gates = self.th = None
+        if self.gemm == GEMM_BF16:
+            self.hidden_bf16 = torch.zeros(2, Mp, 1024, dtype=torch.bfloat16, device=dev)
+            self.th_bf16 = torch.zeros(Mp, 1024, dtype=torch.bfloat16, device=dev)
+            self.u_bf16 = torch.zeros(Mp, 64, dtype=torch.bfloat16, device=dev)
+        else:
+            self.gates = torch.zeros(Mp, 6144, **f32)
+            self.th = torch.zeros(Mp, 1024, **f32)
+        self.q = torch.zeros(N * T, **f32) if (dump_q or self.tau > 0) else None
+        self.gnn_out = torch.empty(N, 16, **f32)
+        self.node_emb = torch.empty(N, 16, **f32)
+        self.node_B = torch.empty(N, 64, **f32)
+        self.policy_c = _lib.Policy(M, Mp, ptr(self.hidden), ptr(self.hidden_bf16), ptr(self.th_bf16), ptr(self.u_bf16),
+                                    ptr(self.u), ptr(self.gates), ptr(self.th), ptr(self.y1), ptr(self.P), ptr(self.A),
+                                    ptr(self.v), ptr(self.last_sel), ptr(self.node_emb), ptr(self.node_B),
+                                    ptr(self.actions), ptr(self.q))
+        # logs + step counter
+        self.max_steps = int(max_steps)
+        self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.score_log = torch.empty(max(self.max_steps, 1), M, **f32) if log_scores and max_steps > 0 else None
+        self.action_log = (torch.empty(max(self.max_steps, 1), M, dtype=torch.int32, device=dev)
+                           if log_actions and max_steps > 0 else None)
+        self.steps_per_graph = int(steps_per_graph)
+        self.steps_done = 0
+        self.plan = None
+        self.init_state_dev = None
+        self.kernel_launches = 0
+
+    # ---- set-up -----------------------------------------------------------------------------
+    def gnn_embed(self):
+        """t=0 embedding (a5): fills gnn_out, node_emb and node_B."""
+        ws = torch.empty(self.lib.ecord_gnn_workspace_bytes(self.g.N), dtype=torch.uint8, device=self.device)
+        check(self.lib.ecord_gnn_embed(C.byref(self.g.c), C.byref(self.w.c), ptr(self.gnn_out), ptr(self.node_emb),
+                                       ptr(self.node_B), ptr(ws), _stream()), "ecord_gnn_embed")
+        self.kernel_launches += 16
+        self._ws = ws
+
+    def env_init(self, init_state):
+        """a2: init_state int8 [N,T] (host numpy / torch, reference layout)."""
+        s = torch.as_tensor(np.ascontiguousarray(np.asarray(init_state).astype(np.int8)))
+        if tuple(s.shape) != (self.g.N, self.T):
+            raise AssertionError(f"init_state must have shape {(self.g.N, self.T)}.  Got {tuple(s.shape)}.")
+        self.init_state_dev = s.to(self.device, non_blocking=False)
+        check(self.lib.ecord_env_init(C.byref(self.g.c), C.byref(self.env_c), ptr(self.init_state_dev), _stream()),
+              "ecord_env_init")
+        self.kernel_launches += 2
+        self.hidden.zero_()
+        if self.hidden_bf16 is not None:
+            self.hidden_bf16.zero_()
+        self.last_sel.zero_()
+        self.step_counter.zero_()
+        self.steps_done = 0
+
+    # ---- step-wise API (tests, log_stats) -----------------------------------------------------
+    def policy_step(self):
+        check(self.lib.ecord_policy_step(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c), C.byref(self.policy_c),
+                                         self.steps_done & 1, self.gemm, _stream()), "ecord_policy_step")
+        self.kernel_launches += 6 if self.gemm == GEMM_FP32 else 4
+
+    def q_select(self, forced_actions=None):
+        fa = None
+        if forced_actions is not None:
+            fa = torch.as_tensor(forced_actions).to(self.device, torch.int32).contiguous().view(-1)
+            assert fa.numel() == self.M
+        check(self.lib.ecord_q_select(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c), C.byref(self.policy_c),
+                                      self.steps_done, self.tau, self.seed, int(self.compat), ptr(fa), _stream()),
+              "ecord_q_select")
+        self.kernel_launches += 1
+        self._fa = fa
+
+    def env_step(self, actions=None):
+        a = self.actions if actions is None else torch.as_tensor(actions).to(self.device, torch.int32).contiguous().view(-1)
+        row = None
+        if self.score_log is not None and self.steps_done < self.max_steps:
+            row = self.score_log[self.steps_done]
+            if self.action_log is not None:
+                self.action_log[self.steps_done].copy_(a)
+        check(self.lib.ecord_env_step(C.byref(self.g.c), C.byref(self.env_c), ptr(a), self.steps_done, ptr(row), _stream()),
+              "ecord_env_step")
+        self.kernel_launches += 1
+        self.steps_done += 1
+        self.step_counter.fill_(self.steps_done)
+
+    def step(self, forced_actions=None):
+        self.policy_step()
+        self.q_select(forced_actions)
+        self.env_step()
+
+    # ---- fused loop -------------------------------------------------------------------------
+    def _make_plan(self):
+        desc = _lib.RolloutDesc(C.pointer(self.g.c), C.pointer(self.env_c), C.pointer(self.w.c), C.pointer(self.policy_c),
+                                self.gemm, int(self.compat), self.tau, self.steps_per_graph, self.seed,
+                                ptr(self.step_counter), ptr(self.score_log), ptr(self.action_log), self.max_steps, 0)
+        out = C.c_void_p()
+        self._plan_stream = torch.cuda.current_stream()
+        check(self.lib.ecord_rollout_plan_create(C.byref(desc), _stream(), C.byref(out)), "ecord_rollout_plan_create")
+        self.plan = out
+
+    def run(self, num_steps):
+        """Enqueue `num_steps` whole steps (asynchronous).  Uses CUDA graphs of `steps_per_graph` steps."""
+        if self.plan is None:
+            self._make_plan()
+        n = C.c_int64(0)
+        check(self.lib.ecord_rollout_plan_run(self.plan, int(num_steps), C.byref(n)), "ecord_rollout_plan_run")
+        self.kernel_launches += n.value
+        self.steps_done += int(num_steps)
+
+    def close(self):
+        if self.plan is not None:
+            self.lib.ecord_rollout_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- views in the reference's layouts (parity checks, logs) ------------------------------
+    def export(self, normalise=False):
+        """(node_features [N,T,3], glob_features [G,T,2], best_states [N,T]) as torch CUDA tensors."""
+        N, G, T = self.g.N, self.g.G, self.T
+        nf = torch.empty(N, T, 3, dtype=torch.float32, device=self.device)
+        gf = torch.empty(G, T, 2, dtype=torch.float32, device=self.device)
+        bs = torch.empty(N, T, dtype=torch.float32, device=self.device)
+        check(self.lib.ecord_env_export(C.byref(self.g.c), C.byref(self.env_c), self.steps_done, int(normalise),
+                                        ptr(nf), ptr(gf), ptr(bs), _stream()), "ecord_env_export")
+        return nf, gf, bs
+
+    def plane_to_nt(self, plane):
+        out = torch.empty(self.g.N, self.T, dtype=torch.float32, device=self.device)
+        check(self.lib.ecord_plane_to_nt(C.byref(self.g.c), self.T, ptr(plane), ptr(out), _stream()), "ecord_plane_to_nt")
+        return out
+
+    def q_values(self):
+        """Q-values of the last q_select in the reference layout [N,T] (needs dump_q=True)."""
+        return self.plane_to_nt(self.q)
+
+    def hidden_state(self):
+        """Current GRU state [G,T,1024]."""
+        return self.hidden[self.steps_done & 1, :self.M].view(self.g.G, self.T, 1024)
+
+    def scores(self):
+        return self.score.view(self.g.G, self.T)
+
+    def best_from_log(self, num_steps):
+        out = torch.empty(self.M, dtype=torch.float32, device=self.device)
+        check(self.lib.ecord_score_log_max(ptr(self.score_log), int(num_steps), self.M, ptr(out), _stream()),
+              "ecord_score_log_max")
+        return out.view(self.g.G, self.T)
+
+    def best_states_batched(self, true_snapshot=False):
+        """[G, n_max, T], -1 padded (tradjectories.py:324-328,378-385).  true_snapshot=False gives the
+        reference's semantics (quirk D); True replays the action log up to each trajectory's best step."""
+        N, G, T = self.g.N, self.g.G, self.T
+        if true_snapshot:
+            if self.action_log is None or self.init_state_dev is None:
+                raise ValueError("true_snapshot needs log_actions=True")
+            plane = torch.empty(N * T, dtype=torch.uint8, device=self.device)
+            check(self.lib.ecord_best_state_snapshot(C.byref(self.g.c), C.byref(self.env_c), ptr(self.init_state_dev),
+                                                     ptr(self.action_log), min(self.steps_done, self.max_steps),
+                                                     ptr(plane), _stream()), "ecord_best_state_snapshot")
+            flat = self.plane_to_nt(plane.float())
+        else:
+            flat = self.export()[2]
+        flat = flat.cpu()
+        out = -torch.ones(G, self.g.n_max, T)
+        ptrs = self.g.tg.np_ptr
+        for gi in range(G):
+            out[gi, :ptrs[gi + 1] - ptrs[gi]] = flat[ptrs[gi]:ptrs[gi + 1]]
+        return out

@@ -1,0 +1,233 @@
+"""B200 drop-in for the reference's solver seam B1.
+
+`B200Solver` keeps the constructor keywords, methods and log contract of
+`ecord.solvers.solver.DQNSolver` as used by the test-time path
+(`experiments/validate.py:167-202` -> `ecord/validate/testing.py:146-230`):
+
+    solver = B200Solver(gnn=..., rnn=..., gnn2rnn=..., node_encoder=..., node_features=..., global_features=...)
+    solver.load("checkpoint.pth"); solver.test()
+    log = solver.rollout(batch, num_tradj, num_steps, tau=0, use_epsilon=False, ...)
+
+but `rollout()` runs entirely on the GPU: one GNN pass, one env-init, then S fused steps as CUDA graphs
+(engine.RolloutState), with a single device->host copy of the score log at the end.
+`gnn`, `rnn`, `gnn2rnn`, `node_encoder` may be torch modules (anything with .state_dict()) or state dicts.
+Training-only arguments are accepted and ignored (the engine is inference-only).
+"""
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import DeviceGraph, DeviceWeights, RolloutState
+from .network import check_state_dicts, state_dicts_from_checkpoint
+from .observations import CANONICAL_GLOB_FEATURES, CANONICAL_NODE_FEATURES, check_canonical
+
+
+def _sd(x):
+    return x.state_dict() if hasattr(x, "state_dict") else x
+
+
+class _ActorShim:
+    """`solver.actor.reset_state()` is called between rollouts by test_solver (testing.py:197)."""
+
+    def __init__(self, solver):
+        self._solver = solver
+
+    def reset_state(self):
+        self._solver._last_state = None
+
+    def test(self):
+        pass
+
+    def train(self):
+        pass
+
+
+class B200Solver:
+    def __init__(self, gnn, rnn, gnn2rnn, node_encoder=None, node_classifier=None,
+                 add_glob_to_nodes=False, add_glob_to_obs=True, detach_gnn_from_rnn=False,
+                 node_features=CANONICAL_NODE_FEATURES, global_features=CANONICAL_GLOB_FEATURES,
+                 allow_reversible_actions=True, intermediate_reward=0, revisit_reward=0,
+                 use_double_q_networks=False, use_gnn_embeddings_from_buffer=False, use_ecodqn=False,
+                 default_actor_idx=None, tau=0, alpha=0, munch_lower_log_clip=-1,
+                 initial_epsilon=1, final_epsilon=0.05, final_epsilon_step=1000, device=None,
+                 # engine options (not in the reference)
+                 gemm="bf16", compat=True, steps_per_graph=16, seed=0):
+        if use_ecodqn or use_double_q_networks:
+            raise NotImplementedError("only the single-Q ECORD actor (Actor_Q, actors/ecord.py:26) is implemented")
+        if node_classifier is not None:
+            raise NotImplementedError("network initialisation head is outside the canonical configuration")
+        if node_encoder is None or add_glob_to_nodes or not add_glob_to_obs:
+            raise NotImplementedError("canonical ECORD wiring expected: node_encoder set, add_glob_to_nodes=False, "
+                                      "add_glob_to_obs=True (experiments/train.py:88-90)")
+        check_canonical(node_features, global_features)
+        if not torch.cuda.is_available():
+            raise _lib.EcordError("B200Solver needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.lib = _lib.load()          # fail loudly, now, if the extension is missing
+        self.tau = tau
+        self.gemm, self.compat, self.steps_per_graph, self.seed = gemm, compat, steps_per_graph, seed
+        self.node_features, self.global_features = node_features, global_features
+        self.is_training = False
+        self.trainable = False
+        self.num_env_steps = self.num_rollouts = self.num_param_steps = 0
+        self.initial_epsilon, self.final_epsilon, self.final_epsilon_step = initial_epsilon, final_epsilon, final_epsilon_step
+        self.set_weights({'gnn': _sd(gnn), 'rnn': _sd(rnn), 'gnn2rnn': _sd(gnn2rnn), 'node_encoder': _sd(node_encoder)})
+        self.actor = _ActorShim(self)
+        self._last_state = None
+        self._graph_cache = (None, None)
+
+    # ---- weights ------------------------------------------------------------------------------
+    def set_weights(self, state_dicts):
+        self.state_dicts = check_state_dicts(state_dicts)
+        self.weights = DeviceWeights(self.state_dicts, self.device, pack_bf16=True)
+
+    def load(self, fname, quiet=False):
+        """Ingest a reference checkpoint written by DQNSolver.save (solver.py:582-617)."""
+        checkpoint = torch.load(fname, map_location="cpu", weights_only=False)
+        self.set_weights(state_dicts_from_checkpoint(checkpoint))
+        for k in ("num_env_steps", "num_rollouts", "num_param_steps", "initial_epsilon", "final_epsilon",
+                  "final_epsilon_step"):
+            if k in checkpoint:
+                setattr(self, k, checkpoint[k])
+        if not quiet:
+            print(f"Loaded DQNSolver checkpoint from {fname} into the B200 engine.")
+
+    def save(self, fname, quiet=False):
+        import os
+        if os.path.splitext(fname)[-1] != '.pth':
+            fname += '.pth'
+        ck = {'actor:checkpoint': {f'{m}:state_dict': sd for m, sd in self.state_dicts.items()},
+              'num_env_steps': self.num_env_steps, 'num_rollouts': self.num_rollouts,
+              'num_param_steps': self.num_param_steps, 'initial_epsilon': self.initial_epsilon,
+              'final_epsilon': self.final_epsilon, 'final_epsilon_step': self.final_epsilon_step}
+        torch.save(ck, fname)
+        return fname
+
+    def train(self):
+        raise NotImplementedError("the B200 engine is inference-only (test-time rollout)")
+
+    def test(self):
+        self.is_training = False
+
+    def set_training(self, is_training):
+        if is_training:
+            self.train()
+
+    # ---- rollout (seam B1) ---------------------------------------------------------------------
+    def _device_graph(self, batch):
+        tg = batch.tg
+        if self._graph_cache[0] is tg:
+            return self._graph_cache[1]
+        dg = DeviceGraph(tg, self.device)
+        self._graph_cache = (tg, dg)
+        return dg
+
+    @torch.no_grad()
+    def rollout(self, batch, num_tradj=1, num_steps=-1, log_stats=False, callbacks=None, use_epsilon=True,
+                use_network_initialisation=False, tau=None, max_time=None, pre_solve_with_greedy=False,
+                post_solve_with_greedy_from_best=False, init_state=None, gemm=None, traj_slice=None):
+        """Same contract as DQNSolver.rollout (solver.py:196-377) for the test-time path.
+        Extra keywords: init_state (int8 [N, num_tradj]) pins the initial spins (the reference draws them
+        from numpy's global RNG, tradjectories.py:64 -- reproduced here when init_state is None);
+        traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU sharding)."""
+        if use_network_initialisation or pre_solve_with_greedy or post_solve_with_greedy_from_best or callbacks:
+            raise NotImplementedError("network initialisation / greedy pre-/post-solve / callbacks are not implemented "
+                                      "by the B200 engine yet (SURVEY.md 8f)")
+        if max_time is not None:
+            raise NotImplementedError("max_time needs a host check per step; not supported by the fused loop")
+        tau = self.tau if tau is None else tau
+        tau = 0.0 if tau is None else float(tau)
+        log = defaultdict(list)
+        t_all = time.time()
+        dg = self._device_graph(batch)
+        N, G = dg.N, dg.G
+        num_graphs = len(batch.info.num_nodes) if batch.info is not None else G
+        assert num_graphs == G
+
+        if num_steps < 0:
+            S = int(abs(num_steps) * int(np.max(dg.num_nodes_list)))   # loop runs to the max (solver.py:306-316)
+        else:
+            S = int(num_steps)
+
+        if init_state is None:
+            init_state = np.random.randint(0, 2, (N, num_tradj), dtype=np.int8)   # tradjectories.py:64
+        else:
+            if torch.is_tensor(init_state):
+                init_state = init_state.cpu().numpy()
+            assert init_state.shape == (N, num_tradj), \
+                f"init_state must have shape {(N, num_tradj)}.  Got {init_state.shape}."
+            init_state = init_state.astype(np.int8)
+        if traj_slice is not None:
+            init_state = np.ascontiguousarray(init_state[:, traj_slice[0]:traj_slice[1]])
+        T = init_state.shape[1]
+
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        state = RolloutState(dg, self.weights, T, gemm=gemm or self.gemm, compat=self.compat, tau=tau, seed=self.seed,
+                             max_steps=S, log_scores=True, log_actions=True, steps_per_graph=self.steps_per_graph,
+                             dump_q=False)
+        ev[0].record()
+        state.gnn_embed()
+        ev[1].record()
+        state.env_init(init_state)
+        init_score = state.scores().clone()
+        ev[2].record()
+
+        per_step = defaultdict(list)
+        if log_stats:
+            # per-step peeks / states need the [G, n_max, T] views each step -> step-wise path
+            for _ in range(S):
+                nf, _, _ = state.export()
+                per_step['peeks'].append(self._flat2batch(dg, nf[..., 1].cpu(), -1e10))
+                per_step['state'].append(self._flat2batch(dg, nf[..., 0].cpu(), -1))
+                state.step()
+                per_step['actions'].append(state.actions.view(G, T).cpu().long())
+        else:
+            state.run(S)
+        ev[3].record()
+        ev[3].synchronize()
+        t_init_emb = ev[0].elapsed_time(ev[1]) * 1e-3
+        t_setup = ev[1].elapsed_time(ev[2]) * 1e-3
+        t_rollout = ev[2].elapsed_time(ev[3]) * 1e-3
+
+        scores = state.score_log[:S].view(S, G, T).cpu() if S > 0 else torch.zeros(0, G, T)
+        init_score = init_score.cpu()
+        best_step = state.best_step.view(G, T).cpu()
+        log['t_init_emb'].append(torch.tensor([t_init_emb]))
+        log['t_setup'].append(torch.tensor([t_setup]))
+        log['init_score'] = init_score
+        dt = t_rollout / max(S, 1)
+        # t_opt: time at which each trajectory reached its best score (solver.py:241-242), from the step index
+        log['t_opt'] = t_init_emb + best_step.float() * dt
+        prev = init_score
+        for s in range(S):
+            log['scores'].append(scores[s])
+            log['scores0'].append(prev)
+            prev = scores[s]
+            log['t_step'].append(dt)
+            log['t_inf'].append(dt)
+        if log_stats:
+            for k, v in per_step.items():
+                log[k] = v
+        log['best_state'] = state.best_states_batched(true_snapshot=not self.compat)
+        log['t_rollout'] = torch.tensor([t_rollout])
+        log['t_tot'] = torch.tensor([t_init_emb + t_rollout])
+        log['kernel_launches'] = state.kernel_launches
+        self._last_state = state
+        self.last_wall = time.time() - t_all
+        return log
+
+    @staticmethod
+    def _flat2batch(dg, arr, fill):
+        G, T = dg.G, arr.shape[1]
+        out = fill * torch.ones(G, dg.n_max, T)
+        p = dg.tg.np_ptr
+        for gi in range(G):
+            out[gi, :p[gi + 1] - p[gi]] = arr[p[gi]:p[gi + 1]]
+        return out
+
+
+# the name the reference's scripts construct (experiments/validate.py:187-200)
+DQNSolver = B200Solver

@@ -1,0 +1,266 @@
+/*
+ * ecord_b200.h -- C ABI of libecord_b200.so, the B200 (sm_100a) rollout engine for ECORD.
+ *
+ * This is the drop-in boundary for the reference's test-time rollout hot path
+ * (SURVEY.md section 8).  Plain C: pointers, sizes and PODs only -- no torch / C++ types.
+ * Reference citations are relative to the upstream tree (tomdbar/ecord).
+ *
+ * Conventions
+ *   - Every entry point returns int: 0 = ok, <0 = argument error (ECORD_E_*), >0 = cudaError_t.
+ *     Nothing throws, exits or prints.  ecord_error_string() names a code.
+ *   - Unless a function says "host", every pointer is caller-allocated DEVICE memory; the library
+ *     allocates nothing on the data path (plans own only their CUDA graphs).  Kernels are enqueued
+ *     on the `stream` argument (a cudaStream_t passed as void*) and do not synchronise.
+ *   - Re-entrant: no global mutable state; one host thread per GPU is the intended use.
+ *   - Vertex ids: "global" = index into the flat batch [0,N); "local" = index inside its graph.
+ *
+ * Device data layout (DESIGN.md "Data layout in HBM")
+ *   The reference keeps AoS node_features f32[N][T][F] on the host (tradjectories.py:150-166).
+ *   Here the per-(vertex,trajectory) state is SoA and TRAJECTORY-MAJOR per graph, so that one
+ *   (graph, trajectory) unit is one contiguous row of n_g elements:
+ *        plane_offset(g, t, v) = graph_ptr[g] * T + t * n_g + v          (v local)
+ *     peek  f32 : cut gain if v flips (reference NodeObservation.PEEK, un-normalised)
+ *     sp    i32 : (last_flip_step << 1) | state      static = steps_done - last_flip_step
+ *     best  u8  : reference "best_states" (only the flipped vertex is recorded on a new best,
+ *                 _tradjectory_step_cy.pyx:142-146)
+ *   Per-(graph,trajectory) scalars are indexed m = g * T + t.
+ */
+#ifndef ECORD_B200_H
+#define ECORD_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECORD_ABI_VERSION 1
+
+/* error codes (<0) */
+#define ECORD_E_NULL      (-1)  /* required pointer is NULL */
+#define ECORD_E_SIZE      (-2)  /* size/shape argument out of range */
+#define ECORD_E_ALIGN     (-3)  /* pointer not aligned as documented */
+#define ECORD_E_UNSUPPORTED (-4)/* feature table / option not supported by this kernel */
+#define ECORD_E_DEVICE    (-5)  /* device is not sm_100 / required driver entry point missing */
+#define ECORD_E_PLAN      (-6)  /* invalid plan handle or plan state */
+
+/* network dimensions (canonical ECORD net, experiments/train.py:55-96) */
+#define ECORD_DIM_GNN   16
+#define ECORD_DIM_NODE  32
+#define ECORD_DIM_MSG   64
+#define ECORD_DIM_H     1024
+#define ECORD_DIM_P1    512
+#define ECORD_DIM_Q     64
+#define ECORD_STATIC_CLIP 40   /* Tradjectories._clip_features_max, tradjectories.py:16 */
+
+/* GRU / projection arithmetic */
+#define ECORD_GEMM_FP32 0   /* CUDA-core fp32 FMA (parity mode; 1e-4 rel vs reference)            */
+#define ECORD_GEMM_BF16 1   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM (2e-2 rel) */
+
+/* ---- graph batch: replaces GraphBatcher/Batch.tg (environment/data.py:53-83) + the CSR views
+ *      Tradjectories builds (tradjectories.py:38-60).  All arrays read-only. ---- */
+typedef struct ecord_graph {
+    int32_t num_graphs;            /* G */
+    int32_t num_nodes;             /* N = sum n_g */
+    int32_t num_edges;             /* E = directed edge count (2 x undirected) */
+    int32_t n_max;                 /* max n_g */
+    const int32_t *graph_ptr;      /* [G+1] vertex offsets (Batch.ptr) */
+    const int32_t *node_graph;     /* [N]   graph id of each vertex (Batch.batch) */
+    const int32_t *row_ptr;        /* [N+1] CSR by source (edge_by_node_ptr) */
+    const int32_t *col;            /* [E]   neighbour, global id, reference edge order (edges_by_node[1]) */
+    const float   *w;              /* [E]   edge weight (edge_attrs_by_node) */
+    const int64_t *graph_edge_ptr; /* [G+1] offsets of each graph's directed edges in [0,E] */
+    const int32_t *in_ptr;         /* [N+1] incoming-edge lists, in global edge order (for scatter_mean) */
+    const int32_t *in_src;         /* [E]   source (global id) of each incoming edge */
+    const float   *in_w;           /* [E]   its weight */
+} ecord_graph;
+
+/* ---- environment state: replaces Tradjectories' arrays (tradjectories.py:78-116) ---- */
+typedef struct ecord_env {
+    int32_t  num_tradj;            /* T */
+    int32_t  _pad;
+    float   *peek;                 /* [N*T] plane */
+    int32_t *sp;                   /* [N*T] plane */
+    uint8_t *best_state;           /* [N*T] plane */
+    float   *score;                /* [G*T] */
+    float   *best_score;           /* [G*T] */
+    int32_t *best_step;            /* [G*T] step count (1-based) at which best_score was reached; 0 = initial */
+} ecord_env;
+
+/* ---- weights: fp32 device tensors in PyTorch layout [out][in], named by the reference's
+ *      state_dict keys.  ---- */
+typedef struct ecord_weights {
+    /* gnn (models/gnn_embedder.py:105-180) */
+    const float *gnn_embed_w, *gnn_embed_b;        /* [16,1],[16] */
+    const float *gnn_snd_w, *gnn_snd_b;            /* [16,16],[16] */
+    const float *gnn_rec_w, *gnn_rec_b;            /* [32,32],[32] */
+    const float *gnn_wih, *gnn_whh, *gnn_bih, *gnn_bhh; /* [48,32],[48,16],[48],[48] */
+    /* gnn2rnn (models/gnn_to_rnn.py:6-18), node_encoder (configs.py:174-192) */
+    const float *g2r_w, *g2r_b;                    /* [16,16],[16] */
+    const float *enc_w, *enc_b;                    /* [16,3],[16] */
+    /* rnn (models/rnn_decoder.py:22-136,313-381) */
+    const float *msg_w, *msg_b;                    /* [64,34],[64] */
+    const float *gru_wih, *gru_whh, *gru_bih, *gru_bhh; /* [3072,64],[3072,1024],[3072],[3072] */
+    const float *p1_w, *p1_b, *ln1_w, *ln1_b;      /* [512,1024],[512],[512],[512] */
+    const float *p2_w, *p2_b, *ln2_w, *ln2_b;      /* [32,512],[32],[32],[32] */
+    const float *v1_w, *v1_b, *v2_w, *v2_b;        /* [32,32],[32],[1,32],[1] */
+    const float *q1_w, *q1_b, *qln_w, *qln_b, *q2_w, *q2_b; /* [64,64],[64],[64],[64],[1,64],[1] */
+    /* derived by ecord_pack_weights() into caller-allocated buffers */
+    void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [16][192][1024] (rows r|z|hn of each 64-unit block)
+                            followed by Wu pack [16][256][64] (rows r|z|0|in) -- tile order of the tcgen05 GRU kernel */
+    void  *p1_w_bf16;    /* bf16 [512][1024] */
+    const float *q_fold; /* HOST f32 [6][64] from ecord_fold_q_host(): C0|C1|C2 (C = Wq[:,48:64] @ W_enc, 64x3) | LN gamma | LN beta |
+                            w_o.  Passed to the Q kernel by value (constant bank), hence a host array. */
+#define ECORD_GRU_PACK_ELEMS (3072 * 1024 + 4096 * 64)
+} ecord_weights;
+
+/* ---- per-rollout policy state and scratch (all caller-allocated) ---- */
+typedef struct ecord_policy {
+    int32_t  rows;        /* M = G*T */
+    int32_t  rows_pad;    /* M rounded up to 128; every [M][*] buffer below has rows_pad rows */
+    float   *hidden;      /* [2][rows_pad][1024] double-buffered GRU state (fp32) */
+    void    *hidden_bf16; /* [2][rows_pad][1024] bf16 mirror (tcgen05 A operand) */
+    void    *th_bf16;     /* [rows_pad][1024] bf16 tanh(h) (projection A operand) */
+    void    *u_bf16;      /* [rows_pad][64] bf16 GRU input */
+    float   *u;           /* [rows_pad][64] GRU input  LReLU(msg_in([last_sel; glob])) */
+    float   *gates;       /* [rows_pad][6144] fp32-mode scratch: gi | gh */
+    float   *th;          /* [rows_pad][1024] fp32-mode tanh(h) */
+    float   *y1;          /* [rows_pad][512] projection pre-LayerNorm */
+    float   *P;           /* [rows_pad][32]  proj_rnn_to_gnn output */
+    float   *A;           /* [rows_pad][64]  Wq[:, :32] @ P + b_q (per-(g,t) part of mlp_out[0]) */
+    float   *v;           /* [rows_pad]      state value + mlp_out bias */
+    float   *last_sel;    /* [rows_pad][32]  embedding of the last selected vertex */
+    const float *node_emb;/* [N][16] gnn2rnn(gnn(x)) (actors/_base.py:218-224) */
+    const float *node_B;  /* [N][64] Wq[:,32:48] @ node_emb + Wq[:,48:64] @ b_enc */
+    int32_t *actions;     /* [rows] local vertex id chosen at the current step */
+    float   *q;           /* [N*T] plane, optional Q-value dump (may be NULL when tau == 0) */
+} ecord_policy;
+
+/* ------------------------------------------------------------------------------------------ */
+int         ecord_version(void);
+const char *ecord_error_string(int code);
+/* sizeof() of the structs above as compiled, so bindings can assert their mirror is in sync:
+ * which = 0 graph, 1 env, 2 weights, 3 policy, 4 rollout_desc */
+int64_t     ecord_abi_sizeof(int which);
+
+/* ---- B3: the reference's native seam.  Same arguments, meaning and in-place semantics as
+ *      step_cy() (_tradjectory_step_cy.pyx:152-171) called from Tradjectories.step()
+ *      (tradjectories.py:387-405); the two trailing sizes are explicit because C has no shapes.
+ *      ecord_step_cy takes HOST buffers (numpy arrays as the reference holds them), copies them to
+ *      the current device, runs the sm_100a kernel and copies the mutated arrays back.
+ *      ecord_step_cy_device is the same on DEVICE buffers in the reference layout, asynchronous. ---- */
+int ecord_step_cy(const int64_t *actions,       /* [G][T] global vertex ids */
+                  float *scores, float *best_scores,          /* [G][T] */
+                  float *best_states,                         /* [N][T] */
+                  float *node_features,                       /* [N][T][num_node_features] */
+                  float *global_features,                     /* [G][T][num_glob_features] */
+                  const int32_t *node_feature_idxs,           /* [5] state,peek,best_state,static,degree (-1 = absent) */
+                  const int32_t *glob_feature_idxs,           /* [6] score_from_best,steps_since_best,num_greedy,steps,max_peek,mean_peek */
+                  const int32_t *edges_by_node,               /* [2][E] */
+                  const float *edge_attrs_by_node,            /* [E] */
+                  const int32_t *edge_by_node_ptr,            /* [N+1] */
+                  int32_t num_nodes, int32_t num_graphs, int32_t num_tradj,
+                  int32_t num_node_features, int32_t num_glob_features);
+int ecord_step_cy_device(const int64_t *actions, float *scores, float *best_scores, float *best_states,
+                         float *node_features, float *global_features,
+                         const int32_t *node_feature_idxs /* host [5] */, const int32_t *glob_feature_idxs /* host [6] */,
+                         const int32_t *edges_by_node, const float *edge_attrs_by_node,
+                         const int32_t *edge_by_node_ptr,
+                         int32_t num_nodes, int32_t num_graphs, int32_t num_tradj,
+                         int32_t num_node_features, int32_t num_glob_features, int32_t num_edges, void *stream);
+
+/* ---- a2: initial scores / peeks from spin states; replaces Tradjectories.__init__ +
+ *      _calc_scores_and_peeks (tradjectories.py:62-116,130-148).
+ *      init_state: i8 [N][T] (reference layout), values in {0,1}. ---- */
+int ecord_env_init(const ecord_graph *g, const ecord_env *env, const int8_t *init_state, void *stream);
+
+/* ---- a3: one environment step on the SoA state; actions are LOCAL ids [G*T] (the engine's own
+ *      layout; Tradjectories.step adds the batch offset, tradjectories.py:389-390).
+ *      step_no = number of steps completed BEFORE this one.  score_log (optional) receives the new
+ *      score [G*T] (solver.py:238 log['scores']). ---- */
+int ecord_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, int32_t step_no,
+                   float *score_log, void *stream);
+
+/* ---- a4 + parity view: materialise the reference's arrays from the SoA state.
+ *      node_features f32 [N][T][3] = (state, peek, static) un-normalised; with normalise != 0 the
+ *      canonical observation instead (peek/n_g, min(static,40)/40; tradjectories.py:336-353);
+ *      glob_features f32 [G][T][2] = (best-score [/n_g], 0) (quirk C); best_states f32 [N][T].
+ *      Any output pointer may be NULL. ---- */
+int ecord_env_export(const ecord_graph *g, const ecord_env *env, int32_t steps_done, int32_t normalise,
+                     float *node_features, float *glob_features, float *best_states, void *stream);
+
+/* ---- a5: t=0 GNN embedding; replaces _ActorBase.initialise_embeddings -> GNNEmbedder.forward +
+ *      GNN2RNN (actors/_base.py:185-237, gnn_embedder.py:133-149,182-199, gnn_to_rnn.py:16-18),
+ *      one pass (the reference's 10 extra timing passes, gnn_embedder.py:201-217, are dropped).
+ *      LayerNorm statistics are batch-wide (quirk B).  gnn_out, node_emb: f32 [N][16];
+ *      node_B: f32 [N][64] (see ecord_policy).  workspace: ecord_gnn_workspace_bytes(N) bytes. ---- */
+size_t ecord_gnn_workspace_bytes(int32_t num_nodes);
+int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
+                    void *workspace, void *stream);
+
+/* ---- weight packing for the tensor-core path (device) and the folded Q-head constants (host arrays in/out) ---- */
+int ecord_pack_weights(const ecord_weights *w, void *stream);
+int ecord_fold_q_host(const float *q1_w /*[64,64]*/, const float *enc_w /*[16,3]*/, const float *qln_w, const float *qln_b,
+                      const float *q2_w /*[1,64]*/, float *out384);
+
+/* ---- a6 + a8 (per-(graph,trajectory) part): msg_in -> GRUCell(64->1024) -> proj_rnn_to_gnn -> val_out;
+ *      replaces _update_internal_state + GRUDecoder.update_embeddings + the P/state-value half of
+ *      _forward_action_value (actors/_base.py:247-269, rnn_decoder.py:369-381,285-311).
+ *      cur = index (0/1) of the hidden buffer holding h_{t-1}; h_t is written to buffer 1-cur. ---- */
+int ecord_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                      int32_t cur, int32_t gemm_mode, void *stream);
+
+/* ---- a7 + a8 (per-vertex part) + a9: Q-values over every vertex of every (graph,trajectory),
+ *      greedy (tau == 0: argmax, lowest index on ties) or soft (tau > 0: exponential-race sampling,
+ *      actors/ecord.py:12-19, Philox stream seeded by (seed, step_no)) selection, and the cache of the
+ *      chosen vertex's embedding for the next step.  compat != 0 reproduces the reference's gather
+ *      with the LOCAL index into the FLAT array (quirk A: ecord.py:167,183 -> _base.py:305-308).
+ *      forced_actions (optional, [G*T] local ids) overrides the selection (teacher forcing). ---- */
+int ecord_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                   int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
+                   void *stream);
+
+/* ---- a10: the S-step loop as CUDA graphs of (policy_step, q_select, env_step); replaces the Python
+ *      loop of DQNSolver.rollout (solvers/solver.py:316-362).  No host round trip per step. ---- */
+typedef struct ecord_rollout_desc {
+    const ecord_graph   *graph;
+    const ecord_env     *env;
+    const ecord_weights *weights;
+    const ecord_policy  *policy;
+    int32_t  gemm_mode;       /* ECORD_GEMM_* */
+    int32_t  compat;          /* quirk A on/off */
+    float    tau;
+    int32_t  steps_per_graph; /* steps unrolled into one CUDA graph (e.g. 16) */
+    uint64_t seed;
+    int32_t *step_counter;    /* device i32[1]: steps completed; the plan advances it */
+    float   *score_log;       /* device f32 [max_steps][G*T] or NULL */
+    int32_t *action_log;      /* device i32 [max_steps][G*T] or NULL */
+    int32_t  max_steps;       /* capacity of the logs */
+    int32_t  _pad;
+} ecord_rollout_desc;
+
+typedef struct ecord_rollout_plan ecord_rollout_plan;   /* opaque */
+int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *stream, ecord_rollout_plan **out);
+/* enqueue `num_steps` more steps on the plan's stream; asynchronous.  launches_out (optional, host)
+ * receives the number of kernels enqueued. */
+int ecord_rollout_plan_run(ecord_rollout_plan *plan, int32_t num_steps, int64_t *launches_out);
+int ecord_rollout_plan_destroy(ecord_rollout_plan *plan);
+
+/* ---- a11 (device part): best score per (g,t) over steps 1..S is env.best_score restricted to s>=1;
+ *      since best_score also covers the initial score, the log-based maximum is provided:
+ *      out_best[g*T+t] = max_s score_log[s][g*T+t]  (validate/testing.py:201). ---- */
+int ecord_score_log_max(const float *score_log, int32_t num_steps, int32_t rows, float *out_best, void *stream);
+
+/* ---- layout helper: trajectory-major plane f32 [N*T] -> the reference's [N][T] ---- */
+int ecord_plane_to_nt(const ecord_graph *g, int32_t num_tradj, const float *plane, float *out, void *stream);
+
+/* ---- true best-state snapshot (what quirk D loses): replays action_log up to best_step.
+ *      out: u8 plane [N*T] ---- */
+int ecord_best_state_snapshot(const ecord_graph *g, const ecord_env *env, const int8_t *init_state,
+                              const int32_t *action_log, int32_t num_steps, uint8_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECORD_B200_H */

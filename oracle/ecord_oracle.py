@@ -97,6 +97,8 @@ def graph_to_edges(g):
     """One graph -> (n, src[], dst[], w[]) in the reference's edge order:
     GraphData.from_networkx (data.py:114-128) relabels nodes to integers in G.nodes order, makes
     the graph directed and lists G.edges; weights come from the 'weight' attribute in that order."""
+    if isinstance(g, tuple) and len(g) == 4:   # (n, src, dst, w): directed edge arrays already in reference order
+        return int(g[0]), np.asarray(g[1], np.int64), np.asarray(g[2], np.int64), np.asarray(g[3], np.float32)
     import networkx as nx
     if isinstance(g, np.ndarray):
         g = nx.from_numpy_array(g)          # graphs/utils.py:19-21
