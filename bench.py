@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- ECORD rollout throughput on B200: rollout steps/sec = graphs x trajectories x steps / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload er500|er10000|ba500|er40] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (GRU update + projection, Q over every vertex, selection, env flip)
+over one rollout batch.  Workload at N=1 = BASELINE.json configs[1]: ER500 (100 graphs G(500,0.15), +-1
+weights, synthesised as SURVEY.md 8d prescribes because the reference's file is not shipped), 50
+trajectories per graph, greedy tau=0; all 100 graphs form one rollout batch (5000 units per step).
+N>1: weak scaling -- every rank runs 50 more trajectories of the same graphs (trajectory sharding,
+ecord_b200/dist.py); the only collective is the final best-cut reduce, inside the timed region.
+
+Prints ONE JSON line (rank 0).  `value`: device-resident throughput (CUDA events, max over ranks).
+`e2e`: the same metric through the public API (B200Solver.rollout) with host inputs/outputs.
+`roofline`: the dominant kernel timed alone with CUDA events.  `cpu_baseline`: the oracle port of the
+reference rollout on the host cores, bounded sample.  `--impl reference` times that CPU path as the
+reference arm (Cython env step from oracle/_ref when present + torch CPU model restated in oracle/).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (kind, n, num_graphs, gen kwargs, T per GPU, description)
+    "er500": ("er", 500, 100, dict(p=0.15, signed=True), 50, "ER500: 100 x G(500,0.15) +-1 weights, 50 tradj/graph/GPU, greedy"),
+    "er200": ("er", 200, 100, dict(p=0.15, signed=True), 50, "ER200: 100 x G(200,0.15) +-1 weights, 50 tradj/graph/GPU, greedy"),
+    "ba500": ("ba", 500, 50, dict(signed=True), 50, "BA500: 50 x BA(500,m=4) +-1 weights, 50 tradj/graph/GPU, greedy"),
+    "er40": ("er", 40, 100, dict(p=0.15, signed=True), 50, "ER40: 100 x G(40,0.15) +-1 weights, 50 tradj/graph/GPU, greedy"),
+    "er10000": ("er", 10000, 10, dict(avg_degree=10, signed=False), 128, "ER10000: 10 x G(10000, deg 10) unit weights, 128 tradj/graph/GPU"),
+    "er2000": ("er", 2000, 10, dict(avg_degree=10, signed=False), 128, "ER2000: 10 x G(2000, deg 10) unit weights, 128 tradj/graph/GPU"),
+}
+F_UNIT = lambda n: 7772480 + 8416 * n            # literal FLOPs per (g,t,step), SURVEY.md 8d
+B_UNIT = lambda n, d: 12 * n + 20 * d + 8268     # compulsory bytes per (g,t,step), SURVEY.md 8d
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p["bf16_tflops"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_graphs(workload, seed0=0):
+    from ecord_b200.graphs import synthetic_set
+    kind, n, G, kw, T, desc = WORKLOADS[workload]
+    return synthetic_set(kind, n, G, seed0=seed0, **kw), n, G, T, desc
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_rollout_rate(graphs_sample, T, steps, use_ref_env=True):
+    """Time the CPU restatement of the reference rollout (oracle) on a bounded sample; returns units/s."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ecord_oracle as orc
+    from ecord_b200.network import random_state_dicts
+    torch.set_num_threads(os.cpu_count())
+    have_ref = False
+    if use_ref_env:
+        try:
+            import build_ref
+            have_ref = build_ref.load_step_cy() is not None
+        except Exception:
+            have_ref = False
+    ob = orc.build_batch([tuple(g) for g in graphs_sample])
+    model = orc.ModelOracle(random_state_dicts(0))
+    init = np.random.RandomState(0).randint(0, 2, (ob.N, T)).astype(np.int8)
+    model.initialise_embeddings(ob, T)
+    env = orc.EnvOracle(ob, T, init, use_ref=have_ref)
+    nf, gf = env.observe()
+
+    def one_step():
+        nonlocal nf, gf
+        model.update_internal_state(gf)
+        q, emb, _ = model.q_values(ob, nf)
+        a = model.select(ob, q, emb)
+        env.step(a.numpy())
+        nf, gf = env.observe()
+
+    one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    return ob.G * T * steps / dt, dt, have_ref
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    graphs, n, G, T, desc = make_graphs(args.workload)
+    gs = max(1, min(G, args.cpu_graphs))
+    # warm-up on the default sample; then bound the sample so that K timed steps end within ~2 minutes
+    rate_w, dt_w, _ = cpu_rollout_rate(graphs[:gs], T, max(args.warmup, 1))
+    est = dt_w / max(args.warmup, 1) * args.steps
+    if est > 120.0:
+        gs = max(1, int(gs * 120.0 / est))
+    sample = graphs[:gs]
+    rate, dt, have_ref = cpu_rollout_rate(sample, T, args.steps)
+    cores = os.cpu_count()
+    sample_s = f"{gs} of {G} graphs x {T} tradj x {args.steps} steps ({'compiled reference Cython step' if have_ref else 'C restatement of the env step'} + torch CPU model, {torch.get_num_threads()} threads)"
+    out = {"impl": "reference", "metric": "rollout steps/sec (graphs x tradj x steps)", "value": rate, "unit": "steps/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": desc, "note": "CPU path; per-step batch is the sample below"},
+           "cpu_baseline": {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample_s},
+           "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from ecord_b200.data import GraphBatcher
+    from ecord_b200.dist import reduce_best, shard_bounds
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    from ecord_b200.network import random_state_dicts
+    from ecord_b200.solver import B200Solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    graphs, n, G, T, desc = make_graphs(args.workload)
+    K, W = args.steps, max(args.warmup, 3)
+    T_total = T * world
+    lo, hi = shard_bounds(T_total, world, rank)
+    sd = random_state_dicts(0)
+    batch = GraphBatcher()(graphs)
+    avg_deg = batch.tg.num_edges / batch.tg.num_nodes
+    # global initial spins, sliced per rank: results do not depend on the GPU count
+    init_all = np.random.RandomState(1234).randint(0, 2, (batch.tg.num_nodes, T_total), dtype=np.int8)
+    init = np.ascontiguousarray(init_all[:, lo:hi])
+
+    weights = DeviceWeights(sd, dev)
+    dg = DeviceGraph(batch.tg, dev)
+    k = args.steps_per_graph
+    st = RolloutState(dg, weights, T, gemm=args.gemm, compat=True, max_steps=W + K + k, steps_per_graph=k)
+    st.gnn_embed()
+    st.env_init(init)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also instantiates the CUDA graphs) ----
+    st.run(W)
+    barrier()
+    launches0 = st.kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps; L2 flushed before every graph launch (outside the events) ----
+    chunks = [k] * (K // k) + ([K % k] if K % k else [])
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for c in chunks:
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); st.run(c); e1.record()
+        evs.append((e0, e1))
+    # final reduce (the path's only collective) is part of the job
+    by_tradj = st.best_from_log(W + K)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    best, by_all = reduce_best(by_tradj, T_total)
+    e3.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms = sum(a.elapsed_time(b) for a, b in evs) + e2.elapsed_time(e3)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = st.kernel_launches - launches0
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    units = G * T_total * K
+    value = units / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (q_select), timed alone with CUDA events on its stream ----
+    roof = None
+    if rank == 0:
+        reps = 30
+        st.q_select(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            a.record(); st.q_select(); b.record(); b.synchronize()
+            tot += a.elapsed_time(b)
+        q_ms = tot / reps
+        tp = {}
+        for nm, fn in (("policy_step", st.policy_step),):
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); b.synchronize()
+            tp[nm] = a.elapsed_time(b) / reps
+        hbm, tf_burst, tf_sus, which = peaks()
+        flops = 8416.0 * dg.N * T                       # literal mlp_out + encoder FLOPs per launch
+        bytes_alg = 12.0 * dg.N * T                     # (state, peek, static) fp32 per (vertex, trajectory)
+        ach = flops / (q_ms * 1e-3) / 1e12
+        roof = {"kernel": "k_q_select", "bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s",
+                "frac": ach / tf_burst, "traffic": None, "peak_source": which + " (bf16 burst; kernel timed alone)",
+                "ms_per_launch": q_ms, "launch_share_of_step": q_ms / (ms / K),
+                "hbm_view": {"achieved_gbs": bytes_alg / (q_ms * 1e-3) / 1e9, "peak_gbs": hbm, "frac": bytes_alg / (q_ms * 1e-3) / 1e9 / hbm},
+                "policy_step_ms": tp["policy_step"],
+                "whole_step": {"flops_per_unit": F_UNIT(n), "bytes_per_unit": B_UNIT(n, avg_deg),
+                               "tensor_bound_units_s": tf_sus * 1e12 / F_UNIT(n), "hbm_bound_units_s": hbm * 1e9 / B_UNIT(n, avg_deg),
+                               "frac_of_binding_bound": (value / world) / min(tf_sus * 1e12 / F_UNIT(n), hbm * 1e9 / B_UNIT(n, avg_deg))}}
+    st.close()
+
+    # ---- e2e: the public API with host buffers (H2D of inputs, D2H of the score log inside the timed region) ----
+    solver = B200Solver(gnn=sd['gnn'], rnn=sd['rnn'], gnn2rnn=sd['gnn2rnn'], node_encoder=sd['node_encoder'],
+                        device=dev, gemm=args.gemm, steps_per_graph=k)
+    Ke = K
+    solver.rollout(batch, num_tradj=T, num_steps=min(Ke, 2 * k), tau=0, use_epsilon=False, init_state=init)   # warm
+    pinned = torch.from_numpy(init).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    log = solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=pinned.numpy())
+    sc = torch.stack(log['scores'], -1).max(-1).values.to(dev)
+    best_e, _ = reduce_best(sc, T_total)
+    best_host = best_e.cpu()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = G * T_total * Ke / float(te.item())
+    h2d = (init.nbytes) / Ke
+    d2h = (G * T * 4 * Ke + dg.N * T * 4 + G * T * 8 + best_host.numel() * 4) / Ke
+
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            gs = max(1, min(G, args.cpu_graphs))
+            rate, dt, have_ref = cpu_rollout_rate(graphs[:gs], T, args.cpu_steps)
+            cb = {"value": rate, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port",
+                  "sample": f"{gs} of {G} graphs x {T} tradj x {args.cpu_steps} steps in {dt:.1f}s "
+                            f"({'compiled reference Cython step (oracle/_ref)' if have_ref else 'C restatement of the env step'}"
+                            f" + torch CPU model, {torch.get_num_threads()} threads)"}
+        out = {"metric": "rollout steps/sec (graphs x tradj x steps)", "value": value, "unit": "steps/s", "n_gpus": world,
+               "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
+               "config": {"workload": desc, "graphs": G, "tradj_total": T_total, "units_per_step": G * T_total,
+                          "parallelism": f"trajectory-sharded x{world}", "gemm": args.gemm,
+                          "l2": "flushed (256 MB write) before every CUDA-graph launch of %d steps, outside the timed events" % k,
+                          "weights": "random-init canonical ECORD network (seed 0)"},
+               "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "note": "B200Solver.rollout incl. graph upload, GNN, env init, H2D init states, D2H score log"},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
+               "wall_s_timed_region": t_wall, "best_cut_mean": float(best.mean().item())}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="er500", choices=sorted(WORKLOADS))
+    ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--steps-per-graph", type=int, default=16)
+    ap.add_argument("--cpu-graphs", type=int, default=10, help="graphs in the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=24, help="steps of the CPU baseline sample (b200 arm)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -26,6 +26,25 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_stream(fn):
+    """Run a RolloutState method on the state's own (non-default) stream.  CUDA graphs cannot be captured on
+    the legacy default stream, so every kernel of a rollout is enqueued on `self.stream`; the caller's current
+    stream is ordered before and after the call, which keeps plain torch code around it correct."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        cur = torch.cuda.current_stream(self.device)
+        if cur == self.stream:
+            return fn(self, *a, **k)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            out = fn(self, *a, **k)
+        cur.wait_stream(self.stream)
+        return out
+    return wrapped
+
+
 class DeviceGraph:
     """Uploads one batch (data.TgBatch) and fills the C struct `ecord_graph`."""
 
@@ -109,6 +128,7 @@ class RolloutState:
         self.g, self.w = dgraph, weights
         dev = dgraph.device
         self.device = dev
+        self.stream = torch.cuda.Stream(device=dev)
         self.T = T = int(num_tradj)
         self.gemm = _GEMM_MODES[gemm]
         if self.gemm == GEMM_BF16 and weights.gru_w_bf16 is None:
@@ -166,6 +186,7 @@ class RolloutState:
         self.kernel_launches = 0
 
     # ---- set-up -----------------------------------------------------------------------------
+    @_on_stream
     def gnn_embed(self):
         """t=0 embedding (a5): fills gnn_out, node_emb and node_B."""
         ws = torch.empty(self.lib.ecord_gnn_workspace_bytes(self.g.N), dtype=torch.uint8, device=self.device)
@@ -174,6 +195,7 @@ class RolloutState:
         self.kernel_launches += 16
         self._ws = ws
 
+    @_on_stream
     def env_init(self, init_state):
         """a2: init_state int8 [N,T] (host numpy / torch, reference layout)."""
         s = torch.as_tensor(np.ascontiguousarray(np.asarray(init_state).astype(np.int8)))
@@ -191,11 +213,13 @@ class RolloutState:
         self.steps_done = 0
 
     # ---- step-wise API (tests, log_stats) -----------------------------------------------------
+    @_on_stream
     def policy_step(self):
         check(self.lib.ecord_policy_step(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c), C.byref(self.policy_c),
                                          self.steps_done & 1, self.gemm, _stream()), "ecord_policy_step")
         self.kernel_launches += 6 if self.gemm == GEMM_FP32 else 4
 
+    @_on_stream
     def q_select(self, forced_actions=None):
         fa = None
         if forced_actions is not None:
@@ -207,6 +231,7 @@ class RolloutState:
         self.kernel_launches += 1
         self._fa = fa
 
+    @_on_stream
     def env_step(self, actions=None):
         a = self.actions if actions is None else torch.as_tensor(actions).to(self.device, torch.int32).contiguous().view(-1)
         row = None
@@ -231,10 +256,10 @@ class RolloutState:
                                 self.gemm, int(self.compat), self.tau, self.steps_per_graph, self.seed,
                                 ptr(self.step_counter), ptr(self.score_log), ptr(self.action_log), self.max_steps, 0)
         out = C.c_void_p()
-        self._plan_stream = torch.cuda.current_stream()
         check(self.lib.ecord_rollout_plan_create(C.byref(desc), _stream(), C.byref(out)), "ecord_rollout_plan_create")
         self.plan = out
 
+    @_on_stream
     def run(self, num_steps):
         """Enqueue `num_steps` whole steps (asynchronous).  Uses CUDA graphs of `steps_per_graph` steps."""
         if self.plan is None:
@@ -256,6 +281,7 @@ class RolloutState:
             pass
 
     # ---- views in the reference's layouts (parity checks, logs) ------------------------------
+    @_on_stream
     def export(self, normalise=False):
         """(node_features [N,T,3], glob_features [G,T,2], best_states [N,T]) as torch CUDA tensors."""
         N, G, T = self.g.N, self.g.G, self.T
@@ -266,6 +292,7 @@ class RolloutState:
                                         ptr(nf), ptr(gf), ptr(bs), _stream()), "ecord_env_export")
         return nf, gf, bs
 
+    @_on_stream
     def plane_to_nt(self, plane):
         out = torch.empty(self.g.N, self.T, dtype=torch.float32, device=self.device)
         check(self.lib.ecord_plane_to_nt(C.byref(self.g.c), self.T, ptr(plane), ptr(out), _stream()), "ecord_plane_to_nt")
@@ -282,12 +309,14 @@ class RolloutState:
     def scores(self):
         return self.score.view(self.g.G, self.T)
 
+    @_on_stream
     def best_from_log(self, num_steps):
         out = torch.empty(self.M, dtype=torch.float32, device=self.device)
         check(self.lib.ecord_score_log_max(ptr(self.score_log), int(num_steps), self.M, ptr(out), _stream()),
               "ecord_score_log_max")
         return out.view(self.g.G, self.T)
 
+    @_on_stream
     def best_states_batched(self, true_snapshot=False):
         """[G, n_max, T], -1 padded (tradjectories.py:324-328,378-385).  true_snapshot=False gives the
         reference's semantics (quirk D); True replays the action log up to each trajectory's best step."""

@@ -1,0 +1,153 @@
+"""Model kernels on the GPU against the reference's recorded tensors (tests/golden/model_trace.npz).
+
+Tolerances (BASELINE.json north_star): fp32 mode 1e-4 relative; bf16 (tcgen05) mode 2e-2 relative, where
+"relative" = max|a-b| / max|b| over the tensor.  Per-step checks are teacher-forced with the reference's
+actions so that an argmax flip cannot mask a numerical comparison."""
+import numpy as np
+import pytest
+import torch
+
+import ecord_oracle as orc
+from ecord_b200.data import GraphBatcher
+from ecord_b200.network import random_state_dicts
+from util import load_gold, rel_err, unpack_graphs
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _setup(gemm, compat=True, dump_q=True):
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    z = load_gold("model_trace.npz")
+    sd = random_state_dicts(int(z["weight_seed"]), perturb_norms=True)
+    dg = DeviceGraph(GraphBatcher()(unpack_graphs(z)).tg)
+    T, S = int(z["T"]), int(z["S"])
+    st = RolloutState(dg, DeviceWeights(sd), T, gemm=gemm, compat=compat, max_steps=S, dump_q=dump_q)
+    st.gnn_embed()
+    st.env_init(z["init_state"])
+    return z, sd, st, dg, T, S
+
+
+def test_gnn_embedding_matches_reference():
+    z, sd, st, dg, T, S = _setup("fp32")
+    assert rel_err(st.gnn_out.cpu().numpy(), z["gnn_emb"]) < 1e-4
+    assert rel_err(st.node_emb.cpu().numpy(), z["init_emb"]) < 1e-4
+
+
+def test_gnn_layernorm_is_batch_wide():
+    """Quirk B: embeddings of a graph depend on the batch it is embedded with (gnn_embedder.py:178,193-199)."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    z = load_gold("model_trace.npz")
+    graphs = unpack_graphs(z)
+    sd = random_state_dicts(int(z["weight_seed"]), perturb_norms=True)
+    w = DeviceWeights(sd)
+    model = orc.ModelOracle(sd)
+    for sub in (graphs[:1], graphs[:3]):
+        dg = DeviceGraph(GraphBatcher()(sub).tg)
+        st = RolloutState(dg, w, 1, gemm="fp32")
+        st.gnn_embed()
+        ref = model.gnn_embed(orc.build_batch(sub)).numpy()
+        assert rel_err(st.gnn_out.cpu().numpy(), ref) < 1e-4
+    # and the two differ from each other by more than the tolerance, as in the reference
+    a = model.gnn_embed(orc.build_batch(graphs[:1])).numpy()
+    b = model.gnn_embed(orc.build_batch(graphs[:3])).numpy()[:a.shape[0]]
+    assert rel_err(a, b) > 1e-4
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "bf16"])
+def test_per_step_tensors_teacher_forced(gemm):
+    z, sd, st, dg, T, S = _setup(gemm)
+    tol = TOL[gemm]
+    for s in range(S):
+        st.policy_step()
+        st.q_select(forced_actions=z["actions"][s].astype(np.int32).reshape(-1))
+        q = st.q_values().cpu().numpy()
+        h = st.hidden[(s + 1) & 1, :st.M].view(dg.G, T, 1024).cpu().numpy()
+        assert rel_err(q, z["q"][s]) < tol, f"q step {s}"
+        assert rel_err(h[..., ::16], z["hidden_slice"][s]) < tol, f"hidden step {s}"
+        assert rel_err(np.linalg.norm(h, axis=-1), z["hidden_norm"][s]) < tol
+        assert rel_err(st.P[:st.M].view(dg.G, T, 32).cpu().numpy(), z["P"][s]) < tol, f"P step {s}"
+        assert rel_err(st.last_sel[:st.M].view(dg.G, T, 32).cpu().numpy(), z["last_sel"][s]) < 1e-5, f"last_sel {s}"
+        st.env_step()
+        assert np.array_equal(st.scores().cpu().numpy(), z["scores"][s])
+
+
+def test_tcgen05_kernels_against_torch_on_identical_operands():
+    """The tensor-core GRU / projection kernels vs torch matmuls fed the SAME bf16-rounded operands: isolates
+    descriptor/layout bugs from precision (fp32 accumulation order is the only difference)."""
+    z, sd, st, dg, T, S = _setup("bf16")
+    r, dev = sd['rnn'], st.device
+    wih = r['graph_rnn.0.weight_ih'].to(dev).bfloat16().float()
+    whh = r['graph_rnn.0.weight_hh'].to(dev).bfloat16().float()
+    w1 = r['proj_rnn_to_gnn.1.weight'].to(dev).bfloat16().float()
+    for s in range(4):
+        st.policy_step()
+        u = st.u_bf16[:st.M].float()
+        hb, h32 = st.hidden_bf16[s & 1, :st.M].float(), st.hidden[s & 1, :st.M]
+        gi = u @ wih.T + r['graph_rnn.0.bias_ih'].to(dev)
+        gh = hb @ whh.T + r['graph_rnn.0.bias_hh'].to(dev)
+        rr = torch.sigmoid(gi[:, :1024] + gh[:, :1024])
+        zz = torch.sigmoid(gi[:, 1024:2048] + gh[:, 1024:2048])
+        nn_ = torch.tanh(gi[:, 2048:] + rr * gh[:, 2048:])
+        want = (h32 - nn_) * zz + nn_
+        got = st.hidden[(s + 1) & 1, :st.M]
+        assert float((got - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+        assert torch.equal(st.hidden_bf16[(s + 1) & 1, :st.M], got.bfloat16())
+        y1 = torch.tanh(got).bfloat16().float() @ w1.T + r['proj_rnn_to_gnn.1.bias'].to(dev)
+        assert float((st.y1[:st.M] - y1).abs().max()) < 2e-3 * float(y1.abs().max())   # tanh rounding to bf16 can differ by 1 ulp
+        st.q_select(forced_actions=z["actions"][s].astype(np.int32).reshape(-1))
+        st.env_step()
+
+
+def test_quirk_a_switch():
+    """compat=False caches the embedding of the vertex actually flipped (global index)."""
+    z, sd, st, dg, T, S = _setup("fp32", compat=False)
+    ob = orc.build_batch(unpack_graphs(z))
+    model = orc.ModelOracle(sd, compat=False)
+    log = orc.rollout(model, ob, T, 6, z["init_state"], record=True)
+    for s in range(6):
+        st.policy_step()
+        st.q_select(forced_actions=log["actions"][s].numpy().astype(np.int32).reshape(-1))
+        assert rel_err(st.q_values().cpu().numpy(), log["q"][s].numpy()) < 1e-4
+        assert rel_err(st.last_sel[:st.M].view(dg.G, T, 32).cpu().numpy(), log["last_sel"][s].numpy()) < 1e-5
+        st.env_step()
+
+
+def test_argmax_ties_resolve_to_lowest_index():
+    """All-equal Q-values (zero weights in the Q head) must select vertex 0 everywhere (torch_scatter CPU semantics)."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    z = load_gold("model_trace.npz")
+    sd = random_state_dicts(3)
+    sd['rnn']['mlp_out.3.weight'].zero_()
+    dg = DeviceGraph(GraphBatcher()(unpack_graphs(z)).tg)
+    st = RolloutState(dg, DeviceWeights(sd), 4, gemm="fp32")
+    st.gnn_embed()
+    st.env_init(np.random.RandomState(0).randint(0, 2, (dg.N, 4)).astype(np.int8))
+    st.policy_step()
+    st.q_select()
+    assert int(st.actions.abs().sum()) == 0
+
+
+def test_tau_sampling_is_distributionally_right():
+    """tau > 0 (actors/ecord.py:12-19): exponential-race sampling == softmax(q / tau) sampling.  The reference draws
+    from torch's RNG so only the distribution can match: chi-square of empirical counts vs softmax probabilities."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    from ecord_b200.graphs import synthetic_set
+    sd = random_state_dicts(11, perturb_norms=True)
+    dg = DeviceGraph(GraphBatcher()(synthetic_set("er", 12, 1, p=0.4)).tg)
+    T = 4096
+    tau = 0.05
+    st = RolloutState(dg, DeviceWeights(sd), T, gemm="fp32", tau=tau, seed=123, dump_q=True)
+    st.gnn_embed()
+    st.env_init(np.zeros((dg.N, T), np.int8))      # identical state in every trajectory -> identical q
+    st.policy_step()
+    st.q_select()
+    q = st.q_values()[:, 0].double().cpu()
+    p = torch.softmax(q / tau, 0).numpy()
+    counts = np.bincount(st.actions.cpu().numpy(), minlength=dg.N)
+    chi2 = float((((counts - T * p) ** 2) / np.maximum(T * p, 1e-9))[p * T > 5].sum())
+    dof = int((p * T > 5).sum()) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+    st2 = RolloutState(dg, DeviceWeights(sd), T, gemm="fp32", tau=tau, seed=123, dump_q=True)
+    st2.gnn_embed(); st2.env_init(np.zeros((dg.N, T), np.int8)); st2.policy_step(); st2.q_select()
+    assert torch.equal(st.actions, st2.actions)     # same seed -> same draw (counter-based Philox)

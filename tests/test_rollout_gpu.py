@@ -1,0 +1,151 @@
+"""Fused rollout (CUDA-graph plan) and the solver / validate API on the GPU."""
+import numpy as np
+import pytest
+import torch
+
+import ecord_oracle as orc
+from ecord_b200.data import GraphBatcher
+from ecord_b200.graphs import synthetic_set
+from ecord_b200.network import random_state_dicts
+from util import load_gold, unpack_graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def _solver(sd, **kw):
+    from ecord_b200.solver import B200Solver
+    return B200Solver(gnn=sd['gnn'], rnn=sd['rnn'], gnn2rnn=sd['gnn2rnn'], node_encoder=sd['node_encoder'], **kw)
+
+
+def test_free_running_greedy_reproduces_reference_trace():
+    """fp32 mode, no teacher forcing: 24 greedy steps through the plan give the reference's actions and scores."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    z = load_gold("model_trace.npz")
+    sd = random_state_dicts(int(z["weight_seed"]), perturb_norms=True)
+    dg = DeviceGraph(GraphBatcher()(unpack_graphs(z)).tg)
+    T, S = int(z["T"]), int(z["S"])
+    st = RolloutState(dg, DeviceWeights(sd), T, gemm="fp32", max_steps=S, steps_per_graph=5)   # 4 graphs of 5 + 4 of 1
+    st.gnn_embed()
+    st.env_init(z["init_state"])
+    st.run(S)
+    acts = st.action_log[:S].view(S, dg.G, T).cpu().numpy()
+    assert np.array_equal(acts, z["actions"].astype(np.int32))
+    assert np.array_equal(st.score_log[:S].view(S, dg.G, T).cpu().numpy(), z["scores"])
+    assert np.array_equal(st.best_states_batched().numpy(), z["best_state"])
+    assert int(st.step_counter.item()) == S
+    # the true snapshot (what quirk D loses) must have exactly the best score as its cut value
+    snap = st.best_states_batched(true_snapshot=True).numpy()
+    ob = orc.build_batch(unpack_graphs(z))
+    flat = np.concatenate([snap[g, :ob.num_nodes_list[g]] for g in range(ob.G)]).astype(np.int8)
+    env = orc.EnvOracle(ob, T, flat)
+    assert np.array_equal(env.scores, st.best_score.view(dg.G, T).cpu().numpy())
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "bf16"])
+def test_plan_equals_stepwise(gemm):
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    graphs = synthetic_set("er", 60, 7, p=0.2)
+    sd = random_state_dicts(5, perturb_norms=True)
+    w = DeviceWeights(sd)
+    dg = DeviceGraph(GraphBatcher()(graphs).tg)
+    T, S = 9, 37
+    init = np.random.RandomState(2).randint(0, 2, (dg.N, T)).astype(np.int8)
+    a = RolloutState(dg, w, T, gemm=gemm, max_steps=S, steps_per_graph=8)
+    b = RolloutState(dg, w, T, gemm=gemm, max_steps=S)
+    for st in (a, b):
+        st.gnn_embed(); st.env_init(init)
+    a.run(20); a.run(S - 20)
+    for _ in range(S):
+        b.step()
+    assert torch.equal(a.action_log[:S], b.action_log[:S])
+    assert torch.equal(a.score_log[:S], b.score_log[:S])
+    assert torch.equal(a.hidden_state(), b.hidden_state())
+    assert torch.equal(a.peek, b.peek) and torch.equal(a.sp, b.sp)
+
+
+def test_config1_best_cut_parity():
+    """BASELINE config 1: ER40 validation set (100 graphs), 80 steps, 50 trajectories, graph batch 50, greedy.
+    Bar (north_star): best cut equal to the reference's on >= 99% of instances (fp32 mode)."""
+    from ecord_b200.testing import TestGraphsConfig, test_solver
+    z = load_gold("config1.npz")
+    graphs = unpack_graphs(z)
+    T, S, bsz = int(z["T"]), int(z["S"]), int(z["bsz"])
+    solver = _solver(random_state_dicts(int(z["weight_seed"])), gemm="fp32")
+    cfg = TestGraphsConfig(graphs=graphs, opt_scores=torch.tensor(z["opts"]), num_steps=S, tradj_per_graph=T, tau=0,
+                           graphs_bsz=bsz, tradj_bsz=T)
+    np.random.seed(int(z["state_seed"]))       # the solver draws initial spins exactly as the reference does
+    log = test_solver(solver, GraphBatcher(), cfg)
+    assert np.array_equal(log["init_score"].numpy(), z["init_score"].astype(np.float32))
+    agree = float((log["scores_max"].numpy() == z["scores_max"]).mean())
+    assert agree >= 0.99, f"best-cut agreement {agree:.3f}"
+    assert log["scores"].shape == (100, T, S) and log["t_step"].shape == (S,)
+    assert np.allclose(log["apx_max"].numpy(), log["scores_max"].numpy() / z["opts"])
+
+
+def test_solver_log_contract_and_checkpoint_roundtrip(tmp_path):
+    """The keys / shapes downstream code reads (SURVEY.md 8b "Log contract"), and DQNSolver.save/load ingestion."""
+    graphs = synthetic_set("er", 30, 3, p=0.3) + synthetic_set("er", 20, 2, p=0.3, seed0=7)     # ragged
+    sd = random_state_dicts(1)
+    solver = _solver(sd, gemm="bf16")
+    batch = GraphBatcher()(graphs)
+    T = 4
+    log = solver.rollout(batch, num_tradj=T, num_steps=-2, use_epsilon=False, tau=0, log_stats=False)
+    S = 2 * 30
+    assert len(log["scores"]) == S and log["scores"][0].shape == (5, T)
+    assert log["init_score"].shape == (5, T) and log["t_opt"].shape == (5, T)
+    assert log["best_state"].shape == (5, 30, T) and (log["best_state"][3:, 20:] == -1).all()
+    for k in ("t_setup", "t_init_emb"):
+        assert isinstance(log[k], list) and log[k][0].shape == (1,)
+    assert len(log["t_step"]) == S and log["t_tot"].shape == (1,) and log["t_rollout"].shape == (1,)
+    # log_stats adds per-step actions / peeks / state in the reference's padded layout
+    log2 = solver.rollout(batch, num_tradj=T, num_steps=5, use_epsilon=False, tau=0, log_stats=True,
+                          init_state=np.zeros((batch.tg.num_nodes, T), np.int8))
+    assert log2["actions"][0].shape == (5, T) and log2["peeks"][0].shape == (5, 30, T) and log2["state"][0].shape == (5, 30, T)
+    assert (log2["peeks"][0][3:, 20:] == -1e10).all()
+    # checkpoint in the reference's format -> load
+    f = solver.save(str(tmp_path / "ck"))
+    other = _solver(random_state_dicts(99), gemm="bf16")
+    other.load(f, quiet=True)
+    a = solver.rollout(batch, num_tradj=T, num_steps=8, use_epsilon=False, tau=0, init_state=np.ones((batch.tg.num_nodes, T), np.int8))
+    b = other.rollout(batch, num_tradj=T, num_steps=8, use_epsilon=False, tau=0, init_state=np.ones((batch.tg.num_nodes, T), np.int8))
+    assert torch.equal(torch.stack(a["scores"]), torch.stack(b["scores"]))
+
+
+def test_unsupported_options_fail_loudly():
+    sd = random_state_dicts(1)
+    from ecord_b200.solver import B200Solver
+    from ecord_b200.observations import NodeObservation
+    with pytest.raises(NotImplementedError):
+        B200Solver(gnn=sd['gnn'], rnn=sd['rnn'], gnn2rnn=sd['gnn2rnn'], node_encoder=sd['node_encoder'],
+                   node_features=[NodeObservation.STATE, NodeObservation.PEEK])
+    solver = _solver(sd)
+    batch = GraphBatcher()(synthetic_set("er", 10, 1, p=0.5))
+    with pytest.raises(NotImplementedError):
+        solver.rollout(batch, num_tradj=2, num_steps=2, post_solve_with_greedy_from_best=True)
+
+
+def test_full_size_er500_properties():
+    """BASELINE configs[1] size (ER500, 50 graphs x 50 trajectories; steps truncated): size-independent properties."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    graphs = synthetic_set("er", 500, 50, p=0.15)
+    dg = DeviceGraph(GraphBatcher()(graphs).tg)
+    T, S = 50, 64
+    st = RolloutState(dg, DeviceWeights(random_state_dicts(0)), T, gemm="bf16", max_steps=S)
+    init = np.random.RandomState(1).randint(0, 2, (dg.N, T)).astype(np.int8)
+    st.gnn_embed(); st.env_init(init); st.run(S)
+    nf, gf, bs = st.export()
+    ob = orc.build_batch(graphs)
+    fresh = orc.EnvOracle(ob, T, nf[..., 0].cpu().numpy().astype(np.int8))
+    assert np.array_equal(fresh.scores, st.scores().cpu().numpy())                 # score == cut of the final spins
+    assert np.array_equal(fresh.node_features[..., 1], nf[..., 1].cpu().numpy())   # peeks == recomputed
+    log = st.score_log[:S].view(S, dg.G, T)
+    init_sc = orc.EnvOracle(ob, T, init).scores
+    assert np.array_equal(np.maximum(log.max(0).values.cpu().numpy(), init_sc), st.best_score.view(dg.G, T).cpu().numpy())
+    acts = st.action_log[:S].view(S, dg.G, T)
+    assert int(acts.min()) >= 0 and int(acts.max()) < 500
+    # static feature == steps since the vertex was last flipped
+    last = torch.zeros(dg.G, T, 500, dtype=torch.long)
+    for s in range(S):
+        last.scatter_(2, acts[s].cpu().long().unsqueeze(-1), s + 1)
+    static = nf[..., 2].cpu().view(dg.G, 500, T).permute(0, 2, 1)
+    assert torch.equal(static.long(), S - last)
