@@ -11,6 +11,10 @@ LIB_PATH = os.path.join(HERE, "libecord_b200.so")
 
 GEMM_FP32 = 0
 GEMM_BF16 = 1
+Q_EXACT = 0
+Q_FAST = 1
+QTILE = 128
+QFOLD_FLOATS = 580
 GRU_PACK_ELEMS = 3072 * 1024 + 4096 * 64
 
 _vp, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
@@ -23,7 +27,8 @@ class EcordError(RuntimeError):
 class Graph(C.Structure):
     _fields_ = [("num_graphs", _i32), ("num_nodes", _i32), ("num_edges", _i32), ("n_max", _i32),
                 ("graph_ptr", _vp), ("node_graph", _vp), ("row_ptr", _vp), ("col", _vp), ("w", _vp),
-                ("graph_edge_ptr", _vp), ("in_ptr", _vp), ("in_src", _vp), ("in_w", _vp)]
+                ("graph_edge_ptr", _vp), ("in_ptr", _vp), ("in_src", _vp), ("in_w", _vp),
+                ("num_qtiles", _i32), ("_pad", _i32), ("qtile_graph", _vp), ("qtile_v0", _vp)]
 
 
 class Env(C.Structure):
@@ -62,12 +67,14 @@ class Weights(C.Structure):
 class Policy(C.Structure):
     _fields_ = [("rows", _i32), ("rows_pad", _i32), ("hidden", _vp), ("hidden_bf16", _vp), ("th_bf16", _vp),
                 ("u_bf16", _vp), ("u", _vp), ("gates", _vp), ("th", _vp), ("y1", _vp), ("P", _vp), ("A", _vp),
-                ("v", _vp), ("last_sel", _vp), ("node_emb", _vp), ("node_B", _vp), ("actions", _vp), ("q", _vp)]
+                ("v", _vp), ("last_sel", _vp), ("node_emb", _vp), ("node_B", _vp), ("actions", _vp), ("q", _vp),
+                ("Ac", _vp), ("LA", _vp), ("node_Bc", _vp), ("node_LB", _vp), ("keys", _vp)]
 
 
 class RolloutDesc(C.Structure):
     _fields_ = [("graph", C.POINTER(Graph)), ("env", C.POINTER(Env)), ("weights", C.POINTER(Weights)),
-                ("policy", C.POINTER(Policy)), ("gemm_mode", _i32), ("compat", _i32), ("tau", _f32),
+                ("policy", C.POINTER(Policy)), ("gemm_mode", _i32), ("q_mode", _i32), ("compat", _i32), ("_pad0", _i32),
+                ("tau", _f32),
                 ("steps_per_graph", _i32), ("seed", _u64), ("step_counter", _vp), ("score_log", _vp),
                 ("action_log", _vp), ("max_steps", _i32), ("_pad", _i32)]
 
@@ -82,13 +89,15 @@ SYMBOLS = {
     "ecord_step_cy_device": (_i32, [_vp] * 11 + [_i32] * 6 + [_vp]),
     "ecord_env_init": (_i32, [_P(Graph), _P(Env), _vp, _vp]),
     "ecord_env_step": (_i32, [_P(Graph), _P(Env), _vp, _i32, _vp, _vp]),
+    "ecord_env_step_fused": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _vp, _vp]),
     "ecord_env_export": (_i32, [_P(Graph), _P(Env), _i32, _i32, _vp, _vp, _vp, _vp]),
     "ecord_gnn_workspace_bytes": (C.c_size_t, [_i32]),
-    "ecord_gnn_embed": (_i32, [_P(Graph), _P(Weights), _vp, _vp, _vp, _vp, _vp]),
+    "ecord_gnn_embed": (_i32, [_P(Graph), _P(Weights), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ecord_pack_weights": (_i32, [_P(Weights), _vp]),
     "ecord_fold_q_host": (_i32, [_vp] * 6),
-    "ecord_policy_step": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _i32, _vp]),
-    "ecord_q_select": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _f32, _u64, _i32, _vp, _vp]),
+    "ecord_policy_step": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _i32, _i32, _vp]),
+    "ecord_policy_pre": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _vp]),
+    "ecord_q_select": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _f32, _u64, _i32, _vp, _i32, _vp]),
     "ecord_rollout_plan_create": (_i32, [_P(RolloutDesc), _vp, _P(_vp)]),
     "ecord_rollout_plan_run": (_i32, [_vp, _i32, _P(_i64)]),
     "ecord_rollout_plan_destroy": (_i32, [_vp]),

@@ -39,3 +39,35 @@ __device__ __forceinline__ long long unit_base(const int32_t *graph_ptr, int g, 
 
 // accurate, deterministic activations (same formulas on every path so modes are comparable)
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// u = LReLU(msg_in([last_sel (32); glob0; 0])) for one row, computed by one warp (lane holds last_sel[lane]).
+// wt = transposed msg_in weight in shared memory [34][64], wb = bias [64].  Outputs u[lane], u[lane+32].
+// (_ActorBase._update_internal_state, actors/_base.py:247-269; rnn_decoder.py:121-124)
+__device__ __forceinline__ void msg_in_row(const float *wt, const float *wb, float x, float glob0, int lane, float &u0,
+                                           float &u1) {
+    float a0 = wb[lane], a1 = wb[lane + 32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float xi = __shfl_sync(0xffffffffu, x, i);
+        a0 = fmaf(wt[i * 64 + lane], xi, a0);
+        a1 = fmaf(wt[i * 64 + lane + 32], xi, a1);
+    }
+    a0 = fmaf(wt[32 * 64 + lane], glob0, a0);     // + wt[33][.] * 0: the 2nd global feature is identically 0 (quirk C)
+    a1 = fmaf(wt[32 * 64 + lane + 32], glob0, a1);
+    u0 = lrelu(a0);
+    u1 = lrelu(a1);
+}
+__device__ __forceinline__ void msg_in_load(const float *__restrict__ msg_w, const float *__restrict__ msg_b, float *wt,
+                                            float *wb) {
+    for (int i = threadIdx.x; i < 34 * 64; i += blockDim.x) wt[i] = msg_w[(i % 64) * 34 + (i / 64)];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) wb[i] = msg_b[i];
+}
+__device__ __forceinline__ void msg_in_store(const ecord_policy &p, int m, int lane, float u0, float u1) {
+    p.u[(long long)m * 64 + lane] = u0;
+    p.u[(long long)m * 64 + lane + 32] = u1;
+    if (p.u_bf16) {
+        __nv_bfloat16 *ub = reinterpret_cast<__nv_bfloat16 *>(p.u_bf16);
+        ub[(long long)m * 64 + lane] = __float2bfloat16(u0);
+        ub[(long long)m * 64 + lane + 32] = __float2bfloat16(u1);
+    }
+}

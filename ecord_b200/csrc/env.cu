@@ -93,6 +93,56 @@ k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, cons
     }
 }
 
+// The same step fused with the NEXT step's msg_in stage (policy.cu k_policy_pre): the warp that just applied the
+// flip holds everything that stage reads -- the new (best - score) and the cached embedding of the chosen vertex.
+__global__ void __launch_bounds__(256)
+k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const int32_t *step_base, int step_off,
+                 float *score_log, int32_t *action_log, int log_stride) {
+    __shared__ float wt[34 * 64];
+    __shared__ float wb[64];
+    msg_in_load(w.msg_w, w.msg_b, wt, wb);
+    __syncthreads();
+    const int T = e.num_tradj;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= g.num_graphs * T) return;
+    const int step_no = (step_base ? *step_base : 0) + step_off;
+    const int gi = m / T, t = m - gi * T;
+    int n;
+    const long long base = unit_base(g.graph_ptr, gi, t, T, n);
+    const int lo = g.graph_ptr[gi];
+    const int a = p.actions[m];
+    const float pa = e.peek[base + a];
+    const int spa = e.sp[base + a];
+    const int sa = spa & 1;
+    const float fa = (float)(2 * sa - 1);
+    const int k1 = g.row_ptr[lo + a + 1];
+    for (int k = g.row_ptr[lo + a] + lane; k < k1; k += 32) {
+        const int nb = g.col[k] - lo;
+        const float fn = (float)(2 * (e.sp[base + nb] & 1) - 1);
+        const float sw = fa * fn * g.w[k];
+        e.peek[base + nb] = e.peek[base + nb] - 2.0f * sw;
+    }
+    float glob0 = 0.0f;
+    if (lane == 0) {
+        const float sc = e.score[m] + pa;
+        e.score[m] = sc;
+        float best = e.best_score[m];
+        const bool new_best = sc > best;
+        if (new_best) { best = sc; e.best_score[m] = sc; e.best_step[m] = step_no + 1; }
+        e.peek[base + a] = -1.0f * pa;
+        e.sp[base + a] = ((step_no + 1) << 1) | (sa ^ 1);
+        if (new_best) e.best_state[base + a] = (uint8_t)(sa ^ 1);
+        if (score_log) score_log[(long long)step_no * log_stride + m] = sc;
+        if (action_log) action_log[(long long)step_no * log_stride + m] = a;
+        glob0 = (best - sc) / (float)n;                      // SCORE_FROM_BEST_NORM of the new observation
+    }
+    glob0 = __shfl_sync(0xffffffffu, glob0, 0);
+    float u0, u1;
+    msg_in_row(wt, wb, p.last_sel[(long long)m * ECORD_DIM_NODE + lane], glob0, lane, u0, u1);
+    msg_in_store(p, m, lane, u0, u1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // a4 / parity view: materialise the reference's arrays.
 // ------------------------------------------------------------------------------------------------
@@ -226,6 +276,26 @@ int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *a
                                                                   action_log, GT);
     ECORD_LAUNCH_CHECK();
     return 0;
+}
+
+int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                          const int32_t *step_base, int step_off, float *score_log, int32_t *action_log, cudaStream_t st) {
+    const int GT = g->num_graphs * env->num_tradj;
+    k_env_step_fused<<<ceil_div((long long)GT * 32, 256), 256, 0, st>>>(*g, *env, *w, *p, step_base, step_off, score_log,
+                                                                        action_log, GT);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ecord_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                                    int32_t step_no, float *score_log, void *stream) {
+    int rc;
+    if ((rc = check_graph(g)) || (rc = check_env(env))) return rc;
+    ECORD_RET_IF(!w || !p || !p->actions || !p->last_sel || !p->u || !w->msg_w || !w->msg_b, ECORD_E_NULL);
+    ECORD_RET_IF(step_no < 0 || p->rows != g->num_graphs * env->num_tradj, ECORD_E_SIZE);
+    const int GT = g->num_graphs * env->num_tradj;
+    float *log0 = score_log ? score_log - (long long)step_no * GT : nullptr;
+    return launch_env_step_fused(g, env, w, p, nullptr, step_no, log0, nullptr, as_stream(stream));
 }
 
 extern "C" int ecord_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, int32_t step_no,

@@ -7,7 +7,8 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B) -> 4-stage smem ring, mbarrier complete_tx
 //   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //               (bf16 x bf16 -> fp32 accumulate in TMEM), tcgen05.commit releases smem stages / signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> fused math -> global
+//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 16 columns at a time) -> registers -> fused math -> global;
+//               warp w reads TMEM lanes 32*(w%4).., the two warps of a lane quarter split the tile's columns
 //
 // GRU tile = 128 rows x 64 hidden units.  The weight rows of one 64-unit block are packed (ecord_pack_weights)
 // as [r | z | hn | in] so ONE accumulator [128 x 256] holds all four gate pre-activations of the block:
@@ -26,7 +27,7 @@ constexpr int BM = 128;          // rows per tile (UMMA_M)
 constexpr int BK = 64;           // bf16 elements per k-chunk = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
-constexpr int kThreads = 192;    // 6 warps
+constexpr int kThreads = 320;    // 10 warps: TMA, MMA, 8 epilogue (two per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,6 +84,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// MUFU.TANH (rel. error ~2^-11): the bf16 path rounds its outputs to 8 mantissa bits anyway
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 struct TcParams {
     // GRU
@@ -182,8 +186,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
             umma_commit(accum_bar);                       // accumulator complete
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                 // which 32 of the tile's 64 output columns
         const int row = m0 + q * 32 + lane;
         mbar_wait(accum_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -194,7 +199,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
             __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + nb * 64;
             __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + nb * 64;
 #pragma unroll 1
-            for (int j0 = 0; j0 < 64; j0 += 16) {
+            for (int j0 = half * 32; j0 < half * 32 + 32; j0 += 16) {
                 float ar[16], az[16], ahn[16], ain[16];
                 tmem_ld16(tbase + j0, ar);
                 tmem_ld16(tbase + 64 + j0, az);
@@ -209,13 +214,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int j = nb * 64 + j0 + i;
-                        const float r = sigmoidf_acc((ar[i] + prm.bhh[j]) + prm.bih[j]);
-                        const float z = sigmoidf_acc((az[i] + prm.bhh[H + j]) + prm.bih[H + j]);
-                        const float n = tanhf(__fadd_rn(ain[i] + prm.bih[2 * H + j], __fmul_rn(ahn[i] + prm.bhh[2 * H + j], r)));
-                        const float hn = __fadd_rn(__fmul_rn(__fsub_rn(hv[i], n), z), n);
+                        const float r = sigmoid_fast((ar[i] + prm.bhh[j]) + prm.bih[j]);
+                        const float z = sigmoid_fast((az[i] + prm.bhh[H + j]) + prm.bih[H + j]);
+                        const float n = tanh_fast(fmaf(ahn[i] + prm.bhh[2 * H + j], r, ain[i] + prm.bih[2 * H + j]));
+                        const float hn = fmaf(hv[i] - n, z, n);
                         hv[i] = hn;
                         ob[i] = __float2bfloat16(hn);
-                        ot[i] = __float2bfloat16(tanhf(hn));
+                        ot[i] = __float2bfloat16(tanh_fast(hn));
                     }
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(hnew + j0 + i) = *reinterpret_cast<float4 *>(&hv[i]);
@@ -228,7 +233,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
         } else {
             float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + nb * 64;
 #pragma unroll 1
-            for (int j0 = 0; j0 < 64; j0 += 16) {
+            for (int j0 = half * 32; j0 < half * 32 + 32; j0 += 16) {
                 float acc[16];
                 tmem_ld16(tbase + j0, acc);
                 tmem_ld_wait();
@@ -322,21 +327,38 @@ extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
     return 0;
 }
 
-// Host-side fold of the node-feature encoder into mlp_out[0] (all arguments are HOST arrays):
-//   C[c][k] = sum_i Wq[c][48+i] W_enc[i][k]   (64 x 3), stored as three planes C0|C1|C2, then gamma|beta|w_o.
+// Host-side fold of the node-feature encoder into mlp_out[0] (all arguments are HOST arrays); layout of `out`
+// is documented at ecord_weights.q_fold:
+//   C[c][k] = sum_i Wq[c][48+i] W_enc[i][k]   (64 x 3), stored as planes C0|C1|C2, then gamma|beta|w_o, then the
+//   channel-centred C planes, LC_k = sum_c w_o[c] gamma[c] Cc[c][k], and sum_c w_o[c] beta[c].
 extern "C" int ecord_fold_q_host(const float *q1_w, const float *enc_w, const float *qln_w, const float *qln_b,
-                                 const float *q2_w, float *out384) {
-    ECORD_RET_IF(!q1_w || !enc_w || !qln_w || !qln_b || !q2_w || !out384, ECORD_E_NULL);
-    for (int c = 0; c < ECORD_DIM_Q; ++c) {
+                                 const float *q2_w, float *out) {
+    ECORD_RET_IF(!q1_w || !enc_w || !qln_w || !qln_b || !q2_w || !out, ECORD_E_NULL);
+    const int Q = ECORD_DIM_Q;
+    double mean[3] = {0, 0, 0};
+    for (int c = 0; c < Q; ++c) {
         for (int k = 0; k < 3; ++k) {
             float a = 0.0f;
-            for (int i = 0; i < 16; ++i) a = fmaf(q1_w[c * ECORD_DIM_Q + 48 + i], enc_w[i * 3 + k], a);
-            out384[k * ECORD_DIM_Q + c] = a;
+            for (int i = 0; i < 16; ++i) a = fmaf(q1_w[c * Q + 48 + i], enc_w[i * 3 + k], a);
+            out[k * Q + c] = a;
+            mean[k] += a;
         }
-        out384[3 * ECORD_DIM_Q + c] = qln_w[c];
-        out384[4 * ECORD_DIM_Q + c] = qln_b[c];
-        out384[5 * ECORD_DIM_Q + c] = q2_w[c];
+        out[3 * Q + c] = qln_w[c];
+        out[4 * Q + c] = qln_b[c];
+        out[5 * Q + c] = q2_w[c];
     }
+    double wb = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        double lc = 0.0;
+        for (int c = 0; c < Q; ++c) {
+            const float cc = (float)((double)out[k * Q + c] - mean[k] / Q);
+            out[384 + k * Q + c] = cc;
+            lc += (double)q2_w[c] * (double)qln_w[c] * (double)cc;
+        }
+        out[576 + k] = (float)lc;
+    }
+    for (int c = 0; c < Q; ++c) wb += (double)q2_w[c] * (double)qln_b[c];
+    out[579] = (float)wb;
     return 0;
 }
 

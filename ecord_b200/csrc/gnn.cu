@@ -164,7 +164,7 @@ __global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__res
 
 // node_emb = W_g x + b_g ; node_B = Wq[:,32:48] node_emb + Wq[:,48:64] b_enc
 __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ x, float *gnn_out, float *node_emb,
-                             float *node_B) {
+                             float *node_B, float *node_Bc, float *node_LB) {
     __shared__ float gw[D * D], gb[D], qb[ECORD_DIM_Q * D], qd[ECORD_DIM_Q];
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) gw[i] = wt.g2r_w[i];
     if (threadIdx.x < D) gb[threadIdx.x] = wt.g2r_b[threadIdx.x];
@@ -188,11 +188,23 @@ __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ 
         e[o] = a;
         node_emb[(long long)v * D + o] = a;
     }
+    float bsum = 0.0f;
     for (int c = 0; c < ECORD_DIM_Q; ++c) {
         float a = qd[c];
 #pragma unroll
         for (int i = 0; i < D; ++i) a = fmaf(qb[c * D + i], e[i], a);
         node_B[(long long)v * ECORD_DIM_Q + c] = a;
+        bsum += a;
+    }
+    if (node_Bc) {     // fast Q kernel operands: B - mean_c(B) and its projection on w_o * gamma
+        const float mean = bsum * (1.0f / ECORD_DIM_Q);
+        float lb = 0.0f;
+        for (int c = 0; c < ECORD_DIM_Q; ++c) {
+            const float bc = node_B[(long long)v * ECORD_DIM_Q + c] - mean;
+            node_Bc[(long long)v * ECORD_DIM_Q + c] = bc;
+            lb = fmaf(wt.q2_w[c] * wt.qln_w[c], bc, lb);
+        }
+        node_LB[v] = lb;
     }
 }
 }  // namespace
@@ -203,7 +215,8 @@ extern "C" size_t ecord_gnn_workspace_bytes(int32_t N) {
 }
 
 extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
-                               void *workspace, void *stream) {
+                               float *node_Bc, float *node_LB, void *workspace, void *stream) {
+    ECORD_RET_IF((node_Bc == nullptr) != (node_LB == nullptr), ECORD_E_NULL);
     ECORD_RET_IF(!g || !w || !node_emb || !node_B || !workspace, ECORD_E_NULL);
     ECORD_RET_IF(g->num_nodes <= 0, ECORD_E_SIZE);
     ECORD_RET_IF(!g->in_ptr || (g->num_edges > 0 && (!g->in_src || !g->in_w)), ECORD_E_NULL);
@@ -230,7 +243,7 @@ extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, flo
         ECORD_LAUNCH_CHECK();
         float *t = cur; cur = nxt; nxt = t;
     }
-    k_gnn_finish<<<nb, TB, 0, st>>>(N, *w, cur, gnn_out, node_emb, node_B);
+    k_gnn_finish<<<nb, TB, 0, st>>>(N, *w, cur, gnn_out, node_emb, node_B, node_Bc, node_LB);
     ECORD_LAUNCH_CHECK();
     return 0;
 }

@@ -36,8 +36,7 @@ __global__ void __launch_bounds__(256)
 k_policy_pre(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p) {
     __shared__ float wt[34 * MSG];   // transposed msg_in weight: wt[i][o]
     __shared__ float wb[MSG];
-    for (int i = threadIdx.x; i < 34 * MSG; i += blockDim.x) wt[i] = w.msg_w[(i % MSG) * 34 + (i / MSG)];
-    if (threadIdx.x < MSG) wb[threadIdx.x] = w.msg_b[threadIdx.x];
+    msg_in_load(w.msg_w, w.msg_b, wt, wb);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -45,24 +44,9 @@ k_policy_pre(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p) {
     const int T = e.num_tradj, gi = m / T;
     const float x = p.last_sel[(long long)m * ND + lane];
     const float glob0 = (e.best_score[m] - e.score[m]) / (float)(g.graph_ptr[gi + 1] - g.graph_ptr[gi]);
-    float a0 = wb[lane], a1 = wb[lane + 32];
-#pragma unroll
-    for (int i = 0; i < ND; ++i) {
-        const float xi = __shfl_sync(0xffffffffu, x, i);
-        a0 = fmaf(wt[i * MSG + lane], xi, a0);
-        a1 = fmaf(wt[i * MSG + lane + 32], xi, a1);
-    }
-    a0 = fmaf(wt[32 * MSG + lane], glob0, a0);
-    a1 = fmaf(wt[32 * MSG + lane + 32], glob0, a1);
-    // + wt[33][.] * 0
-    a0 = lrelu(a0); a1 = lrelu(a1);
-    p.u[(long long)m * MSG + lane] = a0;
-    p.u[(long long)m * MSG + lane + 32] = a1;
-    if (p.u_bf16) {
-        __nv_bfloat16 *ub = reinterpret_cast<__nv_bfloat16 *>(p.u_bf16);
-        ub[(long long)m * MSG + lane] = __float2bfloat16(a0);
-        ub[(long long)m * MSG + lane + 32] = __float2bfloat16(a1);
-    }
+    float u0, u1;
+    msg_in_row(wt, wb, x, glob0, lane, u0, u1);
+    msg_in_store(p, m, lane, u0, u1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -205,17 +189,34 @@ k_policy_tail(ecord_weights w, ecord_policy p) {
         if (lane == 0) p.v[m] = vv + w.v2_b[0];
         p.A[(long long)m * ECORD_DIM_Q + lane] = a0;
         p.A[(long long)m * ECORD_DIM_Q + lane + 32] = a1;
+        if (p.Ac) {   // fast Q kernel operands: A - mean_c(A), and its projection on w_o * gamma
+            const float meanA = warp_sum(a0 + a1) * (1.0f / ECORD_DIM_Q);
+            const float c0 = a0 - meanA, c1 = a1 - meanA;
+            p.Ac[(long long)m * ECORD_DIM_Q + lane] = c0;
+            p.Ac[(long long)m * ECORD_DIM_Q + lane + 32] = c1;
+            const float la = warp_sum(w.q2_w[lane] * w.qln_w[lane] * c0 + w.q2_w[lane + 32] * w.qln_w[lane + 32] * c1);
+            if (lane == 0) p.LA[m] = la;
+        }
     }
 }
 }  // namespace
 
 // the hidden buffer holding the current state is ((*step_base) + step_off) & 1, resolved on the device so that a
 // captured CUDA graph stays valid when replayed at a later step count
-int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                       const int32_t *step_base, int step_off, int gemm_mode, cudaStream_t st) {
-    const int M = p->rows, Mp = p->rows_pad;
-    k_policy_pre<<<ceil_div((long long)M * 32, 256), 256, 0, st>>>(*g, *env, *w, *p);
+int launch_policy_pre(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                      cudaStream_t st) {
+    k_policy_pre<<<ceil_div((long long)p->rows * 32, 256), 256, 0, st>>>(*g, *env, *w, *p);
     ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                       const int32_t *step_base, int step_off, int gemm_mode, int skip_pre, cudaStream_t st) {
+    const int M = p->rows, Mp = p->rows_pad;
+    if (!skip_pre) {
+        int rc = launch_policy_pre(g, env, w, p, st);
+        if (rc) return rc;
+    }
     if (gemm_mode == ECORD_GEMM_FP32) {
         const float *h0 = p->hidden, *h1 = p->hidden + (long long)Mp * H;
         k_sgemm_nt_bias<<<dim3(3072 / 64, Mp / 64), 256, 0, st>>>(p->u, p->u, nullptr, 0, w->gru_wih, w->gru_bih, p->gates,
@@ -239,7 +240,7 @@ int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_w
     return 0;
 }
 
-int policy_kernels_per_step(int gemm_mode) { return gemm_mode == ECORD_GEMM_FP32 ? 6 : 4; }
+int policy_kernels_per_step(int gemm_mode, int skip_pre) { return (gemm_mode == ECORD_GEMM_FP32 ? 6 : 4) - (skip_pre ? 1 : 0); }
 
 int policy_init_attrs() {
     ECORD_CUDA(cudaFuncSetAttribute(k_policy_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
@@ -255,8 +256,16 @@ int check_policy(const ecord_policy *p, int gemm_mode) {
     return 0;
 }
 
+extern "C" int ecord_policy_pre(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                                void *stream) {
+    ECORD_RET_IF(!g || !env || !w || !p, ECORD_E_NULL);
+    ECORD_RET_IF(!p->u || !p->last_sel || !w->msg_w || !w->msg_b, ECORD_E_NULL);
+    ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj, ECORD_E_SIZE);
+    return launch_policy_pre(g, env, w, p, as_stream(stream));
+}
+
 extern "C" int ecord_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                                 int32_t cur, int32_t gemm_mode, void *stream) {
+                                 int32_t cur, int32_t gemm_mode, int32_t skip_pre, void *stream) {
     ECORD_RET_IF(!g || !env || !w, ECORD_E_NULL);
     ECORD_RET_IF(gemm_mode != ECORD_GEMM_FP32 && gemm_mode != ECORD_GEMM_BF16, ECORD_E_UNSUPPORTED);
     ECORD_RET_IF(cur != 0 && cur != 1, ECORD_E_SIZE);
@@ -265,5 +274,6 @@ extern "C" int ecord_policy_step(const ecord_graph *g, const ecord_env *env, con
     ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj, ECORD_E_SIZE);
     if (gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!w->gru_w_bf16 || !w->p1_w_bf16, ECORD_E_NULL);
     if ((rc = policy_init_attrs())) return rc;
-    return launch_policy_step(g, env, w, p, nullptr, cur, gemm_mode, as_stream(stream));
+    ECORD_RET_IF((p->Ac == nullptr) != (p->LA == nullptr), ECORD_E_NULL);
+    return launch_policy_step(g, env, w, p, nullptr, cur, gemm_mode, skip_pre, as_stream(stream));
 }

@@ -180,6 +180,154 @@ k_q_select(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const __
     }
 }
 
+// =================================================================================================
+// ECORD_Q_FAST: the throughput form of the same head.
+//
+// (1) Work decomposition.  The exact kernel streams B[n] (256 B) from L2 for every (vertex, trajectory) row:
+//     N*T*256 B per step.  Here one thread owns ONE vertex, keeps its 64-float operand in registers and loops over
+//     a range of trajectories of its graph, so B is read once per (vertex, step); the per-(g,t) operand A comes
+//     from shared memory as warp-uniform LDS.128 broadcasts.  Grid = (vertex tiles of 128) x (trajectory splits).
+// (2) Arithmetic.  With every operand centred over the 64 channels (Ac, Bc, Cc: rows sum to 0) the LayerNorm mean
+//     vanishes identically, and LeakyReLU(y) = a1 y + a2 |y| (a1 = 0.505, a2 = 0.495) splits the head into a part
+//     LINEAR in the pre-activation -- which folds into three scalars LA[g,t] + LB[n] + LC.f -- and an |.| part:
+//         x_c   = Ac_c + Bc_c + Cc_c . f                         (1 FADD + 3 FFMA)
+//         ss   += x_c^2                                          (1 FFMA)      sigma = sqrt(ss/64 + eps)
+//         acc  += w_c |gamma_c x_c + beta_c sigma|               (1 FMUL + 2 FFMA; |.| is a free operand modifier)
+//         q     = a1 (LA + LB + LC.f)/sigma + a1 sum(w beta) + a2 acc/sigma + b_o + v[g,t]
+//     8 fp32 ops per channel instead of ~12: the same function re-associated (differences ~1e-6 relative).
+// (3) Arg-max across the CTAs that share a (g,t): warp REDUX.MAX on the order-preserving integer image of q,
+//     a ballot picks the lowest vertex among equals, one 64-bit atomicMax per warp on keys[g*T+t].
+// =================================================================================================
+struct QConstFast { float C0[Q], C1[Q], C2[Q], gam[Q], bet[Q], wo[Q]; float LC[3], Wb; };
+constexpr int QT = ECORD_QTILE;      // vertices per CTA = threads per CTA
+constexpr int kMaxTChunk = 32;       // trajectories per CTA (shared-memory A rows)
+
+struct QFastSmem { float A[kMaxTChunk][Q]; float LA[kMaxTChunk], V[kMaxTChunk]; };
+
+__global__ void __launch_bounds__(QT, 3)
+k_q_fast(ecord_graph g, ecord_env e, ecord_policy p, const __grid_constant__ QConstFast K, const float *__restrict__ q2_b,
+         const int32_t *step_base, int step_off, int t_chunk) {
+    __shared__ __align__(16) QFastSmem S;
+    const int tile = blockIdx.x;
+    const int gi = g.qtile_graph[tile], v0 = g.qtile_v0[tile];
+    const int T = e.num_tradj;
+    const int t_lo = blockIdx.y * t_chunk, t_hi = min(T, t_lo + t_chunk);
+    const int steps_done = (step_base ? *step_base : 0) + step_off;
+    const int lo = g.graph_ptr[gi], n = g.graph_ptr[gi + 1] - lo;
+    const int lane = threadIdx.x & 31;
+    // per-(g,t) operands of this CTA's trajectory range -> shared memory
+    for (int i = threadIdx.x; i < (t_hi - t_lo) * (Q / 4); i += QT) {
+        const int tt = i / (Q / 4), c4 = i % (Q / 4);
+        reinterpret_cast<float4 *>(S.A[tt])[c4] =
+            reinterpret_cast<const float4 *>(p.Ac + (long long)(gi * T + t_lo + tt) * Q)[c4];
+    }
+    for (int i = threadIdx.x; i < t_hi - t_lo; i += QT) {
+        S.LA[i] = p.LA[gi * T + t_lo + i];
+        S.V[i] = p.v[gi * T + t_lo + i];
+    }
+    // per-vertex operand -> registers (kept across the trajectory loop)
+    const bool valid = v0 + (int)threadIdx.x < n;
+    const int v = valid ? v0 + (int)threadIdx.x : n - 1;
+    float b[Q];
+    {
+        const float4 *bp = reinterpret_cast<const float4 *>(p.node_Bc + (long long)(lo + v) * Q);
+#pragma unroll
+        for (int c = 0; c < Q / 4; ++c) {
+            const float4 t4 = bp[c];
+            b[4 * c] = t4.x; b[4 * c + 1] = t4.y; b[4 * c + 2] = t4.z; b[4 * c + 3] = t4.w;
+        }
+    }
+    const float lb = p.node_LB[lo + v];
+    const float bo = q2_b[0];
+    __syncthreads();
+
+    const long long base0 = (long long)lo * T + v;
+    int sp = e.sp[base0 + (long long)t_lo * n];
+    float pk = e.peek[base0 + (long long)t_lo * n];
+    for (int t = t_lo; t < t_hi; ++t) {
+        const int sp_c = sp;
+        const float pk_c = pk;
+        if (t + 1 < t_hi) {                       // prefetch the next trajectory's state row entry
+            sp = e.sp[base0 + (long long)(t + 1) * n];
+            pk = e.peek[base0 + (long long)(t + 1) * n];
+        }
+        const float f0 = (float)(sp_c & 1);
+        const float f1 = pk_c / (float)n;
+        const float f2 = fminf((float)(steps_done - (sp_c >> 1)), (float)ECORD_STATIC_CLIP) / (float)ECORD_STATIC_CLIP;
+        const float *As = S.A[t - t_lo];
+        float x[Q];
+        float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < Q; c += 4) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(As + c);
+            x[c + 0] = fmaf(K.C2[c + 0], f2, fmaf(K.C1[c + 0], f1, fmaf(K.C0[c + 0], f0, a4.x + b[c + 0])));
+            x[c + 1] = fmaf(K.C2[c + 1], f2, fmaf(K.C1[c + 1], f1, fmaf(K.C0[c + 1], f0, a4.y + b[c + 1])));
+            x[c + 2] = fmaf(K.C2[c + 2], f2, fmaf(K.C1[c + 2], f1, fmaf(K.C0[c + 2], f0, a4.z + b[c + 2])));
+            x[c + 3] = fmaf(K.C2[c + 3], f2, fmaf(K.C1[c + 3], f1, fmaf(K.C0[c + 3], f0, a4.w + b[c + 3])));
+            ss0 = fmaf(x[c + 0], x[c + 0], ss0); ss1 = fmaf(x[c + 1], x[c + 1], ss1);
+            ss2 = fmaf(x[c + 2], x[c + 2], ss2); ss3 = fmaf(x[c + 3], x[c + 3], ss3);
+        }
+        const float var = ((ss0 + ss1) + (ss2 + ss3)) * (1.0f / Q);
+        const float sigma = sqrtf(var + kLnEps);
+        const float rstd = 1.0f / sigma;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < Q; c += 4) {
+            a0 = fmaf(K.wo[c + 0], fabsf(fmaf(x[c + 0], K.gam[c + 0], K.bet[c + 0] * sigma)), a0);
+            a1 = fmaf(K.wo[c + 1], fabsf(fmaf(x[c + 1], K.gam[c + 1], K.bet[c + 1] * sigma)), a1);
+            a2 = fmaf(K.wo[c + 2], fabsf(fmaf(x[c + 2], K.gam[c + 2], K.bet[c + 2] * sigma)), a2);
+            a3 = fmaf(K.wo[c + 3], fabsf(fmaf(x[c + 3], K.gam[c + 3], K.bet[c + 3] * sigma)), a3);
+        }
+        const float acc = (a0 + a1) + (a2 + a3);
+        const float lin = S.LA[t - t_lo] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
+        const float dot = fmaf(0.505f, fmaf(lin, rstd, K.Wb), 0.495f * acc * rstd);
+        const float q = (dot + bo) + S.V[t - t_lo];
+        if (p.q && valid) p.q[base0 + (long long)t * n] = q;
+        // arg-max: ordered-int max across the warp, lowest vertex among equals, one atomic per warp
+        const uint32_t ord = valid ? f2ord(q) : 0u;
+        const uint32_t mx = __reduce_max_sync(0xffffffffu, ord);
+        const uint32_t bal = __ballot_sync(0xffffffffu, ord == mx);
+        if (lane == 0 && mx != 0u) {
+            const int vbest = v0 + (int)(threadIdx.x & ~31u) + (__ffs(bal) - 1);
+            atomicMax(p.keys + (gi * T + t), ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)vbest));
+        }
+    }
+}
+
+// one warp per (g,t): decode the arg-max key, cache the chosen vertex's embedding, reset the key
+__global__ void __launch_bounds__(256)
+k_select_finish(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const int32_t *step_base, int step_off,
+                int compat, const int32_t *__restrict__ forced) {
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= p.rows) return;
+    const int T = e.num_tradj;
+    const int gi = m / T, t = m - gi * T;
+    const int steps_done = (step_base ? *step_base : 0) + step_off;
+    const unsigned long long key = p.keys[m];
+    int a = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+    if (forced) a = forced[m];
+    const int lo = g.graph_ptr[gi];
+    const int j = compat ? a : lo + a;
+    const int gj = g.node_graph[j];
+    int nj;
+    const long long bj = unit_base(g.graph_ptr, gj, t, T, nj);
+    float f0, f1, f2;
+    features(e, bj + (j - g.graph_ptr[gj]), nj, steps_done, f0, f1, f2);
+    float val;
+    if (lane < 16) val = p.node_emb[(long long)j * 16 + lane];
+    else {
+        const int c = lane - 16;
+        val = w.enc_b[c];
+        val = fmaf(w.enc_w[c * 3 + 0], f0, val);
+        val = fmaf(w.enc_w[c * 3 + 1], f1, val);
+        val = fmaf(w.enc_w[c * 3 + 2], f2, val);
+    }
+    p.last_sel[(long long)m * ECORD_DIM_NODE + lane] = val;
+    __syncwarp();
+    if (lane == 0) { p.actions[m] = a; p.keys[m] = 0ull; }
+}
+
 // plane [N*T] (trajectory-major) -> reference layout [N][T]
 __global__ void k_plane_to_nt(ecord_graph g, int T, const float *__restrict__ plane, float *__restrict__ out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,9 +341,33 @@ __global__ void k_plane_to_nt(ecord_graph g, int T, const float *__restrict__ pl
 
 static int q_block_size(int n_max) { return n_max <= 32 ? 32 : n_max <= 64 ? 64 : n_max <= 128 ? 128 : 256; }
 
+int q_kernels_per_step(int q_mode) { return q_mode == ECORD_Q_FAST ? 2 : 1; }
+
+static int launch_q_fast(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                         const int32_t *step_base, int step_off, int compat, const int32_t *forced, cudaStream_t st) {
+    QConstFast K;
+    memcpy(K.C0, w->q_fold + 384, 3 * Q * sizeof(float));          // centred C planes
+    memcpy(K.gam, w->q_fold + 3 * Q, 3 * Q * sizeof(float));        // gamma | beta | w_o
+    memcpy(K.LC, w->q_fold + 576, 4 * sizeof(float));               // LC[3], Wb
+    const int T = env->num_tradj;
+    // trajectory splits: enough CTAs for >= ~3 waves of (148 SMs x 3 CTAs), at most kMaxTChunk rows of A in smem
+    int splits = ceil_div(3 * 3 * kNumSMs, g->num_qtiles);
+    if (splits > T) splits = T;
+    int t_chunk = ceil_div(T, splits);
+    if (t_chunk > kMaxTChunk) t_chunk = kMaxTChunk;
+    splits = ceil_div(T, t_chunk);
+    k_q_fast<<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
+    ECORD_LAUNCH_CHECK();
+    k_select_finish<<<ceil_div((long long)p->rows * 32, 256), 256, 0, st>>>(*g, *env, *w, *p, step_base, step_off, compat,
+                                                                             forced);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                     const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat, const int32_t *forced,
-                    cudaStream_t st) {
+                    int q_mode, cudaStream_t st) {
+    if (q_mode == ECORD_Q_FAST) return launch_q_fast(g, env, w, p, step_base, step_off, compat, forced, st);
     QConst K;
     static_assert(sizeof(QConst) == 6 * Q * sizeof(float), "QConst must be densely packed");
     memcpy(&K, w->q_fold, sizeof(QConst));      // q_fold is a HOST array (see ecord_weights)
@@ -207,13 +379,19 @@ int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weig
 
 extern "C" int ecord_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                               int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
-                              void *stream) {
+                              int32_t q_mode, void *stream) {
     ECORD_RET_IF(!g || !env || !w || !p, ECORD_E_NULL);
     ECORD_RET_IF(!p->A || !p->v || !p->node_B || !p->node_emb || !p->last_sel || !p->actions || !w->q_fold, ECORD_E_NULL);
     ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj || steps_done < 0, ECORD_E_SIZE);
     ECORD_RET_IF(tau < 0.0f, ECORD_E_SIZE);
     ECORD_RET_IF(tau > 0.0f && !p->q, ECORD_E_NULL);
-    return launch_q_select(g, env, w, p, nullptr, steps_done, tau, seed, compat, forced_actions, as_stream(stream));
+    ECORD_RET_IF(q_mode != ECORD_Q_EXACT && q_mode != ECORD_Q_FAST, ECORD_E_UNSUPPORTED);
+    if (q_mode == ECORD_Q_FAST) {
+        ECORD_RET_IF(tau > 0.0f, ECORD_E_UNSUPPORTED);     // sampling needs the two-pass exact kernel
+        ECORD_RET_IF(!p->Ac || !p->LA || !p->node_Bc || !p->node_LB || !p->keys, ECORD_E_NULL);
+        ECORD_RET_IF(g->num_qtiles <= 0 || !g->qtile_graph || !g->qtile_v0, ECORD_E_NULL);
+    }
+    return launch_q_select(g, env, w, p, nullptr, steps_done, tau, seed, compat, forced_actions, q_mode, as_stream(stream));
 }
 
 extern "C" int ecord_plane_to_nt(const ecord_graph *g, int32_t num_tradj, const float *plane, float *out, void *stream) {

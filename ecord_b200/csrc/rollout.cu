@@ -11,13 +11,16 @@
 #include <new>
 
 int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                       const int32_t *step_base, int step_off, int gemm_mode, cudaStream_t st);
-int policy_kernels_per_step(int gemm_mode);
+                       const int32_t *step_base, int step_off, int gemm_mode, int skip_pre, cudaStream_t st);
+int policy_kernels_per_step(int gemm_mode, int skip_pre);
+int q_kernels_per_step(int q_mode);
+int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                          const int32_t *step_base, int step_off, float *score_log, int32_t *action_log, cudaStream_t st);
 int policy_init_attrs();
 int check_policy(const ecord_policy *p, int gemm_mode);
 int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                     const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat, const int32_t *forced,
-                    cudaStream_t st);
+                    int q_mode, cudaStream_t st);
 int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, const int32_t *step_base,
                     int step_off, float *score_log, int32_t *action_log, cudaStream_t st);
 
@@ -70,12 +73,18 @@ int capture(ecord_rollout_plan *pl, int nsteps, cudaGraphExec_t *out) {
     ECORD_CUDA(cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeRelaxed));
     int rc = 0;
     const ecord_rollout_desc &d = pl->desc;
+    // ECORD_Q_FAST also fuses the next step's msg_in stage into the env-step kernel (u must be primed once with
+    // ecord_policy_pre before the first step); ECORD_Q_EXACT keeps the literal kernel sequence.
+    const int fused = d.q_mode == ECORD_Q_FAST;
     for (int i = 0; i < nsteps && !rc; ++i) {
-        rc = launch_policy_step(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i, d.gemm_mode, pl->stream);
+        rc = launch_policy_step(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i, d.gemm_mode, fused,
+                                pl->stream);
         if (!rc) rc = launch_q_select(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i, d.tau, d.seed,
-                                      d.compat, nullptr, pl->stream);
-        if (!rc) rc = launch_env_step(&pl->graph, &pl->env, pl->policy.actions, d.step_counter, i, d.score_log,
-                                      d.action_log, pl->stream);
+                                      d.compat, nullptr, d.q_mode, pl->stream);
+        if (!rc && fused) rc = launch_env_step_fused(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i,
+                                                     d.score_log, d.action_log, pl->stream);
+        if (!rc && !fused) rc = launch_env_step(&pl->graph, &pl->env, pl->policy.actions, d.step_counter, i, d.score_log,
+                                                d.action_log, pl->stream);
     }
     if (!rc) {
         k_advance<<<1, 1, 0, pl->stream>>>(d.step_counter, nsteps);
@@ -101,6 +110,13 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     if (rc) return rc;
     ECORD_RET_IF(desc->policy->rows != desc->graph->num_graphs * desc->env->num_tradj, ECORD_E_SIZE);
     ECORD_RET_IF(desc->tau > 0.0f && !desc->policy->q, ECORD_E_NULL);
+    ECORD_RET_IF(desc->q_mode != ECORD_Q_EXACT && desc->q_mode != ECORD_Q_FAST, ECORD_E_UNSUPPORTED);
+    if (desc->q_mode == ECORD_Q_FAST) {
+        ECORD_RET_IF(desc->tau > 0.0f, ECORD_E_UNSUPPORTED);
+        ECORD_RET_IF(!desc->policy->Ac || !desc->policy->LA || !desc->policy->node_Bc || !desc->policy->node_LB ||
+                     !desc->policy->keys, ECORD_E_NULL);
+        ECORD_RET_IF(desc->graph->num_qtiles <= 0 || !desc->graph->qtile_graph || !desc->graph->qtile_v0, ECORD_E_NULL);
+    }
     ECORD_RET_IF(!desc->weights->q_fold, ECORD_E_NULL);
     if (desc->gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!desc->weights->gru_w_bf16 || !desc->weights->p1_w_bf16, ECORD_E_NULL);
     if ((rc = policy_init_attrs())) return rc;
@@ -111,7 +127,8 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     pl->desc.graph = &pl->graph; pl->desc.env = &pl->env; pl->desc.weights = &pl->weights; pl->desc.policy = &pl->policy;
     pl->stream = as_stream(stream);
     pl->k = desc->steps_per_graph;
-    pl->kernels_per_step = policy_kernels_per_step(desc->gemm_mode) + 2;
+    pl->kernels_per_step = policy_kernels_per_step(desc->gemm_mode, desc->q_mode == ECORD_Q_FAST) +
+                           q_kernels_per_step(desc->q_mode) + 1;
     pl->exec_k = pl->exec_1 = nullptr;
     pl->steps_enqueued = 0;
     rc = capture(pl, pl->k, &pl->exec_k);

@@ -10,10 +10,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GEMM_BF16, GEMM_FP32, check, ptr
+from ._lib import GEMM_BF16, GEMM_FP32, Q_EXACT, Q_FAST, check, ptr
 from .network import check_state_dicts
 
 _GEMM_MODES = {"fp32": GEMM_FP32, "bf16": GEMM_BF16}
+_Q_MODES = {"exact": Q_EXACT, "fast": Q_FAST}
 
 
 def _require_cuda(device):
@@ -74,9 +75,16 @@ class DeviceGraph:
         self.N, self.G, self.E = N, G, E
         self.n_max = int(tg.num_nodes_list.max())
         self.num_nodes_list = tg.num_nodes_list
+        # vertex tiles for the fast Q kernel
+        tiles_per_graph = (tg.num_nodes_list + _lib.QTILE - 1) // _lib.QTILE
+        tg_ids = np.repeat(np.arange(G), tiles_per_graph).astype(np.int32)
+        starts = np.concatenate([[0], np.cumsum(tiles_per_graph)])[:-1]
+        tv0 = ((np.arange(tg_ids.shape[0]) - np.repeat(starts, tiles_per_graph)) * _lib.QTILE).astype(np.int32)
+        self.qtile_graph, self.qtile_v0 = up(tg_ids), up(tv0)
         self.c = _lib.Graph(G, N, E, self.n_max, ptr(self.graph_ptr), ptr(self.node_graph), ptr(self.row_ptr),
                             ptr(self.col), ptr(self.w), ptr(self.graph_edge_ptr), ptr(self.in_ptr),
-                            ptr(self.in_src), ptr(self.in_w))
+                            ptr(self.in_src), ptr(self.in_w), int(tg_ids.shape[0]), 0, ptr(self.qtile_graph),
+                            ptr(self.qtile_v0))
 
     def plane_index(self, T):
         """int64 [N,T]: plane offset of every (vertex, trajectory) -- host-side layout helper for views."""
@@ -103,7 +111,7 @@ class DeviceWeights:
             kw[field] = ptr(self.t[field])
         # folded Q-head constants (host array, passed to the kernel by value)
         r = sd['rnn']
-        self.q_fold = torch.empty(6 * 64, dtype=torch.float32)
+        self.q_fold = torch.empty(_lib.QFOLD_FLOATS, dtype=torch.float32)
         check(self.lib.ecord_fold_q_host(ptr(r['mlp_out.0.weight']), ptr(sd['node_encoder']['0.weight']),
                                          ptr(r['mlp_out.1.weight']), ptr(r['mlp_out.1.bias']),
                                          ptr(r['mlp_out.3.weight']), ptr(self.q_fold)), "ecord_fold_q_host")
@@ -123,7 +131,7 @@ class RolloutState:
     tests and `log_stats`; `run()` executes whole steps through the CUDA-graph plan."""
 
     def __init__(self, dgraph, weights, num_tradj, gemm="bf16", compat=True, tau=0.0, seed=0,
-                 max_steps=0, log_scores=True, log_actions=True, steps_per_graph=16, dump_q=False):
+                 max_steps=0, log_scores=True, log_actions=True, steps_per_graph=16, dump_q=False, q_mode=None):
         self.lib = _lib.load()
         self.g, self.w = dgraph, weights
         dev = dgraph.device
@@ -134,6 +142,13 @@ class RolloutState:
         if self.gemm == GEMM_BF16 and weights.gru_w_bf16 is None:
             raise ValueError("weights were created with pack_bf16=False")
         self.compat, self.tau, self.seed = bool(compat), float(tau), int(seed)
+        # parity mode = (fp32 GEMM, exact Q); throughput mode = (bf16 tcgen05 GEMM, fast Q).  tau > 0 needs exact Q.
+        if q_mode is None:
+            q_mode = "fast" if (gemm == "bf16" and self.tau == 0.0) else "exact"
+        self.q_mode = _Q_MODES[q_mode]
+        if self.q_mode == Q_FAST and self.tau > 0:
+            raise ValueError("tau > 0 (sampling) requires q_mode='exact'")
+        self.fused = self.q_mode == Q_FAST
         N, G = dgraph.N, dgraph.G
         M = G * T
         Mp = (M + 127) // 128 * 128
@@ -169,10 +184,18 @@ class RolloutState:
         self.gnn_out = torch.empty(N, 16, **f32)
         self.node_emb = torch.empty(N, 16, **f32)
         self.node_B = torch.empty(N, 64, **f32)
+        self.Ac = self.LA = self.node_Bc = self.node_LB = self.keys = None
+        if self.q_mode == Q_FAST:
+            self.Ac = torch.zeros(Mp, 64, **f32)
+            self.LA = torch.zeros(Mp, **f32)
+            self.node_Bc = torch.empty(N, 64, **f32)
+            self.node_LB = torch.empty(N, **f32)
+            self.keys = torch.zeros(M, dtype=torch.int64, device=dev)
         self.policy_c = _lib.Policy(M, Mp, ptr(self.hidden), ptr(self.hidden_bf16), ptr(self.th_bf16), ptr(self.u_bf16),
                                     ptr(self.u), ptr(self.gates), ptr(self.th), ptr(self.y1), ptr(self.P), ptr(self.A),
                                     ptr(self.v), ptr(self.last_sel), ptr(self.node_emb), ptr(self.node_B),
-                                    ptr(self.actions), ptr(self.q))
+                                    ptr(self.actions), ptr(self.q), ptr(self.Ac), ptr(self.LA), ptr(self.node_Bc),
+                                    ptr(self.node_LB), ptr(self.keys))
         # logs + step counter
         self.max_steps = int(max_steps)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -191,7 +214,8 @@ class RolloutState:
         """t=0 embedding (a5): fills gnn_out, node_emb and node_B."""
         ws = torch.empty(self.lib.ecord_gnn_workspace_bytes(self.g.N), dtype=torch.uint8, device=self.device)
         check(self.lib.ecord_gnn_embed(C.byref(self.g.c), C.byref(self.w.c), ptr(self.gnn_out), ptr(self.node_emb),
-                                       ptr(self.node_B), ptr(ws), _stream()), "ecord_gnn_embed")
+                                       ptr(self.node_B), ptr(self.node_Bc), ptr(self.node_LB), ptr(ws), _stream()),
+              "ecord_gnn_embed")
         self.kernel_launches += 16
         self._ws = ws
 
@@ -211,13 +235,19 @@ class RolloutState:
         self.last_sel.zero_()
         self.step_counter.zero_()
         self.steps_done = 0
+        if self.keys is not None:
+            self.keys.zero_()
+        if self.fused:   # prime u = msg_in([0; glob_0]); afterwards the fused env step keeps it current
+            check(self.lib.ecord_policy_pre(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c),
+                                            C.byref(self.policy_c), _stream()), "ecord_policy_pre")
+            self.kernel_launches += 1
 
     # ---- step-wise API (tests, log_stats) -----------------------------------------------------
     @_on_stream
     def policy_step(self):
         check(self.lib.ecord_policy_step(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c), C.byref(self.policy_c),
-                                         self.steps_done & 1, self.gemm, _stream()), "ecord_policy_step")
-        self.kernel_launches += 6 if self.gemm == GEMM_FP32 else 4
+                                         self.steps_done & 1, self.gemm, int(self.fused), _stream()), "ecord_policy_step")
+        self.kernel_launches += (6 if self.gemm == GEMM_FP32 else 4) - int(self.fused)
 
     @_on_stream
     def q_select(self, forced_actions=None):
@@ -226,9 +256,9 @@ class RolloutState:
             fa = torch.as_tensor(forced_actions).to(self.device, torch.int32).contiguous().view(-1)
             assert fa.numel() == self.M
         check(self.lib.ecord_q_select(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c), C.byref(self.policy_c),
-                                      self.steps_done, self.tau, self.seed, int(self.compat), ptr(fa), _stream()),
-              "ecord_q_select")
-        self.kernel_launches += 1
+                                      self.steps_done, self.tau, self.seed, int(self.compat), ptr(fa), self.q_mode,
+                                      _stream()), "ecord_q_select")
+        self.kernel_launches += 2 if self.q_mode == Q_FAST else 1
         self._fa = fa
 
     @_on_stream
@@ -239,8 +269,15 @@ class RolloutState:
             row = self.score_log[self.steps_done]
             if self.action_log is not None:
                 self.action_log[self.steps_done].copy_(a)
-        check(self.lib.ecord_env_step(C.byref(self.g.c), C.byref(self.env_c), ptr(a), self.steps_done, ptr(row), _stream()),
-              "ecord_env_step")
+        if self.fused:
+            if actions is not None:
+                self.actions.copy_(a)
+            check(self.lib.ecord_env_step_fused(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c),
+                                                C.byref(self.policy_c), self.steps_done, ptr(row), _stream()),
+                  "ecord_env_step_fused")
+        else:
+            check(self.lib.ecord_env_step(C.byref(self.g.c), C.byref(self.env_c), ptr(a), self.steps_done, ptr(row),
+                                          _stream()), "ecord_env_step")
         self.kernel_launches += 1
         self.steps_done += 1
         self.step_counter.fill_(self.steps_done)
@@ -253,7 +290,7 @@ class RolloutState:
     # ---- fused loop -------------------------------------------------------------------------
     def _make_plan(self):
         desc = _lib.RolloutDesc(C.pointer(self.g.c), C.pointer(self.env_c), C.pointer(self.w.c), C.pointer(self.policy_c),
-                                self.gemm, int(self.compat), self.tau, self.steps_per_graph, self.seed,
+                                self.gemm, self.q_mode, int(self.compat), 0, self.tau, self.steps_per_graph, self.seed,
                                 ptr(self.step_counter), ptr(self.score_log), ptr(self.action_log), self.max_steps, 0)
         out = C.c_void_p()
         check(self.lib.ecord_rollout_plan_create(C.byref(desc), _stream(), C.byref(out)), "ecord_rollout_plan_create")

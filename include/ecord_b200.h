@@ -74,7 +74,14 @@ typedef struct ecord_graph {
     const int32_t *in_ptr;         /* [N+1] incoming-edge lists, in global edge order (for scatter_mean) */
     const int32_t *in_src;         /* [E]   source (global id) of each incoming edge */
     const float   *in_w;           /* [E]   its weight */
+    /* vertex tiles of ECORD_QTILE vertices for the fast Q kernel: tile i covers vertices
+       [qtile_v0[i], qtile_v0[i] + ECORD_QTILE) (local ids, clipped to n_g) of graph qtile_graph[i] */
+    int32_t num_qtiles;
+    int32_t _pad;
+    const int32_t *qtile_graph;    /* [num_qtiles] */
+    const int32_t *qtile_v0;       /* [num_qtiles] */
 } ecord_graph;
+#define ECORD_QTILE 128
 
 /* ---- environment state: replaces Tradjectories' arrays (tradjectories.py:78-116) ---- */
 typedef struct ecord_env {
@@ -110,8 +117,12 @@ typedef struct ecord_weights {
     void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [16][192][1024] (rows r|z|hn of each 64-unit block)
                             followed by Wu pack [16][256][64] (rows r|z|0|in) -- tile order of the tcgen05 GRU kernel */
     void  *p1_w_bf16;    /* bf16 [512][1024] */
-    const float *q_fold; /* HOST f32 [6][64] from ecord_fold_q_host(): C0|C1|C2 (C = Wq[:,48:64] @ W_enc, 64x3) | LN gamma | LN beta |
-                            w_o.  Passed to the Q kernel by value (constant bank), hence a host array. */
+    const float *q_fold; /* HOST f32 [ECORD_QFOLD_FLOATS] from ecord_fold_q_host():
+                              [0,384)   C0|C1|C2 (C = Wq[:,48:64] @ W_enc, 64x3) | LN gamma | LN beta | w_o
+                              [384,576) the same C with each column centred over the 64 channels (fast Q kernel)
+                              [576,579) LC_k = sum_c w_o[c] gamma[c] Ccentred[c][k];  [579] sum_c w_o[c] beta[c]
+                            Passed to the Q kernels by value (constant bank), hence a host array. */
+#define ECORD_QFOLD_FLOATS 580
 #define ECORD_GRU_PACK_ELEMS (3072 * 1024 + 4096 * 64)
 } ecord_weights;
 
@@ -135,7 +146,18 @@ typedef struct ecord_policy {
     const float *node_B;  /* [N][64] Wq[:,32:48] @ node_emb + Wq[:,48:64] @ b_enc */
     int32_t *actions;     /* [rows] local vertex id chosen at the current step */
     float   *q;           /* [N*T] plane, optional Q-value dump (may be NULL when tau == 0) */
+    /* fast Q kernel (q_mode = ECORD_Q_FAST): channel-centred operands and the linear part of the head */
+    float   *Ac;          /* [rows_pad][64]  A - mean_c(A) */
+    float   *LA;          /* [rows_pad]      sum_c w_o[c] gamma[c] Ac[c] */
+    const float *node_Bc; /* [N][64]         node_B - mean_c(node_B) */
+    const float *node_LB; /* [N]             sum_c w_o[c] gamma[c] node_Bc[c] */
+    unsigned long long *keys; /* [rows]      packed (ordered q << 32 | ~vertex) running arg-max; zero between steps */
 } ecord_policy;
+
+/* Q-head evaluation */
+#define ECORD_Q_EXACT 0   /* one CTA per (g,t); LayerNorm/LeakyReLU/dot evaluated literally (parity mode)             */
+#define ECORD_Q_FAST  1   /* vertex-tiled, per-vertex operands register-resident across trajectories; centred LN and
+                             LeakyReLU(y) = 0.505 y + 0.495 |y| with the linear half folded out (re-associated fp32) */
 
 /* ------------------------------------------------------------------------------------------ */
 int         ecord_version(void);
@@ -181,6 +203,10 @@ int ecord_env_init(const ecord_graph *g, const ecord_env *env, const int8_t *ini
  *      score [G*T] (solver.py:238 log['scores']). ---- */
 int ecord_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, int32_t step_no,
                    float *score_log, void *stream);
+/* the same step (actions = policy->actions) fused with the NEXT step's msg_in stage, which needs exactly the
+ * quantities the flip just produced (best - score) and the cached embedding: saves a launch per step. */
+int ecord_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                         int32_t step_no, float *score_log, void *stream);
 
 /* ---- a4 + parity view: materialise the reference's arrays from the SoA state.
  *      node_features f32 [N][T][3] = (state, peek, static) un-normalised; with normalise != 0 the
@@ -197,19 +223,22 @@ int ecord_env_export(const ecord_graph *g, const ecord_env *env, int32_t steps_d
  *      node_B: f32 [N][64] (see ecord_policy).  workspace: ecord_gnn_workspace_bytes(N) bytes. ---- */
 size_t ecord_gnn_workspace_bytes(int32_t num_nodes);
 int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
-                    void *workspace, void *stream);
+                    float *node_Bc /* [N][64] or NULL */, float *node_LB /* [N] or NULL */, void *workspace, void *stream);
 
 /* ---- weight packing for the tensor-core path (device) and the folded Q-head constants (host arrays in/out) ---- */
 int ecord_pack_weights(const ecord_weights *w, void *stream);
 int ecord_fold_q_host(const float *q1_w /*[64,64]*/, const float *enc_w /*[16,3]*/, const float *qln_w, const float *qln_b,
-                      const float *q2_w /*[1,64]*/, float *out384);
+                      const float *q2_w /*[1,64]*/, float *out /*[ECORD_QFOLD_FLOATS]*/);
 
 /* ---- a6 + a8 (per-(graph,trajectory) part): msg_in -> GRUCell(64->1024) -> proj_rnn_to_gnn -> val_out;
  *      replaces _update_internal_state + GRUDecoder.update_embeddings + the P/state-value half of
  *      _forward_action_value (actors/_base.py:247-269, rnn_decoder.py:369-381,285-311).
  *      cur = index (0/1) of the hidden buffer holding h_{t-1}; h_t is written to buffer 1-cur. ---- */
 int ecord_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                      int32_t cur, int32_t gemm_mode, void *stream);
+                      int32_t cur, int32_t gemm_mode, int32_t skip_pre, void *stream);
+/* the msg_in stage alone: u = LReLU(msg_in([last_sel; glob])).  With skip_pre != 0 ecord_policy_step expects u to be
+ * current: ecord_env_step_fused leaves it so (it recomputes u right after the flip), and this entry primes it at t=0. */
+int ecord_policy_pre(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p, void *stream);
 
 /* ---- a7 + a8 (per-vertex part) + a9: Q-values over every vertex of every (graph,trajectory),
  *      greedy (tau == 0: argmax, lowest index on ties) or soft (tau > 0: exponential-race sampling,
@@ -219,7 +248,7 @@ int ecord_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_we
  *      forced_actions (optional, [G*T] local ids) overrides the selection (teacher forcing). ---- */
 int ecord_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                    int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
-                   void *stream);
+                   int32_t q_mode /* ECORD_Q_*; tau > 0 requires ECORD_Q_EXACT */, void *stream);
 
 /* ---- a10: the S-step loop as CUDA graphs of (policy_step, q_select, env_step); replaces the Python
  *      loop of DQNSolver.rollout (solvers/solver.py:316-362).  No host round trip per step. ---- */
@@ -229,7 +258,9 @@ typedef struct ecord_rollout_desc {
     const ecord_weights *weights;
     const ecord_policy  *policy;
     int32_t  gemm_mode;       /* ECORD_GEMM_* */
+    int32_t  q_mode;          /* ECORD_Q_* */
     int32_t  compat;          /* quirk A on/off */
+    int32_t  _pad0;
     float    tau;
     int32_t  steps_per_graph; /* steps unrolled into one CUDA graph (e.g. 16) */
     uint64_t seed;

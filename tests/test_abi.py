@@ -56,13 +56,17 @@ def test_fold_q_host_matches_numpy(lib):
     rs = np.random.RandomState(0)
     q1, enc = rs.randn(64, 64).astype(np.float32), rs.randn(16, 3).astype(np.float32)
     g, b, wo = rs.randn(64).astype(np.float32), rs.randn(64).astype(np.float32), rs.randn(1, 64).astype(np.float32)
-    out = torch.empty(384)
+    out = torch.empty(_lib.QFOLD_FLOATS)
     p = lambda a: C.c_void_p(a.ctypes.data)
     assert lib.ecord_fold_q_host(p(q1), p(enc), p(g), p(b), p(wo), C.c_void_p(out.data_ptr())) == 0
     Cm = q1[:, 48:64].astype(np.float64) @ enc.astype(np.float64)
     o = out.numpy()
     assert np.allclose(o[:192].reshape(3, 64).T, Cm, atol=1e-5)
-    assert np.array_equal(o[192:256], g) and np.array_equal(o[256:320], b) and np.array_equal(o[320:], wo[0])
+    assert np.array_equal(o[192:256], g) and np.array_equal(o[256:320], b) and np.array_equal(o[320:384], wo[0])
+    Cc = Cm - Cm.mean(0, keepdims=True)                                   # channel-centred planes (fast Q kernel)
+    assert np.allclose(o[384:576].reshape(3, 64).T, Cc, atol=1e-5)
+    assert np.allclose(o[576:579], (wo[0] * g) @ Cc, atol=1e-4)
+    assert np.isclose(o[579], float(wo[0] @ b), atol=1e-5)
 
 
 def test_sass_is_blackwell_native():

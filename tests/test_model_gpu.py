@@ -16,13 +16,13 @@ pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
 
 
-def _setup(gemm, compat=True, dump_q=True):
+def _setup(gemm, compat=True, dump_q=True, q_mode=None):
     from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
     z = load_gold("model_trace.npz")
     sd = random_state_dicts(int(z["weight_seed"]), perturb_norms=True)
     dg = DeviceGraph(GraphBatcher()(unpack_graphs(z)).tg)
     T, S = int(z["T"]), int(z["S"])
-    st = RolloutState(dg, DeviceWeights(sd), T, gemm=gemm, compat=compat, max_steps=S, dump_q=dump_q)
+    st = RolloutState(dg, DeviceWeights(sd), T, gemm=gemm, compat=compat, max_steps=S, dump_q=dump_q, q_mode=q_mode)
     st.gnn_embed()
     st.env_init(z["init_state"])
     return z, sd, st, dg, T, S
@@ -72,6 +72,58 @@ def test_per_step_tensors_teacher_forced(gemm):
         assert np.array_equal(st.scores().cpu().numpy(), z["scores"][s])
 
 
+@pytest.mark.parametrize("compat", [True, False])
+def test_fast_q_kernel_matches_exact_kernel(compat):
+    """ECORD_Q_FAST is the same function re-associated (centred LayerNorm, LeakyReLU split): Q within 1e-5 relative of
+    the literal kernel, identical greedy choices on the reference trace, identical cached embeddings and u."""
+    z, sd, a, dg, T, S = _setup("fp32", compat=compat, q_mode="exact")
+    _, _, b, _, _, _ = _setup("fp32", compat=compat, q_mode="fast")
+    for s in range(S):
+        for st in (a, b):
+            st.policy_step()
+            st.q_select()
+        assert rel_err(b.q_values().cpu().numpy(), a.q_values().cpu().numpy()) < 1e-5, s
+        assert torch.equal(a.actions, b.actions), s
+        assert torch.equal(a.last_sel, b.last_sel) and torch.equal(a.u, b.u), s
+        assert int(b.keys.abs().sum()) == 0                    # finish kernel re-arms the arg-max keys
+        for st in (a, b):
+            st.env_step()
+    assert torch.equal(a.score, b.score) and torch.equal(a.peek, b.peek) and torch.equal(a.sp, b.sp)
+
+
+def test_fast_q_kernel_vertex_tiles_and_trajectory_splits():
+    """Graphs larger than one 128-vertex tile, ragged sizes, T not a multiple of the trajectory chunk."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    from ecord_b200.graphs import synthetic_set
+    graphs = synthetic_set("er", 300, 2, p=0.05) + synthetic_set("er", 129, 1, p=0.1, seed0=5) + synthetic_set("er", 40, 2, p=0.2, seed0=9)
+    sd = random_state_dicts(21, perturb_norms=True)
+    w = DeviceWeights(sd)
+    dg = DeviceGraph(GraphBatcher()(graphs).tg)
+    T = 37
+    init = np.random.RandomState(3).randint(0, 2, (dg.N, T)).astype(np.int8)
+    a = RolloutState(dg, w, T, gemm="fp32", q_mode="exact", dump_q=True)
+    b = RolloutState(dg, w, T, gemm="fp32", q_mode="fast", dump_q=True)
+    for st in (a, b):
+        st.gnn_embed(); st.env_init(init)
+    for s in range(12):
+        for st in (a, b):
+            st.policy_step(); st.q_select()
+        assert rel_err(b.q_values().cpu().numpy(), a.q_values().cpu().numpy()) < 1e-5
+        # arg-max may legitimately differ only where the two best Q-values are within rounding of each other
+        qa = a.q_values()
+        diff = (a.actions != b.actions).nonzero().flatten().cpu().tolist()
+        for m in diff:
+            g_, t_ = divmod(m, T)
+            lo = int(dg.tg.np_ptr[g_])
+            col = qa[lo:int(dg.tg.np_ptr[g_ + 1]), t_]
+            gap = float(col[int(a.actions[m])] - col[int(b.actions[m])])
+            assert abs(gap) < 1e-5 * float(col.abs().max())
+        b.actions.copy_(a.actions); b.last_sel.copy_(a.last_sel)   # keep the two states in lock-step
+        for st in (a, b):
+            st.env_step()
+    assert torch.equal(a.score, b.score)
+
+
 def test_tcgen05_kernels_against_torch_on_identical_operands():
     """The tensor-core GRU / projection kernels vs torch matmuls fed the SAME bf16-rounded operands: isolates
     descriptor/layout bugs from precision (fp32 accumulation order is the only difference)."""
@@ -91,7 +143,8 @@ def test_tcgen05_kernels_against_torch_on_identical_operands():
         nn_ = torch.tanh(gi[:, 2048:] + rr * gh[:, 2048:])
         want = (h32 - nn_) * zz + nn_
         got = st.hidden[(s + 1) & 1, :st.M]
-        assert float((got - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+        # the kernel evaluates sigmoid/tanh with MUFU.TANH (rel. error ~2^-11): compare at that level
+        assert float((got - want).abs().max()) < 2e-3 * max(1.0, float(want.abs().max()))
         assert torch.equal(st.hidden_bf16[(s + 1) & 1, :st.M], got.bfloat16())
         y1 = torch.tanh(got).bfloat16().float() @ w1.T + r['proj_rnn_to_gnn.1.bias'].to(dev)
         assert float((st.y1[:st.M] - y1).abs().max()) < 2e-3 * float(y1.abs().max())   # tanh rounding to bf16 can differ by 1 ulp

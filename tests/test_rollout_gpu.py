@@ -78,7 +78,7 @@ def test_config1_best_cut_parity():
     assert np.array_equal(log["init_score"].numpy(), z["init_score"].astype(np.float32))
     agree = float((log["scores_max"].numpy() == z["scores_max"]).mean())
     assert agree >= 0.99, f"best-cut agreement {agree:.3f}"
-    assert log["scores"].shape == (100, T, S) and log["t_step"].shape == (S,)
+    assert log["scores"].shape == (100, T, S) and log["t_step"].shape == (2 * S,)   # merge_log concatenates graph chunks (testing.py:120-143)
     assert np.allclose(log["apx_max"].numpy(), log["scores_max"].numpy() / z["opts"])
 
 

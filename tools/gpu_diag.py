@@ -115,7 +115,7 @@ def sec_env():
               f"dmax={int(np.bincount(b.tg.np_src).max())}")
 
 
-def _model_setup(gemm, dump_q=True):
+def _model_setup(gemm, dump_q=True, q_mode=None):
     z = load_gold("model_trace.npz")
     graphs = unpack_graphs(z)
     sd = random_state_dicts(int(z["weight_seed"]), perturb_norms=True)
@@ -123,7 +123,7 @@ def _model_setup(gemm, dump_q=True):
     b = GraphBatcher()(graphs)
     dg = DeviceGraph(b.tg)
     T, S = int(z["T"]), int(z["S"])
-    st = RolloutState(dg, w, T, gemm=gemm, compat=True, max_steps=S, dump_q=dump_q)
+    st = RolloutState(dg, w, T, gemm=gemm, compat=True, max_steps=S, dump_q=dump_q, q_mode=q_mode)
     st.gnn_embed()
     st.env_init(z["init_state"])
     return z, st, dg, T, S
@@ -204,6 +204,26 @@ def sec_tc():
         st32.env_step()
 
 
+def sec_qfast():
+    hdr("fast Q kernel vs exact Q kernel (fp32 GEMM for both), teacher-forced")
+    z, sa, dg, T, S = _model_setup("fp32", q_mode="exact")
+    _, sb, _, _, _ = _model_setup("fp32", q_mode="fast")
+    for s in range(S):
+        fa = z["actions"][s].astype(np.int32).reshape(-1)
+        for st in (sa, sb):
+            st.policy_step()
+            st.q_select(forced_actions=None)
+        torch.cuda.synchronize()
+        qa, qb = sa.q_values().cpu().numpy(), sb.q_values().cpu().numpy()
+        print(f"step {s:2d}: q fast vs exact rel {rel_err(qb, qa):.2e}; fast vs reference rel {rel_err(qb, z['q'][s]):.2e}; "
+              f"argmax equal {bool(torch.equal(sa.actions, sb.actions))}; u equal {bool(torch.equal(sa.u, sb.u))}; "
+              f"last_sel rel {rel_err(sb.last_sel.cpu().numpy(), sa.last_sel.cpu().numpy()):.1e}")
+        for st in (sa, sb):
+            st.q_select(forced_actions=fa)
+            st.env_step()
+    print("scores equal:", bool(torch.equal(sa.score, sb.score)), " keys all zero:", int(sb.keys.abs().sum()) == 0)
+
+
 def sec_rollout():
     hdr("free-running greedy rollout through the CUDA-graph plan vs reference (golden model trace)")
     for gemm in ("fp32", "bf16"):
@@ -258,9 +278,9 @@ def sec_perf():
     dg = DeviceGraph(b.tg)
     T = 50
     init = np.random.RandomState(0).randint(0, 2, (dg.N, T)).astype(np.int8)
-    for gemm in ("bf16", "fp32"):
+    for gemm, qm in (("bf16", "fast"), ("bf16", "exact"), ("fp32", "exact")):
         S = 400 if gemm == "bf16" else 48
-        st = RolloutState(dg, w, T, gemm=gemm, max_steps=S + 64)
+        st = RolloutState(dg, w, T, gemm=gemm, max_steps=S + 64, q_mode=qm)
         t0 = time.time(); st.gnn_embed(); torch.cuda.synchronize(); t_gnn = time.time() - t0
         t0 = time.time(); st.env_init(init); torch.cuda.synchronize(); t_init = time.time() - t0
         st.run(16)
@@ -268,7 +288,7 @@ def sec_perf():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); st.run(S); e1.record(); e1.synchronize()
         ms = e0.elapsed_time(e1)
-        print(f"{gemm}: {S} steps in {ms:.2f} ms -> {ms / S * 1e3:.1f} us/step, {dg.G * T * S / ms * 1e3 / 1e6:.2f} M units/s "
+        print(f"{gemm}/{qm}: {S} steps in {ms:.2f} ms -> {ms / S * 1e3:.1f} us/step, {dg.G * T * S / ms * 1e3 / 1e6:.2f} M units/s "
               f"(gnn {t_gnn * 1e3:.1f} ms, env_init {t_init * 1e3:.1f} ms)")
         # per-kernel coarse timing in step-wise mode
         def tm(fn, reps=20):
@@ -280,13 +300,14 @@ def sec_perf():
             bb.record(); bb.synchronize()
             return a.elapsed_time(bb) / reps * 1e3
         print(f"      policy_step {tm(st.policy_step):.1f} us   q_select {tm(st.q_select):.1f} us")
-        acts = st.actions.clone()
-        st2 = st
-        print(f"      env_step    {tm(lambda: st2.lib.ecord_env_step(C.byref(st2.g.c), C.byref(st2.env_c), C.c_void_p(acts.data_ptr()), 0, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))):.1f} us")
+        st.max_steps = 0   # keep env_step from logging while it is timed repeatedly
+        sl, st.score_log = st.score_log, None
+        print(f"      env_step    {tm(st.env_step):.1f} us")
+        st.score_log = sl
         st.close()
 
 
-SECTIONS = {"env": sec_env, "model": sec_model, "tc": sec_tc, "rollout": sec_rollout, "perf": sec_perf}
+SECTIONS = {"env": sec_env, "model": sec_model, "tc": sec_tc, "qfast": sec_qfast, "rollout": sec_rollout, "perf": sec_perf}
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0), flush=True)
