@@ -204,6 +204,7 @@ constexpr int kMaxTChunk = 32;       // trajectories per CTA (shared-memory A ro
 
 struct QFastSmem { float A[kMaxTChunk][Q]; float LA[kMaxTChunk], V[kMaxTChunk]; };
 
+template <bool DUMP_Q>
 __global__ void __launch_bounds__(QT, 3)
 k_q_fast(ecord_graph g, ecord_env e, ecord_policy p, const __grid_constant__ QConstFast K, const float *__restrict__ q2_b,
          const int32_t *step_base, int step_off, int t_chunk) {
@@ -239,22 +240,33 @@ k_q_fast(ecord_graph g, ecord_env e, ecord_policy p, const __grid_constant__ QCo
     }
     const float lb = p.node_LB[lo + v];
     const float bo = q2_b[0];
+    // reciprocal multiplies instead of the IEEE divisions of the exact kernel (<= 1 ulp apart): a division per
+    // row costs ~30 instructions and its slow path is taken whenever peek == 0
+    const float inv_n = 1.0f / (float)n;
+    constexpr float inv_clip = 1.0f / (float)ECORD_STATIC_CLIP;
     __syncthreads();
 
-    const long long base0 = (long long)lo * T + v;
-    int sp = e.sp[base0 + (long long)t_lo * n];
-    float pk = e.peek[base0 + (long long)t_lo * n];
-    for (int t = t_lo; t < t_hi; ++t) {
+    // element (t_lo, v) of this graph's planes; consecutive trajectories are n elements apart
+    const long long base0 = (long long)lo * T + (long long)t_lo * n + v;
+    const int *__restrict__ sp_ptr = e.sp + base0;
+    const float *__restrict__ pk_ptr = e.peek + base0;
+    float *q_ptr = DUMP_Q ? p.q + base0 : nullptr;
+    unsigned long long *key_ptr = p.keys + (gi * T + t_lo);
+    const int nt = t_hi - t_lo;
+    int sp = *sp_ptr;
+    float pk = *pk_ptr;
+    for (int tt = 0; tt < nt; ++tt) {
         const int sp_c = sp;
         const float pk_c = pk;
-        if (t + 1 < t_hi) {                       // prefetch the next trajectory's state row entry
-            sp = e.sp[base0 + (long long)(t + 1) * n];
-            pk = e.peek[base0 + (long long)(t + 1) * n];
+        if (tt + 1 < nt) {                        // prefetch the next trajectory's state row entry
+            sp_ptr += n; pk_ptr += n;
+            sp = *sp_ptr;
+            pk = *pk_ptr;
         }
         const float f0 = (float)(sp_c & 1);
-        const float f1 = pk_c / (float)n;
-        const float f2 = fminf((float)(steps_done - (sp_c >> 1)), (float)ECORD_STATIC_CLIP) / (float)ECORD_STATIC_CLIP;
-        const float *As = S.A[t - t_lo];
+        const float f1 = pk_c * inv_n;
+        const float f2 = fminf((float)(steps_done - (sp_c >> 1)), (float)ECORD_STATIC_CLIP) * inv_clip;
+        const float *As = S.A[tt];
         float x[Q];
         float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
 #pragma unroll
@@ -279,17 +291,17 @@ k_q_fast(ecord_graph g, ecord_env e, ecord_policy p, const __grid_constant__ QCo
             a3 = fmaf(K.wo[c + 3], fabsf(fmaf(x[c + 3], K.gam[c + 3], K.bet[c + 3] * sigma)), a3);
         }
         const float acc = (a0 + a1) + (a2 + a3);
-        const float lin = S.LA[t - t_lo] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
+        const float lin = S.LA[tt] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
         const float dot = fmaf(0.505f, fmaf(lin, rstd, K.Wb), 0.495f * acc * rstd);
-        const float q = (dot + bo) + S.V[t - t_lo];
-        if (p.q && valid) p.q[base0 + (long long)t * n] = q;
+        const float q = (dot + bo) + S.V[tt];
+        if (DUMP_Q) { if (valid) *q_ptr = q; q_ptr += n; }
         // arg-max: ordered-int max across the warp, lowest vertex among equals, one atomic per warp
         const uint32_t ord = valid ? f2ord(q) : 0u;
         const uint32_t mx = __reduce_max_sync(0xffffffffu, ord);
         const uint32_t bal = __ballot_sync(0xffffffffu, ord == mx);
         if (lane == 0 && mx != 0u) {
             const int vbest = v0 + (int)(threadIdx.x & ~31u) + (__ffs(bal) - 1);
-            atomicMax(p.keys + (gi * T + t), ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)vbest));
+            atomicMax(key_ptr + tt, ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)vbest));
         }
     }
 }
@@ -356,7 +368,8 @@ static int launch_q_fast(const ecord_graph *g, const ecord_env *env, const ecord
     int t_chunk = ceil_div(T, splits);
     if (t_chunk > kMaxTChunk) t_chunk = kMaxTChunk;
     splits = ceil_div(T, t_chunk);
-    k_q_fast<<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
+    if (p->q) k_q_fast<true><<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
+    else k_q_fast<false><<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
     ECORD_LAUNCH_CHECK();
     k_select_finish<<<ceil_div((long long)p->rows * 32, 256), 256, 0, st>>>(*g, *env, *w, *p, step_base, step_off, compat,
                                                                              forced);
