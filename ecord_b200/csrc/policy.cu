@@ -115,19 +115,48 @@ __global__ void k_gru_gates(ecord_policy p, const int32_t *step_base, int step_o
 }
 
 // ------------------------------------------------------------------------------------------------
-// tail: y1 [M][512] -> LN512 -> LReLU -> W2 -> LN32 -> LReLU = P ; v ; A.   16 rows per block (8 warps x 2),
-// W2 (64 KB) staged in shared memory once per block.
+// tail: y1 [M][512] -> LN512 -> LReLU -> W2 (512->32) -> LN32 -> LReLU = P ; v = val_out(P) ; A = Wq[:, :32] P + b_q.
+//
+// One warp owns FOUR rows at once so that every W2 element fetched from shared memory feeds four FMAs
+// (LDS : FFMA = 1 : 4, the ratio the SM can sustain), and the 4 x 32 dot products are finished with a
+// reduce-scatter butterfly over the warp (62 shuffles for 64 sums) instead of one 5-step all-reduce per output.
+// 32 rows per block (8 warps); W2 (64 KB) is staged in shared memory once per block.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTailRowsPerWarp = 2;
+constexpr int kTailR = 4;
 constexpr int kTailWarps = 8;
-constexpr int kTailRows = kTailRowsPerWarp * kTailWarps;
+constexpr int kTailRows = kTailR * kTailWarps;
 struct TailSmem {
     float w2[ND * P1];          // [o][i]
     float v1t[ND * ND];         // transposed val_out.1: [i][o]
     float qt[ND * ECORD_DIM_Q]; // transposed Wq[:, :32]: [i][c]
 };
 
-__global__ void __launch_bounds__(kTailWarps * 32)
+// one butterfly level: lanes with (lane & OFF) == 0 keep v[0..N/2), the others keep v[N/2..N)
+template <int N, int OFF>
+__device__ __forceinline__ void reduce_scatter_step(float (&v)[64], bool upper) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float send = upper ? v[i] : v[i + N / 2];
+        const float keep = upper ? v[i + N / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+}
+// 64 per-lane partial sums -> lane L ends with the warp totals of entries 2L and 2L+1 in v[0], v[1]
+__device__ __forceinline__ void reduce_scatter64(float (&v)[64], int lane) {
+    reduce_scatter_step<64, 16>(v, lane & 16);
+    reduce_scatter_step<32, 8>(v, lane & 8);
+    reduce_scatter_step<16, 4>(v, lane & 4);
+    reduce_scatter_step<8, 2>(v, lane & 2);
+    reduce_scatter_step<4, 1>(v, lane & 1);
+}
+__device__ __forceinline__ float group8_sum(float v) {   // all-reduce over the 8 lanes that share a row
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+__global__ void __launch_bounds__(kTailWarps * 32, 2)
 k_policy_tail(ecord_weights w, ecord_policy p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TailSmem &S = *reinterpret_cast<TailSmem *>(smem_raw);
@@ -138,65 +167,132 @@ k_policy_tail(ecord_weights w, ecord_policy p) {
         S.qt[i] = w.q1_w[(i % ECORD_DIM_Q) * ECORD_DIM_Q + (i / ECORD_DIM_Q)];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int rr = 0; rr < kTailRowsPerWarp; ++rr) {
-        const int m = blockIdx.x * kTailRows + warp * kTailRowsPerWarp + rr;
-        if (m >= p.rows) break;
-        // ---- LN512 + LReLU (lane holds elements lane + 32 j) ----
-        float x[16];
+    const int m0 = blockIdx.x * kTailRows + warp * kTailR;
+    if (m0 >= p.rows) return;
+
+    // ---- LN512 + LReLU on 4 rows (lane holds elements lane + 32 j of each) ----
+    float x[kTailR][16];
+#pragma unroll
+    for (int r = 0; r < kTailR; ++r) {
+        const int m = min(m0 + r, p.rows - 1);          // rows past the end are computed on a copy and not stored
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { x[j] = p.y1[(long long)m * P1 + lane + 32 * j]; s += x[j]; }
+        for (int j = 0; j < 16; ++j) { x[r][j] = p.y1[(long long)m * P1 + lane + 32 * j]; s += x[r][j]; }
         const float mean = warp_sum(s) * (1.0f / P1);
         float ss = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { const float d = x[j] - mean; ss = fmaf(d, d, ss); }
+        for (int j = 0; j < 16; ++j) { x[r][j] -= mean; ss = fmaf(x[r][j], x[r][j], ss); }
         const float rstd = rsqrtf(warp_sum(ss) * (1.0f / P1) + kLnEps);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int i = lane + 32 * j;
-            x[j] = lrelu((x[j] - mean) * rstd * w.ln1_w[i] + w.ln1_b[i]);
-        }
-        // ---- W2: 512 -> 32; lane o ends up holding output o ----
-        float mine = 0.0f;
-#pragma unroll 4
-        for (int o = 0; o < ND; ++o) {
-            float a = 0.0f;
+        for (int j = 0; j < 16; ++j) x[r][j] *= rstd;
+    }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a = fmaf(S.w2[o * P1 + lane + 32 * j], x[j], a);
-            a = warp_sum(a);
-            if (lane == o) mine = a;
+    for (int j = 0; j < 16; ++j) {
+        const float gj = w.ln1_w[lane + 32 * j], bj = w.ln1_b[lane + 32 * j];
+#pragma unroll
+        for (int r = 0; r < kTailR; ++r) x[r][j] = lrelu(fmaf(x[r][j], gj, bj));
+    }
+    // ---- W2: 512 -> 32 for 4 rows, two passes of 16 outputs.  After each pass lane L holds, for row L>>3,
+    //      outputs oh*16 + 2*(L&7) + {0,1} ----
+    const int grp = lane >> 3, k8 = lane & 7;           // row within the warp, position within the row's 8 lanes
+    float pre[4];
+#pragma unroll
+    for (int oh = 0; oh < 2; ++oh) {
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+            for (int oo = 0; oo < 16; ++oo) {
+                const float wv = S.w2[(oh * 16 + oo) * P1 + lane + 32 * j];
+#pragma unroll
+                for (int r = 0; r < kTailR; ++r) acc[r * 16 + oo] = fmaf(wv, x[r][j], acc[r * 16 + oo]);
+            }
         }
-        mine += w.p2_b[lane];
-        // ---- LN32 + LReLU ----
-        const float mean2 = warp_sum(mine) * (1.0f / ND);
-        const float d2 = mine - mean2;
-        const float rstd2 = rsqrtf(warp_sum(d2 * d2) * (1.0f / ND) + kLnEps);
-        const float Pv = lrelu(d2 * rstd2 * w.ln2_w[lane] + w.ln2_b[lane]);
-        p.P[(long long)m * ND + lane] = Pv;
-        // ---- state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 ----
-        const float tp = tanhf(Pv);
-        float hv = w.v1_b[lane];
-        float a0 = w.q1_b[lane], a1 = w.q1_b[lane + 32];
+        reduce_scatter64(acc, lane);
+        const int o = oh * 16 + 2 * k8;
+        pre[oh * 2 + 0] = acc[0] + w.p2_b[o];
+        pre[oh * 2 + 1] = acc[1] + w.p2_b[o + 1];
+    }
+    // ---- LN32 + LReLU per row (the row's 32 values live in its 8 lanes x 4 slots) ----
+    const float mean2 = group8_sum((pre[0] + pre[1]) + (pre[2] + pre[3])) * (1.0f / ND);
+    float d[4], ssq = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { d[q] = pre[q] - mean2; ssq = fmaf(d[q], d[q], ssq); }
+    const float rstd2 = rsqrtf(group8_sum(ssq) * (1.0f / ND) + kLnEps);
+    float Pv[4], Tv[4];
+    const int m = m0 + grp;
+    const bool live = m < p.rows;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int o = (q >> 1) * 16 + 2 * k8 + (q & 1);
+        Pv[q] = lrelu(fmaf(d[q] * rstd2, w.ln2_w[o], w.ln2_b[o]));
+        Tv[q] = tanhf(Pv[q]);
+        if (live) p.P[(long long)m * ND + o] = Pv[q];
+    }
+    // ---- every lane of the row group gathers the row's 32 P / tanh(P) values ----
+    float Pa[ND], Ta[ND];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o = (q >> 1) * 16 + 2 * kk + (q & 1);
+            Pa[o] = __shfl_sync(0xffffffffu, Pv[q], grp * 8 + kk);
+            Ta[o] = __shfl_sync(0xffffffffu, Tv[q], grp * 8 + kk);
+        }
+    }
+    // ---- state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 ; lane computes 4 of the 32 hidden units ----
+    float vpart = 0.0f;
+    {
+        float4 hv = *reinterpret_cast<const float4 *>(w.v1_b + k8 * 4);
 #pragma unroll
         for (int i = 0; i < ND; ++i) {
-            const float ti = __shfl_sync(0xffffffffu, tp, i);
-            const float pi = __shfl_sync(0xffffffffu, Pv, i);
-            hv = fmaf(S.v1t[i * ND + lane], ti, hv);
-            a0 = fmaf(S.qt[i * ECORD_DIM_Q + lane], pi, a0);
-            a1 = fmaf(S.qt[i * ECORD_DIM_Q + lane + 32], pi, a1);
+            const float4 wv = *reinterpret_cast<const float4 *>(&S.v1t[i * ND + k8 * 4]);
+            hv.x = fmaf(wv.x, Ta[i], hv.x); hv.y = fmaf(wv.y, Ta[i], hv.y);
+            hv.z = fmaf(wv.z, Ta[i], hv.z); hv.w = fmaf(wv.w, Ta[i], hv.w);
         }
-        const float vv = warp_sum(w.v2_w[lane] * lrelu(hv));
-        if (lane == 0) p.v[m] = vv + w.v2_b[0];
-        p.A[(long long)m * ECORD_DIM_Q + lane] = a0;
-        p.A[(long long)m * ECORD_DIM_Q + lane + 32] = a1;
+        const float4 w2v = *reinterpret_cast<const float4 *>(w.v2_w + k8 * 4);
+        vpart = w2v.x * lrelu(hv.x) + w2v.y * lrelu(hv.y) + w2v.z * lrelu(hv.z) + w2v.w * lrelu(hv.w);
+    }
+    const float vv = group8_sum(vpart) + w.v2_b[0];
+    // ---- A = Wq[:, :32] P + b_q ; lane computes 8 of the 64 channels ----
+    float a[8];
+    {
+        const float4 b0 = *reinterpret_cast<const float4 *>(w.q1_b + k8 * 8);
+        const float4 b1 = *reinterpret_cast<const float4 *>(w.q1_b + k8 * 8 + 4);
+        a[0] = b0.x; a[1] = b0.y; a[2] = b0.z; a[3] = b0.w; a[4] = b1.x; a[5] = b1.y; a[6] = b1.z; a[7] = b1.w;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(&S.qt[i * ECORD_DIM_Q + k8 * 8]);
+            const float4 w1 = *reinterpret_cast<const float4 *>(&S.qt[i * ECORD_DIM_Q + k8 * 8 + 4]);
+            a[0] = fmaf(w0.x, Pa[i], a[0]); a[1] = fmaf(w0.y, Pa[i], a[1]); a[2] = fmaf(w0.z, Pa[i], a[2]);
+            a[3] = fmaf(w0.w, Pa[i], a[3]); a[4] = fmaf(w1.x, Pa[i], a[4]); a[5] = fmaf(w1.y, Pa[i], a[5]);
+            a[6] = fmaf(w1.z, Pa[i], a[6]); a[7] = fmaf(w1.w, Pa[i], a[7]);
+        }
+    }
+    float asum = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) asum += a[q];
+    const float meanA = group8_sum(asum) * (1.0f / ECORD_DIM_Q);
+    float la = 0.0f, ac[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        ac[q] = a[q] - meanA;
+        la = fmaf(w.q2_w[k8 * 8 + q] * w.qln_w[k8 * 8 + q], ac[q], la);
+    }
+    la = group8_sum(la);
+    if (live) {
+        float *Ao = p.A + (long long)m * ECORD_DIM_Q + k8 * 8;
+        *reinterpret_cast<float4 *>(Ao) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4 *>(Ao + 4) = make_float4(a[4], a[5], a[6], a[7]);
         if (p.Ac) {   // fast Q kernel operands: A - mean_c(A), and its projection on w_o * gamma
-            const float meanA = warp_sum(a0 + a1) * (1.0f / ECORD_DIM_Q);
-            const float c0 = a0 - meanA, c1 = a1 - meanA;
-            p.Ac[(long long)m * ECORD_DIM_Q + lane] = c0;
-            p.Ac[(long long)m * ECORD_DIM_Q + lane + 32] = c1;
-            const float la = warp_sum(w.q2_w[lane] * w.qln_w[lane] * c0 + w.q2_w[lane + 32] * w.qln_w[lane + 32] * c1);
-            if (lane == 0) p.LA[m] = la;
+            float *Aco = p.Ac + (long long)m * ECORD_DIM_Q + k8 * 8;
+            *reinterpret_cast<float4 *>(Aco) = make_float4(ac[0], ac[1], ac[2], ac[3]);
+            *reinterpret_cast<float4 *>(Aco + 4) = make_float4(ac[4], ac[5], ac[6], ac[7]);
+            if (k8 == 0) p.LA[m] = la;
         }
+        if (k8 == 0) p.v[m] = vv;
     }
 }
 }  // namespace
