@@ -13,8 +13,11 @@ GEMM_FP32 = 0
 GEMM_BF16 = 1
 Q_EXACT = 0
 Q_FAST = 1
+Q_TC = 2
+QTC_FLOATS = 4736
+QA_STRIDE = 152
 QTILE = 128
-QFOLD_FLOATS = 580
+QFOLD_FLOATS = 588
 GRU_PACK_ELEMS = 3072 * 1024 + 4096 * 64
 
 _vp, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
@@ -61,14 +64,14 @@ WEIGHT_FIELDS = [
 
 
 class Weights(C.Structure):
-    _fields_ = [(f, _vp) for f, _, _ in WEIGHT_FIELDS] + [("gru_w_bf16", _vp), ("p1_w_bf16", _vp), ("q_fold", _vp)]
+    _fields_ = [(f, _vp) for f, _, _ in WEIGHT_FIELDS] + [("gru_w_bf16", _vp), ("p1_w_bf16", _vp), ("q_tc", _vp), ("q_fold", _vp)]
 
 
 class Policy(C.Structure):
     _fields_ = [("rows", _i32), ("rows_pad", _i32), ("hidden", _vp), ("hidden_bf16", _vp), ("th_bf16", _vp),
                 ("u_bf16", _vp), ("u", _vp), ("gates", _vp), ("th", _vp), ("y1", _vp), ("P", _vp), ("A", _vp),
                 ("v", _vp), ("last_sel", _vp), ("node_emb", _vp), ("node_B", _vp), ("actions", _vp), ("q", _vp),
-                ("Ac", _vp), ("LA", _vp), ("node_Bc", _vp), ("node_LB", _vp), ("keys", _vp)]
+                ("Ac", _vp), ("LA", _vp), ("node_Bc", _vp), ("node_LB", _vp), ("keys", _vp), ("qa", _vp), ("node_qv", _vp)]
 
 
 class RolloutDesc(C.Structure):
@@ -92,7 +95,7 @@ SYMBOLS = {
     "ecord_env_step_fused": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _vp, _vp]),
     "ecord_env_export": (_i32, [_P(Graph), _P(Env), _i32, _i32, _vp, _vp, _vp, _vp]),
     "ecord_gnn_workspace_bytes": (C.c_size_t, [_i32]),
-    "ecord_gnn_embed": (_i32, [_P(Graph), _P(Weights), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ecord_gnn_embed": (_i32, [_P(Graph), _P(Weights), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ecord_pack_weights": (_i32, [_P(Weights), _vp]),
     "ecord_fold_q_host": (_i32, [_vp] * 6),
     "ecord_policy_step": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _i32, _i32, _vp]),

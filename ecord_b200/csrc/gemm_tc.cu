@@ -210,6 +210,60 @@ __global__ void k_pack_weights(ecord_weights w) {
     }
 }
 
+// Operands of the tensor-core Q kernel (layout: ecord_weights.q_tc).  One block of 64 threads, thread = channel c.
+// Column means are taken in double and subtracted exactly as ecord_fold_q_host() does, so that the host-side
+// constants (LC, Wb, C^T C) and these device-side operands describe the same centred matrices.
+__global__ void k_pack_qtc(ecord_weights w) {
+    constexpr int Q = ECORD_DIM_Q;
+    __shared__ float raw[Q][20];      // [c][0..15] Wq[c][32+k] | [16..18] C[c][j] | [19] Wq[:,48:64] b_enc
+    __shared__ double mean[20];
+    const int c = threadIdx.x;
+    for (int k = 0; k < 16; ++k) raw[c][k] = w.q1_w[c * Q + 32 + k];
+    for (int j = 0; j < 3; ++j) {
+        float a = 0.0f;
+        for (int i = 0; i < 16; ++i) a = fmaf(w.q1_w[c * Q + 48 + i], w.enc_w[i * 3 + j], a);
+        raw[c][16 + j] = a;
+    }
+    {
+        float a = 0.0f;
+        for (int i = 0; i < 16; ++i) a = fmaf(w.q1_w[c * Q + 48 + i], w.enc_b[i], a);
+        raw[c][19] = a;
+    }
+    __syncthreads();
+    if (c < 20) {
+        double m = 0.0;
+        for (int r = 0; r < Q; ++r) m += (double)raw[r][c];
+        mean[c] = m / Q;
+    }
+    __syncthreads();
+    const float gam = w.qln_w[c];
+    float *out = w.q_tc;
+    for (int k = 0; k < 16; ++k) {
+        const float wg = (float)((double)raw[c][k] - mean[k]);
+        out[1280 + c * 16 + k] = wg;
+        out[c * 16 + k] = tf32_rn(gam * wg);
+    }
+    for (int k = 0; k < 16; ++k)
+        if (c < 16) out[(64 + c) * 16 + k] = 0.0f;
+    for (int j = 0; j < 4; ++j) {
+        const float cc = (float)((double)raw[c][16 + j] - mean[16 + j]);
+        out[2304 + c * 4 + j] = cc;
+        out[2560 + c * 4 + j] = j < 3 ? tf32_rn(gam * cc) : gam;
+    }
+    // shared-memory image of one B-operand buffer of k_q_tc: three [80][8] tf32 blocks (W1 k 0..7 | W1 k 8..15 | W2)
+    // in the K-major SWIZZLE_32B layout; the per-trajectory entries (row 64, W2 slots 4 and 5) stay zero
+    float *img = out + 2816;
+    for (int i = c; i < 3 * 80 * 8; i += ECORD_DIM_Q) img[i] = 0.0f;
+    __syncthreads();
+    auto at = [&](int blk, int r, int k) -> float & {
+        return img[blk * 640 + (r * 32 + ((((k >> 2) ^ (r >> 2)) & 1) << 4) + (k & 3) * 4) / 4];
+    };
+    for (int k = 0; k < 16; ++k) at(k >> 3, c, k & 7) = out[c * 16 + k];
+    for (int j = 0; j < 3; ++j) at(2, c, j) = out[2560 + c * 4 + j];
+    at(2, c, 3) = out[2560 + c * 4 + 1];        // against f1_lo
+    at(2, c, 6) = out[2560 + c * 4 + 2];        // against f2_lo   (slots 4, 5: per-trajectory gamma_c a'_c hi / lo)
+}
+
 }  // namespace
 
 extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
@@ -217,6 +271,11 @@ extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
     const long long n = (long long)3072 * H + (long long)4096 * 64 + (long long)512 * H;
     k_pack_weights<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(*w);
     ECORD_LAUNCH_CHECK();
+    if (w->q_tc) {
+        ECORD_RET_IF(!w->q1_w || !w->enc_w || !w->enc_b || !w->qln_w, ECORD_E_NULL);
+        k_pack_qtc<<<1, ECORD_DIM_Q, 0, as_stream(stream)>>>(*w);
+        ECORD_LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -252,6 +311,14 @@ extern "C" int ecord_fold_q_host(const float *q1_w, const float *enc_w, const fl
     }
     for (int c = 0; c < Q; ++c) wb += (double)q2_w[c] * (double)qln_b[c];
     out[579] = (float)wb;
+    int o = 580;
+    for (int a = 0; a < 3; ++a)
+        for (int b = a; b < 3; ++b) {          // C^T C of the centred planes: 00 01 02 11 12 22
+            double t = 0.0;
+            for (int c = 0; c < Q; ++c) t += (double)out[384 + a * Q + c] * (double)out[384 + b * Q + c];
+            out[o++] = (float)t;
+        }
+    out[586] = out[587] = 0.0f;
     return 0;
 }
 

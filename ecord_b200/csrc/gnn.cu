@@ -164,7 +164,7 @@ __global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__res
 
 // node_emb = W_g x + b_g ; node_B = Wq[:,32:48] node_emb + Wq[:,48:64] b_enc
 __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ x, float *gnn_out, float *node_emb,
-                             float *node_B, float *node_Bc, float *node_LB) {
+                             float *node_B, float *node_Bc, float *node_LB, float *node_qv) {
     __shared__ float gw[D * D], gb[D], qb[ECORD_DIM_Q * D], qd[ECORD_DIM_Q];
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) gw[i] = wt.g2r_w[i];
     if (threadIdx.x < D) gb[threadIdx.x] = wt.g2r_b[threadIdx.x];
@@ -206,6 +206,23 @@ __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ 
         }
         node_LB[v] = lb;
     }
+    if (node_qv) {     // tensor-core Q kernel: b' = Wg emb (the vertex part of the centred pre-activation, without bconst)
+        const float *Wg = wt.q_tc + 1280, *Cc = wt.q_tc + 2304;
+        float bb = 0.0f, cb0 = 0.0f, cb1 = 0.0f, cb2 = 0.0f, lb = 0.0f;
+        for (int c = 0; c < ECORD_DIM_Q; ++c) {
+            float b = 0.0f;
+#pragma unroll
+            for (int i = 0; i < D; ++i) b = fmaf(Wg[c * D + i], e[i], b);
+            bb = fmaf(b, b, bb);
+            cb0 = fmaf(Cc[c * 4 + 0], b, cb0);
+            cb1 = fmaf(Cc[c * 4 + 1], b, cb1);
+            cb2 = fmaf(Cc[c * 4 + 2], b, cb2);
+            lb = fmaf(wt.q2_w[c] * wt.qln_w[c], b + Cc[c * 4 + 3], lb);
+        }
+        float4 *o = reinterpret_cast<float4 *>(node_qv + (long long)v * 8);
+        o[0] = make_float4(bb, cb0, cb1, cb2);
+        o[1] = make_float4(lb, 0.0f, 0.0f, 0.0f);
+    }
 }
 }  // namespace
 
@@ -215,8 +232,9 @@ extern "C" size_t ecord_gnn_workspace_bytes(int32_t N) {
 }
 
 extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
-                               float *node_Bc, float *node_LB, void *workspace, void *stream) {
+                               float *node_Bc, float *node_LB, float *node_qv, void *workspace, void *stream) {
     ECORD_RET_IF((node_Bc == nullptr) != (node_LB == nullptr), ECORD_E_NULL);
+    ECORD_RET_IF(node_qv && (!w || !w->q_tc), ECORD_E_NULL);
     ECORD_RET_IF(!g || !w || !node_emb || !node_B || !workspace, ECORD_E_NULL);
     ECORD_RET_IF(g->num_nodes <= 0, ECORD_E_SIZE);
     ECORD_RET_IF(!g->in_ptr || (g->num_edges > 0 && (!g->in_src || !g->in_w)), ECORD_E_NULL);
@@ -243,7 +261,7 @@ extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, flo
         ECORD_LAUNCH_CHECK();
         float *t = cur; cur = nxt; nxt = t;
     }
-    k_gnn_finish<<<nb, TB, 0, st>>>(N, *w, cur, gnn_out, node_emb, node_B, node_Bc, node_LB);
+    k_gnn_finish<<<nb, TB, 0, st>>>(N, *w, cur, gnn_out, node_emb, node_B, node_Bc, node_LB, node_qv);
     ECORD_LAUNCH_CHECK();
     return 0;
 }

@@ -129,8 +129,13 @@ struct TailSmem {
     float w2[ND * P1];          // [o][i]
     float v1t[ND * ND];         // transposed val_out.1: [i][o]
     float qt[ND * ECORD_DIM_Q]; // transposed Wq[:, :32]: [i][c]
+    float wg[ECORD_DIM_Q * 16]; // tensor-core Q kernel: centred Wq[:,32:48]  [c][k]
+    float cc[ECORD_DIM_Q * 4];  //                        centred C [c][0..2], bconst[c]
 };
 
+__device__ __forceinline__ float tf32_round(float x) {     // round-to-nearest onto the tf32 grid (see tc_common.cuh)
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
 // one butterfly level: lanes with (lane & OFF) == 0 keep v[0..N/2), the others keep v[N/2..N)
 template <int N, int OFF>
 __device__ __forceinline__ void reduce_scatter_step(float (&v)[64], bool upper) {
@@ -165,6 +170,10 @@ k_policy_tail(ecord_weights w, ecord_policy p) {
     for (int i = threadIdx.x; i < ND * ND; i += blockDim.x) S.v1t[i] = w.v1_w[(i % ND) * ND + (i / ND)];
     for (int i = threadIdx.x; i < ND * ECORD_DIM_Q; i += blockDim.x)
         S.qt[i] = w.q1_w[(i % ECORD_DIM_Q) * ECORD_DIM_Q + (i / ECORD_DIM_Q)];
+    if (p.qa) {
+        for (int i = threadIdx.x; i < ECORD_DIM_Q * 16; i += blockDim.x) S.wg[i] = w.q_tc[1280 + i];
+        for (int i = threadIdx.x; i < ECORD_DIM_Q * 4; i += blockDim.x) S.cc[i] = w.q_tc[2304 + i];
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int m0 = blockIdx.x * kTailRows + warp * kTailR;
@@ -294,6 +303,44 @@ k_policy_tail(ecord_weights w, ecord_policy p) {
         }
         if (k8 == 0) p.v[m] = vv;
     }
+    if (p.qa) {
+        // operands of the tensor-core Q kernel (layout: ecord_policy.qa), a' = Ac + bconst.  Each lane holds 8 channels
+        // of its row; the 20 channel sums (Wg^T a', Cc^T a', |a'|^2) are reduced over the row's 8 lanes.
+        float part[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) part[i] = 0.0f;
+        float ga[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int c = k8 * 8 + q;
+            const float ap = ac[q] + S.cc[c * 4 + 3];
+            ga[q] = w.qln_w[c] * ap;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) part[k] = fmaf(S.wg[c * 16 + k], ap, part[k]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) part[16 + j] = fmaf(S.cc[c * 4 + j], ap, part[16 + j]);
+            part[19] = fmaf(ap, ap, part[19]);
+        }
+#pragma unroll
+        for (int i = 0; i < 20; ++i) part[i] = group8_sum(part[i]);
+        if (live) {
+            // (hi, lo) pairs: hi on the tf32 grid, lo the exact remainder -- the kernel stores them as they are
+            float *qo = p.qa + (long long)m * ECORD_QA_STRIDE;
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                const float h0 = tf32_round(ga[q]), h1 = tf32_round(ga[q + 1]);
+                *reinterpret_cast<float4 *>(qo + 2 * (k8 * 8 + q)) = make_float4(h0, ga[q] - h0, h1, ga[q + 1] - h1);
+            }
+#pragma unroll
+            for (int i = 0; i < 19; ++i)
+                if ((i & 7) == k8) qo[128 + i] = tf32_round(part[i]);
+            if (k8 == 3) qo[147] = part[19];
+            if (k8 == 4) qo[148] = la;
+            if (k8 == 5) qo[149] = vv;
+            if (k8 == 6) qo[150] = 0.0f;
+            if (k8 == 7) qo[151] = 0.0f;
+        }
+    }
 }
 }  // namespace
 
@@ -371,5 +418,6 @@ extern "C" int ecord_policy_step(const ecord_graph *g, const ecord_env *env, con
     if (gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!w->gru_w_bf16 || !w->p1_w_bf16, ECORD_E_NULL);
     if ((rc = policy_init_attrs())) return rc;
     ECORD_RET_IF((p->Ac == nullptr) != (p->LA == nullptr), ECORD_E_NULL);
+    ECORD_RET_IF(p->qa && !w->q_tc, ECORD_E_NULL);
     return launch_policy_step(g, env, w, p, nullptr, cur, gemm_mode, skip_pre, as_stream(stream));
 }

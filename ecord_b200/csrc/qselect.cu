@@ -353,7 +353,20 @@ __global__ void k_plane_to_nt(ecord_graph g, int T, const float *__restrict__ pl
 
 static int q_block_size(int n_max) { return n_max <= 32 ? 32 : n_max <= 64 ? 64 : n_max <= 128 ? 128 : 256; }
 
-int q_kernels_per_step(int q_mode) { return q_mode == ECORD_Q_FAST ? 2 : 1; }
+int q_kernels_per_step(int q_mode) { return q_mode == ECORD_Q_EXACT ? 1 : 2; }
+
+// qtc.cu
+int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                const int32_t *step_base, int step_off, cudaStream_t st);
+int qtc_init_attrs();
+
+static int launch_select_finish(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                                const int32_t *step_base, int step_off, int compat, const int32_t *forced, cudaStream_t st) {
+    k_select_finish<<<ceil_div((long long)p->rows * 32, 256), 256, 0, st>>>(*g, *env, *w, *p, step_base, step_off, compat,
+                                                                             forced);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
 
 static int launch_q_fast(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                          const int32_t *step_base, int step_off, int compat, const int32_t *forced, cudaStream_t st) {
@@ -371,22 +384,39 @@ static int launch_q_fast(const ecord_graph *g, const ecord_env *env, const ecord
     if (p->q) k_q_fast<true><<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
     else k_q_fast<false><<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
     ECORD_LAUNCH_CHECK();
-    k_select_finish<<<ceil_div((long long)p->rows * 32, 256), 256, 0, st>>>(*g, *env, *w, *p, step_base, step_off, compat,
-                                                                             forced);
-    ECORD_LAUNCH_CHECK();
-    return 0;
+    return launch_select_finish(g, env, w, p, step_base, step_off, compat, forced, st);
 }
 
 int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                     const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat, const int32_t *forced,
                     int q_mode, cudaStream_t st) {
     if (q_mode == ECORD_Q_FAST) return launch_q_fast(g, env, w, p, step_base, step_off, compat, forced, st);
+    if (q_mode == ECORD_Q_TC) {
+        int rc = launch_q_tc(g, env, w, p, step_base, step_off, st);
+        if (rc) return rc;
+        return launch_select_finish(g, env, w, p, step_base, step_off, compat, forced, st);
+    }
     QConst K;
     static_assert(sizeof(QConst) == 6 * Q * sizeof(float), "QConst must be densely packed");
     memcpy(&K, w->q_fold, sizeof(QConst));      // q_fold is a HOST array (see ecord_weights)
     k_q_select<<<p->rows, q_block_size(g->n_max), 0, st>>>(*g, *env, *w, *p, K, step_base, step_off, tau, seed, compat,
                                                            forced);
     ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+// argument checks shared by ecord_q_select and ecord_rollout_plan_create
+int check_q_mode(const ecord_graph *g, const ecord_weights *w, const ecord_policy *p, int q_mode, float tau) {
+    ECORD_RET_IF(q_mode != ECORD_Q_EXACT && q_mode != ECORD_Q_FAST && q_mode != ECORD_Q_TC, ECORD_E_UNSUPPORTED);
+    if (q_mode == ECORD_Q_EXACT) return 0;
+    ECORD_RET_IF(tau > 0.0f, ECORD_E_UNSUPPORTED);     // sampling needs the two-pass exact kernel
+    ECORD_RET_IF(!p->keys, ECORD_E_NULL);
+    ECORD_RET_IF(g->num_qtiles <= 0 || !g->qtile_graph || !g->qtile_v0, ECORD_E_NULL);
+    if (q_mode == ECORD_Q_FAST) ECORD_RET_IF(!p->Ac || !p->LA || !p->node_Bc || !p->node_LB, ECORD_E_NULL);
+    if (q_mode == ECORD_Q_TC) {
+        ECORD_RET_IF(!p->qa || !p->node_qv || !w->q_tc, ECORD_E_NULL);
+        return qtc_init_attrs();
+    }
     return 0;
 }
 
@@ -398,12 +428,8 @@ extern "C" int ecord_q_select(const ecord_graph *g, const ecord_env *env, const 
     ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj || steps_done < 0, ECORD_E_SIZE);
     ECORD_RET_IF(tau < 0.0f, ECORD_E_SIZE);
     ECORD_RET_IF(tau > 0.0f && !p->q, ECORD_E_NULL);
-    ECORD_RET_IF(q_mode != ECORD_Q_EXACT && q_mode != ECORD_Q_FAST, ECORD_E_UNSUPPORTED);
-    if (q_mode == ECORD_Q_FAST) {
-        ECORD_RET_IF(tau > 0.0f, ECORD_E_UNSUPPORTED);     // sampling needs the two-pass exact kernel
-        ECORD_RET_IF(!p->Ac || !p->LA || !p->node_Bc || !p->node_LB || !p->keys, ECORD_E_NULL);
-        ECORD_RET_IF(g->num_qtiles <= 0 || !g->qtile_graph || !g->qtile_v0, ECORD_E_NULL);
-    }
+    int rc = check_q_mode(g, w, p, q_mode, tau);
+    if (rc) return rc;
     return launch_q_select(g, env, w, p, nullptr, steps_done, tau, seed, compat, forced_actions, q_mode, as_stream(stream));
 }
 

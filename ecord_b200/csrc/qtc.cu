@@ -1,0 +1,373 @@
+// qtc.cu -- ECORD_Q_TC: the per-vertex Q head with its contraction on 5th-gen tensor cores (sm_100a).
+//
+// Same function as qselect.cu (SURVEY.md 8a rows a7 + a8 per-vertex half + a9; reference
+// models/rnn_decoder.py:285-311, actors/ecord.py:78-91,123-193), evaluated in the centred / split form of
+// ECORD_Q_FAST:
+//     x_c   = a'_c[g,t] + b'_c[n] + Cc_c . f[n,t]            a' = Ac + bconst,  b' = Wg node_emb[n]  (channel-centred)
+//     sigma = sqrt(sum_c x_c^2 / 64 + eps)
+//     q     = 0.505 (lin / sigma + Wb) + 0.495 (sum_c w_c |gamma_c x_c + beta_c sigma|) / sigma + b_o + v[g,t]
+//
+// What the tensor core does.  For one tile of 128 vertices of a graph and one trajectory t, the 128 x 64 block
+// gamma_c x_c is a small GEMM  [128 rows] x [K = 24] x [N = 80]  in tf32 with fp32 accumulation in TMEM:
+//     A operand rows (one per vertex, written by the vertex's own thread)
+//         R1 = node_emb[n] (16)                                       shared memory, constant for the CTA
+//         R2 = [ f0  f1_hi  f2_hi  f1_lo | 1  1  f2_lo  0 ]            TENSOR memory (tcgen05.st), rewritten per trajectory
+//                                                                      (hi/lo = exact tf32 split)
+//     B operand rows (one per output column)
+//         c < 64 : [ gamma_c Wg[c][0..15] | gamma_c Cc[c][0..2]  gamma_c Cc[c][1]  ga'_hi  ga'_lo  gamma_c Cc[c][2]  0 ]
+//         c = 64 : [ (Wg^T a')[0..15]     | (Cc^T a')[0..2]      (Cc^T a')[1]      0  0  (Cc^T a')[2]  0 ]  ->  d = a' . (b' + Cc f)
+// Column 64 turns the LayerNorm sum of squares into a quadratic form,
+//     sum_c x_c^2 = |a'|^2 + 2 d + |b' + Cc f|^2,     |b' + Cc f|^2 = bb[n] + 2 cb[n].f + f^T (Cc^T Cc) f,
+// so the CUDA cores are left with 2 FFMA per channel (the |.| sum) instead of 8: ~190 instructions per
+// (vertex, trajectory) row instead of ~550.  Only the per-trajectory entries of the B operand (ga', Wg^T a', Cc^T a':
+// 83 floats from the policy tail) and the 128 R2 rows change between MMAs.
+//
+// CTA = 4 row warps (thread i <-> vertex i of the tile <-> TMEM lane i) + 1 control warp (writes the per-trajectory
+// operand entries, issues tcgen05.mma / commit).  No CTA-wide barrier in the loop: the roles meet on mbarriers
+// (`ready`: R2 written + accumulator drained, 4 warp arrivals; `full`: tcgen05.commit).  Three accumulators are in
+// flight: a row warp hands trajectory t+2 to the tensor core right after reading the accumulator of t out of TMEM,
+// so the MMA latency hides behind two epilogues.
+// Shared-memory operand blocks are [rows][8 tf32] with 32-byte rows in the canonical K-major SWIZZLE_32B layout
+// (16-byte chunk index XOR bit 2 of the row; 8-row groups 256 B apart).  R2 lives in tensor memory because a
+// generic-proxy write to a shared-memory operand needs fence.proxy.async (a MEMBAR) before the MMA may read it,
+// and that fence would drain the row warps' prefetched global loads and arg-max atomics every trajectory.
+#include "tc_common.cuh"
+#include <string.h>
+
+namespace {
+constexpr int Q = ECORD_DIM_Q;        // 64
+constexpr int QT = ECORD_QTILE;       // 128 vertices per tile
+constexpr int QN = 80;                // MMA N (multiple of 16 for M = 128)
+constexpr int QA = ECORD_QA_STRIDE;   // 88
+constexpr int kTcMaxT = 64;           // trajectories per CTA (rows of qa staged in shared memory)
+constexpr int A_BLK = QT * 32;        // bytes of one [128][8] tf32 operand block
+constexpr int B_BLK = QN * 32;        // bytes of one [80][8] block
+constexpr int kQtcThreads = 160;
+constexpr int kNB = 3;                // accumulators / B-operand buffers in flight
+constexpr int kAccStride = QN;        // TMEM columns [0,240): three accumulators
+constexpr int kTmemA = kNB * QN;      // TMEM columns [240,248) / [248,256): the per-trajectory A operand R2, double-buffered
+constexpr int kTmemCols = 256;
+
+constexpr int kRing = 8;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
+constexpr int kImgBytes = 3 * B_BLK;   // packed image of one B-operand buffer: W1 k-block 0 | W1 k-block 1 | W2
+
+struct QTcSmem {
+    uint8_t R1[2][A_BLK];              // A operand, k-blocks 0 and 1 (node_emb), constant for the CTA
+    uint8_t W[kNB][3][B_BLK];          // B operand [buffer][W1 k0 | W1 k1 | W2]
+    float qa[kTcMaxT][QA];             // per-(g,t) rows of ecord_policy.qa
+    int sp[kRing + 1][QT];             // state ring (cp.async), one slot per trajectory in flight
+    float pk[kRing + 1][QT];
+    uint64_t full[kNB];                // MMA -> row warps: accumulator j complete (trajectory tt uses j = tt % 3)
+    uint64_t ready[kNB];               // row warps -> MMA: R2 of trajectory tt written, accumulator j drained
+    uint64_t setup;                    // bulk copies of the set-up landed
+    uint32_t tmem_base;
+};
+
+// epilogue constants, passed by value (constant bank operands of the FFMAs)
+struct QTcConst { float bet[Q], wo[Q], CC[6], LC[3], Wb; };
+
+__device__ __forceinline__ uint32_t sw32(int r, int k) {      // byte offset of element (row r, k) in a SWIZZLE_32B block
+    return (uint32_t)(r * 32 + ((((k >> 2) ^ (r >> 2)) & 1) << 4) + (k & 3) * 4);
+}
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {   // D = f32, A = B = tf32, K-major
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// A operand from tensor memory (lane = row, one 32-bit column per tf32 element)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, float a0, float a1, float a2, float a3, float a4, float a5, float a6,
+                                         float a7) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)),
+                   "r"(__float_as_uint(a3)), "r"(__float_as_uint(a4)), "r"(__float_as_uint(a5)), "r"(__float_as_uint(a6)),
+                   "r"(__float_as_uint(a7)) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool DUMP_Q>
+__global__ void __launch_bounds__(kQtcThreads, 2)
+k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_tc, const __grid_constant__ QTcConst K,
+       const float *__restrict__ q2_b, const int32_t *step_base, int step_off, int t_chunk) {
+    extern __shared__ uint8_t smem_raw[];
+    QTcSmem &S = *reinterpret_cast<QTcSmem *>(smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_row = warp < 4;
+    const int tile = blockIdx.x;
+    const int gi = g.qtile_graph[tile], v0 = g.qtile_v0[tile];
+    const int T = e.num_tradj;
+    const int t_lo = blockIdx.y * t_chunk, nt = min(T, t_lo + t_chunk) - t_lo;
+    const int steps_done = (step_base ? *step_base : 0) + step_off;
+    const int lo = g.graph_ptr[gi], n = g.graph_ptr[gi + 1] - lo;
+    const uint32_t full0 = smem_u32(&S.full[0]), ready0 = smem_u32(&S.ready[0]), setup_bar = smem_u32(&S.setup);
+    constexpr uint32_t idesc = umma_idesc_tf32(QT, QN);
+
+    // ---------------- set-up ----------------
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int j = 0; j < kNB; ++j) { mbar_init(full0 + 8 * j, 1); mbar_init(ready0 + 8 * j, 4); }
+            mbar_init(setup_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // B-operand images (both buffers) and this CTA's qa rows: bulk copies through the async proxy
+            const uint32_t qa_bytes = (uint32_t)nt * QA * 4u;
+            mbar_expect_tx(setup_bar, (uint32_t)kNB * kImgBytes + qa_bytes);
+            for (int j = 0; j < kNB; ++j) bulk_g2s(smem_u32(S.W[j]), q_tc + 2816, kImgBytes, setup_bar);
+            bulk_g2s(smem_u32(S.qa), p.qa + (long long)(gi * T + t_lo) * QA, qa_bytes, setup_bar);
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                     "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // per-vertex: the R1 row (node_emb rounded onto the tf32 grid) and the quadratic-form scalars
+    const bool valid = is_row && v0 + tid < n;
+    const int v = is_row ? min(v0 + tid, n - 1) : 0;
+    float bb = 0.f, cb0 = 0.f, cb1 = 0.f, cb2 = 0.f, lb = 0.f;
+    // state row entries: element (t_lo, v); consecutive trajectories are n elements apart
+    const long long base0 = (long long)lo * T + (long long)t_lo * n + v;
+    const int *__restrict__ sp_ptr = e.sp + base0;          // next trajectory to fetch
+    const float *__restrict__ pk_ptr = e.peek + base0;
+    const uint32_t ring_sp = smem_u32(&S.sp[0][tid & (QT - 1)]), ring_pk = smem_u32(&S.pk[0][tid & (QT - 1)]);
+    if (is_row) {
+        const float4 *ep = reinterpret_cast<const float4 *>(p.node_emb + (long long)(lo + v) * 16);
+        const float4 *qv = reinterpret_cast<const float4 *>(p.node_qv + (long long)(lo + v) * 8);
+        float4 x[4];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) x[c4] = ep[c4];
+        const float4 q0 = qv[0];
+        lb = qv[1].x;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            x[c4].x = tf32_rn(x[c4].x); x[c4].y = tf32_rn(x[c4].y); x[c4].z = tf32_rn(x[c4].z); x[c4].w = tf32_rn(x[c4].w);
+            const int k = c4 * 4;
+            *reinterpret_cast<float4 *>(&S.R1[k >> 3][sw32(tid, k & 7)]) = x[c4];
+        }
+        bb = q0.x; cb0 = 2.0f * q0.y; cb1 = 2.0f * q0.z; cb2 = 2.0f * q0.w;
+        // R1 was written through the generic proxy: make it visible to the tensor core.  This fence is a MEMBAR, so
+        // it sits before the first cp.async; inside the trajectory loop the row warps touch no shared-memory operand
+        // (their per-trajectory operand R2 goes through tensor memory) and never fence.
+        fence_async_smem();
+#pragma unroll
+        for (int j = 0; j < kRing; ++j) {
+            if (j < nt) {
+                cp_async4(ring_sp + (uint32_t)(j * QT * 4), sp_ptr);
+                cp_async4(ring_pk + (uint32_t)(j * QT * 4), pk_ptr);
+                sp_ptr += n; pk_ptr += n;
+            }
+            cp_async_commit();
+        }
+    }
+    const float bo = q2_b[0];
+    const float inv_n = 1.0f / (float)n;
+    constexpr float inv_clip = 1.0f / (float)ECORD_STATIC_CLIP;
+    float *q_ptr = DUMP_Q ? p.q + base0 : nullptr;
+    unsigned long long *key_ptr = p.keys + (gi * T + t_lo);
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                 // barrier inits, TMEM base, R1
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = S.tmem_base;
+
+    if (warp == 4) {
+        // =============== control warp: per-trajectory B-operand entries, MMA issue ===============
+        mbar_wait(setup_bar, 0);
+        // Per-trajectory B-operand entries (qa row, already rounded / split by the policy tail) and where this lane
+        // puts them inside a buffer: two (hi, lo) channel pairs into W2 slots 4|5, plus one row-64 entry.
+        const uint32_t dst_c0 = 2u * B_BLK + sw32(lane, 4), dst_c1 = 2u * B_BLK + sw32(lane + 32, 4);
+        uint32_t dst_r = 0, dst_r2 = 0;       // row 64: Wg^T a' (lanes 0..15), Cc^T a' (lanes 16..18; f1, f2 twice: hi and lo slots)
+        if (lane < 8) dst_r = sw32(Q, lane);
+        else if (lane < 16) dst_r = B_BLK + sw32(Q, lane - 8);
+        else if (lane < 19) dst_r = 2u * B_BLK + sw32(Q, lane - 16);
+        if (lane == 17) dst_r2 = 2u * B_BLK + sw32(Q, 3);
+        if (lane == 18) dst_r2 = 2u * B_BLK + sw32(Q, 6);
+        int j = 0;
+        uint32_t ph = 0;                 // parity of the current use of buffer j
+        for (int tt = 0; tt < nt; ++tt) {
+            // B-operand buffer j was last read by the MMAs of trajectory tt-3
+            if (tt >= kNB) mbar_wait(full0 + 8u * (uint32_t)j, ph ^ 1u);
+            const float *src = S.qa[tt];
+            uint8_t *Wj = S.W[j][0];
+            uint8_t *W1a = Wj, *W1b = Wj + B_BLK, *W2 = Wj + 2 * B_BLK;
+            *reinterpret_cast<float2 *>(Wj + dst_c0) = *reinterpret_cast<const float2 *>(src + 2 * lane);
+            *reinterpret_cast<float2 *>(Wj + dst_c1) = *reinterpret_cast<const float2 *>(src + 2 * (lane + 32));
+            if (lane < 19) {
+                const float val = src[128 + lane];
+                *reinterpret_cast<float *>(Wj + dst_r) = val;
+                if (lane >= 17) *reinterpret_cast<float *>(Wj + dst_r2) = val;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_wait(ready0 + 8u * (uint32_t)j, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + (uint32_t)(j * kAccStride);
+                umma_tf32(d, umma_desc_sw32(smem_u32(S.R1[0])), umma_desc_sw32(smem_u32(W1a)), idesc, 0u);
+                umma_tf32(d, umma_desc_sw32(smem_u32(S.R1[1])), umma_desc_sw32(smem_u32(W1b)), idesc, 1u);
+                umma_tf32_ts(d, tmem_base + (uint32_t)(kTmemA + 8 * (tt & 1)), umma_desc_sw32(smem_u32(W2)), idesc, 1u);
+                umma_commit(full0 + 8u * (uint32_t)j);
+            }
+            __syncwarp();
+            if (++j == kNB) { j = 0; ph ^= 1u; }
+        }
+        // the row warps wait for every accumulator, so all MMAs have completed when they reach the final barrier
+    } else {
+        // =============== row warps: thread <-> vertex <-> TMEM lane ===============
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        // prepare(tt): features of trajectory tt -> R2 row in tensor memory (buffer tt&1); refill the state ring
+        auto prepare = [&](int tt, int jr, float &o0, float &o1, float &o2) {
+            cp_async_wait<kRing - 1>();
+            const int slot = tt % (kRing + 1);
+            const int sp_c = S.sp[slot][tid];
+            const float pk_c = S.pk[slot][tid];
+            if (tt + kRing < nt) {                 // trajectory tt + kRing goes into the slot trajectory tt - 1 vacated
+                const uint32_t off = (uint32_t)(((tt + kRing) % (kRing + 1)) * QT * 4);
+                cp_async4(ring_sp + off, sp_ptr);
+                cp_async4(ring_pk + off, pk_ptr);
+                sp_ptr += n; pk_ptr += n;
+            }
+            cp_async_commit();
+            o0 = (float)(sp_c & 1);
+            o1 = pk_c * inv_n;
+            o2 = fminf((float)(steps_done - (sp_c >> 1)), (float)ECORD_STATIC_CLIP) * inv_clip;
+            const float h1 = tf32_rn(o1), h2 = tf32_rn(o2);
+            tmem_st8(trow + (uint32_t)(kTmemA + 8 * (tt & 1)), o0, h1, h2, o1 - h1, 1.0f, 1.0f, o2 - h2, 0.0f);
+            tmem_st_wait();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready0 + 8u * (uint32_t)jr);
+        };
+        float f0, f1 = 0.f, f2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        prepare(0, 0, f0, f1, f2);
+        if (nt > 1) prepare(1, 1, g0, g1, g2);
+        mbar_wait(setup_bar, 0);          // qa rows (bulk copy) are read by the epilogue
+        int j = 0;
+        uint32_t ph = 0;
+        for (int tt = 0; tt < nt; ++tt) {
+            mbar_wait(full0 + 8u * (uint32_t)j, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = trow + (uint32_t)(j * kAccStride);
+            float gx[Q];
+            tmem_ld16(taddr, gx);
+            tmem_ld16(taddr + 16, gx + 16);
+            tmem_ld16(taddr + 32, gx + 32);
+            tmem_ld16(taddr + 48, gx + 48);
+            const float d = tmem_ld1(taddr + 64);
+            tmem_ld_wait();
+            // The MMAs of trajectory tt are complete (their R2 buffer tt&1 is free) and accumulator (tt+2)%3 was
+            // drained in the previous iteration: hand trajectory tt+2 to the tensor core before the epilogue math,
+            // so that its MMAs have two epilogues to complete in.
+            if (tt + 2 < nt) prepare(tt + 2, j == 0 ? 2 : j - 1, h0, h1, h2);
+            const float *sc = S.qa[tt];
+            // |b' + Cc f|^2 = bb + 2 cb.f + f^T CC f
+            float xx = fmaf(f0, fmaf(K.CC[0], f0, fmaf(2.0f * K.CC[1], f1, fmaf(2.0f * K.CC[2], f2, cb0))), bb);
+            xx = fmaf(f1, fmaf(K.CC[3], f1, fmaf(2.0f * K.CC[4], f2, cb1)), xx);
+            xx = fmaf(f2, fmaf(K.CC[5], f2, cb2), xx);
+            const float ss = fmaxf(fmaf(2.0f, d, sc[147]) + xx, 0.0f);
+            const float var = fmaf(ss, 1.0f / Q, kLnEps);
+            const float rstd = rsqrtf(var);
+            const float sigma = var * rstd;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < Q; c += 4) {
+                a0 = fmaf(K.wo[c + 0], fabsf(fmaf(K.bet[c + 0], sigma, gx[c + 0])), a0);
+                a1 = fmaf(K.wo[c + 1], fabsf(fmaf(K.bet[c + 1], sigma, gx[c + 1])), a1);
+                a2 = fmaf(K.wo[c + 2], fabsf(fmaf(K.bet[c + 2], sigma, gx[c + 2])), a2);
+                a3 = fmaf(K.wo[c + 3], fabsf(fmaf(K.bet[c + 3], sigma, gx[c + 3])), a3);
+            }
+            const float acc = (a0 + a1) + (a2 + a3);
+            const float lin = sc[148] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
+            const float dot = fmaf(0.505f, fmaf(lin, rstd, K.Wb), 0.495f * acc * rstd);
+            const float q = (dot + bo) + sc[149];
+            if (DUMP_Q) { if (valid) *q_ptr = q; q_ptr += n; }
+            // arg-max: ordered-int max across the warp, lowest vertex among equals, one atomic per warp
+            const uint32_t u = __float_as_uint(q);
+            const uint32_t ord = valid ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0u;
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, ord);
+            const uint32_t bal = __ballot_sync(0xffffffffu, ord == mx);
+            if (lane == 0 && mx != 0u) {
+                const int vbest = v0 + warp * 32 + (__ffs(bal) - 1);
+                atomicMax(key_ptr + tt, ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)vbest));
+            }
+            f0 = g0; f1 = g1; f2 = g2;
+            g0 = h0; g1 = h1; g2 = h2;
+            if (++j == kNB) { j = 0; ph ^= 1u; }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+    }
+}
+}  // namespace
+
+int qtc_init_attrs() {
+    // the dynamic request is padded so that at most two CTAs (2 x 256 TMEM columns) share an SM
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    return 0;
+}
+
+// trajectory split that minimises (waves of CTAs) x (set-up + trajectories per CTA)
+static int qtc_t_chunk(int tiles, int T) {
+    const int slots = 2 * kNumSMs, setup = 8;
+    long long best_cost = -1;
+    int best = 1;
+    for (int s = 1; s <= T; ++s) {
+        const int tc = ceil_div(T, s);
+        if (tc > kTcMaxT) continue;
+        const long long waves = ceil_div((long long)tiles * ceil_div(T, tc), slots);
+        const long long cost = waves * (setup + tc);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tc; }
+    }
+    return best;
+}
+
+int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
+                const int32_t *step_base, int step_off, cudaStream_t st) {
+    static_assert(sizeof(QTcSmem) + 256 <= 100 * 1024, "QTcSmem too large");
+    QTcConst K;
+    memcpy(K.bet, w->q_fold + 4 * Q, Q * sizeof(float));
+    memcpy(K.wo, w->q_fold + 5 * Q, Q * sizeof(float));
+    memcpy(K.CC, w->q_fold + 580, 6 * sizeof(float));
+    memcpy(K.LC, w->q_fold + 576, 4 * sizeof(float));     // LC[3], Wb
+    const int T = env->num_tradj;
+    const int t_chunk = qtc_t_chunk(g->num_qtiles, T);
+    const dim3 grid(g->num_qtiles, ceil_div(T, t_chunk));
+    if (p->q) k_q_tc<true><<<grid, kQtcThreads, 100 * 1024, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
+    else k_q_tc<false><<<grid, kQtcThreads, 100 * 1024, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}

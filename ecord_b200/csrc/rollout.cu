@@ -18,6 +18,7 @@ int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecor
                           const int32_t *step_base, int step_off, float *score_log, int32_t *action_log, cudaStream_t st);
 int policy_init_attrs();
 int check_policy(const ecord_policy *p, int gemm_mode);
+int check_q_mode(const ecord_graph *g, const ecord_weights *w, const ecord_policy *p, int q_mode, float tau);
 int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                     const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat, const int32_t *forced,
                     int q_mode, cudaStream_t st);
@@ -75,7 +76,7 @@ int capture(ecord_rollout_plan *pl, int nsteps, cudaGraphExec_t *out) {
     const ecord_rollout_desc &d = pl->desc;
     // ECORD_Q_FAST also fuses the next step's msg_in stage into the env-step kernel (u must be primed once with
     // ecord_policy_pre before the first step); ECORD_Q_EXACT keeps the literal kernel sequence.
-    const int fused = d.q_mode == ECORD_Q_FAST;
+    const int fused = d.q_mode != ECORD_Q_EXACT;
     for (int i = 0; i < nsteps && !rc; ++i) {
         rc = launch_policy_step(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i, d.gemm_mode, fused,
                                 pl->stream);
@@ -110,13 +111,7 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     if (rc) return rc;
     ECORD_RET_IF(desc->policy->rows != desc->graph->num_graphs * desc->env->num_tradj, ECORD_E_SIZE);
     ECORD_RET_IF(desc->tau > 0.0f && !desc->policy->q, ECORD_E_NULL);
-    ECORD_RET_IF(desc->q_mode != ECORD_Q_EXACT && desc->q_mode != ECORD_Q_FAST, ECORD_E_UNSUPPORTED);
-    if (desc->q_mode == ECORD_Q_FAST) {
-        ECORD_RET_IF(desc->tau > 0.0f, ECORD_E_UNSUPPORTED);
-        ECORD_RET_IF(!desc->policy->Ac || !desc->policy->LA || !desc->policy->node_Bc || !desc->policy->node_LB ||
-                     !desc->policy->keys, ECORD_E_NULL);
-        ECORD_RET_IF(desc->graph->num_qtiles <= 0 || !desc->graph->qtile_graph || !desc->graph->qtile_v0, ECORD_E_NULL);
-    }
+    if ((rc = check_q_mode(desc->graph, desc->weights, desc->policy, desc->q_mode, desc->tau))) return rc;
     ECORD_RET_IF(!desc->weights->q_fold, ECORD_E_NULL);
     if (desc->gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!desc->weights->gru_w_bf16 || !desc->weights->p1_w_bf16, ECORD_E_NULL);
     if ((rc = policy_init_attrs())) return rc;
@@ -127,7 +122,7 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     pl->desc.graph = &pl->graph; pl->desc.env = &pl->env; pl->desc.weights = &pl->weights; pl->desc.policy = &pl->policy;
     pl->stream = as_stream(stream);
     pl->k = desc->steps_per_graph;
-    pl->kernels_per_step = policy_kernels_per_step(desc->gemm_mode, desc->q_mode == ECORD_Q_FAST) +
+    pl->kernels_per_step = policy_kernels_per_step(desc->gemm_mode, desc->q_mode != ECORD_Q_EXACT) +
                            q_kernels_per_step(desc->q_mode) + 1;
     pl->exec_k = pl->exec_1 = nullptr;
     pl->steps_enqueued = 0;

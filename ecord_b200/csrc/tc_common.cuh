@@ -68,6 +68,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// round-to-nearest onto the tf32 grid (10 explicit mantissa bits); the tensor core ignores the 13 low bits
+__host__ __device__ __forceinline__ float tf32_rn(float x) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+#else
+    union { float f; uint32_t u; } v; v.f = x; v.u = (v.u + 0x1000u) & 0xffffe000u; return v.f;
+#endif
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // MUFU.TANH (rel. error ~2^-11): the bf16 path rounds its outputs to 8 mantissa bits anyway
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

@@ -10,11 +10,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GEMM_BF16, GEMM_FP32, Q_EXACT, Q_FAST, check, ptr
+from ._lib import GEMM_BF16, GEMM_FP32, Q_EXACT, Q_FAST, Q_TC, check, ptr
 from .network import check_state_dicts
 
 _GEMM_MODES = {"fp32": GEMM_FP32, "bf16": GEMM_BF16}
-_Q_MODES = {"exact": Q_EXACT, "fast": Q_FAST}
+_Q_MODES = {"exact": Q_EXACT, "fast": Q_FAST, "tc": Q_TC}
 
 
 def _require_cuda(device):
@@ -115,11 +115,13 @@ class DeviceWeights:
         check(self.lib.ecord_fold_q_host(ptr(r['mlp_out.0.weight']), ptr(sd['node_encoder']['0.weight']),
                                          ptr(r['mlp_out.1.weight']), ptr(r['mlp_out.1.bias']),
                                          ptr(r['mlp_out.3.weight']), ptr(self.q_fold)), "ecord_fold_q_host")
-        self.gru_w_bf16 = self.p1_w_bf16 = None
+        self.gru_w_bf16 = self.p1_w_bf16 = self.q_tc = None
         if pack_bf16:
+            self.q_tc = torch.zeros(_lib.QTC_FLOATS, dtype=torch.float32, device=self.device)
             self.gru_w_bf16 = torch.empty(_lib.GRU_PACK_ELEMS, dtype=torch.bfloat16, device=self.device)
             self.p1_w_bf16 = torch.empty(512 * 1024, dtype=torch.bfloat16, device=self.device)
-        self.c = _lib.Weights(gru_w_bf16=ptr(self.gru_w_bf16), p1_w_bf16=ptr(self.p1_w_bf16), q_fold=ptr(self.q_fold), **kw)
+        self.c = _lib.Weights(gru_w_bf16=ptr(self.gru_w_bf16), p1_w_bf16=ptr(self.p1_w_bf16), q_tc=ptr(self.q_tc),
+                              q_fold=ptr(self.q_fold), **kw)
         if pack_bf16:
             check(self.lib.ecord_pack_weights(C.byref(self.c), _stream()), "ecord_pack_weights")
 
@@ -142,13 +144,15 @@ class RolloutState:
         if self.gemm == GEMM_BF16 and weights.gru_w_bf16 is None:
             raise ValueError("weights were created with pack_bf16=False")
         self.compat, self.tau, self.seed = bool(compat), float(tau), int(seed)
-        # parity mode = (fp32 GEMM, exact Q); throughput mode = (bf16 tcgen05 GEMM, fast Q).  tau > 0 needs exact Q.
+        # parity mode = (fp32 GEMM, exact Q); throughput mode = (bf16 tcgen05 GEMM, tensor-core Q).  tau > 0 needs exact Q.
         if q_mode is None:
-            q_mode = "fast" if (gemm == "bf16" and self.tau == 0.0) else "exact"
+            q_mode = "tc" if (gemm == "bf16" and self.tau == 0.0) else "exact"
         self.q_mode = _Q_MODES[q_mode]
-        if self.q_mode == Q_FAST and self.tau > 0:
+        if self.q_mode != Q_EXACT and self.tau > 0:
             raise ValueError("tau > 0 (sampling) requires q_mode='exact'")
-        self.fused = self.q_mode == Q_FAST
+        if self.q_mode == Q_TC and weights.q_tc is None:
+            raise ValueError("weights were created with pack_bf16=False")
+        self.fused = self.q_mode != Q_EXACT
         N, G = dgraph.N, dgraph.G
         M = G * T
         Mp = (M + 127) // 128 * 128
@@ -184,18 +188,22 @@ class RolloutState:
         self.gnn_out = torch.empty(N, 16, **f32)
         self.node_emb = torch.empty(N, 16, **f32)
         self.node_B = torch.empty(N, 64, **f32)
-        self.Ac = self.LA = self.node_Bc = self.node_LB = self.keys = None
+        self.Ac = self.LA = self.node_Bc = self.node_LB = self.keys = self.qa = self.node_qv = None
         if self.q_mode == Q_FAST:
             self.Ac = torch.zeros(Mp, 64, **f32)
             self.LA = torch.zeros(Mp, **f32)
             self.node_Bc = torch.empty(N, 64, **f32)
             self.node_LB = torch.empty(N, **f32)
+        if self.q_mode == Q_TC:
+            self.qa = torch.zeros(Mp, _lib.QA_STRIDE, **f32)
+            self.node_qv = torch.empty(N, 8, **f32)
+        if self.q_mode != Q_EXACT:
             self.keys = torch.zeros(M, dtype=torch.int64, device=dev)
         self.policy_c = _lib.Policy(M, Mp, ptr(self.hidden), ptr(self.hidden_bf16), ptr(self.th_bf16), ptr(self.u_bf16),
                                     ptr(self.u), ptr(self.gates), ptr(self.th), ptr(self.y1), ptr(self.P), ptr(self.A),
                                     ptr(self.v), ptr(self.last_sel), ptr(self.node_emb), ptr(self.node_B),
                                     ptr(self.actions), ptr(self.q), ptr(self.Ac), ptr(self.LA), ptr(self.node_Bc),
-                                    ptr(self.node_LB), ptr(self.keys))
+                                    ptr(self.node_LB), ptr(self.keys), ptr(self.qa), ptr(self.node_qv))
         # logs + step counter
         self.max_steps = int(max_steps)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -214,7 +222,8 @@ class RolloutState:
         """t=0 embedding (a5): fills gnn_out, node_emb and node_B."""
         ws = torch.empty(self.lib.ecord_gnn_workspace_bytes(self.g.N), dtype=torch.uint8, device=self.device)
         check(self.lib.ecord_gnn_embed(C.byref(self.g.c), C.byref(self.w.c), ptr(self.gnn_out), ptr(self.node_emb),
-                                       ptr(self.node_B), ptr(self.node_Bc), ptr(self.node_LB), ptr(ws), _stream()),
+                                       ptr(self.node_B), ptr(self.node_Bc), ptr(self.node_LB), ptr(self.node_qv), ptr(ws),
+                                       _stream()),
               "ecord_gnn_embed")
         self.kernel_launches += 16
         self._ws = ws
@@ -258,7 +267,7 @@ class RolloutState:
         check(self.lib.ecord_q_select(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c), C.byref(self.policy_c),
                                       self.steps_done, self.tau, self.seed, int(self.compat), ptr(fa), self.q_mode,
                                       _stream()), "ecord_q_select")
-        self.kernel_launches += 2 if self.q_mode == Q_FAST else 1
+        self.kernel_launches += 1 if self.q_mode == Q_EXACT else 2
         self._fa = fa
 
     @_on_stream

@@ -117,12 +117,21 @@ typedef struct ecord_weights {
     void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [16][192][1024] (rows r|z|hn of each 64-unit block)
                             followed by Wu pack [16][256][64] (rows r|z|0|in) -- tile order of the tcgen05 GRU kernel */
     void  *p1_w_bf16;    /* bf16 [512][1024] */
+    float *q_tc;         /* f32 [ECORD_QTC_FLOATS] operands of the tensor-core Q kernel (ECORD_Q_TC), or NULL:
+                              [0,1280)     W1 operand [80][16]: tf32(gamma_c * Wg[c][k]), rows >= 64 zero
+                              [1280,2304)  Wg [64][16] = Wq[:,32:48] centred over the 64 channels (fp32)
+                              [2304,2560)  [64][4]: Cc[c][0..2] (C = Wq[:,48:64] W_enc, centred), bconst[c] = centred Wq[:,48:64] b_enc
+                              [2560,2816)  [64][4]: tf32(gamma_c * Cc[c][0..2]), gamma_c
+                              [2816,4736)  shared-memory image of the kernel's B operand (3 swizzled [80][8] tf32 blocks)
+                            filled by ecord_pack_weights() */
     const float *q_fold; /* HOST f32 [ECORD_QFOLD_FLOATS] from ecord_fold_q_host():
                               [0,384)   C0|C1|C2 (C = Wq[:,48:64] @ W_enc, 64x3) | LN gamma | LN beta | w_o
                               [384,576) the same C with each column centred over the 64 channels (fast Q kernel)
                               [576,579) LC_k = sum_c w_o[c] gamma[c] Ccentred[c][k];  [579] sum_c w_o[c] beta[c]
+                              [580,586) Ccentred^T Ccentred (3x3 symmetric: 00 01 02 11 12 22); [586,588) unused
                             Passed to the Q kernels by value (constant bank), hence a host array. */
-#define ECORD_QFOLD_FLOATS 580
+#define ECORD_QFOLD_FLOATS 588
+#define ECORD_QTC_FLOATS 4736
 #define ECORD_GRU_PACK_ELEMS (3072 * 1024 + 4096 * 64)
 } ecord_weights;
 
@@ -152,12 +161,22 @@ typedef struct ecord_policy {
     const float *node_Bc; /* [N][64]         node_B - mean_c(node_B) */
     const float *node_LB; /* [N]             sum_c w_o[c] gamma[c] node_Bc[c] */
     unsigned long long *keys; /* [rows]      packed (ordered q << 32 | ~vertex) running arg-max; zero between steps */
+    /* tensor-core Q kernel (q_mode = ECORD_Q_TC); with a' = Ac + bconst:
+         qa[m] = [ (hi, lo) tf32 split of gamma_c a'_c (64 pairs) | tf32 Wg^T a' (16) | tf32 Cc^T a' (3) | |a'|^2 | LA | v | 0 0 ]
+                                                                                                written by the policy tail
+         node_qv[n] = [ |b'|^2 | Cc^T b' (3) | LB | 0 0 0 ],  b' = Wg node_emb[n]             written by ecord_gnn_embed */
+    float   *qa;          /* [rows_pad][ECORD_QA_STRIDE] */
+    float   *node_qv;     /* [N][8] */
 } ecord_policy;
 
 /* Q-head evaluation */
 #define ECORD_Q_EXACT 0   /* one CTA per (g,t); LayerNorm/LeakyReLU/dot evaluated literally (parity mode)             */
+#define ECORD_QA_STRIDE 152
 #define ECORD_Q_FAST  1   /* vertex-tiled, per-vertex operands register-resident across trajectories; centred LN and
                              LeakyReLU(y) = 0.505 y + 0.495 |y| with the linear half folded out (re-associated fp32) */
+#define ECORD_Q_TC    2   /* the same folded head with the 64-channel pre-activation of every (vertex, trajectory) row produced
+                             by tcgen05.mma kind::tf32 (operands built in shared memory, accumulators in TMEM) and only the
+                             |.|-sum left on the CUDA cores; 1e-3 relative (tf32 operands).  tau == 0 only. */
 
 /* ------------------------------------------------------------------------------------------ */
 int         ecord_version(void);
@@ -223,7 +242,8 @@ int ecord_env_export(const ecord_graph *g, const ecord_env *env, int32_t steps_d
  *      node_B: f32 [N][64] (see ecord_policy).  workspace: ecord_gnn_workspace_bytes(N) bytes. ---- */
 size_t ecord_gnn_workspace_bytes(int32_t num_nodes);
 int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
-                    float *node_Bc /* [N][64] or NULL */, float *node_LB /* [N] or NULL */, void *workspace, void *stream);
+                    float *node_Bc /* [N][64] or NULL */, float *node_LB /* [N] or NULL */,
+                    float *node_qv /* [N][8] or NULL; needs w->q_tc */, void *workspace, void *stream);
 
 /* ---- weight packing for the tensor-core path (device) and the folded Q-head constants (host arrays in/out) ---- */
 int ecord_pack_weights(const ecord_weights *w, void *stream);

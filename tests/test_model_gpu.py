@@ -124,6 +124,71 @@ def test_fast_q_kernel_vertex_tiles_and_trajectory_splits():
     assert torch.equal(a.score, b.score)
 
 
+TOL_TC = 2e-3   # tf32 operands (10-bit mantissa, hi/lo split on the per-trajectory terms), fp32 accumulation
+
+
+def _argmax_diffs_are_near_ties(dg, T, qa, a_actions, b_actions, tol):
+    """arg-max may legitimately differ only where the two Q-values are within `tol` (relative) of each other"""
+    diff = (a_actions != b_actions).nonzero().flatten().cpu().tolist()
+    for m in diff:
+        g_, t_ = divmod(m, T)
+        lo = int(dg.tg.np_ptr[g_])
+        col = qa[lo:int(dg.tg.np_ptr[g_ + 1]), t_]
+        gap = float(col[int(a_actions[m])] - col[int(b_actions[m])])
+        assert abs(gap) < tol * float(col.abs().max()), (m, gap)
+    return len(diff)
+
+
+@pytest.mark.parametrize("compat", [True, False])
+def test_tc_q_kernel_matches_exact_kernel(compat):
+    """ECORD_Q_TC (tcgen05 kind::tf32 pre-activations + quadratic-form LayerNorm statistics) vs the literal kernel on
+    the reference trace: Q within TOL_TC relative, choices identical except at near-ties."""
+    z, sd, a, dg, T, S = _setup("fp32", compat=compat, q_mode="exact")
+    _, _, b, _, _, _ = _setup("fp32", compat=compat, q_mode="tc")
+    worst = 0.0
+    for s in range(S):
+        for st in (a, b):
+            st.policy_step()
+            st.q_select()
+        qa, qb = a.q_values(), b.q_values()
+        worst = max(worst, rel_err(qb.cpu().numpy(), qa.cpu().numpy()))
+        assert worst < TOL_TC, (s, worst)
+        _argmax_diffs_are_near_ties(dg, T, qa, a.actions, b.actions, 2 * TOL_TC)
+        assert int(b.keys.abs().sum()) == 0
+        b.actions.copy_(a.actions); b.last_sel.copy_(a.last_sel); b.u.copy_(a.u)   # lock-step
+        if b.u_bf16 is not None:
+            b.u_bf16.copy_(a.u_bf16)
+        for st in (a, b):
+            st.env_step()
+    assert torch.equal(a.score, b.score) and torch.equal(a.peek, b.peek) and torch.equal(a.sp, b.sp)
+
+
+def test_tc_q_kernel_vertex_tiles_and_trajectory_splits():
+    """Graphs larger than one 128-vertex tile, ragged sizes, partial tiles, odd trajectory counts."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    from ecord_b200.graphs import synthetic_set
+    graphs = synthetic_set("er", 300, 2, p=0.05) + synthetic_set("er", 129, 1, p=0.1, seed0=5) + synthetic_set("er", 40, 2, p=0.2, seed0=9)
+    sd = random_state_dicts(21, perturb_norms=True)
+    w = DeviceWeights(sd)
+    dg = DeviceGraph(GraphBatcher()(graphs).tg)
+    for T in (37, 1, 130):
+        init = np.random.RandomState(3).randint(0, 2, (dg.N, T)).astype(np.int8)
+        a = RolloutState(dg, w, T, gemm="fp32", q_mode="exact", dump_q=True)
+        b = RolloutState(dg, w, T, gemm="fp32", q_mode="tc", dump_q=True)
+        for st in (a, b):
+            st.gnn_embed(); st.env_init(init)
+        for s in range(8):
+            for st in (a, b):
+                st.policy_step(); st.q_select()
+            qa = a.q_values()
+            assert rel_err(b.q_values().cpu().numpy(), qa.cpu().numpy()) < TOL_TC, (T, s)
+            _argmax_diffs_are_near_ties(dg, T, qa, a.actions, b.actions, 2 * TOL_TC)
+            b.actions.copy_(a.actions); b.last_sel.copy_(a.last_sel)
+            for st in (a, b):
+                st.env_step()
+        assert torch.equal(a.score, b.score)
+
+
 def test_tcgen05_kernels_against_torch_on_identical_operands():
     """The tensor-core GRU / projection kernels vs torch matmuls fed the SAME bf16-rounded operands: isolates
     descriptor/layout bugs from precision (fp32 accumulation order is the only difference)."""
