@@ -24,9 +24,10 @@
 //
 // CTA = 4 row warps (thread i <-> vertex i of the tile <-> TMEM lane i) + 1 control warp (writes the per-trajectory
 // operand entries, issues tcgen05.mma / commit).  No CTA-wide barrier in the loop: the roles meet on mbarriers
-// (`ready`: R2 written + accumulator drained, 4 warp arrivals; `full`: tcgen05.commit).  Three accumulators are in
-// flight: a row warp hands trajectory t+2 to the tensor core right after reading the accumulator of t out of TMEM,
-// so the MMA latency hides behind two epilogues.
+// (`ready`: R2 written + accumulator drained, 4 warp arrivals; `full`: tcgen05.commit).  A CTA owns 128 TMEM columns
+// (one accumulator + R2) so that FOUR CTAs share an SM: a row warp hands trajectory t+1 to the tensor core right
+// after reading the accumulator of t out of TMEM, its MMAs overlap the epilogue math of t, and the other CTAs'
+// warps cover what latency remains (the kernel is latency-, not issue-bound: see profiles/).
 // Shared-memory operand blocks are [rows][8 tf32] with 32-byte rows in the canonical K-major SWIZZLE_32B layout
 // (16-byte chunk index XOR bit 2 of the row; 8-row groups 256 B apart).  R2 lives in tensor memory because a
 // generic-proxy write to a shared-memory operand needs fence.proxy.async (a MEMBAR) before the MMA may read it,
@@ -39,26 +40,25 @@ constexpr int Q = ECORD_DIM_Q;        // 64
 constexpr int QT = ECORD_QTILE;       // 128 vertices per tile
 constexpr int QN = 80;                // MMA N (multiple of 16 for M = 128)
 constexpr int QA = ECORD_QA_STRIDE;   // 88
-constexpr int kTcMaxT = 64;           // trajectories per CTA (rows of qa staged in shared memory)
+constexpr int kTcMaxT = 32;           // trajectories per CTA (rows of qa staged in shared memory)
+constexpr int kCtasPerSM = 4;         // 4 x 128 TMEM columns; shared memory and registers are sized for it
 constexpr int A_BLK = QT * 32;        // bytes of one [128][8] tf32 operand block
 constexpr int B_BLK = QN * 32;        // bytes of one [80][8] block
 constexpr int kQtcThreads = 160;
-constexpr int kNB = 3;                // accumulators / B-operand buffers in flight
-constexpr int kAccStride = QN;        // TMEM columns [0,240): three accumulators
-constexpr int kTmemA = kNB * QN;      // TMEM columns [240,248) / [248,256): the per-trajectory A operand R2, double-buffered
-constexpr int kTmemCols = 256;
+constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,88): the per-trajectory A operand R2
+constexpr int kTmemCols = 128;
 
 constexpr int kRing = 8;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
 constexpr int kImgBytes = 3 * B_BLK;   // packed image of one B-operand buffer: W1 k-block 0 | W1 k-block 1 | W2
 
 struct QTcSmem {
     uint8_t R1[2][A_BLK];              // A operand, k-blocks 0 and 1 (node_emb), constant for the CTA
-    uint8_t W[kNB][3][B_BLK];          // B operand [buffer][W1 k0 | W1 k1 | W2]
+    uint8_t W[3][B_BLK];               // B operand: W1 k0 | W1 k1 | W2
     float qa[kTcMaxT][QA];             // per-(g,t) rows of ecord_policy.qa
     int sp[kRing + 1][QT];             // state ring (cp.async), one slot per trajectory in flight
     float pk[kRing + 1][QT];
-    uint64_t full[kNB];                // MMA -> row warps: accumulator j complete (trajectory tt uses j = tt % 3)
-    uint64_t ready[kNB];               // row warps -> MMA: R2 of trajectory tt written, accumulator j drained
+    uint64_t full;                     // MMA -> row warps: accumulator complete (one phase per trajectory)
+    uint64_t ready;                    // row warps -> MMA: R2 written, accumulator drained (4 warp arrivals per trajectory)
     uint64_t setup;                    // bulk copies of the set-up landed
     uint32_t tmem_base;
 };
@@ -100,6 +100,25 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, float a0, float a1, flo
                    "r"(__float_as_uint(a3)), "r"(__float_as_uint(a4)), "r"(__float_as_uint(a5)), "r"(__float_as_uint(a6)),
                    "r"(__float_as_uint(a7)) : "memory");
 }
+// packed fp32 pairs (sm_100 FFMA2)
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long abs2(unsigned long long v) {
+    float a, b;
+    unpack2(v, a, b);
+    return pack2(fabsf(a), fabsf(b));
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -117,7 +136,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool DUMP_Q>
-__global__ void __launch_bounds__(kQtcThreads, 2)
+__global__ void __launch_bounds__(kQtcThreads, kCtasPerSM)
 k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_tc, const __grid_constant__ QTcConst K,
        const float *__restrict__ q2_b, const int32_t *step_base, int step_off, int t_chunk) {
     extern __shared__ uint8_t smem_raw[];
@@ -130,19 +149,20 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
     const int t_lo = blockIdx.y * t_chunk, nt = min(T, t_lo + t_chunk) - t_lo;
     const int steps_done = (step_base ? *step_base : 0) + step_off;
     const int lo = g.graph_ptr[gi], n = g.graph_ptr[gi + 1] - lo;
-    const uint32_t full0 = smem_u32(&S.full[0]), ready0 = smem_u32(&S.ready[0]), setup_bar = smem_u32(&S.setup);
+    const uint32_t full0 = smem_u32(&S.full), ready0 = smem_u32(&S.ready), setup_bar = smem_u32(&S.setup);
     constexpr uint32_t idesc = umma_idesc_tf32(QT, QN);
 
     // ---------------- set-up ----------------
     if (warp == 4) {
         if (lane == 0) {
-            for (int j = 0; j < kNB; ++j) { mbar_init(full0 + 8 * j, 1); mbar_init(ready0 + 8 * j, 4); }
+            mbar_init(full0, 1);
+            mbar_init(ready0, 4);
             mbar_init(setup_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             // B-operand images (both buffers) and this CTA's qa rows: bulk copies through the async proxy
             const uint32_t qa_bytes = (uint32_t)nt * QA * 4u;
-            mbar_expect_tx(setup_bar, (uint32_t)kNB * kImgBytes + qa_bytes);
-            for (int j = 0; j < kNB; ++j) bulk_g2s(smem_u32(S.W[j]), q_tc + 2816, kImgBytes, setup_bar);
+            mbar_expect_tx(setup_bar, (uint32_t)kImgBytes + qa_bytes);
+            bulk_g2s(smem_u32(S.W), q_tc + 2816, kImgBytes, setup_bar);
             bulk_g2s(smem_u32(S.qa), p.qa + (long long)(gi * T + t_lo) * QA, qa_bytes, setup_bar);
         }
         __syncwarp();
@@ -211,14 +231,14 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
         else if (lane < 19) dst_r = 2u * B_BLK + sw32(Q, lane - 16);
         if (lane == 17) dst_r2 = 2u * B_BLK + sw32(Q, 3);
         if (lane == 18) dst_r2 = 2u * B_BLK + sw32(Q, 6);
-        int j = 0;
-        uint32_t ph = 0;                 // parity of the current use of buffer j
+        uint8_t *Wj = S.W[0];
+        const uint64_t dR1a = umma_desc_sw32(smem_u32(S.R1[0])), dR1b = umma_desc_sw32(smem_u32(S.R1[1]));
+        const uint64_t dW1a = umma_desc_sw32(smem_u32(Wj)), dW1b = umma_desc_sw32(smem_u32(Wj + B_BLK)),
+                       dW2 = umma_desc_sw32(smem_u32(Wj + 2 * B_BLK));
         for (int tt = 0; tt < nt; ++tt) {
-            // B-operand buffer j was last read by the MMAs of trajectory tt-3
-            if (tt >= kNB) mbar_wait(full0 + 8u * (uint32_t)j, ph ^ 1u);
+            // the B operand was last read by the MMAs of trajectory tt-1
+            if (tt >= 1) mbar_wait(full0, (uint32_t)(tt - 1) & 1u);
             const float *src = S.qa[tt];
-            uint8_t *Wj = S.W[j][0];
-            uint8_t *W1a = Wj, *W1b = Wj + B_BLK, *W2 = Wj + 2 * B_BLK;
             *reinterpret_cast<float2 *>(Wj + dst_c0) = *reinterpret_cast<const float2 *>(src + 2 * lane);
             *reinterpret_cast<float2 *>(Wj + dst_c1) = *reinterpret_cast<const float2 *>(src + 2 * (lane + 32));
             if (lane < 19) {
@@ -229,23 +249,21 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                mbar_wait(ready0 + 8u * (uint32_t)j, ph);
+                mbar_wait(ready0, (uint32_t)tt & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d = tmem_base + (uint32_t)(j * kAccStride);
-                umma_tf32(d, umma_desc_sw32(smem_u32(S.R1[0])), umma_desc_sw32(smem_u32(W1a)), idesc, 0u);
-                umma_tf32(d, umma_desc_sw32(smem_u32(S.R1[1])), umma_desc_sw32(smem_u32(W1b)), idesc, 1u);
-                umma_tf32_ts(d, tmem_base + (uint32_t)(kTmemA + 8 * (tt & 1)), umma_desc_sw32(smem_u32(W2)), idesc, 1u);
-                umma_commit(full0 + 8u * (uint32_t)j);
+                umma_tf32(tmem_base, dR1a, dW1a, idesc, 0u);
+                umma_tf32(tmem_base, dR1b, dW1b, idesc, 1u);
+                umma_tf32_ts(tmem_base, tmem_base + (uint32_t)kTmemA, dW2, idesc, 1u);
+                umma_commit(full0);
             }
             __syncwarp();
-            if (++j == kNB) { j = 0; ph ^= 1u; }
         }
         // the row warps wait for every accumulator, so all MMAs have completed when they reach the final barrier
     } else {
         // =============== row warps: thread <-> vertex <-> TMEM lane ===============
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         // prepare(tt): features of trajectory tt -> R2 row in tensor memory (buffer tt&1); refill the state ring
-        auto prepare = [&](int tt, int jr, float &o0, float &o1, float &o2) {
+        auto prepare = [&](int tt, float &o0, float &o1, float &o2) {
             cp_async_wait<kRing - 1>();
             const int slot = tt % (kRing + 1);
             const int sp_c = S.sp[slot][tid];
@@ -261,33 +279,28 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             o1 = pk_c * inv_n;
             o2 = fminf((float)(steps_done - (sp_c >> 1)), (float)ECORD_STATIC_CLIP) * inv_clip;
             const float h1 = tf32_rn(o1), h2 = tf32_rn(o2);
-            tmem_st8(trow + (uint32_t)(kTmemA + 8 * (tt & 1)), o0, h1, h2, o1 - h1, 1.0f, 1.0f, o2 - h2, 0.0f);
+            tmem_st8(trow + (uint32_t)kTmemA, o0, h1, h2, o1 - h1, 1.0f, 1.0f, o2 - h2, 0.0f);
             tmem_st_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(ready0 + 8u * (uint32_t)jr);
+            if (lane == 0) mbar_arrive(ready0);
         };
-        float f0, f1 = 0.f, f2 = 0.f, g0 = 0.f, g1 = 0.f, g2 = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f;
-        prepare(0, 0, f0, f1, f2);
-        if (nt > 1) prepare(1, 1, g0, g1, g2);
+        float f0, f1, f2, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        prepare(0, f0, f1, f2);
         mbar_wait(setup_bar, 0);          // qa rows (bulk copy) are read by the epilogue
-        int j = 0;
-        uint32_t ph = 0;
         for (int tt = 0; tt < nt; ++tt) {
-            mbar_wait(full0 + 8u * (uint32_t)j, ph);
+            mbar_wait(full0, (uint32_t)tt & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = trow + (uint32_t)(j * kAccStride);
             float gx[Q];
-            tmem_ld16(taddr, gx);
-            tmem_ld16(taddr + 16, gx + 16);
-            tmem_ld16(taddr + 32, gx + 32);
-            tmem_ld16(taddr + 48, gx + 48);
-            const float d = tmem_ld1(taddr + 64);
+            tmem_ld16(trow, gx);
+            tmem_ld16(trow + 16, gx + 16);
+            tmem_ld16(trow + 32, gx + 32);
+            tmem_ld16(trow + 48, gx + 48);
+            const float d = tmem_ld1(trow + 64);
             tmem_ld_wait();
-            // The MMAs of trajectory tt are complete (their R2 buffer tt&1 is free) and accumulator (tt+2)%3 was
-            // drained in the previous iteration: hand trajectory tt+2 to the tensor core before the epilogue math,
-            // so that its MMAs have two epilogues to complete in.
-            if (tt + 2 < nt) prepare(tt + 2, j == 0 ? 2 : j - 1, h0, h1, h2);
+            // accumulator drained, MMAs of trajectory tt complete (R2 free): hand trajectory tt+1 to the tensor core
+            // before the epilogue math, which its MMAs overlap
+            if (tt + 1 < nt) prepare(tt + 1, g0, g1, g2);
             const float *sc = S.qa[tt];
             // |b' + Cc f|^2 = bb + 2 cb.f + f^T CC f
             float xx = fmaf(f0, fmaf(K.CC[0], f0, fmaf(2.0f * K.CC[1], f1, fmaf(2.0f * K.CC[2], f2, cb0))), bb);
@@ -297,14 +310,20 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             const float var = fmaf(ss, 1.0f / Q, kLnEps);
             const float rstd = rsqrtf(var);
             const float sigma = var * rstd;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            // sum_c w_c |gamma_c x_c + beta_c sigma| on packed fp32 pairs (FFMA2 with |.| and scalar-broadcast operands):
+            // 64 instructions for the 64 channels
+            const unsigned long long sig2 = pack2(sigma, sigma);
+            unsigned long long acc01 = 0ull, acc23 = 0ull;
 #pragma unroll
             for (int c = 0; c < Q; c += 4) {
-                a0 = fmaf(K.wo[c + 0], fabsf(fmaf(K.bet[c + 0], sigma, gx[c + 0])), a0);
-                a1 = fmaf(K.wo[c + 1], fabsf(fmaf(K.bet[c + 1], sigma, gx[c + 1])), a1);
-                a2 = fmaf(K.wo[c + 2], fabsf(fmaf(K.bet[c + 2], sigma, gx[c + 2])), a2);
-                a3 = fmaf(K.wo[c + 3], fabsf(fmaf(K.bet[c + 3], sigma, gx[c + 3])), a3);
+                const unsigned long long y01 = fma2(pack2(K.bet[c + 0], K.bet[c + 1]), sig2, pack2(gx[c + 0], gx[c + 1]));
+                const unsigned long long y23 = fma2(pack2(K.bet[c + 2], K.bet[c + 3]), sig2, pack2(gx[c + 2], gx[c + 3]));
+                acc01 = fma2(pack2(K.wo[c + 0], K.wo[c + 1]), abs2(y01), acc01);
+                acc23 = fma2(pack2(K.wo[c + 2], K.wo[c + 3]), abs2(y23), acc23);
             }
+            float a0, a1, a2, a3;
+            unpack2(acc01, a0, a1);
+            unpack2(acc23, a2, a3);
             const float acc = (a0 + a1) + (a2 + a3);
             const float lin = sc[148] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
             const float dot = fmaf(0.505f, fmaf(lin, rstd, K.Wb), 0.495f * acc * rstd);
@@ -320,8 +339,6 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
                 atomicMax(key_ptr + tt, ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)vbest));
             }
             f0 = g0; f1 = g1; f2 = g2;
-            g0 = h0; g1 = h1; g2 = h2;
-            if (++j == kNB) { j = 0; ph ^= 1u; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -333,16 +350,18 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
 }
 }  // namespace
 
+constexpr int kQtcSmemBytes = 52 * 1024;
+
 int qtc_init_attrs() {
-    // the dynamic request is padded so that at most two CTAs (2 x 256 TMEM columns) share an SM
-    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    // the dynamic request is padded so that at most four CTAs (4 x 128 TMEM columns) share an SM
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
     return 0;
 }
 
 // trajectory split that minimises (waves of CTAs) x (set-up + trajectories per CTA)
 static int qtc_t_chunk(int tiles, int T) {
-    const int slots = 2 * kNumSMs, setup = 8;
+    const int slots = kCtasPerSM * kNumSMs, setup = 6;
     long long best_cost = -1;
     int best = 1;
     for (int s = 1; s <= T; ++s) {
@@ -357,7 +376,7 @@ static int qtc_t_chunk(int tiles, int T) {
 
 int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                 const int32_t *step_base, int step_off, cudaStream_t st) {
-    static_assert(sizeof(QTcSmem) + 256 <= 100 * 1024, "QTcSmem too large");
+    static_assert(sizeof(QTcSmem) + 256 <= kQtcSmemBytes, "QTcSmem too large");
     QTcConst K;
     memcpy(K.bet, w->q_fold + 4 * Q, Q * sizeof(float));
     memcpy(K.wo, w->q_fold + 5 * Q, Q * sizeof(float));
@@ -366,8 +385,8 @@ int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights 
     const int T = env->num_tradj;
     const int t_chunk = qtc_t_chunk(g->num_qtiles, T);
     const dim3 grid(g->num_qtiles, ceil_div(T, t_chunk));
-    if (p->q) k_q_tc<true><<<grid, kQtcThreads, 100 * 1024, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
-    else k_q_tc<false><<<grid, kQtcThreads, 100 * 1024, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
+    if (p->q) k_q_tc<true><<<grid, kQtcThreads, kQtcSmemBytes, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
+    else k_q_tc<false><<<grid, kQtcThreads, kQtcSmemBytes, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
