@@ -21,35 +21,45 @@
 #include "tc_common.cuh"
 
 namespace {
-// MODE 0 = GRU (first chunk N=256 from (mapA0=u, mapB0=Wu), then 16 chunks N=192 from (h[cur], Wh)), 256 TMEM cols
-// MODE 1 = PROJ (16 chunks N=64 from (th, W1)), 64 TMEM cols
+// MODE 0 = GRU : tile = 128 rows x 64 hidden units; k-chunk 0 (N=256) from (u, Wu), then 16 chunks (N=192) from
+//                (h[cur], Wh); accumulator = 256 TMEM columns, two accumulators = all 512 columns
+// MODE 1 = PROJ: tile = 128 rows x 128 outputs; 16 chunks (N=128) from (th, W1); accumulator = 128 columns
+//
+// Persistent: grid = min(#tiles, #SMs); CTA b works on tiles b, b + grid, ...  The accumulator is double-buffered in
+// TMEM (tmem_full / tmem_empty barriers), so the epilogue of tile i (TMEM -> registers -> GRU cell -> global) runs
+// while TMA + MMA already work on tile i+1; the epilogue warps prefetch the old hidden state before they wait.
+template <int MODE> struct TcCfg;
+template <> struct TcCfg<0> { static constexpr int N_FIRST = 256, N_MAIN = 192, B_ROWS = 256, ACC_COLS = 256, TILE_N = 64; };
+template <> struct TcCfg<1> { static constexpr int N_FIRST = 0, N_MAIN = 128, B_ROWS = 128, ACC_COLS = 128, TILE_N = 128; };
+
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
           const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-          const __grid_constant__ CUtensorMap mapB, TcParams prm) {
-    constexpr int N_FIRST = MODE == 0 ? 256 : 0;
-    constexpr int N_MAIN = MODE == 0 ? 192 : 64;
-    constexpr int B_ROWS = MODE == 0 ? 256 : 64;             // smem rows reserved per stage for B
-    constexpr int TMEM_COLS = MODE == 0 ? 256 : 64;
-    constexpr int A_BYTES = BM * BK * 2, B_BYTES = B_ROWS * BK * 2;
+          const __grid_constant__ CUtensorMap mapB, TcParams prm, int num_tiles, int nblk) {
+    using C = TcCfg<MODE>;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
+    constexpr int TMEM_COLS = 2 * C::ACC_COLS;
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 4];
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024-byte alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nb = blockIdx.x;            // output-column block
-    const int m0 = blockIdx.y * BM;
     const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
 
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]), accum_bar = smem_u32(&bars[2 * kStages]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * kStages]), tempty0 = smem_u32(&bars[2 * kStages + 2]);
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kThreads / 32 - 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -68,107 +78,132 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
             const CUtensorMap *mapA = (MODE == 0) ? (cur ? &mapA1 : &mapA0) : &mapA0;
             tmap_prefetch(mapA); tmap_prefetch(&mapB);
             if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int s = c % kStages;
-                const uint32_t ph = (uint32_t)(c / kStages) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                if (MODE == 0 && c == 0) {
-                    mbar_expect_tx(full0 + 8 * s, A_BYTES + N_FIRST * BK * 2);
-                    tma_load_2d(a_dst, &mapU, full0 + 8 * s, 0, m0);
-                    tma_load_2d(b_dst, &mapWu, full0 + 8 * s, 0, nb * N_FIRST);
-                } else {
-                    const int kc = (MODE == 0 ? c - 1 : c) * BK;
-                    mbar_expect_tx(full0 + 8 * s, A_BYTES + N_MAIN * BK * 2);
-                    tma_load_2d(a_dst, mapA, full0 + 8 * s, kc, m0);
-                    tma_load_2d(b_dst, &mapB, full0 + 8 * s, kc, nb * N_MAIN);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / nblk) * BM, nb = tile % nblk;
+                for (int c = 0; c < NCHUNK; ++c, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                    if (MODE == 0 && c == 0) {
+                        mbar_expect_tx(full0 + 8 * s, A_BYTES + C::N_FIRST * BK * 2);
+                        tma_load_2d(a_dst, &mapU, full0 + 8 * s, 0, m0);
+                        tma_load_2d(b_dst, &mapWu, full0 + 8 * s, 0, nb * C::N_FIRST);
+                    } else {
+                        const int kc = (MODE == 0 ? c - 1 : c) * BK;
+                        mbar_expect_tx(full0 + 8 * s, A_BYTES + C::N_MAIN * BK * 2);
+                        tma_load_2d(a_dst, mapA, full0 + 8 * s, kc, m0);
+                        tma_load_2d(b_dst, &mapB, full0 + 8 * s, kc, nb * C::N_MAIN);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int s = c % kStages;
-                const uint32_t ph = (uint32_t)(c / kStages) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+                mbar_wait(tempty0 + 8 * ab, aph ^ 1u);            // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
-                const uint32_t idesc = (MODE == 0 && c == 0) ? umma_idesc(BM, 256) : umma_idesc(BM, N_MAIN);
+                const uint32_t acc = tmem_d + ab * C::ACC_COLS;
+                for (int c = 0; c < NCHUNK; ++c, ++it) {
+                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+                    const uint32_t idesc = (MODE == 0 && c == 0) ? umma_idesc(BM, 256) : umma_idesc(BM, C::N_MAIN);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
-                    umma_bf16(tmem_d, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
+                        umma_bf16(acc, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8 * s);              // frees the smem stage once these MMAs retire
                 }
-                umma_commit(empty0 + 8 * s);              // frees the smem stage once these MMAs retire
+                umma_commit(tfull0 + 8 * ab);                 // accumulator complete
             }
-            umma_commit(accum_bar);                       // accumulator complete
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                 // which 32 of the tile's 64 output columns
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16);
-        if (MODE == 0) {
-            const float *hold = prm.hidden + ((size_t)cur * prm.rows_pad + row) * H + nb * 64;
-            float *hnew = const_cast<float *>(prm.hidden) + ((size_t)(1 - cur) * prm.rows_pad + row) * H + nb * 64;
-            __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + nb * 64;
-            __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + nb * 64;
-#pragma unroll 1
-            for (int j0 = half * 32; j0 < half * 32 + 32; j0 += 16) {
-                float ar[16], az[16], ahn[16], ain[16];
-                tmem_ld16(tbase + j0, ar);
-                tmem_ld16(tbase + 64 + j0, az);
-                tmem_ld16(tbase + 128 + j0, ahn);
-                tmem_ld16(tbase + 192 + j0, ain);
-                tmem_ld_wait();
-                if (row < prm.rows) {
-                    float hv[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + j0 + i);
-                    __align__(16) __nv_bfloat16 ob[16], ot[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int j = nb * 64 + j0 + i;
-                        const float r = sigmoid_fast((ar[i] + prm.bhh[j]) + prm.bih[j]);
-                        const float z = sigmoid_fast((az[i] + prm.bhh[H + j]) + prm.bih[H + j]);
-                        const float n = tanh_fast(fmaf(ahn[i] + prm.bhh[2 * H + j], r, ain[i] + prm.bih[2 * H + j]));
-                        const float hn = fmaf(hv[i] - n, z, n);
-                        hv[i] = hn;
-                        ob[i] = __float2bfloat16(hn);
-                        ot[i] = __float2bfloat16(tanh_fast(hn));
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(hnew + j0 + i) = *reinterpret_cast<float4 *>(&hv[i]);
-                    *reinterpret_cast<uint4 *>(hb + j0) = *reinterpret_cast<uint4 *>(&ob[0]);
-                    *reinterpret_cast<uint4 *>(hb + j0 + 8) = *reinterpret_cast<uint4 *>(&ob[8]);
-                    *reinterpret_cast<uint4 *>(tb + j0) = *reinterpret_cast<uint4 *>(&ot[0]);
-                    *reinterpret_cast<uint4 *>(tb + j0 + 8) = *reinterpret_cast<uint4 *>(&ot[8]);
-                }
-            }
-        } else {
-            float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + nb * 64;
-#pragma unroll 1
-            for (int j0 = half * 32; j0 < half * 32 + 32; j0 += 16) {
-                float acc[16];
-                tmem_ld16(tbase + j0, acc);
-                tmem_ld_wait();
+        const int half = (warp - 2) >> 2;                 // which half of the tile's output columns
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int m0 = (tile / nblk) * BM, nb = tile % nblk;
+            const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+            const int row = m0 + q * 32 + lane;
+            const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + ab * C::ACC_COLS;
+            if (MODE == 0) {
+                const int j00 = nb * 64 + half * 32;          // first hidden unit of this thread
+                const float *hold = prm.hidden + ((size_t)cur * prm.rows_pad + row) * H + j00;
+                float *hnew = const_cast<float *>(prm.hidden) + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
+                __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
+                __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + j00;
+                float hv[32];                                 // old state, fetched while the MMAs run
                 if (row < prm.rows) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const int j = nb * 64 + j0 + i;
-                        float4 o = make_float4(acc[i] + prm.p1_b[j], acc[i + 1] + prm.p1_b[j + 1], acc[i + 2] + prm.p1_b[j + 2],
-                                               acc[i + 3] + prm.p1_b[j + 3]);
-                        *reinterpret_cast<float4 *>(yrow + j0 + i) = o;
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + i);
+                }
+                mbar_wait(tfull0 + 8 * ab, aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 16) {
+                    const int j0 = half * 32 + jj;
+                    float ar[16], az[16], ahn[16], ain[16];
+                    tmem_ld16(tbase + j0, ar);
+                    tmem_ld16(tbase + 64 + j0, az);
+                    tmem_ld16(tbase + 128 + j0, ahn);
+                    tmem_ld16(tbase + 192 + j0, ain);
+                    tmem_ld_wait();
+                    if (row < prm.rows) {
+                        __align__(16) __nv_bfloat16 ob[16], ot[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int j = j00 + jj + i;
+                            const float r = sigmoid_fast((ar[i] + prm.bhh[j]) + prm.bih[j]);
+                            const float z = sigmoid_fast((az[i] + prm.bhh[H + j]) + prm.bih[H + j]);
+                            const float n = tanh_fast(fmaf(ahn[i] + prm.bhh[2 * H + j], r, ain[i] + prm.bih[2 * H + j]));
+                            const float hn = fmaf(hv[jj + i] - n, z, n);
+                            hv[jj + i] = hn;
+                            ob[i] = __float2bfloat16(hn);
+                            ot[i] = __float2bfloat16(tanh_fast(hn));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(hnew + jj + i) = *reinterpret_cast<float4 *>(&hv[jj + i]);
+                        *reinterpret_cast<uint4 *>(hb + jj) = *reinterpret_cast<uint4 *>(&ob[0]);
+                        *reinterpret_cast<uint4 *>(hb + jj + 8) = *reinterpret_cast<uint4 *>(&ob[8]);
+                        *reinterpret_cast<uint4 *>(tb + jj) = *reinterpret_cast<uint4 *>(&ot[0]);
+                        *reinterpret_cast<uint4 *>(tb + jj + 8) = *reinterpret_cast<uint4 *>(&ot[8]);
+                    }
+                }
+            } else {
+                const int c00 = nb * C::TILE_N + half * (C::TILE_N / 2);
+                float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + c00;
+                mbar_wait(tfull0 + 8 * ab, aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < C::TILE_N / 2; jj += 16) {
+                    float acc[16];
+                    tmem_ld16(tbase + half * (C::TILE_N / 2) + jj, acc);
+                    tmem_ld_wait();
+                    if (row < prm.rows) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const int j = c00 + jj + i;
+                            float4 o = make_float4(acc[i] + prm.p1_b[j], acc[i + 1] + prm.p1_b[j + 1], acc[i + 2] + prm.p1_b[j + 2],
+                                                   acc[i + 3] + prm.p1_b[j + 3]);
+                            *reinterpret_cast<float4 *>(yrow + jj + i) = o;
+                        }
                     }
                 }
             }
+            // this warp has read its part of the accumulator: hand it back to the MMA issuer
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta(tempty0 + 8 * ab);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -180,7 +215,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + (MODE == 0 ? 256 : 64) * BK * 2) + 1024; }
+constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_ROWS * BK * 2) + 1024; }
 
 // ---------------------------------------------------------------------------------------------
 // weight packing (device): fp32 PyTorch layout -> bf16 tile-permuted, plus the folded encoder constants
@@ -347,7 +382,9 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     prm.th_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->th_bf16);
     prm.bih = w->gru_bih; prm.bhh = w->gru_bhh;
     prm.rows = p->rows; prm.rows_pad = Mp; prm.step_base = step_base; prm.step_off = step_off;
-    k_gemm_tc<0><<<dim3(H / 64, Mp / BM), kThreads, tc_smem_bytes<0>(), st>>>(mU, mWu, mA0, mA1, mB, prm);
+    const int nblk = H / 64, num_tiles = nblk * (Mp / BM);
+    k_gemm_tc<0><<<num_tiles < kNumSMs ? num_tiles : kNumSMs, kThreads, tc_smem_bytes<0>(), st>>>(mU, mWu, mA0, mA1, mB, prm,
+                                                                                              num_tiles, nblk);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
@@ -359,10 +396,12 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t 
     const int Mp = p->rows_pad;
     CUtensorMap mA, mB;
     if ((rc = make_map(enc, &mA, p->th_bf16, Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, 64))) return rc;
+    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, 128))) return rc;
     TcParams prm{};
     prm.p1_b = w->p1_b; prm.y1 = p->y1; prm.rows = p->rows; prm.rows_pad = Mp;
-    k_gemm_tc<1><<<dim3(ECORD_DIM_P1 / 64, Mp / BM), kThreads, tc_smem_bytes<1>(), st>>>(mA, mB, mA, mA, mB, prm);
+    const int nblk = ECORD_DIM_P1 / 128, num_tiles = nblk * (Mp / BM);
+    k_gemm_tc<1><<<num_tiles < kNumSMs ? num_tiles : kNumSMs, kThreads, tc_smem_bytes<1>(), st>>>(mA, mB, mA, mA, mB, prm,
+                                                                                              num_tiles, nblk);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
