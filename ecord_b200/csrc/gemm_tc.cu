@@ -285,18 +285,31 @@ __global__ void k_pack_qtc(ecord_weights w) {
         out[2304 + c * 4 + j] = cc;
         out[2560 + c * 4 + j] = j < 3 ? tf32_rn(gam * cc) : gam;
     }
-    // shared-memory image of one B-operand buffer of k_q_tc: three [80][8] tf32 blocks (W1 k 0..7 | W1 k 8..15 | W2)
-    // in the K-major SWIZZLE_32B layout; the per-trajectory entries (row 64, W2 slots 4 and 5) stay zero
+    // shared-memory image of the B operand of k_q_tc: six [80][8] tf32 blocks in the K-major SWIZZLE_32B layout
+    //   0,1: hi(gamma_c Wg[c][k]) k 0..7 | 8..15     2,3: the lo parts     4: W2 hi     5: W2 lo
+    // (hi = value rounded onto the tf32 grid, lo = tf32(value - hi)).  W2 hi slots: [C0 C1 C2 C1 | . . C2 0] against
+    // R2 = [f0 f1h f2h f1l | 1 1 f2l 0]; W2 lo slots: [C0 C1 C2 0 | 0 0 0 0] against [f0 f1h f2h 0 ...].
+    // The per-trajectory entries (row 64 everywhere, W2-hi slots 4 and 5) stay zero here.
     float *img = out + 2816;
-    for (int i = c; i < 3 * 80 * 8; i += ECORD_DIM_Q) img[i] = 0.0f;
+    for (int i = c; i < 6 * 80 * 8; i += ECORD_DIM_Q) img[i] = 0.0f;
     __syncthreads();
     auto at = [&](int blk, int r, int k) -> float & {
         return img[blk * 640 + (r * 32 + ((((k >> 2) ^ (r >> 2)) & 1) << 4) + (k & 3) * 4) / 4];
     };
-    for (int k = 0; k < 16; ++k) at(k >> 3, c, k & 7) = out[c * 16 + k];
-    for (int j = 0; j < 3; ++j) at(2, c, j) = out[2560 + c * 4 + j];
-    at(2, c, 3) = out[2560 + c * 4 + 1];        // against f1_lo
-    at(2, c, 6) = out[2560 + c * 4 + 2];        // against f2_lo   (slots 4, 5: per-trajectory gamma_c a'_c hi / lo)
+    for (int k = 0; k < 16; ++k) {
+        const float v = gam * out[1280 + c * 16 + k];
+        const float hi = tf32_rn(v);
+        at(k >> 3, c, k & 7) = hi;
+        at(2 + (k >> 3), c, k & 7) = tf32_rn(v - hi);
+    }
+    for (int j = 0; j < 3; ++j) {
+        const float v = gam * out[2304 + c * 4 + j];
+        const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
+        at(4, c, j) = hi;
+        at(5, c, j) = lo;
+        if (j == 1) at(4, c, 3) = hi;       // against f1_lo
+        if (j == 2) at(4, c, 6) = hi;       // against f2_lo
+    }
 }
 
 }  // namespace

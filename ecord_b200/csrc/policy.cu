@@ -115,18 +115,19 @@ __global__ void k_gru_gates(ecord_policy p, const int32_t *step_base, int step_o
 }
 
 // ------------------------------------------------------------------------------------------------
-// tail: y1 [M][512] -> LN512 -> LReLU -> W2 (512->32) -> LN32 -> LReLU = P ; v = val_out(P) ; A = Wq[:, :32] P + b_q.
+// tail: y1 [M][512] -> LN512 -> LReLU -> W2 (512->32) -> LN32 -> LReLU = P ; v = val_out(P) ; A = Wq[:, :32] P + b_q,
+// plus the per-(g,t) operands of the fast / tensor-core Q kernels.
 //
-// One warp owns FOUR rows at once so that every W2 element fetched from shared memory feeds four FMAs
-// (LDS : FFMA = 1 : 4, the ratio the SM can sustain), and the 4 x 32 dot products are finished with a
-// reduce-scatter butterfly over the warp (62 shuffles for 64 sums) instead of one 5-step all-reduce per output.
-// 32 rows per block (8 warps); W2 (64 KB) is staged in shared memory once per block.
+// One warp per row, grid-stride over rows, one 16-warp CTA per SM with every weight staged in shared memory once.
+// The row is held as 16 values per lane (four float4, coalesced); W2 is read as LDS.128 (one load feeds four FMAs);
+// the 32 dot products and the 20 Q-operand sums are finished with a reduce-scatter butterfly (31 shuffles for 32
+// sums) instead of one 5-step all-reduce each.  The code is a short loop, not an unrolled program: the previous
+// 4-rows-per-warp version ran 4000 straight-line instructions once per warp and stalled on instruction fetch.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTailR = 4;
-constexpr int kTailWarps = 8;
-constexpr int kTailRows = kTailR * kTailWarps;
+constexpr int kTailWarps = 16;
 struct TailSmem {
     float w2[ND * P1];          // [o][i]
+    float ln1g[P1], ln1b[P1];
     float v1t[ND * ND];         // transposed val_out.1: [i][o]
     float qt[ND * ECORD_DIM_Q]; // transposed Wq[:, :32]: [i][c]
     float wg[ECORD_DIM_Q * 16]; // tensor-core Q kernel: centred Wq[:,32:48]  [c][k]
@@ -138,7 +139,7 @@ __device__ __forceinline__ float tf32_round(float x) {     // round-to-nearest o
 }
 // one butterfly level: lanes with (lane & OFF) == 0 keep v[0..N/2), the others keep v[N/2..N)
 template <int N, int OFF>
-__device__ __forceinline__ void reduce_scatter_step(float (&v)[64], bool upper) {
+__device__ __forceinline__ void reduce_scatter_step(float (&v)[32], bool upper) {
 #pragma unroll
     for (int i = 0; i < N / 2; ++i) {
         const float send = upper ? v[i] : v[i + N / 2];
@@ -146,27 +147,26 @@ __device__ __forceinline__ void reduce_scatter_step(float (&v)[64], bool upper) 
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
     }
 }
-// 64 per-lane partial sums -> lane L ends with the warp totals of entries 2L and 2L+1 in v[0], v[1]
-__device__ __forceinline__ void reduce_scatter64(float (&v)[64], int lane) {
-    reduce_scatter_step<64, 16>(v, lane & 16);
-    reduce_scatter_step<32, 8>(v, lane & 8);
-    reduce_scatter_step<16, 4>(v, lane & 4);
-    reduce_scatter_step<8, 2>(v, lane & 2);
-    reduce_scatter_step<4, 1>(v, lane & 1);
-}
-__device__ __forceinline__ float group8_sum(float v) {   // all-reduce over the 8 lanes that share a row
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    return v;
+// 32 per-lane partial sums -> lane L returns the warp total of entry L
+__device__ __forceinline__ float reduce_scatter32(float (&v)[32], int lane) {
+    reduce_scatter_step<32, 16>(v, lane & 16);
+    reduce_scatter_step<16, 8>(v, lane & 8);
+    reduce_scatter_step<8, 4>(v, lane & 4);
+    reduce_scatter_step<4, 2>(v, lane & 2);
+    reduce_scatter_step<2, 1>(v, lane & 1);
+    return v[0];
 }
 
-__global__ void __launch_bounds__(kTailWarps * 32, 2)
+__global__ void __launch_bounds__(kTailWarps * 32, 1)
 k_policy_tail(ecord_weights w, ecord_policy p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TailSmem &S = *reinterpret_cast<TailSmem *>(smem_raw);
-    for (int i = threadIdx.x; i < ND * P1 / 4; i += blockDim.x)
-        reinterpret_cast<float4 *>(S.w2)[i] = reinterpret_cast<const float4 *>(w.p2_w)[i];
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(w.p2_w);
+        float4 *dst = reinterpret_cast<float4 *>(S.w2);
+        for (int i = threadIdx.x; i < ND * P1 / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    for (int i = threadIdx.x; i < P1; i += blockDim.x) { S.ln1g[i] = w.ln1_w[i]; S.ln1b[i] = w.ln1_b[i]; }
     for (int i = threadIdx.x; i < ND * ND; i += blockDim.x) S.v1t[i] = w.v1_w[(i % ND) * ND + (i / ND)];
     for (int i = threadIdx.x; i < ND * ECORD_DIM_Q; i += blockDim.x)
         S.qt[i] = w.q1_w[(i % ECORD_DIM_Q) * ECORD_DIM_Q + (i / ECORD_DIM_Q)];
@@ -176,169 +176,118 @@ k_policy_tail(ecord_weights w, ecord_policy p) {
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int m0 = blockIdx.x * kTailRows + warp * kTailR;
-    if (m0 >= p.rows) return;
+    // per-lane constants: lane o owns output o of the 32-wide stages, channels (lane, lane + 32) of the 64-wide ones
+    const float b2 = w.p2_b[lane], g2 = w.ln2_w[lane], be2 = w.ln2_b[lane];
+    const float vb1 = w.v1_b[lane], vw2 = w.v2_w[lane], vb2 = w.v2_b[0];
+    const float qb0 = w.q1_b[lane], qb1 = w.q1_b[lane + 32];
+    const float wog0 = w.q2_w[lane] * w.qln_w[lane], wog1 = w.q2_w[lane + 32] * w.qln_w[lane + 32];
+    const float gq0 = w.qln_w[lane], gq1 = w.qln_w[lane + 32];
 
-    // ---- LN512 + LReLU on 4 rows (lane holds elements lane + 32 j of each) ----
-    float x[kTailR][16];
-#pragma unroll
-    for (int r = 0; r < kTailR; ++r) {
-        const int m = min(m0 + r, p.rows - 1);          // rows past the end are computed on a copy and not stored
+    for (int m = blockIdx.x * kTailWarps + warp; m < p.rows; m += gridDim.x * kTailWarps) {
+        // ---- LN512 + LReLU: lane holds elements 4*(lane + 32k) .. +3, k = 0..3 ----
+        float x[16];
+        const float4 *yr = reinterpret_cast<const float4 *>(p.y1 + (long long)m * P1);
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { x[r][j] = p.y1[(long long)m * P1 + lane + 32 * j]; s += x[r][j]; }
+        for (int k = 0; k < 4; ++k) {
+            const float4 t4 = yr[lane + 32 * k];
+            x[4 * k] = t4.x; x[4 * k + 1] = t4.y; x[4 * k + 2] = t4.z; x[4 * k + 3] = t4.w;
+            s += (t4.x + t4.y) + (t4.z + t4.w);
+        }
         const float mean = warp_sum(s) * (1.0f / P1);
         float ss = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { x[r][j] -= mean; ss = fmaf(x[r][j], x[r][j], ss); }
+        for (int j = 0; j < 16; ++j) { x[j] -= mean; ss = fmaf(x[j], x[j], ss); }
         const float rstd = rsqrtf(warp_sum(ss) * (1.0f / P1) + kLnEps);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[r][j] *= rstd;
-    }
+        for (int k = 0; k < 4; ++k) {
+            const float4 g4 = *reinterpret_cast<const float4 *>(&S.ln1g[4 * (lane + 32 * k)]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&S.ln1b[4 * (lane + 32 * k)]);
+            x[4 * k + 0] = lrelu(fmaf(x[4 * k + 0] * rstd, g4.x, b4.x));
+            x[4 * k + 1] = lrelu(fmaf(x[4 * k + 1] * rstd, g4.y, b4.y));
+            x[4 * k + 2] = lrelu(fmaf(x[4 * k + 2] * rstd, g4.z, b4.z));
+            x[4 * k + 3] = lrelu(fmaf(x[4 * k + 3] * rstd, g4.w, b4.w));
+        }
+        // ---- W2: 512 -> 32; per-lane partials over its 16 elements, reduce-scatter: lane o gets output o ----
+        float part[32];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const float gj = w.ln1_w[lane + 32 * j], bj = w.ln1_b[lane + 32 * j];
+        for (int o = 0; o < ND; ++o) {
+            const float4 *wr = reinterpret_cast<const float4 *>(&S.w2[o * P1]);
+            float a = 0.0f;
 #pragma unroll
-        for (int r = 0; r < kTailR; ++r) x[r][j] = lrelu(fmaf(x[r][j], gj, bj));
-    }
-    // ---- W2: 512 -> 32 for 4 rows, two passes of 16 outputs.  After each pass lane L holds, for row L>>3,
-    //      outputs oh*16 + 2*(L&7) + {0,1} ----
-    const int grp = lane >> 3, k8 = lane & 7;           // row within the warp, position within the row's 8 lanes
-    float pre[4];
-#pragma unroll
-    for (int oh = 0; oh < 2; ++oh) {
-        float acc[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) acc[i] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-#pragma unroll
-            for (int oo = 0; oo < 16; ++oo) {
-                const float wv = S.w2[(oh * 16 + oo) * P1 + lane + 32 * j];
-#pragma unroll
-                for (int r = 0; r < kTailR; ++r) acc[r * 16 + oo] = fmaf(wv, x[r][j], acc[r * 16 + oo]);
+            for (int k = 0; k < 4; ++k) {
+                const float4 w4 = wr[lane + 32 * k];
+                a = fmaf(w4.x, x[4 * k], a); a = fmaf(w4.y, x[4 * k + 1], a);
+                a = fmaf(w4.z, x[4 * k + 2], a); a = fmaf(w4.w, x[4 * k + 3], a);
             }
+            part[o] = a;
         }
-        reduce_scatter64(acc, lane);
-        const int o = oh * 16 + 2 * k8;
-        pre[oh * 2 + 0] = acc[0] + w.p2_b[o];
-        pre[oh * 2 + 1] = acc[1] + w.p2_b[o + 1];
-    }
-    // ---- LN32 + LReLU per row (the row's 32 values live in its 8 lanes x 4 slots) ----
-    const float mean2 = group8_sum((pre[0] + pre[1]) + (pre[2] + pre[3])) * (1.0f / ND);
-    float d[4], ssq = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { d[q] = pre[q] - mean2; ssq = fmaf(d[q], d[q], ssq); }
-    const float rstd2 = rsqrtf(group8_sum(ssq) * (1.0f / ND) + kLnEps);
-    float Pv[4], Tv[4];
-    const int m = m0 + grp;
-    const bool live = m < p.rows;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int o = (q >> 1) * 16 + 2 * k8 + (q & 1);
-        Pv[q] = lrelu(fmaf(d[q] * rstd2, w.ln2_w[o], w.ln2_b[o]));
-        Tv[q] = tanhf(Pv[q]);
-        if (live) p.P[(long long)m * ND + o] = Pv[q];
-    }
-    // ---- every lane of the row group gathers the row's 32 P / tanh(P) values ----
-    float Pa[ND], Ta[ND];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int o = (q >> 1) * 16 + 2 * kk + (q & 1);
-            Pa[o] = __shfl_sync(0xffffffffu, Pv[q], grp * 8 + kk);
-            Ta[o] = __shfl_sync(0xffffffffu, Tv[q], grp * 8 + kk);
-        }
-    }
-    // ---- state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 ; lane computes 4 of the 32 hidden units ----
-    float vpart = 0.0f;
-    {
-        float4 hv = *reinterpret_cast<const float4 *>(w.v1_b + k8 * 4);
+        const float pre = reduce_scatter32(part, lane) + b2;
+        // ---- LN32 + LReLU ----
+        const float mean2 = warp_sum(pre) * (1.0f / ND);
+        const float d2 = pre - mean2;
+        const float rstd2 = rsqrtf(warp_sum(d2 * d2) * (1.0f / ND) + kLnEps);
+        const float Pv = lrelu(fmaf(d2 * rstd2, g2, be2));
+        p.P[(long long)m * ND + lane] = Pv;
+        // ---- state value v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 ;  A = Wq[:, :32] P + b_q ----
+        const float tp = tanhf(Pv);
+        float hv = vb1, a0 = qb0, a1 = qb1;
 #pragma unroll
         for (int i = 0; i < ND; ++i) {
-            const float4 wv = *reinterpret_cast<const float4 *>(&S.v1t[i * ND + k8 * 4]);
-            hv.x = fmaf(wv.x, Ta[i], hv.x); hv.y = fmaf(wv.y, Ta[i], hv.y);
-            hv.z = fmaf(wv.z, Ta[i], hv.z); hv.w = fmaf(wv.w, Ta[i], hv.w);
+            const float ti = __shfl_sync(0xffffffffu, tp, i);
+            const float pi = __shfl_sync(0xffffffffu, Pv, i);
+            hv = fmaf(S.v1t[i * ND + lane], ti, hv);
+            a0 = fmaf(S.qt[i * ECORD_DIM_Q + lane], pi, a0);
+            a1 = fmaf(S.qt[i * ECORD_DIM_Q + lane + 32], pi, a1);
         }
-        const float4 w2v = *reinterpret_cast<const float4 *>(w.v2_w + k8 * 4);
-        vpart = w2v.x * lrelu(hv.x) + w2v.y * lrelu(hv.y) + w2v.z * lrelu(hv.z) + w2v.w * lrelu(hv.w);
-    }
-    const float vv = group8_sum(vpart) + w.v2_b[0];
-    // ---- A = Wq[:, :32] P + b_q ; lane computes 8 of the 64 channels ----
-    float a[8];
-    {
-        const float4 b0 = *reinterpret_cast<const float4 *>(w.q1_b + k8 * 8);
-        const float4 b1 = *reinterpret_cast<const float4 *>(w.q1_b + k8 * 8 + 4);
-        a[0] = b0.x; a[1] = b0.y; a[2] = b0.z; a[3] = b0.w; a[4] = b1.x; a[5] = b1.y; a[6] = b1.z; a[7] = b1.w;
-#pragma unroll
-        for (int i = 0; i < ND; ++i) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(&S.qt[i * ECORD_DIM_Q + k8 * 8]);
-            const float4 w1 = *reinterpret_cast<const float4 *>(&S.qt[i * ECORD_DIM_Q + k8 * 8 + 4]);
-            a[0] = fmaf(w0.x, Pa[i], a[0]); a[1] = fmaf(w0.y, Pa[i], a[1]); a[2] = fmaf(w0.z, Pa[i], a[2]);
-            a[3] = fmaf(w0.w, Pa[i], a[3]); a[4] = fmaf(w1.x, Pa[i], a[4]); a[5] = fmaf(w1.y, Pa[i], a[5]);
-            a[6] = fmaf(w1.z, Pa[i], a[6]); a[7] = fmaf(w1.w, Pa[i], a[7]);
+        const float vv = warp_sum(vw2 * lrelu(hv)) + vb2;
+        if (lane == 0) p.v[m] = vv;
+        p.A[(long long)m * ECORD_DIM_Q + lane] = a0;
+        p.A[(long long)m * ECORD_DIM_Q + lane + 32] = a1;
+        if (!p.Ac && !p.qa) continue;
+        // ---- Q-kernel operands: A centred over the 64 channels and its projection on w_o * gamma ----
+        const float meanA = warp_sum(a0 + a1) * (1.0f / ECORD_DIM_Q);
+        const float c0 = a0 - meanA, c1 = a1 - meanA;
+        const float la = warp_sum(fmaf(wog0, c0, wog1 * c1));
+        if (p.Ac) {
+            p.Ac[(long long)m * ECORD_DIM_Q + lane] = c0;
+            p.Ac[(long long)m * ECORD_DIM_Q + lane + 32] = c1;
+            if (lane == 0) p.LA[m] = la;
         }
-    }
-    float asum = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) asum += a[q];
-    const float meanA = group8_sum(asum) * (1.0f / ECORD_DIM_Q);
-    float la = 0.0f, ac[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        ac[q] = a[q] - meanA;
-        la = fmaf(w.q2_w[k8 * 8 + q] * w.qln_w[k8 * 8 + q], ac[q], la);
-    }
-    la = group8_sum(la);
-    if (live) {
-        float *Ao = p.A + (long long)m * ECORD_DIM_Q + k8 * 8;
-        *reinterpret_cast<float4 *>(Ao) = make_float4(a[0], a[1], a[2], a[3]);
-        *reinterpret_cast<float4 *>(Ao + 4) = make_float4(a[4], a[5], a[6], a[7]);
-        if (p.Ac) {   // fast Q kernel operands: A - mean_c(A), and its projection on w_o * gamma
-            float *Aco = p.Ac + (long long)m * ECORD_DIM_Q + k8 * 8;
-            *reinterpret_cast<float4 *>(Aco) = make_float4(ac[0], ac[1], ac[2], ac[3]);
-            *reinterpret_cast<float4 *>(Aco + 4) = make_float4(ac[4], ac[5], ac[6], ac[7]);
-            if (k8 == 0) p.LA[m] = la;
-        }
-        if (k8 == 0) p.v[m] = vv;
-    }
-    if (p.qa) {
-        // operands of the tensor-core Q kernel (layout: ecord_policy.qa), a' = Ac + bconst.  Each lane holds 8 channels
-        // of its row; the 20 channel sums (Wg^T a', Cc^T a', |a'|^2) are reduced over the row's 8 lanes.
-        float part[20];
-#pragma unroll
-        for (int i = 0; i < 20; ++i) part[i] = 0.0f;
-        float ga[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int c = k8 * 8 + q;
-            const float ap = ac[q] + S.cc[c * 4 + 3];
-            ga[q] = w.qln_w[c] * ap;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) part[k] = fmaf(S.wg[c * 16 + k], ap, part[k]);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) part[16 + j] = fmaf(S.cc[c * 4 + j], ap, part[16 + j]);
-            part[19] = fmaf(ap, ap, part[19]);
-        }
-#pragma unroll
-        for (int i = 0; i < 20; ++i) part[i] = group8_sum(part[i]);
-        if (live) {
-            // (hi, lo) pairs: hi on the tf32 grid, lo the exact remainder -- the kernel stores them as they are
+        if (p.qa) {
+            // tensor-core Q kernel (layout: ecord_policy.qa), a' = Ac + bconst
+            const float ap0 = c0 + S.cc[lane * 4 + 3], ap1 = c1 + S.cc[(lane + 32) * 4 + 3];
             float *qo = p.qa + (long long)m * ECORD_QA_STRIDE;
-#pragma unroll
-            for (int q = 0; q < 8; q += 2) {
-                const float h0 = tf32_round(ga[q]), h1 = tf32_round(ga[q + 1]);
-                *reinterpret_cast<float4 *>(qo + 2 * (k8 * 8 + q)) = make_float4(h0, ga[q] - h0, h1, ga[q + 1] - h1);
+            {   // (hi, lo) pairs: hi on the tf32 grid, lo the exact remainder -- the kernel stores them as they are
+                const float ga0 = gq0 * ap0, ga1 = gq1 * ap1;
+                const float h0 = tf32_round(ga0), h1 = tf32_round(ga1);
+                *reinterpret_cast<float2 *>(qo + 2 * lane) = make_float2(h0, ga0 - h0);
+                *reinterpret_cast<float2 *>(qo + 2 * (lane + 32)) = make_float2(h1, ga1 - h1);
             }
 #pragma unroll
-            for (int i = 0; i < 19; ++i)
-                if ((i & 7) == k8) qo[128 + i] = tf32_round(part[i]);
-            if (k8 == 3) qo[147] = part[19];
-            if (k8 == 4) qo[148] = la;
-            if (k8 == 5) qo[149] = vv;
-            if (k8 == 6) qo[150] = 0.0f;
-            if (k8 == 7) qo[151] = 0.0f;
+            for (int k4 = 0; k4 < 4; ++k4) {          // Wg^T a'
+                const float4 u0 = *reinterpret_cast<const float4 *>(&S.wg[lane * 16 + 4 * k4]);
+                const float4 u1 = *reinterpret_cast<const float4 *>(&S.wg[(lane + 32) * 16 + 4 * k4]);
+                part[4 * k4 + 0] = fmaf(u0.x, ap0, u1.x * ap1); part[4 * k4 + 1] = fmaf(u0.y, ap0, u1.y * ap1);
+                part[4 * k4 + 2] = fmaf(u0.z, ap0, u1.z * ap1); part[4 * k4 + 3] = fmaf(u0.w, ap0, u1.w * ap1);
+            }
+            {                                          // Cc^T a', |a'|^2
+                const float4 u0 = *reinterpret_cast<const float4 *>(&S.cc[lane * 4]);
+                const float4 u1 = *reinterpret_cast<const float4 *>(&S.cc[(lane + 32) * 4]);
+                part[16] = fmaf(u0.x, ap0, u1.x * ap1); part[17] = fmaf(u0.y, ap0, u1.y * ap1);
+                part[18] = fmaf(u0.z, ap0, u1.z * ap1);
+                part[19] = fmaf(ap0, ap0, ap1 * ap1);
+            }
+#pragma unroll
+            for (int i = 20; i < 32; ++i) part[i] = 0.0f;
+            const float tot = reduce_scatter32(part, lane);      // lane i: entry i
+            const float hi = tf32_round(tot), lo = tf32_round(tot - hi);
+            if (lane < 16) { qo[128 + lane] = hi; qo[144 + lane] = lo; }
+            else if (lane < 19) { qo[160 + lane - 16] = hi; qo[163 + lane - 16] = lo; }
+            else if (lane == 19) qo[166] = tot;
+            else if (lane == 20) qo[167] = la;
+            else if (lane == 21) qo[168] = vv;
+            else if (lane < 25) qo[147 + lane] = 0.0f;
         }
     }
 }
@@ -378,7 +327,7 @@ int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_w
         rc = launch_proj1_tc(w, p, st);
         if (rc) return rc;
     }
-    k_policy_tail<<<ceil_div(M, kTailRows), kTailWarps * 32, sizeof(TailSmem), st>>>(*w, *p);
+    k_policy_tail<<<min(kNumSMs, ceil_div(M, kTailWarps)), kTailWarps * 32, sizeof(TailSmem), st>>>(*w, *p);
     ECORD_LAUNCH_CHECK();
     return 0;
 }

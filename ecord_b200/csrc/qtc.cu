@@ -8,7 +8,10 @@
 //     q     = 0.505 (lin / sigma + Wb) + 0.495 (sum_c w_c |gamma_c x_c + beta_c sigma|) / sigma + b_o + v[g,t]
 //
 // What the tensor core does.  For one tile of 128 vertices of a graph and one trajectory t, the 128 x 64 block
-// gamma_c x_c is a small GEMM  [128 rows] x [K = 24] x [N = 80]  in tf32 with fp32 accumulation in TMEM:
+// gamma_c x_c is a small GEMM  [128 rows] x [K] x [N = 80]  in tf32 with fp32 accumulation in TMEM.  Every operand
+// is split into a tf32 hi part and a lo remainder and the products hi.hi + lo.hi + hi.lo are accumulated (8 MMAs of
+// K = 8 per trajectory), which makes the result fp32-grade: plain tf32 (10-bit mantissa) puts a fixed per-vertex
+// bias of ~3e-4 on Q, enough to change which vertex wins the arg-max.  Logical operands:
 //     A operand rows (one per vertex, written by the vertex's own thread)
 //         R1 = node_emb[n] (16)                                       shared memory, constant for the CTA
 //         R2 = [ f0  f1_hi  f2_hi  f1_lo | 1  1  f2_lo  0 ]            TENSOR memory (tcgen05.st), rewritten per trajectory
@@ -40,20 +43,20 @@ constexpr int Q = ECORD_DIM_Q;        // 64
 constexpr int QT = ECORD_QTILE;       // 128 vertices per tile
 constexpr int QN = 80;                // MMA N (multiple of 16 for M = 128)
 constexpr int QA = ECORD_QA_STRIDE;   // 88
-constexpr int kTcMaxT = 32;           // trajectories per CTA (rows of qa staged in shared memory)
+constexpr int kTcMaxT = 25;           // trajectories per CTA (rows of qa staged in shared memory)
 constexpr int kCtasPerSM = 4;         // 4 x 128 TMEM columns; shared memory and registers are sized for it
 constexpr int A_BLK = QT * 32;        // bytes of one [128][8] tf32 operand block
 constexpr int B_BLK = QN * 32;        // bytes of one [80][8] block
 constexpr int kQtcThreads = 160;
-constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,88): the per-trajectory A operand R2
+constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,96): the per-trajectory A operand R2 (K = 16)
 constexpr int kTmemCols = 128;
 
-constexpr int kRing = 8;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
-constexpr int kImgBytes = 3 * B_BLK;   // packed image of one B-operand buffer: W1 k-block 0 | W1 k-block 1 | W2
+constexpr int kRing = 6;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
+constexpr int kImgBytes = 6 * B_BLK;   // packed image of the B operand: W1 hi (2 k-blocks) | W1 lo (2) | W2 hi | W2 lo
 
 struct QTcSmem {
-    uint8_t R1[2][A_BLK];              // A operand, k-blocks 0 and 1 (node_emb), constant for the CTA
-    uint8_t W[3][B_BLK];               // B operand: W1 k0 | W1 k1 | W2
+    uint8_t R1[4][A_BLK];              // A operand (node_emb): hi k 0..7 | hi k 8..15 | lo k 0..7 | lo k 8..15; constant for the CTA
+    uint8_t W[6][B_BLK];               // B operand: W1 hi k0 | W1 hi k1 | W1 lo k0 | W1 lo k1 | W2 hi | W2 lo
     float qa[kTcMaxT][QA];             // per-(g,t) rows of ecord_policy.qa
     int sp[kRing + 1][QT];             // state ring (cp.async), one slot per trajectory in flight
     float pk[kRing + 1][QT];
@@ -189,9 +192,12 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
         lb = qv[1].x;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-            x[c4].x = tf32_rn(x[c4].x); x[c4].y = tf32_rn(x[c4].y); x[c4].z = tf32_rn(x[c4].z); x[c4].w = tf32_rn(x[c4].w);
+            // hi on the tf32 grid, lo the exact remainder (the tensor core drops its 13 low bits: 2^-22 relative)
+            const float4 hi = make_float4(tf32_rn(x[c4].x), tf32_rn(x[c4].y), tf32_rn(x[c4].z), tf32_rn(x[c4].w));
+            const float4 lo = make_float4(x[c4].x - hi.x, x[c4].y - hi.y, x[c4].z - hi.z, x[c4].w - hi.w);
             const int k = c4 * 4;
-            *reinterpret_cast<float4 *>(&S.R1[k >> 3][sw32(tid, k & 7)]) = x[c4];
+            *reinterpret_cast<float4 *>(&S.R1[k >> 3][sw32(tid, k & 7)]) = hi;
+            *reinterpret_cast<float4 *>(&S.R1[2 + (k >> 3)][sw32(tid, k & 7)]) = lo;
         }
         bb = q0.x; cb0 = 2.0f * q0.y; cb1 = 2.0f * q0.z; cb2 = 2.0f * q0.w;
         // R1 was written through the generic proxy: make it visible to the tensor core.  This fence is a MEMBAR, so
@@ -222,38 +228,54 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
     if (warp == 4) {
         // =============== control warp: per-trajectory B-operand entries, MMA issue ===============
         mbar_wait(setup_bar, 0);
-        // Per-trajectory B-operand entries (qa row, already rounded / split by the policy tail) and where this lane
-        // puts them inside a buffer: two (hi, lo) channel pairs into W2 slots 4|5, plus one row-64 entry.
-        const uint32_t dst_c0 = 2u * B_BLK + sw32(lane, 4), dst_c1 = 2u * B_BLK + sw32(lane + 32, 4);
-        uint32_t dst_r = 0, dst_r2 = 0;       // row 64: Wg^T a' (lanes 0..15), Cc^T a' (lanes 16..18; f1, f2 twice: hi and lo slots)
-        if (lane < 8) dst_r = sw32(Q, lane);
-        else if (lane < 16) dst_r = B_BLK + sw32(Q, lane - 8);
-        else if (lane < 19) dst_r = 2u * B_BLK + sw32(Q, lane - 16);
-        if (lane == 17) dst_r2 = 2u * B_BLK + sw32(Q, 3);
-        if (lane == 18) dst_r2 = 2u * B_BLK + sw32(Q, 6);
-        uint8_t *Wj = S.W[0];
-        const uint64_t dR1a = umma_desc_sw32(smem_u32(S.R1[0])), dR1b = umma_desc_sw32(smem_u32(S.R1[1]));
-        const uint64_t dW1a = umma_desc_sw32(smem_u32(Wj)), dW1b = umma_desc_sw32(smem_u32(Wj + B_BLK)),
-                       dW2 = umma_desc_sw32(smem_u32(Wj + 2 * B_BLK));
+        // Per-trajectory B-operand entries (qa row, already split into tf32 hi / lo by the policy tail) and where this
+        // lane puts them: two (hi, lo) channel pairs into W2-hi slots 4|5, plus row-64 entries (column d).
+        uint8_t *Wb = S.W[0];
+        const uint32_t dst_c0 = 4u * B_BLK + sw32(lane, 4), dst_c1 = 4u * B_BLK + sw32(lane + 32, 4);
+        uint32_t dst_h = 0, dst_l = 0, dst_h2 = 0;
+        int src_h = 0, src_l = 0;
+        if (lane < 16) {                          // Wg^T a': hi -> W1 hi row 64, lo -> W1 lo row 64
+            dst_h = (uint32_t)(lane >> 3) * B_BLK + sw32(Q, lane & 7);
+            dst_l = dst_h + 2u * B_BLK;
+            src_h = 128 + lane; src_l = 144 + lane;
+        } else if (lane < 19) {                   // Cc^T a': hi -> W2 hi row 64 (f1, f2 also against their lo slots), lo -> W2 lo
+            const int j = lane - 16;
+            dst_h = 4u * B_BLK + sw32(Q, j);
+            dst_l = 5u * B_BLK + sw32(Q, j);
+            dst_h2 = j == 1 ? 4u * B_BLK + sw32(Q, 3) : j == 2 ? 4u * B_BLK + sw32(Q, 6) : dst_h;
+            src_h = 160 + j; src_l = 163 + j;
+        }
+        uint64_t dA[4], dB[6];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dA[i] = umma_desc_sw32(smem_u32(S.R1[i]));
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dB[i] = umma_desc_sw32(smem_u32(S.W[i]));
         for (int tt = 0; tt < nt; ++tt) {
             // the B operand was last read by the MMAs of trajectory tt-1
             if (tt >= 1) mbar_wait(full0, (uint32_t)(tt - 1) & 1u);
             const float *src = S.qa[tt];
-            *reinterpret_cast<float2 *>(Wj + dst_c0) = *reinterpret_cast<const float2 *>(src + 2 * lane);
-            *reinterpret_cast<float2 *>(Wj + dst_c1) = *reinterpret_cast<const float2 *>(src + 2 * (lane + 32));
+            *reinterpret_cast<float2 *>(Wb + dst_c0) = *reinterpret_cast<const float2 *>(src + 2 * lane);
+            *reinterpret_cast<float2 *>(Wb + dst_c1) = *reinterpret_cast<const float2 *>(src + 2 * (lane + 32));
             if (lane < 19) {
-                const float val = src[128 + lane];
-                *reinterpret_cast<float *>(Wj + dst_r) = val;
-                if (lane >= 17) *reinterpret_cast<float *>(Wj + dst_r2) = val;
+                const float vh = src[src_h], vl = src[src_l];
+                *reinterpret_cast<float *>(Wb + dst_h) = vh;
+                *reinterpret_cast<float *>(Wb + dst_l) = vl;
+                if (lane >= 17) *reinterpret_cast<float *>(Wb + dst_h2) = vh;
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
                 mbar_wait(ready0, (uint32_t)tt & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                umma_tf32(tmem_base, dR1a, dW1a, idesc, 0u);
-                umma_tf32(tmem_base, dR1b, dW1b, idesc, 1u);
-                umma_tf32_ts(tmem_base, tmem_base + (uint32_t)kTmemA, dW2, idesc, 1u);
+                // x = (e_hi + e_lo)(W_hi + W_lo) ~ e_hi W_hi + e_lo W_hi + e_hi W_lo  (the lo.lo term is 2^-22 relative)
+                umma_tf32(tmem_base, dA[0], dB[0], idesc, 0u);
+                umma_tf32(tmem_base, dA[1], dB[1], idesc, 1u);
+                umma_tf32(tmem_base, dA[2], dB[0], idesc, 1u);
+                umma_tf32(tmem_base, dA[3], dB[1], idesc, 1u);
+                umma_tf32(tmem_base, dA[0], dB[2], idesc, 1u);
+                umma_tf32(tmem_base, dA[1], dB[3], idesc, 1u);
+                umma_tf32_ts(tmem_base, tmem_base + (uint32_t)kTmemA, dB[4], idesc, 1u);
+                umma_tf32_ts(tmem_base, tmem_base + (uint32_t)kTmemA + 8u, dB[5], idesc, 1u);
                 umma_commit(full0);
             }
             __syncwarp();
@@ -280,6 +302,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             o2 = fminf((float)(steps_done - (sp_c >> 1)), (float)ECORD_STATIC_CLIP) * inv_clip;
             const float h1 = tf32_rn(o1), h2 = tf32_rn(o2);
             tmem_st8(trow + (uint32_t)kTmemA, o0, h1, h2, o1 - h1, 1.0f, 1.0f, o2 - h2, 0.0f);
+            tmem_st8(trow + (uint32_t)kTmemA + 8u, o0, h1, h2, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);     // against the lo parts of C
             tmem_st_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -306,7 +329,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             float xx = fmaf(f0, fmaf(K.CC[0], f0, fmaf(2.0f * K.CC[1], f1, fmaf(2.0f * K.CC[2], f2, cb0))), bb);
             xx = fmaf(f1, fmaf(K.CC[3], f1, fmaf(2.0f * K.CC[4], f2, cb1)), xx);
             xx = fmaf(f2, fmaf(K.CC[5], f2, cb2), xx);
-            const float ss = fmaxf(fmaf(2.0f, d, sc[147]) + xx, 0.0f);
+            const float ss = fmaxf(fmaf(2.0f, d, sc[166]) + xx, 0.0f);
             const float var = fmaf(ss, 1.0f / Q, kLnEps);
             const float rstd = rsqrtf(var);
             const float sigma = var * rstd;
@@ -325,9 +348,9 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             unpack2(acc01, a0, a1);
             unpack2(acc23, a2, a3);
             const float acc = (a0 + a1) + (a2 + a3);
-            const float lin = sc[148] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
+            const float lin = sc[167] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
             const float dot = fmaf(0.505f, fmaf(lin, rstd, K.Wb), 0.495f * acc * rstd);
-            const float q = (dot + bo) + sc[149];
+            const float q = (dot + bo) + sc[168];
             if (DUMP_Q) { if (valid) *q_ptr = q; q_ptr += n; }
             // arg-max: ordered-int max across the warp, lowest vertex among equals, one atomic per warp
             const uint32_t u = __float_as_uint(q);
@@ -350,7 +373,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
 }
 }  // namespace
 
-constexpr int kQtcSmemBytes = 52 * 1024;
+constexpr int kQtcSmemBytes = 56 * 1024;
 
 int qtc_init_attrs() {
     // the dynamic request is padded so that at most four CTAs (4 x 128 TMEM columns) share an SM

@@ -124,7 +124,7 @@ def test_fast_q_kernel_vertex_tiles_and_trajectory_splits():
     assert torch.equal(a.score, b.score)
 
 
-TOL_TC = 2e-3   # tf32 operands (10-bit mantissa, hi/lo split on the per-trajectory terms), fp32 accumulation
+TOL_TC = 2e-5   # tf32 hi/lo operand split (3-term products), fp32 accumulation: fp32-grade
 
 
 def _argmax_diffs_are_near_ties(dg, T, qa, a_actions, b_actions, tol):
