@@ -55,43 +55,96 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML is polled
+    in-process (pynvml, initialised before the warm-up so that its start-up cost stays outside the timed region);
+    `nvidia-smi -lms` in a subprocess is the fallback.  Only samples taken between mark_begin() and mark_end()
+    are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index, period_s=0.01):
+        self.rows, self.idx, self.period = [], gpu_index, period_s
+        self.t0 = self.t1 = None
+        self.stop_flag = False
+        self.mode, self.proc, self.th = None, None, None
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES if it is set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                ids = [x.strip() for x in vis.split(",") if x.strip()]
+                if self.idx < len(ids) and ids[self.idx].isdigit():
+                    phys = int(ids[self.idx])
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = nv
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.mode = "smi"
+            self.th = threading.Thread(target=self._read_smi, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll_nvml(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-                for nm, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), mhz, self.max_mhz, pw, [k for k, b in bits.items() if mask & b]))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+            time.sleep(self.period)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]), float(r[3]),
+                                  [nm for nm, v in zip(names, r[4:8]) if v.lower().startswith("active")]))
+            except Exception:
+                pass
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.02)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if self.t0 is None or (self.t0 <= r[0] <= (self.t1 or 1e30))]
+        if not rows:                                   # region shorter than one poll: take the nearest sample
+            rows = self.rows[-1:]
+        sm = [r[1] for r in rows]
+        reasons = sorted({x for r in rows for x in r[4]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "power_w_max": max(r[3] for r in rows) if rows else None, "samples": len(rows), "reasons": reasons,
+                "source": self.mode}
 
 
 def make_graphs(workload, seed0=0):
@@ -204,17 +257,19 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also instantiates the CUDA graphs) ----
-    st.run(W)
-    barrier()
-    launches0 = st.kernel_launches
+    # ---- warm-up (also instantiates the CUDA graphs, NCCL and the clock sampler) ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    st.run(W)
+    reduce_best(st.best_from_log(W), T_total)          # first collective call sets NCCL up: keep that out of the timing
+    barrier()
+    launches0 = st.kernel_launches
     # ---- timed region: exactly K steps; L2 flushed before every graph launch (outside the events) ----
     chunks = [k] * (K // k) + ([K % k] if K % k else [])
     evs = []
     barrier()
+    sampler.mark_begin()
     t_wall0 = time.perf_counter()
     for c in chunks:
         flush.fill_(1)
@@ -229,6 +284,7 @@ def run_b200(args):
     e3.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
     ms = sum(a.elapsed_time(b) for a, b in evs) + e2.elapsed_time(e3)
     clocks = sampler.stop() if rank == 0 else None
     launches = st.kernel_launches - launches0
