@@ -14,8 +14,8 @@ GEMM_BF16 = 1
 Q_EXACT = 0
 Q_FAST = 1
 Q_TC = 2
-QTC_FLOATS = 6656
-QA_STRIDE = 172
+QTC_FLOATS = 4736
+QA_STRIDE = 92
 QTILE = 128
 QFOLD_FLOATS = 588
 GRU_PACK_ELEMS = 3072 * 1024 + 4096 * 64

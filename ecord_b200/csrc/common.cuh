@@ -30,6 +30,26 @@ __device__ __forceinline__ int warp_sum_int(int v) {
     return v;
 }
 
+// packed fp32 pairs (sm_100 FFMA2)
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long abs2(unsigned long long v) {
+    float a, b;
+    unpack2(v, a, b);
+    return pack2(fabsf(a), fabsf(b));
+}
+
 // plane offset of unit (g,t): graph_ptr[g]*T + t*n_g   (see include/ecord_b200.h)
 __device__ __forceinline__ long long unit_base(const int32_t *graph_ptr, int g, int t, int T, int &n) {
     const int lo = graph_ptr[g];

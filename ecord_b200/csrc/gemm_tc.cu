@@ -19,6 +19,7 @@
 // operand) and tanh(h') (bf16, PROJ's A operand).  h is double-buffered: buffer (s & 1) holds the state after s steps.
 
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 // MODE 0 = GRU : tile = 128 rows x 64 hidden units; k-chunk 0 (N=256) from (u, Wu), then 16 chunks (N=192) from
@@ -276,39 +277,36 @@ __global__ void k_pack_qtc(ecord_weights w) {
     for (int k = 0; k < 16; ++k) {
         const float wg = (float)((double)raw[c][k] - mean[k]);
         out[1280 + c * 16 + k] = wg;
-        out[c * 16 + k] = tf32_rn(gam * wg);
+        out[c * 16 + k] = 0.0f;
     }
-    for (int k = 0; k < 16; ++k)
-        if (c < 16) out[(64 + c) * 16 + k] = 0.0f;
     for (int j = 0; j < 4; ++j) {
         const float cc = (float)((double)raw[c][16 + j] - mean[16 + j]);
         out[2304 + c * 4 + j] = cc;
-        out[2560 + c * 4 + j] = j < 3 ? tf32_rn(gam * cc) : gam;
+        out[2560 + c * 4 + j] = 0.0f;
     }
-    // shared-memory image of the B operand of k_q_tc: six [80][8] tf32 blocks in the K-major SWIZZLE_32B layout
-    //   0,1: hi(gamma_c Wg[c][k]) k 0..7 | 8..15     2,3: the lo parts     4: W2 hi     5: W2 lo
-    // (hi = value rounded onto the tf32 grid, lo = tf32(value - hi)).  W2 hi slots: [C0 C1 C2 C1 | . . C2 0] against
-    // R2 = [f0 f1h f2h f1l | 1 1 f2l 0]; W2 lo slots: [C0 C1 C2 0 | 0 0 0 0] against [f0 f1h f2h 0 ...].
-    // The per-trajectory entries (row 64 everywhere, W2-hi slots 4 and 5) stay zero here.
-    float *img = out + 2816;
-    for (int i = c; i < 6 * 80 * 8; i += ECORD_DIM_Q) img[i] = 0.0f;
+    // shared-memory image of the B operand of k_q_tc: three [80][16] fp16 blocks in the K-major SWIZZLE_32B layout
+    //   0: hi(gamma_c Wg[c][k])   1: lo(...)   2: W2 = [C0h C1h C2h C1h . . C2h 0 | C0l C1l C2l 0 0 0 0 0], C = gamma_c Cc[c]
+    // (hi = fp16(value), lo = fp16(value - hi)).  The per-trajectory entries (row 64 everywhere, W2 halves 4 and 5)
+    // stay zero here.
+    __half *img = reinterpret_cast<__half *>(out + 2816);
+    for (int i = c; i < 3 * 80 * 16; i += ECORD_DIM_Q) img[i] = __float2half_rn(0.0f);
     __syncthreads();
-    auto at = [&](int blk, int r, int k) -> float & {
-        return img[blk * 640 + (r * 32 + ((((k >> 2) ^ (r >> 2)) & 1) << 4) + (k & 3) * 4) / 4];
+    auto at = [&](int blk, int r, int k) -> __half & {
+        return img[blk * 1280 + (r * 32 + ((((k >> 3) ^ (r >> 2)) & 1) << 4) + (k & 7) * 2) / 2];
     };
     for (int k = 0; k < 16; ++k) {
         const float v = gam * out[1280 + c * 16 + k];
-        const float hi = tf32_rn(v);
-        at(k >> 3, c, k & 7) = hi;
-        at(2 + (k >> 3), c, k & 7) = tf32_rn(v - hi);
+        const __half hi = __float2half_rn(v);
+        at(0, c, k) = hi;
+        at(1, c, k) = __float2half_rn(v - __half2float(hi));
     }
     for (int j = 0; j < 3; ++j) {
         const float v = gam * out[2304 + c * 4 + j];
-        const float hi = tf32_rn(v), lo = tf32_rn(v - hi);
-        at(4, c, j) = hi;
-        at(5, c, j) = lo;
-        if (j == 1) at(4, c, 3) = hi;       // against f1_lo
-        if (j == 2) at(4, c, 6) = hi;       // against f2_lo
+        const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+        at(2, c, j) = hi;
+        at(2, c, 8 + j) = lo;
+        if (j == 1) at(2, c, 3) = hi;       // against f1_lo
+        if (j == 2) at(2, c, 6) = hi;       // against f2_lo
     }
 }
 

@@ -16,6 +16,7 @@
 //   ECORD_GEMM_FP32: CUDA-core FMA SGEMM below (parity mode),
 //   ECORD_GEMM_BF16: tcgen05/TMA kernels in gemm_tc.cu (throughput mode).
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 // gemm_tc.cu
 int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, cudaStream_t st);
@@ -134,8 +135,11 @@ struct TailSmem {
     float cc[ECORD_DIM_Q * 4];  //                        centred C [c][0..2], bconst[c]
 };
 
-__device__ __forceinline__ float tf32_round(float x) {     // round-to-nearest onto the tf32 grid (see tc_common.cuh)
-    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+// fp16 hi / lo split of an fp32 value packed as (hi | lo << 16): x ~ hi + lo to ~2^-22 relative (see qtc.cu)
+__device__ __forceinline__ uint32_t split_h2(float x) {
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
 }
 // one butterfly level: lanes with (lane & OFF) == 0 keep v[0..N/2), the others keep v[N/2..N)
 template <int N, int OFF>
@@ -258,11 +262,10 @@ k_policy_tail(ecord_weights w, ecord_policy p) {
             // tensor-core Q kernel (layout: ecord_policy.qa), a' = Ac + bconst
             const float ap0 = c0 + S.cc[lane * 4 + 3], ap1 = c1 + S.cc[(lane + 32) * 4 + 3];
             float *qo = p.qa + (long long)m * ECORD_QA_STRIDE;
-            {   // (hi, lo) pairs: hi on the tf32 grid, lo the exact remainder -- the kernel stores them as they are
-                const float ga0 = gq0 * ap0, ga1 = gq1 * ap1;
-                const float h0 = tf32_round(ga0), h1 = tf32_round(ga1);
-                *reinterpret_cast<float2 *>(qo + 2 * lane) = make_float2(h0, ga0 - h0);
-                *reinterpret_cast<float2 *>(qo + 2 * (lane + 32)) = make_float2(h1, ga1 - h1);
+            uint32_t *qw = reinterpret_cast<uint32_t *>(qo);
+            {   // fp16 (hi, lo) pairs of gamma_c a'_c, one 32-bit word per channel -- the kernel copies them as they are
+                qw[lane] = split_h2(gq0 * ap0);
+                qw[lane + 32] = split_h2(gq1 * ap1);
             }
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {          // Wg^T a'
@@ -281,13 +284,27 @@ k_policy_tail(ecord_weights w, ecord_policy p) {
 #pragma unroll
             for (int i = 20; i < 32; ++i) part[i] = 0.0f;
             const float tot = reduce_scatter32(part, lane);      // lane i: entry i
-            const float hi = tf32_round(tot), lo = tf32_round(tot - hi);
-            if (lane < 16) { qo[128 + lane] = hi; qo[144 + lane] = lo; }
-            else if (lane < 19) { qo[160 + lane - 16] = hi; qo[163 + lane - 16] = lo; }
-            else if (lane == 19) qo[166] = tot;
-            else if (lane == 20) qo[167] = la;
-            else if (lane == 21) qo[168] = vv;
-            else if (lane < 25) qo[147 + lane] = 0.0f;
+            // row 64 of the B operand (column d), as fp16 words: lanes gather the two halves of their word by shuffle
+            const uint32_t hl = split_h2(tot);                   // this entry's (hi | lo << 16)
+            const uint32_t e0 = __shfl_sync(0xffffffffu, hl, (2 * lane) & 31), e1 = __shfl_sync(0xffffffffu, hl, (2 * lane + 1) & 31);
+            const uint32_t c0 = __shfl_sync(0xffffffffu, hl, 16), c1 = __shfl_sync(0xffffffffu, hl, 17),
+                           c2 = __shfl_sync(0xffffffffu, hl, 18);
+            if (lane < 8) {                                      // Wg^T a': entries 2l, 2l+1 -> hi word and lo word
+                qw[64 + lane] = (e0 & 0xffffu) | (e1 << 16);
+                qw[72 + lane] = (e0 >> 16) | (e1 & 0xffff0000u);
+            } else if (lane == 8) {                              // Cc^T a' -> [ca0h ca1h ca2h ca1h 0 0 ca2h 0 | ca0l ca1l ca2l 0 ...]
+                qw[80] = (c0 & 0xffffu) | (c1 << 16);
+                qw[81] = (c2 & 0xffffu) | (c1 << 16);
+                qw[82] = 0u;
+                qw[83] = c2 & 0xffffu;
+                qw[84] = (c0 >> 16) | (c1 & 0xffff0000u);
+                qw[85] = c2 >> 16;
+                qw[86] = 0u;
+                qw[87] = 0u;
+            } else if (lane == 19) qo[88] = tot;
+            else if (lane == 20) qo[89] = la;
+            else if (lane == 21) qo[90] = vv;
+            else if (lane == 22) qo[91] = 0.0f;
         }
     }
 }

@@ -8,34 +8,37 @@
 //     q     = 0.505 (lin / sigma + Wb) + 0.495 (sum_c w_c |gamma_c x_c + beta_c sigma|) / sigma + b_o + v[g,t]
 //
 // What the tensor core does.  For one tile of 128 vertices of a graph and one trajectory t, the 128 x 64 block
-// gamma_c x_c is a small GEMM  [128 rows] x [K] x [N = 80]  in tf32 with fp32 accumulation in TMEM.  Every operand
-// is split into a tf32 hi part and a lo remainder and the products hi.hi + lo.hi + hi.lo are accumulated (8 MMAs of
-// K = 8 per trajectory), which makes the result fp32-grade: plain tf32 (10-bit mantissa) puts a fixed per-vertex
-// bias of ~3e-4 on Q, enough to change which vertex wins the arg-max.  Logical operands:
+// gamma_c x_c is a small GEMM  [128 rows] x [K] x [N = 80]  with fp32 accumulation in TMEM.  Every operand is split
+// into an fp16 hi part and an fp16 lo remainder and the products hi.hi + lo.hi + hi.lo are accumulated (4 MMAs of
+// K = 16, kind::f16, per trajectory), which makes the result fp32-grade (~1e-6 relative; operands must stay below
+// the fp16 range, 65504).  A single low-precision product (tf32 or bf16) puts a fixed per-vertex bias of ~3e-4 on Q,
+// enough to change which vertex wins the arg-max and to degrade the rollout.  Logical operands:
 //     A operand rows (one per vertex, written by the vertex's own thread)
-//         R1 = node_emb[n] (16)                                       shared memory, constant for the CTA
-//         R2 = [ f0  f1_hi  f2_hi  f1_lo | 1  1  f2_lo  0 ]            TENSOR memory (tcgen05.st), rewritten per trajectory
-//                                                                      (hi/lo = exact tf32 split)
-//     B operand rows (one per output column)
-//         c < 64 : [ gamma_c Wg[c][0..15] | gamma_c Cc[c][0..2]  gamma_c Cc[c][1]  ga'_hi  ga'_lo  gamma_c Cc[c][2]  0 ]
-//         c = 64 : [ (Wg^T a')[0..15]     | (Cc^T a')[0..2]      (Cc^T a')[1]      0  0  (Cc^T a')[2]  0 ]  ->  d = a' . (b' + Cc f)
+//         R1 = node_emb[n] (16), hi block and lo block                shared memory, constant for the CTA
+//         R2 = [ f0 f1h f2h f1l 1 1 f2l 0 | f0 f1h f2h 0 0 0 0 0 ]    TENSOR memory (tcgen05.st), rewritten per trajectory
+//     B operand rows (one per output column), blocks W1 hi, W1 lo, W2
+//         c < 64 : W1 = gamma_c Wg[c][0..15];   W2 = [ C0h C1h C2h C1h ga'_hi ga'_lo C2h 0 | C0l C1l C2l 0 ... ]  (C = gamma_c Cc[c])
+//         c = 64 : W1 = (Wg^T a')[0..15];       W2 = [ ca0h ca1h ca2h ca1h 0 0 ca2h 0 | ca0l ca1l ca2l 0 ... ]  (ca = Cc^T a')
+//                                                                              ->  d = a' . (b' + Cc f)
+//     MMAs: R1h.W1h + R1l.W1h + R1h.W1l + R2.W2
 // Column 64 turns the LayerNorm sum of squares into a quadratic form,
 //     sum_c x_c^2 = |a'|^2 + 2 d + |b' + Cc f|^2,     |b' + Cc f|^2 = bb[n] + 2 cb[n].f + f^T (Cc^T Cc) f,
-// so the CUDA cores are left with 2 FFMA per channel (the |.| sum) instead of 8: ~190 instructions per
-// (vertex, trajectory) row instead of ~550.  Only the per-trajectory entries of the B operand (ga', Wg^T a', Cc^T a':
-// 83 floats from the policy tail) and the 128 R2 rows change between MMAs.
+// so the CUDA cores are left with the |.| sum: 64 packed FFMA2 per (vertex, trajectory) row instead of ~500 FFMA.
+// Only the per-trajectory entries of the B operand (ga', Wg^T a', Cc^T a': 88 words from the policy tail) and the
+// 128 R2 rows change between MMAs.
 //
-// CTA = 4 row warps (thread i <-> vertex i of the tile <-> TMEM lane i) + 1 control warp (writes the per-trajectory
+// CTA = 4 row warps (thread i <-> vertex i of the tile <-> TMEM lane i) + 1 control warp (copies the per-trajectory
 // operand entries, issues tcgen05.mma / commit).  No CTA-wide barrier in the loop: the roles meet on mbarriers
 // (`ready`: R2 written + accumulator drained, 4 warp arrivals; `full`: tcgen05.commit).  A CTA owns 128 TMEM columns
 // (one accumulator + R2) so that FOUR CTAs share an SM: a row warp hands trajectory t+1 to the tensor core right
 // after reading the accumulator of t out of TMEM, its MMAs overlap the epilogue math of t, and the other CTAs'
 // warps cover what latency remains (the kernel is latency-, not issue-bound: see profiles/).
-// Shared-memory operand blocks are [rows][8 tf32] with 32-byte rows in the canonical K-major SWIZZLE_32B layout
+// Shared-memory operand blocks are [rows][16 fp16] with 32-byte rows in the canonical K-major SWIZZLE_32B layout
 // (16-byte chunk index XOR bit 2 of the row; 8-row groups 256 B apart).  R2 lives in tensor memory because a
 // generic-proxy write to a shared-memory operand needs fence.proxy.async (a MEMBAR) before the MMA may read it,
 // and that fence would drain the row warps' prefetched global loads and arg-max atomics every trajectory.
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 #include <string.h>
 
 namespace {
@@ -43,20 +46,20 @@ constexpr int Q = ECORD_DIM_Q;        // 64
 constexpr int QT = ECORD_QTILE;       // 128 vertices per tile
 constexpr int QN = 80;                // MMA N (multiple of 16 for M = 128)
 constexpr int QA = ECORD_QA_STRIDE;   // 88
-constexpr int kTcMaxT = 25;           // trajectories per CTA (rows of qa staged in shared memory)
+constexpr int kTcMaxT = 32;           // trajectories per CTA (rows of qa staged in shared memory)
 constexpr int kCtasPerSM = 4;         // 4 x 128 TMEM columns; shared memory and registers are sized for it
-constexpr int A_BLK = QT * 32;        // bytes of one [128][8] tf32 operand block
-constexpr int B_BLK = QN * 32;        // bytes of one [80][8] block
+constexpr int A_BLK = QT * 32;        // bytes of one [128][16] fp16 operand block
+constexpr int B_BLK = QN * 32;        // bytes of one [80][16] block
 constexpr int kQtcThreads = 160;
-constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,96): the per-trajectory A operand R2 (K = 16)
+constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,88): the per-trajectory A operand R2 (16 fp16)
 constexpr int kTmemCols = 128;
 
-constexpr int kRing = 6;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
-constexpr int kImgBytes = 6 * B_BLK;   // packed image of the B operand: W1 hi (2 k-blocks) | W1 lo (2) | W2 hi | W2 lo
+constexpr int kRing = 8;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
+constexpr int kImgBytes = 3 * B_BLK;   // packed image of the B operand: W1 hi | W1 lo | W2
 
 struct QTcSmem {
-    uint8_t R1[4][A_BLK];              // A operand (node_emb): hi k 0..7 | hi k 8..15 | lo k 0..7 | lo k 8..15; constant for the CTA
-    uint8_t W[6][B_BLK];               // B operand: W1 hi k0 | W1 hi k1 | W1 lo k0 | W1 lo k1 | W2 hi | W2 lo
+    uint8_t R1[2][A_BLK];              // A operand (node_emb): hi | lo; constant for the CTA
+    uint8_t W[3][B_BLK];               // B operand: W1 hi | W1 lo | W2
     float qa[kTcMaxT][QA];             // per-(g,t) rows of ecord_policy.qa
     int sp[kRing + 1][QT];             // state ring (cp.async), one slot per trajectory in flight
     float pk[kRing + 1][QT];
@@ -69,58 +72,45 @@ struct QTcSmem {
 // epilogue constants, passed by value (constant bank operands of the FFMAs)
 struct QTcConst { float bet[Q], wo[Q], CC[6], LC[3], Wb; };
 
-__device__ __forceinline__ uint32_t sw32(int r, int k) {      // byte offset of element (row r, k) in a SWIZZLE_32B block
-    return (uint32_t)(r * 32 + ((((k >> 2) ^ (r >> 2)) & 1) << 4) + (k & 3) * 4);
+__device__ __forceinline__ uint32_t sw32(int r, int k) {      // byte offset of fp16 element (row r, k) in a SWIZZLE_32B block
+    return (uint32_t)(r * 32 + ((((k >> 3) ^ (r >> 2)) & 1) << 4) + (k & 7) * 2);
 }
 __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
 }
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {   // D = f32, A = B = tf32, K-major
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {   // D = f32, A = B = fp16, K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-// A operand from tensor memory (lane = row, one 32-bit column per tf32 element)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+// A operand from tensor memory (lane = row, two fp16 elements per 32-bit column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// fp16 hi / lo split of an fp32 value: x ~ hi + lo with |x - hi - lo| <= 2^-22 |x| (or 3e-8 absolute below 2^-3)
+__device__ __forceinline__ void split_h(float x, __half &hi, __half &lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     uint32_t r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, float a0, float a1, float a2, float a3, float a4, float a5, float a6,
-                                         float a7) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                         uint32_t a5, uint32_t a6, uint32_t a7) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(a2)),
-                   "r"(__float_as_uint(a3)), "r"(__float_as_uint(a4)), "r"(__float_as_uint(a5)), "r"(__float_as_uint(a6)),
-                   "r"(__float_as_uint(a7)) : "memory");
-}
-// packed fp32 pairs (sm_100 FFMA2)
-__device__ __forceinline__ unsigned long long pack2(float a, float b) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ unsigned long long abs2(unsigned long long v) {
-    float a, b;
-    unpack2(v, a, b);
-    return pack2(fabsf(a), fabsf(b));
+                 ::"r"(taddr), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -153,7 +143,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
     const int steps_done = (step_base ? *step_base : 0) + step_off;
     const int lo = g.graph_ptr[gi], n = g.graph_ptr[gi + 1] - lo;
     const uint32_t full0 = smem_u32(&S.full), ready0 = smem_u32(&S.ready), setup_bar = smem_u32(&S.setup);
-    constexpr uint32_t idesc = umma_idesc_tf32(QT, QN);
+    constexpr uint32_t idesc = umma_idesc_f16(QT, QN);
 
     // ---------------- set-up ----------------
     if (warp == 4) {
@@ -173,7 +163,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
                      "r"((uint32_t)kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // per-vertex: the R1 row (node_emb rounded onto the tf32 grid) and the quadratic-form scalars
+    // per-vertex: the R1 row (node_emb as fp16 hi + lo) and the quadratic-form scalars
     const bool valid = is_row && v0 + tid < n;
     const int v = is_row ? min(v0 + tid, n - 1) : 0;
     float bb = 0.f, cb0 = 0.f, cb1 = 0.f, cb2 = 0.f, lb = 0.f;
@@ -190,14 +180,22 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
         for (int c4 = 0; c4 < 4; ++c4) x[c4] = ep[c4];
         const float4 q0 = qv[0];
         lb = qv[1].x;
+        // the vertex's R1 row: 16 fp16 hi values (32 bytes = two swizzled 16-byte chunks) and the 16 lo remainders
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            // hi on the tf32 grid, lo the exact remainder (the tensor core drops its 13 low bits: 2^-22 relative)
-            const float4 hi = make_float4(tf32_rn(x[c4].x), tf32_rn(x[c4].y), tf32_rn(x[c4].z), tf32_rn(x[c4].w));
-            const float4 lo = make_float4(x[c4].x - hi.x, x[c4].y - hi.y, x[c4].z - hi.z, x[c4].w - hi.w);
-            const int k = c4 * 4;
-            *reinterpret_cast<float4 *>(&S.R1[k >> 3][sw32(tid, k & 7)]) = hi;
-            *reinterpret_cast<float4 *>(&S.R1[2 + (k >> 3)][sw32(tid, k & 7)]) = lo;
+        for (int c8 = 0; c8 < 2; ++c8) {
+            const float e[8] = {x[2 * c8].x, x[2 * c8].y, x[2 * c8].z, x[2 * c8].w,
+                                x[2 * c8 + 1].x, x[2 * c8 + 1].y, x[2 * c8 + 1].z, x[2 * c8 + 1].w};
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __half h0, l0, h1, l1;
+                split_h(e[2 * i], h0, l0);
+                split_h(e[2 * i + 1], h1, l1);
+                wh[i] = pack_h2(h0, h1);
+                wl[i] = pack_h2(l0, l1);
+            }
+            *reinterpret_cast<uint4 *>(&S.R1[0][sw32(tid, 8 * c8)]) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            *reinterpret_cast<uint4 *>(&S.R1[1][sw32(tid, 8 * c8)]) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
         bb = q0.x; cb0 = 2.0f * q0.y; cb1 = 2.0f * q0.z; cb2 = 2.0f * q0.w;
         // R1 was written through the generic proxy: make it visible to the tensor core.  This fence is a MEMBAR, so
@@ -228,54 +226,32 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
     if (warp == 4) {
         // =============== control warp: per-trajectory B-operand entries, MMA issue ===============
         mbar_wait(setup_bar, 0);
-        // Per-trajectory B-operand entries (qa row, already split into tf32 hi / lo by the policy tail) and where this
-        // lane puts them: two (hi, lo) channel pairs into W2-hi slots 4|5, plus row-64 entries (column d).
+        // Per-trajectory B-operand entries: the qa row holds them as ready-made 32-bit words (fp16 pairs, see
+        // ecord_policy.qa); this lane copies two channel words (ga' hi|lo -> W2 halves 4|5 of rows c, c+32) and, for
+        // lane < 24, one word of row 64 (column d): W1 hi (lanes 0..7), W1 lo (8..15), W2 (16..23).
         uint8_t *Wb = S.W[0];
-        const uint32_t dst_c0 = 4u * B_BLK + sw32(lane, 4), dst_c1 = 4u * B_BLK + sw32(lane + 32, 4);
-        uint32_t dst_h = 0, dst_l = 0, dst_h2 = 0;
-        int src_h = 0, src_l = 0;
-        if (lane < 16) {                          // Wg^T a': hi -> W1 hi row 64, lo -> W1 lo row 64
-            dst_h = (uint32_t)(lane >> 3) * B_BLK + sw32(Q, lane & 7);
-            dst_l = dst_h + 2u * B_BLK;
-            src_h = 128 + lane; src_l = 144 + lane;
-        } else if (lane < 19) {                   // Cc^T a': hi -> W2 hi row 64 (f1, f2 also against their lo slots), lo -> W2 lo
-            const int j = lane - 16;
-            dst_h = 4u * B_BLK + sw32(Q, j);
-            dst_l = 5u * B_BLK + sw32(Q, j);
-            dst_h2 = j == 1 ? 4u * B_BLK + sw32(Q, 3) : j == 2 ? 4u * B_BLK + sw32(Q, 6) : dst_h;
-            src_h = 160 + j; src_l = 163 + j;
-        }
-        uint64_t dA[4], dB[6];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dA[i] = umma_desc_sw32(smem_u32(S.R1[i]));
-#pragma unroll
-        for (int i = 0; i < 6; ++i) dB[i] = umma_desc_sw32(smem_u32(S.W[i]));
+        const uint32_t dst_c0 = 2u * B_BLK + sw32(lane, 4), dst_c1 = 2u * B_BLK + sw32(lane + 32, 4);
+        const uint32_t dst_r = (uint32_t)(lane >> 3) * B_BLK + sw32(Q, 2 * (lane & 7));
+        const uint64_t dA0 = umma_desc_sw32(smem_u32(S.R1[0])), dA1 = umma_desc_sw32(smem_u32(S.R1[1]));
+        const uint64_t dB0 = umma_desc_sw32(smem_u32(S.W[0])), dB1 = umma_desc_sw32(smem_u32(S.W[1])),
+                       dB2 = umma_desc_sw32(smem_u32(S.W[2]));
         for (int tt = 0; tt < nt; ++tt) {
             // the B operand was last read by the MMAs of trajectory tt-1
             if (tt >= 1) mbar_wait(full0, (uint32_t)(tt - 1) & 1u);
-            const float *src = S.qa[tt];
-            *reinterpret_cast<float2 *>(Wb + dst_c0) = *reinterpret_cast<const float2 *>(src + 2 * lane);
-            *reinterpret_cast<float2 *>(Wb + dst_c1) = *reinterpret_cast<const float2 *>(src + 2 * (lane + 32));
-            if (lane < 19) {
-                const float vh = src[src_h], vl = src[src_l];
-                *reinterpret_cast<float *>(Wb + dst_h) = vh;
-                *reinterpret_cast<float *>(Wb + dst_l) = vl;
-                if (lane >= 17) *reinterpret_cast<float *>(Wb + dst_h2) = vh;
-            }
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(S.qa[tt]);
+            *reinterpret_cast<uint32_t *>(Wb + dst_c0) = src[lane];
+            *reinterpret_cast<uint32_t *>(Wb + dst_c1) = src[lane + 32];
+            if (lane < 24) *reinterpret_cast<uint32_t *>(Wb + dst_r) = src[64 + lane];
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
                 mbar_wait(ready0, (uint32_t)tt & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // x = (e_hi + e_lo)(W_hi + W_lo) ~ e_hi W_hi + e_lo W_hi + e_hi W_lo  (the lo.lo term is 2^-22 relative)
-                umma_tf32(tmem_base, dA[0], dB[0], idesc, 0u);
-                umma_tf32(tmem_base, dA[1], dB[1], idesc, 1u);
-                umma_tf32(tmem_base, dA[2], dB[0], idesc, 1u);
-                umma_tf32(tmem_base, dA[3], dB[1], idesc, 1u);
-                umma_tf32(tmem_base, dA[0], dB[2], idesc, 1u);
-                umma_tf32(tmem_base, dA[1], dB[3], idesc, 1u);
-                umma_tf32_ts(tmem_base, tmem_base + (uint32_t)kTmemA, dB[4], idesc, 1u);
-                umma_tf32_ts(tmem_base, tmem_base + (uint32_t)kTmemA + 8u, dB[5], idesc, 1u);
+                umma_f16(tmem_base, dA0, dB0, idesc, 0u);
+                umma_f16(tmem_base, dA1, dB0, idesc, 1u);
+                umma_f16(tmem_base, dA0, dB1, idesc, 1u);
+                umma_f16_ts(tmem_base, tmem_base + (uint32_t)kTmemA, dB2, idesc, 1u);
                 umma_commit(full0);
             }
             __syncwarp();
@@ -300,9 +276,14 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             o0 = (float)(sp_c & 1);
             o1 = pk_c * inv_n;
             o2 = fminf((float)(steps_done - (sp_c >> 1)), (float)ECORD_STATIC_CLIP) * inv_clip;
-            const float h1 = tf32_rn(o1), h2 = tf32_rn(o2);
-            tmem_st8(trow + (uint32_t)kTmemA, o0, h1, h2, o1 - h1, 1.0f, 1.0f, o2 - h2, 0.0f);
-            tmem_st8(trow + (uint32_t)kTmemA + 8u, o0, h1, h2, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f);     // against the lo parts of C
+            __half f1h, f1l, f2h, f2l;
+            split_h(o1, f1h, f1l);
+            split_h(o2, f2h, f2l);
+            const __half hz = __ushort_as_half((unsigned short)0), h1 = __ushort_as_half((unsigned short)0x3c00);   // 0, 1
+            const __half f0h = (sp_c & 1) ? h1 : hz;
+            const uint32_t w0 = pack_h2(f0h, f1h);
+            tmem_st8(trow + (uint32_t)kTmemA, w0, pack_h2(f2h, f1l), pack_h2(h1, h1), pack_h2(f2l, hz),
+                     w0, pack_h2(f2h, hz), 0u, 0u);
             tmem_st_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -329,7 +310,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             float xx = fmaf(f0, fmaf(K.CC[0], f0, fmaf(2.0f * K.CC[1], f1, fmaf(2.0f * K.CC[2], f2, cb0))), bb);
             xx = fmaf(f1, fmaf(K.CC[3], f1, fmaf(2.0f * K.CC[4], f2, cb1)), xx);
             xx = fmaf(f2, fmaf(K.CC[5], f2, cb2), xx);
-            const float ss = fmaxf(fmaf(2.0f, d, sc[166]) + xx, 0.0f);
+            const float ss = fmaxf(fmaf(2.0f, d, sc[88]) + xx, 0.0f);
             const float var = fmaf(ss, 1.0f / Q, kLnEps);
             const float rstd = rsqrtf(var);
             const float sigma = var * rstd;
@@ -348,9 +329,9 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             unpack2(acc01, a0, a1);
             unpack2(acc23, a2, a3);
             const float acc = (a0 + a1) + (a2 + a3);
-            const float lin = sc[167] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
+            const float lin = sc[89] + lb + fmaf(K.LC[2], f2, fmaf(K.LC[1], f1, K.LC[0] * f0));
             const float dot = fmaf(0.505f, fmaf(lin, rstd, K.Wb), 0.495f * acc * rstd);
-            const float q = (dot + bo) + sc[168];
+            const float q = (dot + bo) + sc[90];
             if (DUMP_Q) { if (valid) *q_ptr = q; q_ptr += n; }
             // arg-max: ordered-int max across the warp, lowest vertex among equals, one atomic per warp
             const uint32_t u = __float_as_uint(q);

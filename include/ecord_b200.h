@@ -118,12 +118,12 @@ typedef struct ecord_weights {
                             followed by Wu pack [16][256][64] (rows r|z|0|in) -- tile order of the tcgen05 GRU kernel */
     void  *p1_w_bf16;    /* bf16 [512][1024] */
     float *q_tc;         /* f32 [ECORD_QTC_FLOATS] operands of the tensor-core Q kernel (ECORD_Q_TC), or NULL:
-                              [0,1280)     W1 operand [80][16]: tf32(gamma_c * Wg[c][k]), rows >= 64 zero
+                              [0,1280)     reserved
                               [1280,2304)  Wg [64][16] = Wq[:,32:48] centred over the 64 channels (fp32)
                               [2304,2560)  [64][4]: Cc[c][0..2] (C = Wq[:,48:64] W_enc, centred), bconst[c] = centred Wq[:,48:64] b_enc
-                              [2560,2816)  [64][4]: tf32(gamma_c * Cc[c][0..2]), gamma_c
-                              [2816,6656)  shared-memory image of the kernel's B operand: 6 swizzled [80][8] tf32 blocks
-                                           (W1 hi k0..7 | W1 hi k8..15 | W1 lo k0..7 | W1 lo k8..15 | W2 hi | W2 lo)
+                              [2560,2816)  reserved
+                              [2816,4736)  shared-memory image of the kernel's B operand: 3 swizzled [80][16] fp16 blocks
+                                           (W1 hi | W1 lo | W2), 7680 bytes
                             filled by ecord_pack_weights() */
     const float *q_fold; /* HOST f32 [ECORD_QFOLD_FLOATS] from ecord_fold_q_host():
                               [0,384)   C0|C1|C2 (C = Wq[:,48:64] @ W_enc, 64x3) | LN gamma | LN beta | w_o
@@ -132,7 +132,7 @@ typedef struct ecord_weights {
                               [580,586) Ccentred^T Ccentred (3x3 symmetric: 00 01 02 11 12 22); [586,588) unused
                             Passed to the Q kernels by value (constant bank), hence a host array. */
 #define ECORD_QFOLD_FLOATS 588
-#define ECORD_QTC_FLOATS 6656
+#define ECORD_QTC_FLOATS 4736
 #define ECORD_GRU_PACK_ELEMS (3072 * 1024 + 4096 * 64)
 } ecord_weights;
 
@@ -163,9 +163,9 @@ typedef struct ecord_policy {
     const float *node_LB; /* [N]             sum_c w_o[c] gamma[c] node_Bc[c] */
     unsigned long long *keys; /* [rows]      packed (ordered q << 32 | ~vertex) running arg-max; zero between steps */
     /* tensor-core Q kernel (q_mode = ECORD_Q_TC); with a' = Ac + bconst:
-         qa[m] = [ (hi, lo) tf32 split of gamma_c a'_c (64 pairs) | Wg^T a' hi (16) | lo (16) | Cc^T a' hi (3) | lo (3) |
-                   |a'|^2 | LA | v | 0 0 0 ]
-                                                                                                written by the policy tail
+         qa[m] = 92 32-bit words: [0,64) fp16 pairs (hi, lo) of gamma_c a'_c | [64,72) Wg^T a' hi (16 fp16) | [72,80) lo |
+                 [80,88) row 64 of W2: fp16 [ca0h ca1h ca2h ca1h 0 0 ca2h 0 | ca0l ca1l ca2l 0 0 0 0 0], ca = Cc^T a' |
+                 f32 |a'|^2 | f32 LA | f32 v | 0                                            written by the policy tail
          node_qv[n] = [ |b'|^2 | Cc^T b' (3) | LB | 0 0 0 ],  b' = Wg node_emb[n]             written by ecord_gnn_embed */
     float   *qa;          /* [rows_pad][ECORD_QA_STRIDE] */
     float   *node_qv;     /* [N][8] */
@@ -173,13 +173,14 @@ typedef struct ecord_policy {
 
 /* Q-head evaluation */
 #define ECORD_Q_EXACT 0   /* one CTA per (g,t); LayerNorm/LeakyReLU/dot evaluated literally (parity mode)             */
-#define ECORD_QA_STRIDE 172
+#define ECORD_QA_STRIDE 92
 #define ECORD_Q_FAST  1   /* vertex-tiled, per-vertex operands register-resident across trajectories; centred LN and
                              LeakyReLU(y) = 0.505 y + 0.495 |y| with the linear half folded out (re-associated fp32) */
 #define ECORD_Q_TC    2   /* the same folded head with the 64-channel pre-activation of every (vertex, trajectory) row produced
                              by tcgen05.mma kind::tf32 (operands built in shared memory, accumulators in TMEM) and only the
-                             |.|-sum left on the CUDA cores.  Every operand is split into tf32 hi + lo parts (3-term products),
-                             so the result is fp32-grade (~1e-6 relative).  tau == 0 only. */
+                             |.|-sum left on the CUDA cores.  Every operand is split into fp16 hi + lo parts (3-term products,
+                             kind::f16), so the result is fp32-grade (~1e-6 relative) as long as |operands| < 65504.
+                             tau == 0 only. */
 
 /* ------------------------------------------------------------------------------------------ */
 int         ecord_version(void);
