@@ -19,6 +19,7 @@ QA_STRIDE = 92
 QTILE = 128
 QFOLD_FLOATS = 588
 GRU_PACK_ELEMS = 3072 * 1024 + 4096 * 64
+P1_PACK_ELEMS = 512 * 1024 + 32 * 512
 
 _vp, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["env.cu", "gnn.cu", "policy.cu", "gemm_tc.cu", "qselect.cu", "qtc.cu", "rollout.cu"]
+SOURCES = ["env.cu", "gnn.cu", "policy.cu", "gemm_tc.cu", "tail_tc.cu", "qselect.cu", "qtc.cu", "rollout.cu"]
 LIB = os.path.join(HERE, "libecord_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -225,7 +225,7 @@ __global__ void k_pack_weights(ecord_weights w) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     __nv_bfloat16 *wh = reinterpret_cast<__nv_bfloat16 *>(w.gru_w_bf16);
     __nv_bfloat16 *wu = wh + (size_t)3072 * H;
-    const long long n_wh = (long long)3072 * H, n_wu = (long long)4096 * 64, n_p1 = (long long)512 * H;
+    const long long n_wh = (long long)3072 * H, n_wu = (long long)4096 * 64, n_p1 = (long long)512 * H, n_p2 = 32 * 512;
     if (i < n_wh) {                               // Wh pack: row = jb*192 + gate*64 + jj  <-  W_hh[gate*1024 + jb*64 + jj]
         const int row = (int)(i / H), k = (int)(i % H);
         const int jb = row / 192, gate = (row % 192) / 64, jj = row % 64;
@@ -243,6 +243,9 @@ __global__ void k_pack_weights(ecord_weights w) {
     } else if (i < n_wh + n_wu + n_p1) {
         const long long t = i - n_wh - n_wu;
         reinterpret_cast<__nv_bfloat16 *>(w.p1_w_bf16)[t] = __float2bfloat16(w.p1_w[t]);
+    } else if (i < n_wh + n_wu + n_p1 + n_p2) {   // proj_rnn_to_gnn.4 weight [32][512], behind W1
+        const long long t = i - n_wh - n_wu - n_p1;
+        reinterpret_cast<__nv_bfloat16 *>(w.p1_w_bf16)[n_p1 + t] = __float2bfloat16(w.p2_w[t]);
     }
 }
 
@@ -313,8 +316,8 @@ __global__ void k_pack_qtc(ecord_weights w) {
 }  // namespace
 
 extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
-    ECORD_RET_IF(!w || !w->gru_w_bf16 || !w->p1_w_bf16 || !w->gru_whh || !w->gru_wih || !w->p1_w, ECORD_E_NULL);
-    const long long n = (long long)3072 * H + (long long)4096 * 64 + (long long)512 * H;
+    ECORD_RET_IF(!w || !w->gru_w_bf16 || !w->p1_w_bf16 || !w->gru_whh || !w->gru_wih || !w->p1_w || !w->p2_w, ECORD_E_NULL);
+    const long long n = (long long)3072 * H + (long long)4096 * 64 + (long long)512 * H + 32 * 512;
     k_pack_weights<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(*w);
     ECORD_LAUNCH_CHECK();
     if (w->q_tc) {

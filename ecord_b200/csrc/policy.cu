@@ -22,6 +22,9 @@
 int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, cudaStream_t st);
 int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st);
 int tc_init_attrs();
+// tail_tc.cu
+int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st);
+int tail_tc_init_attrs();
 
 namespace {
 constexpr int H = ECORD_DIM_H;      // 1024
@@ -343,6 +346,7 @@ int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_w
         if (rc) return rc;
         rc = launch_proj1_tc(w, p, st);
         if (rc) return rc;
+        return launch_tail_tc(w, p, st);          // LN512 -> W2 on tcgen05 -> LN32, value head, Q-kernel operands
     }
     k_policy_tail<<<min(kNumSMs, ceil_div(M, kTailWarps)), kTailWarps * 32, sizeof(TailSmem), st>>>(*w, *p);
     ECORD_LAUNCH_CHECK();
@@ -353,6 +357,8 @@ int policy_kernels_per_step(int gemm_mode, int skip_pre) { return (gemm_mode == 
 
 int policy_init_attrs() {
     ECORD_CUDA(cudaFuncSetAttribute(k_policy_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+    int rc = tail_tc_init_attrs();
+    if (rc) return rc;
     return tc_init_attrs();
 }
 

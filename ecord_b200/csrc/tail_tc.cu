@@ -1,0 +1,307 @@
+// tail_tc.cu -- the per-(graph,trajectory) tail of the policy step with its 512 -> 32 contraction on tcgen05
+// (throughput mode; the fp32 parity mode keeps k_policy_tail in policy.cu).
+//
+//   y1 [M][512] -> LN512 -> LReLU -> W2 (512 -> 32) -> LN32 -> LReLU = P ;  v = val_out(P) ;  A = Wq[:, :32] P + b_q
+//   + the per-(g,t) operands of the fast / tensor-core Q kernels          (models/rnn_decoder.py:84-90,108-119,285-311)
+//
+// One CTA per block of 128 rows:
+//   phase 1  16 warps, one row at a time per warp: LayerNorm(512) + LeakyReLU in registers (16 values per lane),
+//            result rounded to bf16 and written to shared memory as the A operand of the MMA -- eight [128][64]
+//            K-major SWIZZLE_128B sub-tiles, the layout TMA would produce
+//   phase 2  W2 (bf16, eight [32][64] sub-tiles fetched by TMA during phase 1) x A: 32 tcgen05.mma (M=128, N=32, K=16),
+//            accumulator [128][32] fp32 in TMEM
+//   phase 3  thread i <-> row i <-> TMEM lane i: LayerNorm(32), value head, A and the Q-kernel operands, all weights
+//            read as warp-uniform (broadcast) LDS.128
+// The warp-per-row CUDA-core version spends its time streaming W2 (64 KB) out of shared memory once per row
+// (5000 x 64 KB per step) and in shuffle reductions; here W2 is read by the tensor core once per 128 rows.
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+constexpr int P1 = ECORD_DIM_P1;     // 512
+constexpr int ND = ECORD_DIM_NODE;   // 32
+constexpr int QC = ECORD_DIM_Q;      // 64
+constexpr int kTtThreads = 512;
+constexpr int A_SUB = BM * 128;      // bytes of one [128][64] bf16 sub-tile
+constexpr int W_SUB = ND * 128;      // bytes of one [32][64] bf16 sub-tile
+
+struct TailTcSmem {
+    uint8_t act[8][A_SUB];           // 128 KB
+    uint8_t w2[8][W_SUB];            // 32 KB
+    float ln1g[P1], ln1b[P1];
+    float v1[ND * ND];               // val_out.1 weight [j][o]
+    float q1[QC * ND];               // Wq[:, :32]  [c][o]
+    float wg[QC * 16];               // centred Wq[:,32:48] [c][k]
+    float cc[QC * 4];                // centred C [c][0..2], bconst[c]
+    float colsum[ND + 1];            // sum_c Wq[c][o]; [32] = sum_c b_q[c]
+    uint64_t bar_w, bar_mma;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t split_h2(float x) {     // fp16 (hi | lo << 16), see qtc.cu
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+}
+
+__global__ void __launch_bounds__(kTtThreads, 1)
+k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_policy p) {
+    extern __shared__ uint8_t smem_raw[];
+    TailTcSmem &S = *reinterpret_cast<TailTcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * BM;
+    const uint32_t bar_w = smem_u32(&S.bar_w), bar_mma = smem_u32(&S.bar_mma);
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tmap_prefetch(&mapW2);
+        mbar_expect_tx(bar_w, 8 * W_SUB);
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) tma_load_2d(smem_u32(S.w2[kb]), &mapW2, bar_w, kb * 64, 0);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(32u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < P1; i += kTtThreads) { S.ln1g[i] = w.ln1_w[i]; S.ln1b[i] = w.ln1_b[i]; }
+    for (int i = tid; i < ND * ND; i += kTtThreads) S.v1[i] = w.v1_w[i];
+    for (int i = tid; i < QC * ND; i += kTtThreads) S.q1[i] = w.q1_w[(i / ND) * QC + (i % ND)];
+    if (p.qa) {
+        for (int i = tid; i < QC * 16; i += kTtThreads) S.wg[i] = w.q_tc[1280 + i];
+        for (int i = tid; i < QC * 4; i += kTtThreads) S.cc[i] = w.q_tc[2304 + i];
+    }
+    if (tid <= ND) {
+        float s = 0.0f;
+        for (int c = 0; c < QC; ++c) s += tid < ND ? w.q1_w[c * QC + tid] : w.q1_b[c];
+        S.colsum[tid] = s;
+    }
+    __syncthreads();
+
+    // ---------------- phase 1: LN512 + LReLU -> bf16 A operand ----------------
+    // (the next row's 2 KB are requested before the current row is reduced: a warp's 8 rows would otherwise pay
+    //  8 serial memory latencies)
+    {
+        constexpr int NW = kTtThreads / 32;
+        auto row_ptr = [&](int r) {
+            return reinterpret_cast<const float4 *>(p.y1 + (long long)min(m0 + r, p.rows - 1) * P1);   // rows past the end:
+        };                                                                       // the last row again, never stored
+        float4 nx[4];
+        {
+            const float4 *yr = row_ptr(warp);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nx[k] = yr[lane + 32 * k];
+        }
+        for (int r = warp; r < BM; r += NW) {
+            float x[16];
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                x[4 * k] = nx[k].x; x[4 * k + 1] = nx[k].y; x[4 * k + 2] = nx[k].z; x[4 * k + 3] = nx[k].w;
+                s += (nx[k].x + nx[k].y) + (nx[k].z + nx[k].w);
+            }
+            if (r + NW < BM) {
+                const float4 *yr = row_ptr(r + NW);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nx[k] = yr[lane + 32 * k];
+            }
+            const float mean = warp_sum(s) * (1.0f / P1);
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { x[j] -= mean; ss = fmaf(x[j], x[j], ss); }
+            const float rstd = rsqrtf(warp_sum(ss) * (1.0f / P1) + kLnEps);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = 4 * (lane + 32 * k);               // first of this lane's 4 consecutive elements
+                const float4 g4 = *reinterpret_cast<const float4 *>(&S.ln1g[i]);
+                const float4 b4 = *reinterpret_cast<const float4 *>(&S.ln1b[i]);
+                const float y0 = lrelu(fmaf(x[4 * k + 0] * rstd, g4.x, b4.x)), y1 = lrelu(fmaf(x[4 * k + 1] * rstd, g4.y, b4.y));
+                const float y2 = lrelu(fmaf(x[4 * k + 2] * rstd, g4.z, b4.z)), y3 = lrelu(fmaf(x[4 * k + 3] * rstd, g4.w, b4.w));
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
+                // K-major SWIZZLE_128B: sub-tile i/64, row r (128 B), 16-byte chunk ((i%64)/8) ^ (r%8)
+                const uint32_t off = (uint32_t)(r * 128 + (((((i & 63) >> 3) ^ (r & 7)) & 7) << 4) + (i & 7) * 2);
+                *reinterpret_cast<uint2 *>(&S.act[i >> 6][off]) =
+                    make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = S.tmem_base;
+
+    // ---------------- phase 2: [128 x 512] x [512 x 32] on the tensor core ----------------
+    if (tid == 0) {
+        mbar_wait(bar_w, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr uint32_t idesc = umma_idesc(BM, ND);
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+            const uint32_t a_src = smem_u32(S.act[kb]), b_src = smem_u32(S.w2[kb]);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(tmem_d, umma_desc(a_src + k * UMMA_K * 2), umma_desc(b_src + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(bar_mma);
+    }
+
+    // ---------------- phase 3: four threads per row (row = TMEM lane 32 (warp % 4) + lane, part = warp / 4) ----------------
+    // Each part redoes the cheap LN32, then takes 8 of the 32 value-head units and 16 of the 64 Q channels; the 22
+    // per-row partial sums are combined through shared memory (the A-operand tile is free once the MMAs have completed).
+    {
+        const int rloc = (warp & 3) * 32 + lane, part = warp >> 2;
+        const int m = m0 + rloc;
+        const bool live = m < p.rows;
+        mbar_wait(bar_mma, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float P[ND];
+        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+        tmem_ld16(taddr, P);
+        tmem_ld16(taddr + 16, P + 16);
+        tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        // LN32 + LReLU
+        float s = 0.0f;
+#pragma unroll
+        for (int o = 0; o < ND; ++o) { P[o] += w.p2_b[o]; s += P[o]; }
+        const float mean = s * (1.0f / ND);
+        float ss = 0.0f;
+#pragma unroll
+        for (int o = 0; o < ND; ++o) { P[o] -= mean; ss = fmaf(P[o], P[o], ss); }
+        const float rstd = rsqrtf(ss * (1.0f / ND) + kLnEps);
+#pragma unroll
+        for (int o = 0; o < ND; ++o) P[o] = lrelu(fmaf(P[o] * rstd, w.ln2_w[o], w.ln2_b[o]));
+        if (live && part == 0) {
+#pragma unroll
+            for (int o = 0; o < ND; o += 4)
+                *reinterpret_cast<float4 *>(p.P + (long long)m * ND + o) = make_float4(P[o], P[o + 1], P[o + 2], P[o + 3]);
+        }
+        float acc[22];                                        // Wg^T a' (16) | Cc^T a' (3) | |a'|^2 | LA | v   (partial sums)
+#pragma unroll
+        for (int i = 0; i < 22; ++i) acc[i] = 0.0f;
+        // state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 -- this part's 8 hidden units
+        {
+            float tp[ND];
+#pragma unroll
+            for (int o = 0; o < ND; ++o) tp[o] = tanh_fast(P[o]);     // MUFU.TANH: this is the bf16-tolerance path
+#pragma unroll 2
+            for (int jj = 0; jj < 8; ++jj) {
+                const int j = part * 8 + jj;
+                const float4 *vr = reinterpret_cast<const float4 *>(&S.v1[j * ND]);
+                float h0 = w.v1_b[j], h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+#pragma unroll
+                for (int o4 = 0; o4 < ND / 4; ++o4) {
+                    const float4 v4 = vr[o4];
+                    h0 = fmaf(v4.x, tp[4 * o4], h0); h1 = fmaf(v4.y, tp[4 * o4 + 1], h1);
+                    h2 = fmaf(v4.z, tp[4 * o4 + 2], h2); h3 = fmaf(v4.w, tp[4 * o4 + 3], h3);
+                }
+                acc[21] = fmaf(w.v2_w[j], lrelu((h0 + h1) + (h2 + h3)), acc[21]);
+            }
+        }
+        // mean over the 64 channels of A = Wq[:, :32] P + b_q, without forming A: (sum_c b_q[c] + sum_o colsum[o] P[o]) / 64
+        float sa = S.colsum[ND];                              // sum_c b_q[c]
+#pragma unroll
+        for (int o = 0; o < ND; ++o) sa = fmaf(S.colsum[o], P[o], sa);
+        const float meanA = sa * (1.0f / QC);
+        // this part's 16 channels: a_c, then everything that is linear in it
+        float *Ao = p.A + (long long)m * QC;
+        float *Aco = p.Ac ? p.Ac + (long long)m * QC : nullptr;
+        uint32_t *qw = p.qa ? reinterpret_cast<uint32_t *>(p.qa + (long long)m * ECORD_QA_STRIDE) : nullptr;
+#pragma unroll 2
+        for (int cc_ = 0; cc_ < 16; ++cc_) {
+            const int c = part * 16 + cc_;
+            const float4 *qr = reinterpret_cast<const float4 *>(&S.q1[c * ND]);
+            float a0 = w.q1_b[c], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+            for (int o4 = 0; o4 < ND / 4; ++o4) {
+                const float4 q4 = qr[o4];
+                a0 = fmaf(q4.x, P[4 * o4], a0); a1 = fmaf(q4.y, P[4 * o4 + 1], a1);
+                a2 = fmaf(q4.z, P[4 * o4 + 2], a2); a3 = fmaf(q4.w, P[4 * o4 + 3], a3);
+            }
+            const float a = (a0 + a1) + (a2 + a3);
+            const float ac = a - meanA;
+            acc[20] = fmaf(w.q2_w[c] * w.qln_w[c], ac, acc[20]);
+            if (live) {
+                if (!qw) Ao[c] = a;               // A itself is read by the exact Q kernel only
+                if (Aco) Aco[c] = ac;
+            }
+            if (qw) {
+                const float4 cc4 = *reinterpret_cast<const float4 *>(&S.cc[c * 4]);
+                const float ap = ac + cc4.w;
+                if (live) qw[c] = split_h2(w.qln_w[c] * ap);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 g4 = *reinterpret_cast<const float4 *>(&S.wg[c * 16 + 4 * k4]);
+                    acc[4 * k4] = fmaf(g4.x, ap, acc[4 * k4]); acc[4 * k4 + 1] = fmaf(g4.y, ap, acc[4 * k4 + 1]);
+                    acc[4 * k4 + 2] = fmaf(g4.z, ap, acc[4 * k4 + 2]); acc[4 * k4 + 3] = fmaf(g4.w, ap, acc[4 * k4 + 3]);
+                }
+                acc[16] = fmaf(cc4.x, ap, acc[16]); acc[17] = fmaf(cc4.y, ap, acc[17]); acc[18] = fmaf(cc4.z, ap, acc[18]);
+                acc[19] = fmaf(ap, ap, acc[19]);
+            }
+        }
+        // combine the four parts of each row: red[i][part][row] (conflict-free), summed by part 0
+        float *red = reinterpret_cast<float *>(S.act);
+        if (part) {
+#pragma unroll
+            for (int i = 0; i < 22; ++i) red[(i * 3 + part - 1) * BM + rloc] = acc[i];
+        }
+        __syncthreads();
+        if (part == 0 && live) {
+#pragma unroll
+            for (int i = 0; i < 22; ++i) acc[i] += (red[(i * 3) * BM + rloc] + red[(i * 3 + 1) * BM + rloc]) + red[(i * 3 + 2) * BM + rloc];
+            const float vv = acc[21] + w.v2_b[0];
+            p.v[m] = vv;
+            if (p.LA) p.LA[m] = acc[20];
+            if (qw) {
+                uint32_t e[19];
+#pragma unroll
+                for (int i = 0; i < 19; ++i) e[i] = split_h2(acc[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                 // Wg^T a': hi words, lo words
+                    qw[64 + j] = (e[2 * j] & 0xffffu) | (e[2 * j + 1] << 16);
+                    qw[72 + j] = (e[2 * j] >> 16) | (e[2 * j + 1] & 0xffff0000u);
+                }
+                // row 64 of W2: fp16 [ca0h ca1h ca2h ca1h 0 0 ca2h 0 | ca0l ca1l ca2l 0 0 0 0 0]
+                qw[80] = (e[16] & 0xffffu) | (e[17] << 16);
+                qw[81] = (e[18] & 0xffffu) | (e[17] << 16);
+                qw[82] = 0u;
+                qw[83] = e[18] & 0xffffu;
+                qw[84] = (e[16] >> 16) | (e[17] & 0xffff0000u);
+                qw[85] = e[18] >> 16;
+                qw[86] = 0u;
+                qw[87] = 0u;
+                float *qo = reinterpret_cast<float *>(qw);
+                qo[88] = acc[19];
+                qo[89] = acc[20];
+                qo[90] = vv;
+                qo[91] = 0.0f;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(32u) : "memory");
+    }
+}
+}  // namespace
+
+int tail_tc_init_attrs() {
+    ECORD_CUDA(cudaFuncSetAttribute(k_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailTcSmem) + 1024));
+    return 0;
+}
+
+int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st) {
+    PFN_encodeTiled enc;
+    int rc = get_encoder(&enc);
+    if (rc) return rc;
+    CUtensorMap mW2;
+    const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(w->p1_w_bf16) + (size_t)ECORD_DIM_P1 * H;
+    if ((rc = make_map(enc, &mW2, w2, ND, P1, ND))) return rc;
+    k_tail_tc<<<p->rows_pad / BM, kTtThreads, sizeof(TailTcSmem) + 1024, st>>>(mW2, *w, *p);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}

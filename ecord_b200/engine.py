@@ -119,7 +119,7 @@ class DeviceWeights:
         if pack_bf16:
             self.q_tc = torch.zeros(_lib.QTC_FLOATS, dtype=torch.float32, device=self.device)
             self.gru_w_bf16 = torch.empty(_lib.GRU_PACK_ELEMS, dtype=torch.bfloat16, device=self.device)
-            self.p1_w_bf16 = torch.empty(512 * 1024, dtype=torch.bfloat16, device=self.device)
+            self.p1_w_bf16 = torch.empty(_lib.P1_PACK_ELEMS, dtype=torch.bfloat16, device=self.device)
         self.c = _lib.Weights(gru_w_bf16=ptr(self.gru_w_bf16), p1_w_bf16=ptr(self.p1_w_bf16), q_tc=ptr(self.q_tc),
                               q_fold=ptr(self.q_fold), **kw)
         if pack_bf16:

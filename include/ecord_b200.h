@@ -116,7 +116,8 @@ typedef struct ecord_weights {
     /* derived by ecord_pack_weights() into caller-allocated buffers */
     void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [16][192][1024] (rows r|z|hn of each 64-unit block)
                             followed by Wu pack [16][256][64] (rows r|z|0|in) -- tile order of the tcgen05 GRU kernel */
-    void  *p1_w_bf16;    /* bf16 [512][1024] */
+    void  *p1_w_bf16;    /* bf16, ECORD_P1_PACK_ELEMS elements: proj_rnn_to_gnn.1 weight [512][1024] followed by
+                            proj_rnn_to_gnn.4 weight [32][512] */
     float *q_tc;         /* f32 [ECORD_QTC_FLOATS] operands of the tensor-core Q kernel (ECORD_Q_TC), or NULL:
                               [0,1280)     reserved
                               [1280,2304)  Wg [64][16] = Wq[:,32:48] centred over the 64 channels (fp32)
@@ -134,6 +135,7 @@ typedef struct ecord_weights {
 #define ECORD_QFOLD_FLOATS 588
 #define ECORD_QTC_FLOATS 4736
 #define ECORD_GRU_PACK_ELEMS (3072 * 1024 + 4096 * 64)
+#define ECORD_P1_PACK_ELEMS (512 * 1024 + 32 * 512)
 } ecord_weights;
 
 /* ---- per-rollout policy state and scratch (all caller-allocated) ---- */
