@@ -295,7 +295,9 @@ def run_b200(args):
     units = G * T_total * K
     value = units / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (q_select), timed alone with CUDA events on its stream ----
+    # ---- roofline of the dominant kernel: the tensor-core Q kernel (ecord_q_select = k_q_tc + the 5 us k_select_finish),
+    #      timed alone with CUDA events (torch's current stream is ordered around the state's own stream), L2 flushed
+    #      before every launch.  Algorithmic work per launch: 8416 FLOP and 12 B per (vertex, trajectory). ----
     roof = None
     if rank == 0:
         reps = 30
@@ -308,21 +310,31 @@ def run_b200(args):
             tot += a.elapsed_time(b)
         q_ms = tot / reps
         tp = {}
-        for nm, fn in (("policy_step", st.policy_step),):
+        for nm, fn in (("policy_step", st.policy_step), ("env_step", st.env_step)):
             a.record()
             for _ in range(reps):
                 fn()
             b.record(); b.synchronize()
             tp[nm] = a.elapsed_time(b) / reps
         hbm, tf_burst, tf_sus, which = peaks()
-        flops = 8416.0 * dg.N * T                       # literal mlp_out + encoder FLOPs per launch
-        bytes_alg = 12.0 * dg.N * T                     # (state, peek, static) fp32 per (vertex, trajectory)
+        rows = float(dg.N) * T
+        flops = 8416.0 * rows                           # literal mlp_out + encoder FLOPs per launch
+        bytes_alg = 12.0 * rows                         # (state, peek, static) fp32 per (vertex, trajectory)
         ach = flops / (q_ms * 1e-3) / 1e12
-        roof = {"kernel": "k_q_select", "bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s",
-                "frac": ach / tf_burst, "traffic": None, "peak_source": which + " (bf16 burst; kernel timed alone)",
+        traffic = None
+        try:                                            # dram bytes per launch of this kernel from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get("k_q_tc")
+        except Exception:
+            traffic = None
+        qname = {"tc": "k_q_tc (tcgen05 kind::f16) + k_select_finish", "fast": "k_q_fast + k_select_finish",
+                 "exact": "k_q_select"}[{2: "tc", 1: "fast", 0: "exact"}[st.q_mode]]
+        roof = {"kernel": qname, "bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s",
+                "frac": ach / tf_burst, "traffic": traffic, "peak_source": which + " (bf16 burst; kernel timed alone)",
+                "algorithmic": {"flops_per_row": 8416, "bytes_per_row": 12, "rows_per_launch": rows},
                 "ms_per_launch": q_ms, "launch_share_of_step": q_ms / (ms / K),
                 "hbm_view": {"achieved_gbs": bytes_alg / (q_ms * 1e-3) / 1e9, "peak_gbs": hbm, "frac": bytes_alg / (q_ms * 1e-3) / 1e9 / hbm},
-                "policy_step_ms": tp["policy_step"],
+                "policy_step_ms": tp["policy_step"], "env_step_ms": tp["env_step"],
                 "whole_step": {"flops_per_unit": F_UNIT(n), "bytes_per_unit": B_UNIT(n, avg_deg),
                                "tensor_bound_units_s": tf_sus * 1e12 / F_UNIT(n), "hbm_bound_units_s": hbm * 1e9 / B_UNIT(n, avg_deg),
                                "frac_of_binding_bound": (value / world) / min(tf_sus * 1e12 / F_UNIT(n), hbm * 1e9 / B_UNIT(n, avg_deg))}}
@@ -376,7 +388,7 @@ def run_b200(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=800)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="er500", choices=sorted(WORKLOADS))

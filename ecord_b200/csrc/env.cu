@@ -33,23 +33,31 @@ __global__ void k_env_init_peek(ecord_graph g, ecord_env e, const int8_t *__rest
     e.best_state[o] = (uint8_t)s0[idx];  // tradjectories.py:116
 }
 
-__global__ void k_env_init_score(ecord_graph g, ecord_env e, const int8_t *__restrict__ s0) {
+// One warp per (g,t): lanes stride over the graph's vertices, each sums its vertices' edge terms, then a warp sum.
+// (fp32 sums of +-1 / small-integer weights are exact in any order; the reference's own summation order for
+// non-integer weights is a torch segment reduction that nothing pins.)
+__global__ void __launch_bounds__(256)
+k_env_init_score(ecord_graph g, ecord_env e, const int8_t *__restrict__ s0) {
     const int T = e.num_tradj;
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (m >= g.num_graphs * T) return;
     const int gi = m / T, t = m % T;
     float acc = 0.0f;
-    for (int v = g.graph_ptr[gi]; v < g.graph_ptr[gi + 1]; ++v) {
+    for (int v = g.graph_ptr[gi] + lane; v < g.graph_ptr[gi + 1]; v += 32) {
         const int sv = s0[(long long)v * T + t];
         for (int k = g.row_ptr[v]; k < g.row_ptr[v + 1]; ++k) {
             const int su = s0[(long long)g.col[k] * T + t];
             acc += g.w[k] * (float)((sv + su) & 1);
         }
     }
-    const float sc = 0.5f * acc;
-    e.score[m] = sc;
-    e.best_score[m] = sc;   // tradjectories.py:81
-    e.best_step[m] = 0;
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float sc = 0.5f * acc;
+        e.score[m] = sc;
+        e.best_score[m] = sc;   // tradjectories.py:81
+        e.best_step[m] = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -264,7 +272,7 @@ extern "C" int ecord_env_init(const ecord_graph *g, const ecord_env *env, const 
     const int GT = g->num_graphs * env->num_tradj;
     k_env_init_peek<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state);
     ECORD_LAUNCH_CHECK();
-    k_env_init_score<<<ceil_div(GT, 64), 64, 0, as_stream(stream)>>>(*g, *env, init_state);
+    k_env_init_score<<<ceil_div((long long)GT * 32, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
