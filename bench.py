@@ -310,7 +310,7 @@ def run_b200(args):
             tot += a.elapsed_time(b)
         q_ms = tot / reps
         tp = {}
-        for nm, fn in (("policy_step", st.policy_step), ("env_step", st.env_step)):
+        for nm, fn in (("policy_step", st.policy_step),):
             a.record()
             for _ in range(reps):
                 fn()
@@ -334,7 +334,7 @@ def run_b200(args):
                 "algorithmic": {"flops_per_row": 8416, "bytes_per_row": 12, "rows_per_launch": rows},
                 "ms_per_launch": q_ms, "launch_share_of_step": q_ms / (ms / K),
                 "hbm_view": {"achieved_gbs": bytes_alg / (q_ms * 1e-3) / 1e9, "peak_gbs": hbm, "frac": bytes_alg / (q_ms * 1e-3) / 1e9 / hbm},
-                "policy_step_ms": tp["policy_step"], "env_step_ms": tp["env_step"],
+                "policy_step_ms": tp["policy_step"],
                 "whole_step": {"flops_per_unit": F_UNIT(n), "bytes_per_unit": B_UNIT(n, avg_deg),
                                "tensor_bound_units_s": tf_sus * 1e12 / F_UNIT(n), "hbm_bound_units_s": hbm * 1e9 / B_UNIT(n, avg_deg),
                                "frac_of_binding_bound": (value / world) / min(tf_sus * 1e12 / F_UNIT(n), hbm * 1e9 / B_UNIT(n, avg_deg))}}
@@ -346,16 +346,20 @@ def run_b200(args):
     Ke = K
     solver.rollout(batch, num_tradj=T, num_steps=min(Ke, 2 * k), tau=0, use_epsilon=False, init_state=init)   # warm
     pinned = torch.from_numpy(init).pin_memory()
-    barrier()
-    t0 = time.perf_counter()
-    log = solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=pinned.numpy())
-    sc = torch.stack(log['scores'], -1).max(-1).values.to(dev)
-    best_e, _ = reduce_best(sc, T_total)
-    best_host = best_e.cpu()
-    barrier()
-    te = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_times = []
+    for _ in range(3):                  # median of three: a rollout allocates its state, and the caching allocator's
+        barrier()                       # occasional cudaMalloc / graph teardown shows up as a multi-ms outlier
+        t0 = time.perf_counter()
+        log = solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=pinned.numpy())
+        sc = torch.stack(log['scores'], -1).max(-1).values.to(dev)
+        best_e, _ = reduce_best(sc, T_total)
+        best_host = best_e.cpu()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_times.append(float(te.item()))
+    te = torch.tensor([sorted(e2e_times)[1]], device=dev)
     e2e_val = G * T_total * Ke / float(te.item())
     h2d = (init.nbytes) / Ke
     d2h = (G * T * 4 * Ke + dg.N * T * 4 + G * T * 8 + best_host.numel() * 4) / Ke
@@ -377,7 +381,8 @@ def run_b200(args):
                           "l2": "flushed (256 MB write) before every CUDA-graph launch of %d steps, outside the timed events" % k,
                           "weights": "random-init canonical ECORD network (seed 0)"},
                "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "note": "B200Solver.rollout incl. graph upload, GNN, env init, H2D init states, D2H score log"},
+                       "note": "B200Solver.rollout incl. GNN, env init, H2D init states, D2H score log; median of 3 calls",
+                       "calls_s": e2e_times},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
                "wall_s_timed_region": t_wall, "best_cut_mean": float(best.mean().item())}
         print(json.dumps(out), flush=True)

@@ -7,8 +7,8 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B) -> 4-stage smem ring, mbarrier complete_tx
 //   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //               (bf16 x bf16 -> fp32 accumulate in TMEM), tcgen05.commit releases smem stages / signals the epilogue
-//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 16 columns at a time) -> registers -> fused math -> global;
-//               warp w reads TMEM lanes 32*(w%4).., the two warps of a lane quarter split the tile's columns
+//   warps 2..17 epilogue: tcgen05.ld (32 lanes x 16 columns at a time) -> registers -> fused math -> global;
+//               warp w reads TMEM lanes 32*(w%4).., the four warps of a lane quarter split the tile's columns
 //
 // GRU tile = 128 rows x 64 hidden units.  The weight rows of one 64-unit block are packed (ecord_pack_weights)
 // as [r | z | hn | in] so ONE accumulator [128 x 256] holds all four gate pre-activations of the block:
@@ -20,6 +20,7 @@
 
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 // MODE 0 = GRU : tile = 128 rows x 64 hidden units; k-chunk 0 (N=256) from (u, Wu), then 16 chunks (N=192) from
@@ -51,6 +52,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kStages + 4];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[2][4][64];       // GRU gate biases of the tile in flight (r, z combined; hn; in)
 
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024-byte alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,7 +129,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
     } else {
         // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                 // which half of the tile's output columns
+        const int part = (warp - 2) >> 2;                 // which quarter of the tile's output columns
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
             const int m0 = (tile / nblk) * BM, nb = tile % nblk;
@@ -135,21 +137,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
             const int row = m0 + q * 32 + lane;
             const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + ab * C::ACC_COLS;
             if (MODE == 0) {
-                const int j00 = nb * 64 + half * 32;          // first hidden unit of this thread
+                const int j00 = nb * 64 + part * 16;          // first hidden unit of this thread
                 const float *hold = prm.hidden + ((size_t)cur * prm.rows_pad + row) * H + j00;
                 float *hnew = const_cast<float *>(prm.hidden) + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
                 __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
                 __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + j00;
-                float hv[32];                                 // old state, fetched while the MMAs run
+                float hv[16];                                 // old state, fetched while the MMAs run
                 if (row < prm.rows) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + i);
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + i);
+                }
+                {   // this tile's 4 x 64 gate biases -> shared memory (read back as warp-uniform broadcasts)
+                    const int e = threadIdx.x - 64, gsel = e >> 6, j = nb * 64 + (e & 63);
+                    if (e < 256)
+                        bias_s[ab][gsel][e & 63] = gsel == 0 ? prm.bih[j] + prm.bhh[j]
+                                                 : gsel == 1 ? prm.bih[H + j] + prm.bhh[H + j]
+                                                 : gsel == 2 ? prm.bhh[2 * H + j] : prm.bih[2 * H + j];
+                    asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");
                 }
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int jj = 0; jj < 32; jj += 16) {
-                    const int j0 = half * 32 + jj;
+                for (int jj = 0; jj < 16; jj += 16) {
+                    const int j0 = part * 16 + jj;
                     float ar[16], az[16], ahn[16], ain[16];
                     tmem_ld16(tbase + j0, ar);
                     tmem_ld16(tbase + 64 + j0, az);
@@ -160,10 +170,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
                         __align__(16) __nv_bfloat16 ob[16], ot[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const int j = j00 + jj + i;
-                            const float r = sigmoid_fast((ar[i] + prm.bhh[j]) + prm.bih[j]);
-                            const float z = sigmoid_fast((az[i] + prm.bhh[H + j]) + prm.bih[H + j]);
-                            const float n = tanh_fast(fmaf(ahn[i] + prm.bhh[2 * H + j], r, ain[i] + prm.bih[2 * H + j]));
+                            const int jl = part * 16 + jj + i;      // unit within the tile's 64
+                            const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
+                            const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
+                            const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
                             const float hn = fmaf(hv[jj + i] - n, z, n);
                             hv[jj + i] = hn;
                             ob[i] = __float2bfloat16(hn);
@@ -178,14 +188,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
                     }
                 }
             } else {
-                const int c00 = nb * C::TILE_N + half * (C::TILE_N / 2);
+                const int c00 = nb * C::TILE_N + part * (C::TILE_N / 4);
                 float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + c00;
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int jj = 0; jj < C::TILE_N / 2; jj += 16) {
+                for (int jj = 0; jj < C::TILE_N / 4; jj += 16) {
                     float acc[16];
-                    tmem_ld16(tbase + half * (C::TILE_N / 2) + jj, acc);
+                    tmem_ld16(tbase + part * (C::TILE_N / 4) + jj, acc);
                     tmem_ld_wait();
                     if (row < prm.rows) {
 #pragma unroll
@@ -212,11 +222,252 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
     }
 }
 
+// =================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster (= the two SMs of a TPC) work on a 256-row tile.
+// Each CTA owns 128 rows (its own A tile, accumulator and epilogue -- exactly as above) but holds only HALF of the
+// weight tile: the leader's single tcgen05.mma.cta_group::2 (M = 256) reads A from both CTAs and the two B halves
+// from the two shared memories.  Per k-chunk an SM therefore ingests 16 KB + 12 KB instead of 16 KB + 24 KB: the
+// single-CTA kernel is bound by the L2 -> SM path (435 MB per GRU launch), not by the tensor pipe.
+//   - TMA: every CTA loads its own A rows and its half of B; all four loads complete_tx on the LEADER's full barrier
+//   - MMA: issued by the leader only; tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers
+//   - tmem_empty lives in the leader and collects the 8 epilogue warps of both CTAs (remote mbarrier arrive)
+// =================================================================================================
+constexpr int kStages2 = 4;      // the pair kernel's stages are 28-32 KB (half of B per CTA): six fit in 192 KB
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
+           const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+           const __grid_constant__ CUtensorMap mapB, TcParams prm, int num_tiles, int nblk) {
+    // num_tiles = number of 256-row x TILE_N pair tiles; cluster c works on tiles c, c + #clusters, ...
+    using C = TcCfg<MODE>;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS / 2 * BK * 2;      // per CTA: own A rows, half of B
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
+    constexpr int TMEM_COLS = 2 * C::ACC_COLS;
+
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kStages2 + 4];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[2][4][64];       // GRU gate biases of the tile in flight (r, z combined; hn; in)
+
+    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
+
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages2]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * kStages2]), tempty0 = smem_u32(&bars[2 * kStages2 + 2]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * (kThreads / 32 - 2)); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                     "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                    // both CTAs' barriers are initialised before anything remote touches them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            const CUtensorMap *mapA = (MODE == 0) ? (cur ? &mapA1 : &mapA0) : &mapA0;
+            tmap_prefetch(mapA); tmap_prefetch(&mapB);
+            if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
+            const uint32_t lfull0 = mapa_u32(full0, 0);            // the leader's full barriers
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int m0 = (tile / nblk) * (2 * BM) + (int)rank * BM, nb = tile % nblk;
+                for (int c = 0; c < NCHUNK; ++c, ++it) {
+                    const uint32_t s = it % kStages2, ph = (it / kStages2) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);            // local: released by the leader's multicast commit
+                    const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                    const bool first = MODE == 0 && c == 0;
+                    const int n_rows = first ? C::N_FIRST : C::N_MAIN;
+                    if (prm.debug & 4) {            // no TMA traffic: the leader completes the phase by itself
+                        if (rank == 0) mbar_arrive_cta(full0 + 8 * s);
+                        continue;
+                    }
+                    if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + n_rows / 2 * BK * 2));
+                    if (first) {
+                        tma_load_2d_pair(a_dst, &mapU, lfull0 + 8 * s, 0, m0);
+                        tma_load_2d_pair(b_dst, &mapWu, lfull0 + 8 * s, 0, nb * n_rows + (int)rank * (n_rows / 2));
+                    } else {
+                        const int kc = (MODE == 0 ? c - 1 : c) * BK;
+                        tma_load_2d_pair(a_dst, mapA, lfull0 + 8 * s, kc, m0);
+                        tma_load_2d_pair(b_dst, &mapB, lfull0 + 8 * s, kc, nb * n_rows + (int)rank * (n_rows / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            uint32_t it = 0, lt = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+                const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+                mbar_wait(tempty0 + 8 * ab, aph ^ 1u);            // both CTAs' epilogues have drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_d + ab * C::ACC_COLS;
+                for (int c = 0; c < NCHUNK; ++c, ++it) {
+                    const uint32_t s = it % kStages2, ph = (it / kStages2) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
+                    const uint32_t idesc = (MODE == 0 && c == 0) ? umma_idesc(2 * BM, 256) : umma_idesc(2 * BM, C::N_MAIN);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
+                        if (!(prm.debug & 1)) umma_bf16_pair(acc, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_pair(empty0 + 8 * s);         // frees the stage in both CTAs
+                }
+                umma_commit_pair(tfull0 + 8 * ab);            // accumulator complete, both CTAs
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..9, both CTAs; identical to the single-CTA kernel) =====================
+        const int q = warp & 3;
+        const int part = (warp - 2) >> 2;
+        const uint32_t ltempty0 = mapa_u32(tempty0, 0);            // the leader's tmem_empty barriers
+        uint32_t lt = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+            const int m0 = (tile / nblk) * (2 * BM) + (int)rank * BM, nb = tile % nblk;
+            const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
+            const int row = m0 + q * 32 + lane;
+            const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + ab * C::ACC_COLS;
+            if (MODE == 0) {
+                const int j00 = nb * 64 + part * 16;
+                const float *hold = prm.hidden + ((size_t)cur * prm.rows_pad + row) * H + j00;
+                float *hnew = const_cast<float *>(prm.hidden) + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
+                __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
+                __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + j00;
+                float hv[16];                                 // old state, fetched while the MMAs run
+                if (row < prm.rows) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + i);
+                }
+                {   // this tile's 4 x 64 gate biases -> shared memory (read back as warp-uniform broadcasts)
+                    const int e = threadIdx.x - 64, gsel = e >> 6, j = nb * 64 + (e & 63);
+                    if (e < 256)
+                        bias_s[ab][gsel][e & 63] = gsel == 0 ? prm.bih[j] + prm.bhh[j]
+                                                 : gsel == 1 ? prm.bih[H + j] + prm.bhh[H + j]
+                                                 : gsel == 2 ? prm.bhh[2 * H + j] : prm.bih[2 * H + j];
+                    asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");
+                }
+                mbar_wait(tfull0 + 8 * ab, aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < ((prm.debug & 2) ? 0 : 16); jj += 16) {
+                    const int j0 = part * 16 + jj;
+                    float ar[16], az[16], ahn[16], ain[16];
+                    tmem_ld16(tbase + j0, ar);
+                    tmem_ld16(tbase + 64 + j0, az);
+                    tmem_ld16(tbase + 128 + j0, ahn);
+                    tmem_ld16(tbase + 192 + j0, ain);
+                    tmem_ld_wait();
+                    if (row < prm.rows) {
+                        __align__(16) __nv_bfloat16 ob[16], ot[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int jl = part * 16 + jj + i;      // unit within the tile's 64
+                            const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
+                            const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
+                            const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
+                            const float hn = fmaf(hv[jj + i] - n, z, n);
+                            hv[jj + i] = hn;
+                            ob[i] = __float2bfloat16(hn);
+                            ot[i] = __float2bfloat16(tanh_fast(hn));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(hnew + jj + i) = *reinterpret_cast<float4 *>(&hv[jj + i]);
+                        *reinterpret_cast<uint4 *>(hb + jj) = *reinterpret_cast<uint4 *>(&ob[0]);
+                        *reinterpret_cast<uint4 *>(hb + jj + 8) = *reinterpret_cast<uint4 *>(&ob[8]);
+                        *reinterpret_cast<uint4 *>(tb + jj) = *reinterpret_cast<uint4 *>(&ot[0]);
+                        *reinterpret_cast<uint4 *>(tb + jj + 8) = *reinterpret_cast<uint4 *>(&ot[8]);
+                    }
+                }
+            } else {
+                const int c00 = nb * C::TILE_N + part * (C::TILE_N / 4);
+                float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + c00;
+                mbar_wait(tfull0 + 8 * ab, aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < C::TILE_N / 4; jj += 16) {
+                    float acc[16];
+                    tmem_ld16(tbase + part * (C::TILE_N / 4) + jj, acc);
+                    tmem_ld_wait();
+                    if (row < prm.rows) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const int j = c00 + jj + i;
+                            float4 o = make_float4(acc[i] + prm.p1_b[j], acc[i + 1] + prm.p1_b[j + 1], acc[i + 2] + prm.p1_b[j + 2],
+                                                   acc[i + 3] + prm.p1_b[j + 3]);
+                            *reinterpret_cast<float4 *>(yrow + jj + i) = o;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(ltempty0 + 8 * ab);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                    // nothing remote may still target this CTA's barriers / shared memory
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_ROWS * BK * 2) + 1024; }
+template <int MODE>
+constexpr int tc2_smem_bytes() { return kStages2 * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024; }
+// ECORD_GEMM_PAIR=0 selects the single-CTA kernels (A/B comparisons); rows_pad must be a multiple of 256 for the pair kernels
+static bool use_pair(int rows_pad) {
+    static const int env = [] { const char *e = getenv("ECORD_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    return env != 0 && (rows_pad % (2 * BM)) == 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // weight packing (device): fp32 PyTorch layout -> bf16 tile-permuted, plus the folded encoder constants
@@ -374,6 +625,8 @@ extern "C" int ecord_fold_q_host(const float *q1_w, const float *enc_w, const fl
 int tc_init_attrs() {
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<0>()));
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
+    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0>()));
+    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1>()));
     return 0;
 }
 
@@ -387,15 +640,24 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     const __nv_bfloat16 *hb = reinterpret_cast<const __nv_bfloat16 *>(p->hidden_bf16);
     CUtensorMap mU, mWu, mA0, mA1, mB;
     if ((rc = make_map(enc, &mU, p->u_bf16, Mp, 64, BM))) return rc;
-    if ((rc = make_map(enc, &mWu, wu, 4096, 64, 256))) return rc;
+    const bool pair = use_pair(Mp);
+    if ((rc = make_map(enc, &mWu, wu, 4096, 64, pair ? 128 : 256))) return rc;
     if ((rc = make_map(enc, &mA0, hb, Mp, H, BM))) return rc;
     if ((rc = make_map(enc, &mA1, hb + (size_t)Mp * H, Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mB, wh, 3072, H, 192))) return rc;
+    if ((rc = make_map(enc, &mB, wh, 3072, H, pair ? 96 : 192))) return rc;
     TcParams prm{};
     prm.hidden = p->hidden; prm.hidden_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->hidden_bf16);
     prm.th_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->th_bf16);
     prm.bih = w->gru_bih; prm.bhh = w->gru_bhh;
     prm.rows = p->rows; prm.rows_pad = Mp; prm.step_base = step_base; prm.step_off = step_off;
+    { static const int dbg = [] { const char *e = getenv("ECORD_TC_DEBUG"); return e ? atoi(e) : 0; }(); prm.debug = dbg; }
+    if (pair) {
+        const int nblk2 = H / 64, tiles2 = nblk2 * (Mp / (2 * BM));
+        const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
+        k_gemm_tc2<0><<<2 * clusters, kThreads, tc2_smem_bytes<0>(), st>>>(mU, mWu, mA0, mA1, mB, prm, tiles2, nblk2);
+        ECORD_LAUNCH_CHECK();
+        return 0;
+    }
     const int nblk = H / 64, num_tiles = nblk * (Mp / BM);
     k_gemm_tc<0><<<num_tiles < kNumSMs ? num_tiles : kNumSMs, kThreads, tc_smem_bytes<0>(), st>>>(mU, mWu, mA0, mA1, mB, prm,
                                                                                               num_tiles, nblk);
@@ -410,9 +672,17 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t 
     const int Mp = p->rows_pad;
     CUtensorMap mA, mB;
     if ((rc = make_map(enc, &mA, p->th_bf16, Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, 128))) return rc;
+    const bool pair = use_pair(Mp);
+    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, pair ? 64 : 128))) return rc;
     TcParams prm{};
     prm.p1_b = w->p1_b; prm.y1 = p->y1; prm.rows = p->rows; prm.rows_pad = Mp;
+    if (pair) {
+        const int nblk2 = ECORD_DIM_P1 / 128, tiles2 = nblk2 * (Mp / (2 * BM));
+        const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
+        k_gemm_tc2<1><<<2 * clusters, kThreads, tc2_smem_bytes<1>(), st>>>(mA, mB, mA, mA, mB, prm, tiles2, nblk2);
+        ECORD_LAUNCH_CHECK();
+        return 0;
+    }
     const int nblk = ECORD_DIM_P1 / 128, num_tiles = nblk * (Mp / BM);
     k_gemm_tc<1><<<num_tiles < kNumSMs ? num_tiles : kNumSMs, kThreads, tc_smem_bytes<1>(), st>>>(mA, mB, mA, mA, mB, prm,
                                                                                               num_tiles, nblk);

@@ -12,7 +12,7 @@ constexpr int BM = 128;          // rows per tile (UMMA_M)
 constexpr int BK = 64;           // bf16 elements per k-chunk = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
-constexpr int kThreads = 320;    // 10 warps: TMA, MMA, 8 epilogue (two per TMEM lane quarter)
+constexpr int kThreads = 576;    // 18 warps: TMA, MMA, 16 epilogue (four per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -93,6 +93,7 @@ struct TcParams {
     int rows, rows_pad;
     const int32_t *step_base;     // device step counter (or NULL)
     int step_off;
+    int debug;                    // diagnostics (ECORD_TC_DEBUG): 1 = no MMA issue, 2 = no epilogue math, 4 = no TMA
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

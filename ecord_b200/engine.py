@@ -155,7 +155,7 @@ class RolloutState:
         self.fused = self.q_mode != Q_EXACT
         N, G = dgraph.N, dgraph.G
         M = G * T
-        Mp = (M + 127) // 128 * 128
+        Mp = (M + 255) // 256 * 256          # 256: the tcgen05 GEMMs run on CTA pairs (cta_group::2, 256-row tiles)
         self.M, self.Mp = M, Mp
         f32 = dict(dtype=torch.float32, device=dev)
         # environment (trajectory-major planes)

@@ -141,7 +141,8 @@ typedef struct ecord_weights {
 /* ---- per-rollout policy state and scratch (all caller-allocated) ---- */
 typedef struct ecord_policy {
     int32_t  rows;        /* M = G*T */
-    int32_t  rows_pad;    /* M rounded up to 128; every [M][*] buffer below has rows_pad rows */
+    int32_t  rows_pad;    /* M rounded up to a multiple of 128 (256 selects the CTA-pair tcgen05 GEMM kernels);
+                             every [M][*] buffer below has rows_pad rows */
     float   *hidden;      /* [2][rows_pad][1024] double-buffered GRU state (fp32) */
     void    *hidden_bf16; /* [2][rows_pad][1024] bf16 mirror (tcgen05 A operand) */
     void    *th_bf16;     /* [rows_pad][1024] bf16 tanh(h) (projection A operand) */
