@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/ecord_b200.h"
 
 #define ECORD_RET_IF(cond, code) do { if (cond) return (code); } while (0)
@@ -12,6 +13,26 @@
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL): the kernels of one rollout step form a strictly serial chain, and each
+// has a few microseconds of work that does not depend on its predecessor (barrier / TMEM set-up, staging constant
+// weights into shared memory).  Launched with the attribute below, a kernel may become resident while its predecessor
+// drains; pdl_wait() blocks until the predecessor has completed and its memory is visible, so every read or write of
+// step data must come after it.  Outside a PDL launch both device calls are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const int enabled = [] { const char *e = getenv("ECORD_PDL"); return e ? atoi(e) : 1; }();   // ECORD_PDL=0: plain launches (A/B)
+    cfg.attrs = attr; cfg.numAttrs = enabled ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define ECORD_PDL_LAUNCH(...) do { cudaError_t _e = launch_pdl(__VA_ARGS__); if (_e != cudaSuccess) return (int)_e; } while (0)
 
 constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
 constexpr float kLeaky = 0.01f;       // nn.LeakyReLU default slope

@@ -110,6 +110,8 @@ k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, co
     __shared__ float wb[64];
     msg_in_load(w.msg_w, w.msg_b, wt, wb);
     __syncthreads();
+    pdl_wait();                         // the chosen actions come from the selection kernel (no early trigger: the next
+                                        // kernel is the 148-CTA GRU, whose early residency only gets in the way)
     const int T = e.num_tradj;
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -289,7 +291,7 @@ int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *a
 int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                           const int32_t *step_base, int step_off, float *score_log, int32_t *action_log, cudaStream_t st) {
     const int GT = g->num_graphs * env->num_tradj;
-    k_env_step_fused<<<ceil_div((long long)GT * 32, 256), 256, 0, st>>>(*g, *env, *w, *p, step_base, step_off, score_log,
+    ECORD_PDL_LAUNCH(k_env_step_fused, dim3(ceil_div((long long)GT * 32, 256)), dim3(256), (size_t)0, st, *g, *env, *w, *p, step_base, step_off, score_log,
                                                                         action_log, GT);
     ECORD_LAUNCH_CHECK();
     return 0;

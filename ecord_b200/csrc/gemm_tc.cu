@@ -56,7 +56,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
 
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024-byte alignment
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
 
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]);
     const uint32_t tfull0 = smem_u32(&bars[2 * kStages]), tempty0 = smem_u32(&bars[2 * kStages + 2]);
@@ -74,6 +73,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
+    pdl_launch_dependents();
+    pdl_wait();                             // everything below reads / writes step data
+    const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -282,7 +284,6 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-    const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
 
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages2]);
     const uint32_t tfull0 = smem_u32(&bars[2 * kStages2]), tempty0 = smem_u32(&bars[2 * kStages2 + 2]);
@@ -301,6 +302,10 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     cluster_sync_all();                    // both CTAs' barriers are initialised before anything remote touches them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_smem;
+    if (prm.debug & 8) num_tiles = 0;       // diagnostics: prologue + teardown only
+    pdl_launch_dependents();
+    pdl_wait();                             // everything below reads / writes step data
+    const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
@@ -654,14 +659,13 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     if (pair) {
         const int nblk2 = H / 64, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        k_gemm_tc2<0><<<2 * clusters, kThreads, tc2_smem_bytes<0>(), st>>>(mU, mWu, mA0, mA1, mB, prm, tiles2, nblk2);
-        ECORD_LAUNCH_CHECK();
+        ECORD_PDL_LAUNCH(k_gemm_tc2<0>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0>(), st, mU, mWu, mA0, mA1, mB, prm,
+                         tiles2, nblk2);
         return 0;
     }
     const int nblk = H / 64, num_tiles = nblk * (Mp / BM);
-    k_gemm_tc<0><<<num_tiles < kNumSMs ? num_tiles : kNumSMs, kThreads, tc_smem_bytes<0>(), st>>>(mU, mWu, mA0, mA1, mB, prm,
-                                                                                              num_tiles, nblk);
-    ECORD_LAUNCH_CHECK();
+    ECORD_PDL_LAUNCH(k_gemm_tc<0>, dim3(num_tiles < kNumSMs ? num_tiles : kNumSMs), dim3(kThreads), (size_t)tc_smem_bytes<0>(), st,
+                     mU, mWu, mA0, mA1, mB, prm, num_tiles, nblk);
     return 0;
 }
 
@@ -679,13 +683,12 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t 
     if (pair) {
         const int nblk2 = ECORD_DIM_P1 / 128, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        k_gemm_tc2<1><<<2 * clusters, kThreads, tc2_smem_bytes<1>(), st>>>(mA, mB, mA, mA, mB, prm, tiles2, nblk2);
-        ECORD_LAUNCH_CHECK();
+        ECORD_PDL_LAUNCH(k_gemm_tc2<1>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<1>(), st, mA, mB, mA, mA, mB, prm,
+                         tiles2, nblk2);
         return 0;
     }
     const int nblk = ECORD_DIM_P1 / 128, num_tiles = nblk * (Mp / BM);
-    k_gemm_tc<1><<<num_tiles < kNumSMs ? num_tiles : kNumSMs, kThreads, tc_smem_bytes<1>(), st>>>(mA, mB, mA, mA, mB, prm,
-                                                                                              num_tiles, nblk);
-    ECORD_LAUNCH_CHECK();
+    ECORD_PDL_LAUNCH(k_gemm_tc<1>, dim3(num_tiles < kNumSMs ? num_tiles : kNumSMs), dim3(kThreads), (size_t)tc_smem_bytes<1>(), st,
+                     mA, mB, mA, mA, mB, prm, num_tiles, nblk);
     return 0;
 }

@@ -312,6 +312,8 @@ k_select_finish(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, con
                 int compat, const int32_t *__restrict__ forced) {
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (m >= p.rows) return;
     const int T = e.num_tradj;
     const int gi = m / T, t = m - gi * T;
@@ -362,9 +364,8 @@ int qtc_init_attrs();
 
 static int launch_select_finish(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                                 const int32_t *step_base, int step_off, int compat, const int32_t *forced, cudaStream_t st) {
-    k_select_finish<<<ceil_div((long long)p->rows * 32, 256), 256, 0, st>>>(*g, *env, *w, *p, step_base, step_off, compat,
-                                                                             forced);
-    ECORD_LAUNCH_CHECK();
+    ECORD_PDL_LAUNCH(k_select_finish, dim3(ceil_div((long long)p->rows * 32, 256)), dim3(256), (size_t)0, st, *g, *env, *w, *p,
+                     step_base, step_off, compat, forced);
     return 0;
 }
 

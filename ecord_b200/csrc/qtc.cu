@@ -140,8 +140,8 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
     const int gi = g.qtile_graph[tile], v0 = g.qtile_v0[tile];
     const int T = e.num_tradj;
     const int t_lo = blockIdx.y * t_chunk, nt = min(T, t_lo + t_chunk) - t_lo;
-    const int steps_done = (step_base ? *step_base : 0) + step_off;
     const int lo = g.graph_ptr[gi], n = g.graph_ptr[gi + 1] - lo;
+    pdl_launch_dependents();
     const uint32_t full0 = smem_u32(&S.full), ready0 = smem_u32(&S.ready), setup_bar = smem_u32(&S.setup);
     constexpr uint32_t idesc = umma_idesc_f16(QT, QN);
 
@@ -152,10 +152,12 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             mbar_init(ready0, 4);
             mbar_init(setup_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            // B-operand images (both buffers) and this CTA's qa rows: bulk copies through the async proxy
+            // B-operand image (constant) and this CTA's qa rows (written by the policy tail: after the PDL wait):
+            // bulk copies through the async proxy
             const uint32_t qa_bytes = (uint32_t)nt * QA * 4u;
             mbar_expect_tx(setup_bar, (uint32_t)kImgBytes + qa_bytes);
             bulk_g2s(smem_u32(S.W), q_tc + 2816, kImgBytes, setup_bar);
+            pdl_wait();
             bulk_g2s(smem_u32(S.qa), p.qa + (long long)(gi * T + t_lo) * QA, qa_bytes, setup_bar);
         }
         __syncwarp();
@@ -202,6 +204,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
         // it sits before the first cp.async; inside the trajectory loop the row warps touch no shared-memory operand
         // (their per-trajectory operand R2 goes through tensor memory) and never fence.
         fence_async_smem();
+        pdl_wait();                     // the state planes and step counter belong to the step: predecessor kernels first
 #pragma unroll
         for (int j = 0; j < kRing; ++j) {
             if (j < nt) {
@@ -212,6 +215,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             cp_async_commit();
         }
     }
+    const int steps_done = (step_base ? *step_base : 0) + step_off;      // (row threads: after their pdl_wait)
     const float bo = q2_b[0];
     const float inv_n = 1.0f / (float)n;
     constexpr float inv_clip = 1.0f / (float)ECORD_STATIC_CLIP;
@@ -389,8 +393,11 @@ int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights 
     const int T = env->num_tradj;
     const int t_chunk = qtc_t_chunk(g->num_qtiles, T);
     const dim3 grid(g->num_qtiles, ceil_div(T, t_chunk));
-    if (p->q) k_q_tc<true><<<grid, kQtcThreads, kQtcSmemBytes, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
-    else k_q_tc<false><<<grid, kQtcThreads, kQtcSmemBytes, st>>>(*g, *env, *p, w->q_tc, K, w->q2_b, step_base, step_off, t_chunk);
-    ECORD_LAUNCH_CHECK();
+    if (p->q)
+        ECORD_PDL_LAUNCH(k_q_tc<true>, grid, dim3(kQtcThreads), (size_t)kQtcSmemBytes, st, *g, *env, *p, (const float *)w->q_tc, K,
+                         w->q2_b, step_base, step_off, t_chunk);
+    else
+        ECORD_PDL_LAUNCH(k_q_tc<false>, grid, dim3(kQtcThreads), (size_t)kQtcSmemBytes, st, *g, *env, *p, (const float *)w->q_tc, K,
+                         w->q2_b, step_base, step_off, t_chunk);
     return 0;
 }

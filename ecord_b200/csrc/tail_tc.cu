@@ -79,6 +79,8 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         S.colsum[tid] = s;
     }
     __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();                             // y1 comes from the projection kernel
 
     // ---------------- phase 1: LN512 + LReLU -> bf16 A operand ----------------
     // (the next row's 2 KB are requested before the current row is reduced: a warp's 8 rows would otherwise pay
@@ -301,7 +303,6 @@ int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t s
     CUtensorMap mW2;
     const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(w->p1_w_bf16) + (size_t)ECORD_DIM_P1 * H;
     if ((rc = make_map(enc, &mW2, w2, ND, P1, ND))) return rc;
-    k_tail_tc<<<p->rows_pad / BM, kTtThreads, sizeof(TailTcSmem) + 1024, st>>>(mW2, *w, *p);
-    ECORD_LAUNCH_CHECK();
+    ECORD_PDL_LAUNCH(k_tail_tc, dim3(p->rows_pad / BM), dim3(kTtThreads), sizeof(TailTcSmem) + 1024, st, mW2, *w, *p);
     return 0;
 }

@@ -3,6 +3,8 @@
 Tolerances (BASELINE.json north_star): fp32 mode 1e-4 relative; bf16 (tcgen05) mode 2e-2 relative, where
 "relative" = max|a-b| / max|b| over the tensor.  Per-step checks are teacher-forced with the reference's
 actions so that an argmax flip cannot mask a numerical comparison."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,6 +16,8 @@ from util import load_gold, rel_err, unpack_graphs
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-4, "bf16": 2e-2}
+TESTS_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT_DIR = os.path.dirname(TESTS_DIR)
 
 
 def _setup(gemm, compat=True, dump_q=True, q_mode=None):
@@ -269,3 +273,38 @@ def test_tau_sampling_is_distributionally_right():
     st2 = RolloutState(dg, DeviceWeights(sd), T, gemm="fp32", tau=tau, seed=123, dump_q=True)
     st2.gnn_embed(); st2.env_init(np.zeros((dg.N, T), np.int8)); st2.policy_step(); st2.q_select()
     assert torch.equal(st.actions, st2.actions)     # same seed -> same draw (counter-based Philox)
+
+
+def test_gemm_variants_agree_in_subprocesses():
+    """The CTA-pair (cta_group::2) tcgen05 kernels, the single-CTA ones (ECORD_GEMM_PAIR=0) and plain launches
+    (ECORD_PDL=0, no programmatic dependent launch) compute the same rollout: the switches are read once per process,
+    so each variant runs in its own interpreter and prints a digest of hidden state, scores and actions."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, hashlib
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np, torch
+from ecord_b200.data import GraphBatcher
+from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+from ecord_b200.graphs import synthetic_set
+from ecord_b200.network import random_state_dicts
+graphs = synthetic_set("er", 150, 3, p=0.1)
+w = DeviceWeights(random_state_dicts(5, perturb_norms=True))
+dg = DeviceGraph(GraphBatcher()(graphs).tg)
+T = 70
+st = RolloutState(dg, w, T, gemm="bf16", max_steps=40)
+st.gnn_embed(); st.env_init(np.random.RandomState(2).randint(0, 2, (dg.N, T)).astype(np.int8))
+st.run(37); torch.cuda.synchronize()
+h = hashlib.sha1()
+for t in (st.hidden[:, :st.M], st.score, st.action_log[:37], st.peek):
+    h.update(t.cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest())
+''' % (ROOT_DIR, TESTS_DIR)
+    digests = {}
+    for name, env in (("pair+pdl", {}), ("single", {"ECORD_GEMM_PAIR": "0"}), ("no-pdl", {"ECORD_PDL": "0"})):
+        e = dict(os.environ); e.update(env)
+        out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests[name] = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0]
+    assert len(set(digests.values())) == 1, digests
