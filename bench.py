@@ -359,6 +359,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_times.append(float(te.item()))
+        e2e_dev = {k: float(torch.as_tensor(log[k]).flatten()[0]) for k in ("t_init_emb", "t_setup", "t_rollout")}
     te = torch.tensor([sorted(e2e_times)[1]], device=dev)
     e2e_val = G * T_total * Ke / float(te.item())
     h2d = (init.nbytes) / Ke
@@ -382,7 +383,7 @@ def run_b200(args):
                           "weights": "random-init canonical ECORD network (seed 0)"},
                "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "note": "B200Solver.rollout incl. GNN, env init, H2D init states, D2H score log; median of 3 calls",
-                       "calls_s": e2e_times},
+                       "calls_s": e2e_times, "device_s_last_call": e2e_dev},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
                "wall_s_timed_region": t_wall, "best_cut_mean": float(best.mean().item())}
         print(json.dumps(out), flush=True)

@@ -67,6 +67,8 @@ def test_fold_q_host_matches_numpy(lib):
     assert np.allclose(o[384:576].reshape(3, 64).T, Cc, atol=1e-5)
     assert np.allclose(o[576:579], (wo[0] * g) @ Cc, atol=1e-4)
     assert np.isclose(o[579], float(wo[0] @ b), atol=1e-5)
+    CC = Cc.T @ Cc                                                        # tensor-core Q kernel: 3x3 Gram matrix, upper triangle
+    assert np.allclose(o[580:586], [CC[0, 0], CC[0, 1], CC[0, 2], CC[1, 1], CC[1, 2], CC[2, 2]], atol=1e-5)
 
 
 def test_sass_is_blackwell_native():
@@ -78,6 +80,8 @@ def test_sass_is_blackwell_native():
         import pytest
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    # tcgen05.mma (single CTA and cta_group::2), TMA loads, TMEM load / store, multicast commit, packed fp32 FMA
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMALDG.2D.2CTA", "LDTM", "STTM", "UTCBAR.2CTA.MULTICAST", "FFMA2",
+                     "UBLKCP"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout

@@ -82,6 +82,27 @@ def test_config1_best_cut_parity():
     assert np.allclose(log["apx_max"].numpy(), log["scores_max"].numpy() / z["opts"])
 
 
+def test_config1_best_cut_throughput_mode():
+    """The same config through the throughput path (tcgen05 bf16 GRU / projection / tail, fp16-split tensor-core Q):
+    bf16 rounding of the recurrent update can change a near-tie arg-max, so the bar here is agreement of the best cut
+    on >= 97% of the graphs (measured 99-100%) and of the per-graph mean-over-trajectories within 1%."""
+    from ecord_b200.testing import TestGraphsConfig, test_solver
+    z = load_gold("config1.npz")
+    graphs = unpack_graphs(z)
+    T, S, bsz = int(z["T"]), int(z["S"]), int(z["bsz"])
+    solver = _solver(random_state_dicts(int(z["weight_seed"])), gemm="bf16")
+    cfg = TestGraphsConfig(graphs=graphs, opt_scores=torch.tensor(z["opts"]), num_steps=S, tradj_per_graph=T, tau=0,
+                           graphs_bsz=bsz, tradj_bsz=T)
+    np.random.seed(int(z["state_seed"]))
+    log = test_solver(solver, GraphBatcher(), cfg)
+    agree = float((log["scores_max"].numpy() == z["scores_max"]).mean())
+    print(f"throughput mode: best-cut agreement with the reference on {agree:.3f} of the graphs")
+    assert agree >= 0.97, f"best-cut agreement {agree:.3f}"
+    if "scores_mean" in z.files:
+        rel = np.abs(log["scores_mean"].numpy() - z["scores_mean"]) / np.maximum(np.abs(z["scores_mean"]), 1.0)
+        assert float(rel.mean()) < 0.01
+
+
 def test_solver_log_contract_and_checkpoint_roundtrip(tmp_path):
     """The keys / shapes downstream code reads (SURVEY.md 8b "Log contract"), and DQNSolver.save/load ingestion."""
     graphs = synthetic_set("er", 30, 3, p=0.3) + synthetic_set("er", 20, 2, p=0.3, seed0=7)     # ragged
