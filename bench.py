@@ -394,7 +394,7 @@ def run_b200(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=800)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps; default = the config's rollout length 4*|V|, capped at 2000")
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="er500", choices=sorted(WORKLOADS))
@@ -404,6 +404,8 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-steps", type=int, default=24, help="steps of the CPU baseline sample (b200 arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps <= 0:
+        args.steps = min(4 * WORKLOADS[args.workload][1], 2000) if args.impl == "b200" else 8
     if args.impl == "reference":
         run_reference(args)
     else:

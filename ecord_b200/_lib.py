@@ -94,6 +94,9 @@ SYMBOLS = {
     "ecord_env_init": (_i32, [_P(Graph), _P(Env), _vp, _vp]),
     "ecord_env_step": (_i32, [_P(Graph), _P(Env), _vp, _i32, _vp, _vp]),
     "ecord_env_step_fused": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _vp, _vp]),
+    "ecord_greedy_select": (_i32, [_P(Graph), _P(Env), _f32, _u64, _i32, _vp, _vp, _vp]),
+    "ecord_env_reset_state": (_i32, [_P(Graph), _P(Env), _vp, _i32, _vp]),
+    "ecord_env_rebase_clock": (_i32, [_P(Graph), _P(Env), _i32, _vp]),
     "ecord_env_export": (_i32, [_P(Graph), _P(Env), _i32, _i32, _vp, _vp, _vp, _vp]),
     "ecord_gnn_workspace_bytes": (C.c_size_t, [_i32]),
     "ecord_gnn_embed": (_i32, [_P(Graph), _P(Weights), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

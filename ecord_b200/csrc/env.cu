@@ -60,6 +60,57 @@ k_env_init_score(ecord_graph g, ecord_env e, const int8_t *__restrict__ s0) {
     }
 }
 
+// Re-initialise spins, peeks and scores from given spins (init_state i8 [N][T]) or, with init_state == NULL, from the
+// best-state plane -- greedy_solve(init_from_best=True), solvers/solver.py:39-43: scores and node features are rebuilt
+// (static counters restart: last_flip_step = steps_done), best_score / best_state / best_step are NOT touched.
+__global__ void k_env_reset_peek(ecord_graph g, ecord_env e, const int8_t *__restrict__ s0, int steps_done) {
+    const int T = e.num_tradj;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)g.num_nodes * T) return;
+    const int v = (int)(idx / T), t = (int)(idx % T);
+    const int gi = g.node_graph[v];
+    int n;
+    const long long ub = unit_base(g.graph_ptr, gi, t, T, n);
+    const int lo = g.graph_ptr[gi];
+    auto spin = [&](int u) -> int { return s0 ? (int)s0[(long long)u * T + t] : (int)e.best_state[ub + (u - lo)]; };
+    const int sv = spin(v);
+    const float si = (float)(2 * sv - 1);
+    float acc = 0.0f;
+    for (int k = g.row_ptr[v]; k < g.row_ptr[v + 1]; ++k) acc += g.w[k] * si * (float)(2 * spin(g.col[k]) - 1);
+    e.peek[ub + (v - lo)] = acc;
+    e.sp[ub + (v - lo)] = steps_done * 2 + sv;
+}
+__global__ void __launch_bounds__(256)
+k_env_reset_score(ecord_graph g, ecord_env e) {          // after k_env_reset_peek: the cut of the spins now in sp
+    const int T = e.num_tradj;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= g.num_graphs * T) return;
+    const int gi = m / T, t = m % T;
+    int n;
+    const long long ub = unit_base(g.graph_ptr, gi, t, T, n);
+    const int lo = g.graph_ptr[gi];
+    float acc = 0.0f;
+    for (int v = lo + lane; v < lo + n; v += 32) {
+        const int sv = e.sp[ub + (v - lo)] & 1;
+        for (int k = g.row_ptr[v]; k < g.row_ptr[v + 1]; ++k)
+            acc += g.w[k] * (float)((sv + (e.sp[ub + (g.col[k] - lo)] & 1)) & 1);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) e.score[m] = 0.5f * acc;
+}
+// shift the environment clock back by `by` steps (after a greedy pre-solve the rollout starts at step 0 again, but the
+// "steps since last flip" features must keep counting from the greedy flips): last_flip_step -= by, best_step -= by
+__global__ void k_env_rebase(ecord_graph g, ecord_env e, int by) {
+    const long long NT = (long long)g.num_nodes * e.num_tradj;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < NT) {
+        const int sp = e.sp[idx];
+        e.sp[idx] = ((sp >> 1) - by) * 2 + (sp & 1);
+    }
+    if (idx < (long long)g.num_graphs * e.num_tradj) e.best_step[idx] -= by;
+}
+
 // ------------------------------------------------------------------------------------------------
 // a3: one step on the SoA state.  One warp per (g,t).
 // ------------------------------------------------------------------------------------------------
@@ -306,6 +357,29 @@ extern "C" int ecord_env_step_fused(const ecord_graph *g, const ecord_env *env, 
     const int GT = g->num_graphs * env->num_tradj;
     float *log0 = score_log ? score_log - (long long)step_no * GT : nullptr;
     return launch_env_step_fused(g, env, w, p, nullptr, step_no, log0, nullptr, as_stream(stream));
+}
+
+extern "C" int ecord_env_reset_state(const ecord_graph *g, const ecord_env *env, const int8_t *init_state, int32_t steps_done,
+                                     void *stream) {
+    ECORD_RET_IF(!g || !env, ECORD_E_NULL);
+    ECORD_RET_IF(!env->peek || !env->sp || !env->score || (!init_state && !env->best_state), ECORD_E_NULL);
+    ECORD_RET_IF(env->num_tradj <= 0 || steps_done < 0, ECORD_E_SIZE);
+    const long long NT = (long long)g->num_nodes * env->num_tradj;
+    const int GT = g->num_graphs * env->num_tradj;
+    k_env_reset_peek<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state, steps_done);
+    ECORD_LAUNCH_CHECK();
+    k_env_reset_score<<<ceil_div((long long)GT * 32, 256), 256, 0, as_stream(stream)>>>(*g, *env);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ecord_env_rebase_clock(const ecord_graph *g, const ecord_env *env, int32_t by, void *stream) {
+    ECORD_RET_IF(!g || !env || !env->sp || !env->best_step, ECORD_E_NULL);
+    ECORD_RET_IF(by < 0, ECORD_E_SIZE);
+    const long long NT = (long long)g->num_nodes * env->num_tradj;
+    k_env_rebase<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(*g, *env, by);
+    ECORD_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int ecord_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, int32_t step_no,

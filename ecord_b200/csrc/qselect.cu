@@ -21,6 +21,7 @@
 // reduction a plain max with "lowest index wins on ties" (torch_scatter CPU semantics).
 #include "common.cuh"
 #include <string.h>
+#include <math.h>
 
 namespace {
 constexpr int Q = ECORD_DIM_Q;   // 64
@@ -342,6 +343,45 @@ k_select_finish(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, con
     if (lane == 0) { p.actions[m] = a; p.keys[m] = 0ull; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Greedy local search on the peeks (reference solvers/solver.py:38-95 greedy_solve).
+// One CTA per (g,t): the action is drawn by the reference's exponential race on peek / max(tau, 1e-9)
+// (solver.py:64 + scatter_softmax_sample): at tau = 0 every vertex below the maximum gets exp(-inf) = 0, so the draw is
+// uniform over the vertices of maximal peek.  at_local_min[m] = (max peek <= 0) for the state BEFORE the flip.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_greedy_select(ecord_graph g, ecord_env e, float inv_tau, uint64_t seed, int step_no, int32_t *__restrict__ actions,
+                int32_t *__restrict__ at_local_min) {
+    __shared__ unsigned long long red[32];
+    const int m = blockIdx.x;
+    const int T = e.num_tradj;
+    const int gi = m / T, t = m - gi * T;
+    int n;
+    const long long base = unit_base(g.graph_ptr, gi, t, T, n);
+    unsigned long long key = 0ull;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        const unsigned long long k = pack_key(e.peek[base + v], v);
+        key = k > key ? k : key;
+    }
+    key = block_max_key(key, red);
+    const uint32_t ord = (uint32_t)(key >> 32);
+    const float pmax = __uint_as_float((ord & 0x80000000u) ? (ord & 0x7FFFFFFFu) : ~ord);
+    unsigned long long k2 = 0ull;
+    for (int v = threadIdx.x; v < n; v += blockDim.x) {
+        const float x = (e.peek[base + v] - pmax) * inv_tau;                    // <= 0; 0 exactly for the maxima
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)v, (uint32_t)m, (uint32_t)step_no, 0x47524459u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float z = -logf(uniform01_open(r.x)) / expf(x);                   // inf where exp underflows
+        const unsigned long long k = pack_key(-z, v);
+        k2 = k > k2 ? k : k2;
+    }
+    k2 = block_max_key(k2, red);
+    if (threadIdx.x == 0) {
+        actions[m] = (int)(0xFFFFFFFFu - (uint32_t)(k2 & 0xFFFFFFFFull));
+        if (at_local_min) at_local_min[m] = pmax <= 0.0f ? 1 : 0;
+    }
+}
+
 // plane [N*T] (trajectory-major) -> reference layout [N][T]
 __global__ void k_plane_to_nt(ecord_graph g, int T, const float *__restrict__ plane, float *__restrict__ out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,6 +472,17 @@ extern "C" int ecord_q_select(const ecord_graph *g, const ecord_env *env, const 
     int rc = check_q_mode(g, w, p, q_mode, tau);
     if (rc) return rc;
     return launch_q_select(g, env, w, p, nullptr, steps_done, tau, seed, compat, forced_actions, q_mode, as_stream(stream));
+}
+
+extern "C" int ecord_greedy_select(const ecord_graph *g, const ecord_env *env, float tau, uint64_t seed, int32_t step_no,
+                                   int32_t *actions, int32_t *at_local_min, void *stream) {
+    ECORD_RET_IF(!g || !env || !actions, ECORD_E_NULL);
+    ECORD_RET_IF(tau < 0.0f || step_no < 0 || env->num_tradj <= 0, ECORD_E_SIZE);
+    const float inv_tau = 1.0f / fmaxf(tau, 1e-9f);                 // solver.py:64  peeks / max(tau, 1e-9)
+    k_greedy_select<<<g->num_graphs * env->num_tradj, q_block_size(g->n_max), 0, as_stream(stream)>>>(
+        *g, *env, inv_tau, seed, step_no, actions, at_local_min);
+    ECORD_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int ecord_plane_to_nt(const ecord_graph *g, int32_t num_tradj, const float *plane, float *out, void *stream) {

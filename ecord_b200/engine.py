@@ -291,6 +291,52 @@ class RolloutState:
         self.steps_done += 1
         self.step_counter.fill_(self.steps_done)
 
+    # ---- greedy local search on the peeks (reference solvers/solver.py:38-95) -----------
+    @_on_stream
+    def greedy_solve(self, init_from_best=False, tau=0.0, max_iters=None, rebase=False):
+        """greedy_solve(env, tau, init_from_best): every trajectory flips a vertex of maximal peek (uniformly at random
+        among ties) until each of them has been at a local optimum at some point; trajectories that got there early
+        keep stepping, exactly as the reference's `while not done.all()` loop does.  The flips are environment steps
+        (scores, best scores and the static counters move) but not rollout steps: nothing is logged and the policy
+        state is untouched.  rebase=True (pre-solve) puts the environment clock back to the rollout's step 0
+        afterwards.  Returns the number of steps taken."""
+        M = self.M
+        clock = self.steps_done
+        if init_from_best:
+            check(self.lib.ecord_env_reset_state(C.byref(self.g.c), C.byref(self.env_c), None, clock, _stream()),
+                  "ecord_env_reset_state")
+        acts = torch.empty(M, dtype=torch.int32, device=self.device)
+        flags = torch.empty(M, dtype=torch.int32, device=self.device)
+
+        def select(step_no):
+            check(self.lib.ecord_greedy_select(C.byref(self.g.c), C.byref(self.env_c), float(tau), self.seed + 0x9E3779B9,
+                                               step_no, ptr(acts), ptr(flags), _stream()), "ecord_greedy_select")
+            self.kernel_launches += 1
+
+        select(clock)
+        done = flags.clone()
+        iters = 0
+        while not bool(done.all()):                       # one 4-byte D2H per step: the loop length is data dependent
+            if max_iters is not None and iters >= max_iters:
+                break
+            check(self.lib.ecord_env_step(C.byref(self.g.c), C.byref(self.env_c), ptr(acts), clock + iters, None, _stream()),
+                  "ecord_env_step")
+            self.kernel_launches += 1
+            iters += 1
+            select(clock + iters)
+            done |= flags
+        if rebase and iters:
+            check(self.lib.ecord_env_rebase_clock(C.byref(self.g.c), C.byref(self.env_c), iters, _stream()),
+                  "ecord_env_rebase_clock")
+            self.kernel_launches += 1
+        elif not rebase:
+            self.env_clock_extra = getattr(self, "env_clock_extra", 0) + iters
+        if self.fused:      # the msg_in input of the next policy step depends on (best - score): refresh it
+            check(self.lib.ecord_policy_pre(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c),
+                                            C.byref(self.policy_c), _stream()), "ecord_policy_pre")
+            self.kernel_launches += 1
+        return iters
+
     def step(self, forced_actions=None):
         self.policy_step()
         self.q_select(forced_actions)

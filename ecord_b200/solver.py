@@ -133,9 +133,9 @@ class B200Solver:
         Extra keywords: init_state (int8 [N, num_tradj]) pins the initial spins (the reference draws them
         from numpy's global RNG, tradjectories.py:64 -- reproduced here when init_state is None);
         traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU sharding)."""
-        if use_network_initialisation or pre_solve_with_greedy or post_solve_with_greedy_from_best or callbacks:
-            raise NotImplementedError("network initialisation / greedy pre-/post-solve / callbacks are not implemented "
-                                      "by the B200 engine yet (SURVEY.md 8f)")
+        if use_network_initialisation or callbacks:
+            raise NotImplementedError("network initialisation / callbacks are not implemented by the B200 engine yet "
+                                      "(SURVEY.md 8f)")
         if max_time is not None:
             raise NotImplementedError("max_time needs a host check per step; not supported by the fused loop")
         tau = self.tau if tau is None else tau
@@ -172,6 +172,8 @@ class B200Solver:
         state.gnn_embed()
         ev[1].record()
         state.env_init(init_state)
+        if pre_solve_with_greedy:                       # solver.py:294-295: greedy_solve(env, init_from_best=False)
+            log['greedy_pre_steps'] = state.greedy_solve(init_from_best=False, rebase=True)
         init_score = state.scores().clone()
         ev[2].record()
 
@@ -186,6 +188,10 @@ class B200Solver:
                 per_step['actions'].append(state.actions.view(G, T).cpu().long())
         else:
             state.run(S)
+        post_scores = None
+        if post_solve_with_greedy_from_best:            # solver.py:367-371: greedy from the best states + one more log entry
+            log['greedy_post_steps'] = state.greedy_solve(init_from_best=True)
+            post_scores = state.scores().clone()
         ev[3].record()
         ev[3].synchronize()
         t_init_emb = ev[0].elapsed_time(ev[1]) * 1e-3
@@ -208,6 +214,10 @@ class B200Solver:
             prev = scores[s]
             log['t_step'].append(dt)
             log['t_inf'].append(dt)
+        if post_scores is not None:                     # log_step(env, -ones, ...) of solver.py:369-371
+            log['scores'].append(post_scores.cpu())
+            if log_stats:
+                per_step['actions'].append(-torch.ones(G, T, dtype=torch.long))
         if log_stats:
             for k, v in per_step.items():
                 log[k] = v

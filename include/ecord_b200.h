@@ -234,6 +234,22 @@ int ecord_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *ac
 int ecord_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                          int32_t step_no, float *score_log, void *stream);
 
+/* ---- (8f rank 1) greedy local search on the peeks: greedy_solve (solvers/solver.py:38-95), used by
+ *      DQNSolver.rollout(pre_solve_with_greedy / post_solve_with_greedy_from_best) (solver.py:294-295,367-371).
+ *      ecord_greedy_select draws, per (g,t), the reference's sample argmin_n -log(U_n) / exp((peek_n - max peek) / max(tau,1e-9))
+ *      (solver.py:64, scatter_softmax_sample :30-36; Philox stream (seed, step_no)): uniform over the vertices of maximal
+ *      peek at tau = 0.  actions: LOCAL ids [G*T]; at_local_min (optional) [G*T]: 1 where max peek <= 0 (solver.py:45,75-77).
+ *      The caller applies the actions with ecord_env_step and loops until every unit has been at a local optimum.
+ *      ecord_env_reset_state rebuilds peeks / scores / static counters from spins (i8 [N][T]) or, with NULL, from the
+ *      best-state plane (init_from_best, solver.py:39-43) and leaves best_score / best_state / best_step untouched.
+ *      ecord_env_rebase_clock moves the environment clock back by `by` steps (last_flip_step -= by, best_step -= by): after a
+ *      pre-solve the rollout restarts at step 0 while the static-steps feature keeps counting from the greedy flips. ---- */
+int ecord_greedy_select(const ecord_graph *g, const ecord_env *env, float tau, uint64_t seed, int32_t step_no,
+                        int32_t *actions, int32_t *at_local_min, void *stream);
+int ecord_env_reset_state(const ecord_graph *g, const ecord_env *env, const int8_t *init_state /* or NULL */,
+                          int32_t steps_done, void *stream);
+int ecord_env_rebase_clock(const ecord_graph *g, const ecord_env *env, int32_t by, void *stream);
+
 /* ---- a4 + parity view: materialise the reference's arrays from the SoA state.
  *      node_features f32 [N][T][3] = (state, peek, static) un-normalised; with normalise != 0 the
  *      canonical observation instead (peek/n_g, min(static,40)/40; tradjectories.py:336-353);

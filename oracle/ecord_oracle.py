@@ -189,6 +189,60 @@ class EnvOracle:
                                   ctypes.c_int32(ob.N), ctypes.c_int32(ob.G), ctypes.c_int32(self.T),
                                   ctypes.c_int32(self.Fn), ctypes.c_int32(self.Fg), ctypes.c_int32(ob.E))
 
+    # ---- greedy local search on the peeks (solvers/solver.py:38-95 greedy_solve), SURVEY.md 8f rank 1 ----
+    def reinit_from_best(self):
+        """init_from_best=True (solver.py:39-43): spins <- best_states, scores and peeks recomputed, the node
+        features re-initialised (static counters back to 0); best_scores / best_states are left alone."""
+        ob = self.ob
+        states = np.ascontiguousarray(self.best_states.astype(np.int8))
+        scores = np.zeros((ob.G, self.T), np.float32)
+        peeks = np.zeros((ob.N, self.T), np.float32)
+        _lib().oracle_scores_and_peeks(_p(states), _p(ob.edges_by_node), _p(ob.edge_w), _p(ob.edge_ptr),
+                                       _p(ob.graph_edge_ptr), _p(scores), _p(peeks), ctypes.c_int32(ob.N),
+                                       ctypes.c_int32(ob.G), ctypes.c_int32(self.T), ctypes.c_int32(ob.E))
+        self.scores = scores
+        nf = np.zeros_like(self.node_features)
+        nf[..., self.node_idx[0]] = states
+        nf[..., self.node_idx[1]] = peeks
+        if self.node_idx[2] >= 0:
+            nf[..., self.node_idx[2]] = states
+        self.node_features = nf
+
+    def greedy_solve(self, rng=None, init_from_best=False, max_iters=100000):
+        """Every trajectory keeps flipping a vertex of maximal peek -- uniformly at random among ties, which is what
+        the reference's scatter_softmax_sample(peeks / 1e-9) amounts to at tau = 0 -- until every one of them has
+        been at a local optimum (max peek <= 0) at some point; trajectories that got there early keep stepping
+        (solver.py:62-86).  Returns (number of steps, whether any arg-max was tied)."""
+        rng = rng or np.random.RandomState(0)
+        ob = self.ob
+        if init_from_best:
+            self.reinit_from_best()
+
+        def select():
+            pk = self.node_features[..., self.node_idx[1]]                      # [N,T]
+            acts = np.zeros((ob.G, self.T), np.int64)
+            lm = np.zeros((ob.G, self.T), bool)
+            tie = False
+            for g in range(ob.G):
+                blk = pk[ob.ptr[g]:ob.ptr[g + 1]]                               # [n,T]
+                mx = blk.max(0)
+                lm[g] = mx <= 0
+                for t in range(self.T):
+                    cand = np.flatnonzero(blk[:, t] == mx[t])
+                    tie |= cand.size > 1
+                    acts[g, t] = cand[rng.randint(cand.size)] if cand.size > 1 else cand[0]
+            return acts, lm, tie
+
+        acts, done, tied = select()
+        it = 0
+        while not done.all() and it < max_iters:
+            self.step(acts)
+            acts, lm, tie = select()
+            tied |= tie
+            done |= lm
+            it += 1
+        return it, tied
+
     # canonical observation normalisation (tradjectories.py:336-376): peek / n_g, min(static,40)/40,
     # (best - score) / n_g; glob column 1 stays 0 (quirk C).
     def observe(self):

@@ -142,7 +142,7 @@ def test_unsupported_options_fail_loudly():
     solver = _solver(sd)
     batch = GraphBatcher()(synthetic_set("er", 10, 1, p=0.5))
     with pytest.raises(NotImplementedError):
-        solver.rollout(batch, num_tradj=2, num_steps=2, post_solve_with_greedy_from_best=True)
+        solver.rollout(batch, num_tradj=2, num_steps=2, use_network_initialisation=True)
 
 
 def test_full_size_er500_properties():
@@ -170,3 +170,97 @@ def test_full_size_er500_properties():
         last.scatter_(2, acts[s].cpu().long().unsqueeze(-1), s + 1)
     static = nf[..., 2].cpu().view(dg.G, 500, T).permute(0, 2, 1)
     assert torch.equal(static.long(), S - last)
+
+
+# ---- greedy pre-/post-solve (reference solvers/solver.py:38-95, 294-295, 367-371) ----
+def _greedy_state(gemm="fp32"):
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    z = load_gold("greedy_trace.npz")
+    graphs = unpack_graphs(z)
+    dg = DeviceGraph(GraphBatcher()(graphs).tg)
+    st = RolloutState(dg, DeviceWeights(random_state_dicts(0)), int(z["T"]), gemm=gemm, max_steps=16)
+    st.gnn_embed(); st.env_init(z["init_state"])
+    return z, graphs, dg, st
+
+
+def test_greedy_solve_matches_reference_on_tie_free_graphs():
+    """Distinct dyadic weights -> no ties -> greedy_solve is deterministic: the engine must reproduce the unmodified
+    reference's scores after the solve, after 7 scripted steps + greedy_solve(init_from_best=True), and its best scores
+    (fixture written by oracle/check_greedy.py, which also asserts reference == oracle)."""
+    z, graphs, dg, st = _greedy_state()
+    T = int(z["T"])
+    iters = st.greedy_solve()
+    assert iters == int(z["steps"])
+    assert np.array_equal(st.scores().cpu().numpy(), z["scores_after_greedy"])
+    rs = np.random.RandomState(int(z["scripted_seed"]))
+    for i in range(int(z["scripted_steps"])):
+        a = np.stack([rs.randint(0, int(n), T) for n in dg.num_nodes_list])
+        st.env_step(a.astype(np.int32).reshape(-1))
+    iters2 = st.greedy_solve(init_from_best=True)
+    assert iters2 == int(z["steps_post"])
+    assert np.array_equal(st.scores().cpu().numpy(), z["scores_after_post"])
+    assert np.array_equal(st.best_score.view(dg.G, T).cpu().numpy(), z["best_after_post"])
+    # the state is self-consistent: score == cut of the spins, peeks == recomputed
+    nf, _, _ = st.export()
+    fresh = orc.EnvOracle(orc.build_batch(graphs), T, nf[..., 0].cpu().numpy().astype(np.int8))
+    assert np.array_equal(fresh.scores, st.scores().cpu().numpy())
+    assert np.array_equal(fresh.node_features[..., 1], nf[..., 1].cpu().numpy())
+
+
+def test_greedy_tie_break_is_uniform_and_reaches_local_optima():
+    """+-1 weights: ties everywhere.  (1) On a perfect matching with all spins equal every vertex has peek +1: the first
+    action must be (roughly) uniform over the vertices.  (2) After the solve every unit has been at a local optimum:
+    its best score is >= the score of a fresh single-flip local search bound, and the state stays self-consistent."""
+    import networkx as nx
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    n, T = 16, 4096
+    g = nx.Graph(); g.add_nodes_from(range(n))
+    for i in range(0, n, 2):
+        g.add_edge(i, i + 1, weight=1.0)
+    dg = DeviceGraph(GraphBatcher()([g]).tg)
+    st = RolloutState(dg, DeviceWeights(random_state_dicts(0)), T, gemm="fp32", max_steps=4)
+    st.gnn_embed(); st.env_init(np.zeros((n, T), np.int8))
+    acts = torch.empty(T, dtype=torch.int32, device="cuda"); flags = torch.empty_like(acts)
+    import ctypes as C
+    from ecord_b200._lib import check, ptr
+    check(st.lib.ecord_greedy_select(C.byref(dg.c), C.byref(st.env_c), 0.0, 7, 0, ptr(acts), ptr(flags), None))
+    torch.cuda.synchronize()
+    counts = np.bincount(acts.cpu().numpy(), minlength=n)
+    assert counts.min() > 0.7 * T / n and counts.max() < 1.3 * T / n, counts
+    assert int(flags.sum()) == 0
+    iters = st.greedy_solve()
+    assert iters >= n // 2                                     # every edge has to be cut: one flip per pair
+    assert torch.all(st.best_score == n // 2)                  # the optimum of a perfect matching
+    graphs = synthetic_set("er", 80, 4, p=0.1)
+    dg = DeviceGraph(GraphBatcher()(graphs).tg)
+    T = 16
+    st = RolloutState(dg, DeviceWeights(random_state_dicts(0)), T, gemm="bf16", max_steps=4)
+    init = np.random.RandomState(4).randint(0, 2, (dg.N, T)).astype(np.int8)
+    st.gnn_embed(); st.env_init(init)
+    s0 = st.scores().clone()
+    st.greedy_solve()
+    assert torch.all(st.best_score.view(dg.G, T) >= s0)
+    nf, _, _ = st.export()
+    fresh = orc.EnvOracle(orc.build_batch(graphs), T, nf[..., 0].cpu().numpy().astype(np.int8))
+    assert np.array_equal(fresh.scores, st.scores().cpu().numpy())
+    assert np.array_equal(fresh.node_features[..., 1], nf[..., 1].cpu().numpy())
+
+
+def test_rollout_with_greedy_pre_and_post_solve():
+    """DQNSolver.rollout(pre_solve_with_greedy=True, post_solve_with_greedy_from_best=True): init_score is taken after the
+    pre-solve, one extra `scores` entry is logged after the post-solve, and both can only help the best cut."""
+    graphs = synthetic_set("er", 60, 5, p=0.12)
+    batch = GraphBatcher()(graphs)
+    T, S = 8, 20
+    init = np.random.RandomState(9).randint(0, 2, (batch.tg.num_nodes, T)).astype(np.int8)
+    for gemm in ("fp32", "bf16"):
+        solver = _solver(random_state_dicts(3), gemm=gemm)
+        plain = solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init)
+        both = solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init,
+                              pre_solve_with_greedy=True, post_solve_with_greedy_from_best=True)
+        assert len(plain['scores']) == S and len(both['scores']) == S + 1
+        assert both['greedy_pre_steps'] > 0
+        assert torch.all(both['init_score'] >= plain['init_score'])
+        best_plain = torch.stack(plain['scores'], -1).max(-1).values
+        best_both = torch.maximum(torch.stack(both['scores'], -1).max(-1).values, both['init_score'])
+        assert best_both.mean() >= best_plain.mean()
