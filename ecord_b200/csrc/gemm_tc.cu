@@ -235,6 +235,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
 //   - tmem_empty lives in the leader and collects the 8 epilogue warps of both CTAs (remote mbarrier arrive)
 // =================================================================================================
 constexpr int kStages2 = 4;      // the pair kernel's stages are 28-32 KB (half of B per CTA): six fit in 192 KB
+__device__ __forceinline__ bool elect_one() {          // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -309,10 +314,13 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
+        // the whole warp walks the loop converged (uniform registers, no divergence bookkeeping); one elected lane issues
+        {
             const CUtensorMap *mapA = (MODE == 0) ? (cur ? &mapA1 : &mapA0) : &mapA0;
-            tmap_prefetch(mapA); tmap_prefetch(&mapB);
-            if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
+            if (lane == 0) {
+                tmap_prefetch(mapA); tmap_prefetch(&mapB);
+                if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
+            }
             const uint32_t lfull0 = mapa_u32(full0, 0);            // the leader's full barriers
             uint32_t it = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -323,25 +331,28 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
                     const bool first = MODE == 0 && c == 0;
                     const int n_rows = first ? C::N_FIRST : C::N_MAIN;
-                    if (prm.debug & 4) {            // no TMA traffic: the leader completes the phase by itself
-                        if (rank == 0) mbar_arrive_cta(full0 + 8 * s);
-                        continue;
+                    if (elect_one()) {
+                        if (prm.debug & 4) {            // no TMA traffic: the leader completes the phase by itself
+                            if (rank == 0) mbar_arrive_cta(full0 + 8 * s);
+                        } else {
+                            if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + n_rows / 2 * BK * 2));
+                            if (first) {
+                                tma_load_2d_pair(a_dst, &mapU, lfull0 + 8 * s, 0, m0);
+                                tma_load_2d_pair(b_dst, &mapWu, lfull0 + 8 * s, 0, nb * n_rows + (int)rank * (n_rows / 2));
+                            } else {
+                                const int kc = (MODE == 0 ? c - 1 : c) * BK;
+                                tma_load_2d_pair(a_dst, mapA, lfull0 + 8 * s, kc, m0);
+                                tma_load_2d_pair(b_dst, &mapB, lfull0 + 8 * s, kc, nb * n_rows + (int)rank * (n_rows / 2));
+                            }
+                        }
                     }
-                    if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + n_rows / 2 * BK * 2));
-                    if (first) {
-                        tma_load_2d_pair(a_dst, &mapU, lfull0 + 8 * s, 0, m0);
-                        tma_load_2d_pair(b_dst, &mapWu, lfull0 + 8 * s, 0, nb * n_rows + (int)rank * (n_rows / 2));
-                    } else {
-                        const int kc = (MODE == 0 ? c - 1 : c) * BK;
-                        tma_load_2d_pair(a_dst, mapA, lfull0 + 8 * s, kc, m0);
-                        tma_load_2d_pair(b_dst, &mapB, lfull0 + 8 * s, kc, nb * n_rows + (int)rank * (n_rows / 2));
-                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {                    // converged warp, elected lane issues (see the producer)
             uint32_t it = 0, lt = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
                 const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
@@ -354,14 +365,17 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
                     const uint32_t idesc = (MODE == 0 && c == 0) ? umma_idesc(2 * BM, 256) : umma_idesc(2 * BM, C::N_MAIN);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
-                        if (!(prm.debug & 1)) umma_bf16_pair(acc, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
+                            if (!(prm.debug & 1)) umma_bf16_pair(acc, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit_pair(empty0 + 8 * s);         // frees the stage in both CTAs
+                        if (c == NCHUNK - 1) umma_commit_pair(tfull0 + 8 * ab);            // accumulator complete, both CTAs
                     }
-                    umma_commit_pair(empty0 + 8 * s);         // frees the stage in both CTAs
+                    __syncwarp();
                 }
-                umma_commit_pair(tfull0 + 8 * ab);            // accumulator complete, both CTAs
             }
         }
     } else {
