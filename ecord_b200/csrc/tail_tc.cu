@@ -4,16 +4,19 @@
 //   y1 [M][512] -> LN512 -> LReLU -> W2 (512 -> 32) -> LN32 -> LReLU = P ;  v = val_out(P) ;  A = Wq[:, :32] P + b_q
 //   + the per-(g,t) operands of the fast / tensor-core Q kernels          (models/rnn_decoder.py:84-90,108-119,285-311)
 //
-// One CTA per block of 128 rows:
-//   phase 1  16 warps, one row at a time per warp: LayerNorm(512) + LeakyReLU in registers (16 values per lane),
-//            result rounded to bf16 and written to shared memory as the A operand of the MMA -- eight [128][64]
-//            K-major SWIZZLE_128B sub-tiles, the layout TMA would produce
+// One CTA per block of R = 32 or 64 rows (the MMA still has M = 128: the unused A rows are whatever shared memory
+// holds, their accumulator lanes are never read), so that a few thousand rows spread over all SMs:
+//   phase 1  16 warps, R/16 rows each (both requested up front): LayerNorm(512) + LeakyReLU in registers (16 values
+//            per lane), result rounded to bf16 and written to shared memory as the A operand of the MMA -- eight
+//            [128][64] K-major SWIZZLE_128B sub-tiles, the layout TMA would produce
 //   phase 2  W2 (bf16, eight [32][64] sub-tiles fetched by TMA during phase 1) x A: 32 tcgen05.mma (M=128, N=32, K=16),
 //            accumulator [128][32] fp32 in TMEM
-//   phase 3  thread i <-> row i <-> TMEM lane i: LayerNorm(32), value head, A and the Q-kernel operands, all weights
-//            read as warp-uniform (broadcast) LDS.128
+//   phase 3  R threads (thread <-> row <-> TMEM lane) read the accumulator, apply LayerNorm(32) and publish P, tanh(P)
+//            and the channel mean of A in shared memory; then all 512 threads work, 512/R per row: each takes
+//            32/(512/R) value-head units and 64/(512/R) Q channels (weights as warp-uniform broadcast LDS.128) and the
+//            22 per-row sums are combined through shared memory
 // The warp-per-row CUDA-core version spends its time streaming W2 (64 KB) out of shared memory once per row
-// (5000 x 64 KB per step) and in shuffle reductions; here W2 is read by the tensor core once per 128 rows.
+// (5000 x 64 KB per step) and in shuffle reductions; here W2 is read by the tensor core once per CTA.
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 
@@ -34,6 +37,8 @@ struct TailTcSmem {
     float wg[QC * 16];               // centred Wq[:,32:48] [c][k]
     float cc[QC * 4];                // centred C [c][0..2], bconst[c]
     float colsum[ND + 1];            // sum_c Wq[c][o]; [32] = sum_c b_q[c]
+    float Ps[64][ND + 1], Ts[64][ND + 1];   // P and tanh(P) of the CTA's rows (padded: conflict-free row reads)
+    float meanA[64];
     uint64_t bar_w, bar_mma;
     uint32_t tmem_base;
 };
@@ -45,11 +50,11 @@ __device__ __forceinline__ uint32_t split_h2(float x) {     // fp16 (hi | lo << 
 }
 
 __global__ void __launch_bounds__(kTtThreads, 1)
-k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_policy p) {
+k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_policy p, int R) {
     extern __shared__ uint8_t smem_raw[];
     TailTcSmem &S = *reinterpret_cast<TailTcSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * BM;
+    const int m0 = blockIdx.x * R;
     const uint32_t bar_w = smem_u32(&S.bar_w), bar_mma = smem_u32(&S.bar_mma);
 
     if (tid == 0) {
@@ -90,29 +95,30 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         auto row_ptr = [&](int r) {
             return reinterpret_cast<const float4 *>(p.y1 + (long long)min(m0 + r, p.rows - 1) * P1);   // rows past the end:
         };                                                                       // the last row again, never stored
-        float4 nx[4];
-        {
-            const float4 *yr = row_ptr(warp);
+        const int nrow = R / NW;                         // 2 or 4 rows per warp, all requested before the first reduction
+        float4 nx[4][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) nx[k] = yr[lane + 32 * k];
-        }
-        for (int r = warp; r < BM; r += NW) {
+        for (int j = 0; j < 4; ++j)
+            if (j < nrow) {
+                const float4 *yr = row_ptr(warp + j * NW);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) nx[j][k] = yr[lane + 32 * k];
+            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nrow) break;
+            const int r = warp + j * NW;
             float x[16];
             float s = 0.0f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                x[4 * k] = nx[k].x; x[4 * k + 1] = nx[k].y; x[4 * k + 2] = nx[k].z; x[4 * k + 3] = nx[k].w;
-                s += (nx[k].x + nx[k].y) + (nx[k].z + nx[k].w);
-            }
-            if (r + NW < BM) {
-                const float4 *yr = row_ptr(r + NW);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) nx[k] = yr[lane + 32 * k];
+                x[4 * k] = nx[j][k].x; x[4 * k + 1] = nx[j][k].y; x[4 * k + 2] = nx[j][k].z; x[4 * k + 3] = nx[j][k].w;
+                s += (nx[j][k].x + nx[j][k].y) + (nx[j][k].z + nx[j][k].w);
             }
             const float mean = warp_sum(s) * (1.0f / P1);
             float ss = 0.0f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { x[j] -= mean; ss = fmaf(x[j], x[j], ss); }
+            for (int i = 0; i < 16; ++i) { x[i] -= mean; ss = fmaf(x[i], x[i], ss); }
             const float rstd = rsqrtf(warp_sum(ss) * (1.0f / P1) + kLnEps);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -150,22 +156,17 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         umma_commit(bar_mma);
     }
 
-    // ---------------- phase 3: four threads per row (row = TMEM lane 32 (warp % 4) + lane, part = warp / 4) ----------------
-    // Each part redoes the cheap LN32, then takes 8 of the 32 value-head units and 16 of the 64 Q channels; the 22
-    // per-row partial sums are combined through shared memory (the A-operand tile is free once the MMAs have completed).
-    {
-        const int rloc = (warp & 3) * 32 + lane, part = warp >> 2;
-        const int m = m0 + rloc;
-        const bool live = m < p.rows;
+    // ---------------- phase 3a: R threads read the accumulator (thread <-> row <-> TMEM lane), LN32, publish ----------------
+    if (tid < R) {
+        const int m = m0 + tid;
         mbar_wait(bar_mma, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float P[ND];
-        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
         tmem_ld16(taddr, P);
         tmem_ld16(taddr + 16, P + 16);
         tmem_ld_wait();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        // LN32 + LReLU
         float s = 0.0f;
 #pragma unroll
         for (int o = 0; o < ND; ++o) { P[o] += w.p2_b[o]; s += P[o]; }
@@ -174,47 +175,58 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
 #pragma unroll
         for (int o = 0; o < ND; ++o) { P[o] -= mean; ss = fmaf(P[o], P[o], ss); }
         const float rstd = rsqrtf(ss * (1.0f / ND) + kLnEps);
+        float sa = S.colsum[ND];                              // sum_c b_q[c]
 #pragma unroll
-        for (int o = 0; o < ND; ++o) P[o] = lrelu(fmaf(P[o] * rstd, w.ln2_w[o], w.ln2_b[o]));
-        if (live && part == 0) {
+        for (int o = 0; o < ND; ++o) {
+            P[o] = lrelu(fmaf(P[o] * rstd, w.ln2_w[o], w.ln2_b[o]));
+            S.Ps[tid][o] = P[o];
+            S.Ts[tid][o] = tanh_fast(P[o]);                   // MUFU.TANH: this is the bf16-tolerance path
+            sa = fmaf(S.colsum[o], P[o], sa);
+        }
+        // mean over the 64 channels of A = Wq[:, :32] P + b_q, without forming A
+        S.meanA[tid] = sa * (1.0f / QC);
+        if (m < p.rows) {
 #pragma unroll
             for (int o = 0; o < ND; o += 4)
                 *reinterpret_cast<float4 *>(p.P + (long long)m * ND + o) = make_float4(P[o], P[o + 1], P[o + 2], P[o + 3]);
         }
+    }
+    __syncthreads();          // (the MMAs have completed: the A-operand tile is free for the reduction below)
+
+    // ---------------- phase 3b: 512 / R threads per row ----------------
+    {
+        const int nparts = kTtThreads / R;                    // 16 or 8
+        const int rloc = tid % R, part = tid / R;             // part is warp-uniform (R is a multiple of 32)
+        const int m = m0 + rloc;
+        const bool live = m < p.rows;
+        float P[ND], Tp[ND];
+#pragma unroll
+        for (int o = 0; o < ND; ++o) { P[o] = S.Ps[rloc][o]; Tp[o] = S.Ts[rloc][o]; }
+        const float meanA = S.meanA[rloc];
         float acc[22];                                        // Wg^T a' (16) | Cc^T a' (3) | |a'|^2 | LA | v   (partial sums)
 #pragma unroll
         for (int i = 0; i < 22; ++i) acc[i] = 0.0f;
-        // state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 -- this part's 8 hidden units
-        {
-            float tp[ND];
+        // state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 -- this part's value-head units
+        const int nv = ND / nparts;
+        for (int jj = 0; jj < nv; ++jj) {
+            const int j = part * nv + jj;
+            const float4 *vr = reinterpret_cast<const float4 *>(&S.v1[j * ND]);
+            float h0 = w.v1_b[j], h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
 #pragma unroll
-            for (int o = 0; o < ND; ++o) tp[o] = tanh_fast(P[o]);     // MUFU.TANH: this is the bf16-tolerance path
-#pragma unroll 2
-            for (int jj = 0; jj < 8; ++jj) {
-                const int j = part * 8 + jj;
-                const float4 *vr = reinterpret_cast<const float4 *>(&S.v1[j * ND]);
-                float h0 = w.v1_b[j], h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
-#pragma unroll
-                for (int o4 = 0; o4 < ND / 4; ++o4) {
-                    const float4 v4 = vr[o4];
-                    h0 = fmaf(v4.x, tp[4 * o4], h0); h1 = fmaf(v4.y, tp[4 * o4 + 1], h1);
-                    h2 = fmaf(v4.z, tp[4 * o4 + 2], h2); h3 = fmaf(v4.w, tp[4 * o4 + 3], h3);
-                }
-                acc[21] = fmaf(w.v2_w[j], lrelu((h0 + h1) + (h2 + h3)), acc[21]);
+            for (int o4 = 0; o4 < ND / 4; ++o4) {
+                const float4 v4 = vr[o4];
+                h0 = fmaf(v4.x, Tp[4 * o4], h0); h1 = fmaf(v4.y, Tp[4 * o4 + 1], h1);
+                h2 = fmaf(v4.z, Tp[4 * o4 + 2], h2); h3 = fmaf(v4.w, Tp[4 * o4 + 3], h3);
             }
+            acc[21] = fmaf(w.v2_w[j], lrelu((h0 + h1) + (h2 + h3)), acc[21]);
         }
-        // mean over the 64 channels of A = Wq[:, :32] P + b_q, without forming A: (sum_c b_q[c] + sum_o colsum[o] P[o]) / 64
-        float sa = S.colsum[ND];                              // sum_c b_q[c]
-#pragma unroll
-        for (int o = 0; o < ND; ++o) sa = fmaf(S.colsum[o], P[o], sa);
-        const float meanA = sa * (1.0f / QC);
-        // this part's 16 channels: a_c, then everything that is linear in it
+        // this part's Q channels: a_c, then everything that is linear in it
         float *Ao = p.A + (long long)m * QC;
         float *Aco = p.Ac ? p.Ac + (long long)m * QC : nullptr;
         uint32_t *qw = p.qa ? reinterpret_cast<uint32_t *>(p.qa + (long long)m * ECORD_QA_STRIDE) : nullptr;
-#pragma unroll 2
-        for (int cc_ = 0; cc_ < 16; ++cc_) {
-            const int c = part * 16 + cc_;
+        const int nc = QC / nparts;
+        for (int cc_ = 0; cc_ < nc; ++cc_) {
+            const int c = part * nc + cc_;
             const float4 *qr = reinterpret_cast<const float4 *>(&S.q1[c * ND]);
             float a0 = w.q1_b[c], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
@@ -244,16 +256,18 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
                 acc[19] = fmaf(ap, ap, acc[19]);
             }
         }
-        // combine the four parts of each row: red[i][part][row] (conflict-free), summed by part 0
+        // combine the parts of each row: red[i][part][row] (conflict-free), summed by part 0
         float *red = reinterpret_cast<float *>(S.act);
         if (part) {
 #pragma unroll
-            for (int i = 0; i < 22; ++i) red[(i * 3 + part - 1) * BM + rloc] = acc[i];
+            for (int i = 0; i < 22; ++i) red[(i * 15 + part - 1) * 64 + rloc] = acc[i];
         }
         __syncthreads();
         if (part == 0 && live) {
+            for (int q = 0; q < nparts - 1; ++q) {
 #pragma unroll
-            for (int i = 0; i < 22; ++i) acc[i] += (red[(i * 3) * BM + rloc] + red[(i * 3 + 1) * BM + rloc]) + red[(i * 3 + 2) * BM + rloc];
+                for (int i = 0; i < 22; ++i) acc[i] += red[(i * 15 + q) * 64 + rloc];
+            }
             const float vv = acc[21] + w.v2_b[0];
             p.v[m] = vv;
             if (p.LA) p.LA[m] = acc[20];
@@ -303,6 +317,8 @@ int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t s
     CUtensorMap mW2;
     const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(w->p1_w_bf16) + (size_t)ECORD_DIM_P1 * H;
     if ((rc = make_map(enc, &mW2, w2, ND, P1, ND))) return rc;
-    ECORD_PDL_LAUNCH(k_tail_tc, dim3(p->rows_pad / BM), dim3(kTtThreads), sizeof(TailTcSmem) + 1024, st, mW2, *w, *p);
+    // 32 rows per CTA while that stays within one wave of CTAs (one per SM: the A-operand tile is 128 KB), else 64
+    const int R = ceil_div(p->rows, 32) <= kNumSMs ? 32 : 64;
+    ECORD_PDL_LAUNCH(k_tail_tc, dim3(ceil_div(p->rows, R)), dim3(kTtThreads), sizeof(TailTcSmem) + 1024, st, mW2, *w, *p, R);
     return 0;
 }
