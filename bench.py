@@ -351,7 +351,7 @@ def run_b200(args):
         barrier()                       # occasional cudaMalloc / graph teardown shows up as a multi-ms outlier
         t0 = time.perf_counter()
         log = solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=pinned.numpy())
-        sc = torch.stack(log['scores'], -1).max(-1).values.to(dev)
+        sc = log['best_score_by_tradj'].to(dev)          # == torch.stack(log['scores'], -1).max(-1).values, reduced on the device
         best_e, _ = reduce_best(sc, T_total)
         best_host = best_e.cpu()
         barrier()

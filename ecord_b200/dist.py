@@ -51,8 +51,10 @@ def rollout_sharded(solver, batch, num_tradj, num_steps, init_state, tau=0.0, gr
     lo, hi = shard_bounds(num_tradj, world, rank)
     log = solver.rollout(batch, num_tradj=num_tradj, num_steps=num_steps, tau=tau, use_epsilon=False,
                          init_state=init_state, traj_slice=(lo, hi))
-    scores = torch.stack(log['scores'], -1)                 # [G, T_local, S]
-    by_tradj = scores.max(-1).values.to(solver.device)
+    if 'best_score_by_tradj' in log:                        # reduced on the device by the engine
+        by_tradj = log['best_score_by_tradj'].to(solver.device)
+    else:
+        by_tradj = torch.stack(log['scores'], -1).max(-1).values.to(solver.device)   # [G, T_local, S] -> [G, T_local]
     best, by_all = reduce_best(by_tradj, num_tradj, group)
     log['scores_max'] = best.cpu()
     log['scores_mean'] = by_all.mean(-1).cpu()

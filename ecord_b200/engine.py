@@ -86,6 +86,21 @@ class DeviceGraph:
                             ptr(self.in_src), ptr(self.in_w), int(tg_ids.shape[0]), 0, ptr(self.qtile_graph),
                             ptr(self.qtile_v0))
 
+    def padded_row_index(self):
+        """int64 [N] on the device: row of vertex v in a [G * n_max, ...] padded array (graph * n_max + local id)."""
+        if getattr(self, "_pad_idx", None) is None:
+            ptrs = torch.from_numpy(self.tg.np_ptr.astype(np.int64))
+            gid = torch.repeat_interleave(torch.arange(self.G), torch.from_numpy(self.num_nodes_list.astype(np.int64)))
+            self._pad_idx = (gid * self.n_max + (torch.arange(self.N) - ptrs[:-1][gid])).to(self.device)
+        return self._pad_idx
+
+    def pinned_buffer(self, shape):
+        """A cached page-locked float32 host buffer (results are copied out of it by the caller)."""
+        cache = self.__dict__.setdefault("_pinned", {})
+        if shape not in cache:
+            cache[shape] = torch.empty(shape, dtype=torch.float32).pin_memory()
+        return cache[shape]
+
     def plane_index(self, T):
         """int64 [N,T]: plane offset of every (vertex, trajectory) -- host-side layout helper for views."""
         ptrs = torch.from_numpy(self.tg.np_ptr)
@@ -231,7 +246,7 @@ class RolloutState:
     @_on_stream
     def env_init(self, init_state):
         """a2: init_state int8 [N,T] (host numpy / torch, reference layout)."""
-        s = torch.as_tensor(np.ascontiguousarray(np.asarray(init_state).astype(np.int8)))
+        s = torch.as_tensor(np.ascontiguousarray(np.asarray(init_state), dtype=np.int8))
         if tuple(s.shape) != (self.g.N, self.T):
             raise AssertionError(f"init_state must have shape {(self.g.N, self.T)}.  Got {tuple(s.shape)}.")
         self.init_state_dev = s.to(self.device, non_blocking=False)
@@ -374,10 +389,11 @@ class RolloutState:
 
     # ---- views in the reference's layouts (parity checks, logs) ------------------------------
     @_on_stream
-    def export(self, normalise=False):
-        """(node_features [N,T,3], glob_features [G,T,2], best_states [N,T]) as torch CUDA tensors."""
+    def export(self, normalise=False, nodes=True):
+        """(node_features [N,T,3], glob_features [G,T,2], best_states [N,T]) as torch CUDA tensors
+        (nodes=False skips the node features: None is returned in their place)."""
         N, G, T = self.g.N, self.g.G, self.T
-        nf = torch.empty(N, T, 3, dtype=torch.float32, device=self.device)
+        nf = torch.empty(N, T, 3, dtype=torch.float32, device=self.device) if nodes else None
         gf = torch.empty(G, T, 2, dtype=torch.float32, device=self.device)
         bs = torch.empty(N, T, dtype=torch.float32, device=self.device)
         check(self.lib.ecord_env_export(C.byref(self.g.c), C.byref(self.env_c), self.steps_done, int(normalise),
@@ -422,10 +438,11 @@ class RolloutState:
                                                      ptr(plane), _stream()), "ecord_best_state_snapshot")
             flat = self.plane_to_nt(plane.float())
         else:
-            flat = self.export()[2]
-        flat = flat.cpu()
-        out = -torch.ones(G, self.g.n_max, T)
-        ptrs = self.g.tg.np_ptr
-        for gi in range(G):
-            out[gi, :ptrs[gi + 1] - ptrs[gi]] = flat[ptrs[gi]:ptrs[gi + 1]]
-        return out
+            flat = self.export(nodes=False)[2]
+        # pad to [G, n_max, T] on the device (one index_copy), then a single D2H into a cached pinned buffer
+        pad = torch.full((G * self.g.n_max, T), -1.0, dtype=torch.float32, device=self.device)
+        pad.index_copy_(0, self.g.padded_row_index(), flat)
+        host = self.g.pinned_buffer((G, self.g.n_max, T))
+        host.copy_(pad.view(G, self.g.n_max, T), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.clone()

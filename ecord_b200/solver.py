@@ -159,7 +159,7 @@ class B200Solver:
                 init_state = init_state.cpu().numpy()
             assert init_state.shape == (N, num_tradj), \
                 f"init_state must have shape {(N, num_tradj)}.  Got {init_state.shape}."
-            init_state = init_state.astype(np.int8)
+            init_state = np.asarray(init_state, dtype=np.int8)
         if traj_slice is not None:
             init_state = np.ascontiguousarray(init_state[:, traj_slice[0]:traj_slice[1]])
         T = init_state.shape[1]
@@ -221,6 +221,10 @@ class B200Solver:
         if log_stats:
             for k, v in per_step.items():
                 log[k] = v
+        if S > 0:       # engine extra: max over the logged steps per trajectory, reduced on the device (testing.py:201 needs it)
+            log['best_score_by_tradj'] = state.best_from_log(S).cpu()
+            if post_scores is not None:
+                log['best_score_by_tradj'] = torch.maximum(log['best_score_by_tradj'], post_scores.cpu())
         log['best_state'] = state.best_states_batched(true_snapshot=not self.compat)
         log['t_rollout'] = torch.tensor([t_rollout])
         log['t_tot'] = torch.tensor([t_init_emb + t_rollout])
