@@ -136,8 +136,6 @@ class B200Solver:
         if use_network_initialisation or callbacks:
             raise NotImplementedError("network initialisation / callbacks are not implemented by the B200 engine yet "
                                       "(SURVEY.md 8f)")
-        if max_time is not None:
-            raise NotImplementedError("max_time needs a host check per step; not supported by the fused loop")
         tau = self.tau if tau is None else tau
         tau = 0.0 if tau is None else float(tau)
         log = defaultdict(list)
@@ -186,8 +184,25 @@ class B200Solver:
                 per_step['state'].append(self._flat2batch(dg, nf[..., 0].cpu(), -1))
                 state.step()
                 per_step['actions'].append(state.actions.view(G, T).cpu().long())
-        else:
+        elif max_time is None:
             state.run(S)
+        else:
+            # solver.py:318-320: stop once the accumulated time (embedding + steps) reaches max_time.  The fused loop is
+            # checked between CUDA-graph launches, i.e. with a granularity of `steps_per_graph` steps (the reference
+            # checks every step).
+            ev[1].synchronize()
+            t_used = ev[0].elapsed_time(ev[1]) * 1e-3
+            done_steps = 0
+            while done_steps < S:
+                if t_used >= max_time:
+                    print(f"Max time exceeded, terminating optimisation after {done_steps} steps.")
+                    break
+                c = min(self.steps_per_graph, S - done_steps)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); state.run(c); e1.record(); e1.synchronize()
+                t_used += e0.elapsed_time(e1) * 1e-3
+                done_steps += c
+            S = done_steps
         post_scores = None
         if post_solve_with_greedy_from_best:            # solver.py:367-371: greedy from the best states + one more log entry
             log['greedy_post_steps'] = state.greedy_solve(init_from_best=True)

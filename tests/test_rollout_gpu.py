@@ -264,3 +264,20 @@ def test_rollout_with_greedy_pre_and_post_solve():
         best_plain = torch.stack(plain['scores'], -1).max(-1).values
         best_both = torch.maximum(torch.stack(both['scores'], -1).max(-1).values, both['init_score'])
         assert best_both.mean() >= best_plain.mean()
+
+
+def test_max_time_stops_the_rollout_between_graph_launches():
+    """DQNSolver.rollout(max_time=...) (solver.py:318-320): the loop stops once embedding + step time reaches the budget;
+    the engine checks between CUDA-graph launches (16 steps), and the log is truncated consistently."""
+    graphs = synthetic_set("er", 200, 20, p=0.1)
+    batch = GraphBatcher()(graphs)
+    solver = _solver(random_state_dicts(3), gemm="bf16")
+    T, S = 16, 4000
+    init = np.random.RandomState(2).randint(0, 2, (batch.tg.num_nodes, T)).astype(np.int8)
+    solver.rollout(batch, num_tradj=T, num_steps=32, tau=0, use_epsilon=False, init_state=init)      # warm-up
+    log = solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init, max_time=0.02)
+    n = len(log['scores'])
+    assert 16 <= n < S and n % 16 == 0
+    assert len(log['t_step']) == n and log['best_score_by_tradj'].shape == (20, T)
+    full = solver.rollout(batch, num_tradj=T, num_steps=n, tau=0, use_epsilon=False, init_state=init)
+    assert torch.equal(torch.stack(full['scores']), torch.stack(log['scores']))     # same steps as an un-timed rollout
