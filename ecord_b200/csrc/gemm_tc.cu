@@ -25,14 +25,16 @@
 namespace {
 // MODE 0 = GRU : tile = 128 rows x 64 hidden units; k-chunk 0 (N=256) from (u, Wu), then 16 chunks (N=192) from
 //                (h[cur], Wh); accumulator = 256 TMEM columns, two accumulators = all 512 columns
-// MODE 1 = PROJ: tile = 128 rows x 128 outputs; 16 chunks (N=128) from (th, W1); accumulator = 128 columns
+// MODE 1 = PROJ: tile = 128 rows x 176 outputs; 16 chunks (N=176) from (th, W1); accumulator = 176 of 256 columns
 //
 // Persistent: grid = min(#tiles, #SMs); CTA b works on tiles b, b + grid, ...  The accumulator is double-buffered in
 // TMEM (tmem_full / tmem_empty barriers), so the epilogue of tile i (TMEM -> registers -> GRU cell -> global) runs
 // while TMA + MMA already work on tile i+1; the epilogue warps prefetch the old hidden state before they wait.
 template <int MODE> struct TcCfg;
 template <> struct TcCfg<0> { static constexpr int N_FIRST = 256, N_MAIN = 192, B_ROWS = 256, ACC_COLS = 256, TILE_N = 64; };
-template <> struct TcCfg<1> { static constexpr int N_FIRST = 0, N_MAIN = 128, B_ROWS = 128, ACC_COLS = 128, TILE_N = 128; };
+// PROJ: 512 outputs as three column blocks of 176 (the last one runs 16 columns past the matrix: TMA zero-fills them, the
+// epilogue drops them): 3 x 20 pair tiles fit one wave of 74 clusters, where 4 x 20 tiles of 128 needed two
+template <> struct TcCfg<1> { static constexpr int N_FIRST = 0, N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
 
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -47,7 +49,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
-    constexpr int TMEM_COLS = 2 * C::ACC_COLS;
+    constexpr int TMEM_COLS = 2 * C::ACC_COLS;          // 512 for both modes
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kStages + 4];
@@ -190,22 +192,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
                     }
                 }
             } else {
-                const int c00 = nb * C::TILE_N + part * (C::TILE_N / 4);
+                constexpr int PC = C::TILE_N / 4;                 // 44 columns per warp: 11 groups of 4
+                const int c00 = nb * C::TILE_N + part * PC;
                 float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + c00;
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float acc[PC];
 #pragma unroll
-                for (int jj = 0; jj < C::TILE_N / 4; jj += 16) {
-                    float acc[16];
-                    tmem_ld16(tbase + part * (C::TILE_N / 4) + jj, acc);
-                    tmem_ld_wait();
-                    if (row < prm.rows) {
+                for (int jj = 0; jj < PC; jj += 4) tmem_ld4(tbase + part * PC + jj, acc + jj);
+                tmem_ld_wait();
+                if (row < prm.rows) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const int j = c00 + jj + i;
-                            float4 o = make_float4(acc[i] + prm.p1_b[j], acc[i + 1] + prm.p1_b[j + 1], acc[i + 2] + prm.p1_b[j + 2],
-                                                   acc[i + 3] + prm.p1_b[j + 3]);
-                            *reinterpret_cast<float4 *>(yrow + jj + i) = o;
+                    for (int jj = 0; jj < PC; jj += 4) {
+                        const int j = c00 + jj;
+                        if (j < ECORD_DIM_P1) {                   // the last block's tail columns do not exist
+                            const float4 b4 = *reinterpret_cast<const float4 *>(prm.p1_b + j);
+                            *reinterpret_cast<float4 *>(yrow + jj) =
+                                make_float4(acc[jj] + b4.x, acc[jj + 1] + b4.y, acc[jj + 2] + b4.z, acc[jj + 3] + b4.w);
                         }
                     }
                 }
@@ -278,7 +281,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS / 2 * BK * 2;      // per CTA: own A rows, half of B
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
-    constexpr int TMEM_COLS = 2 * C::ACC_COLS;
+    constexpr int TMEM_COLS = 2 * C::ACC_COLS;          // 512 for both modes
 
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kStages2 + 4];
@@ -441,22 +444,23 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     }
                 }
             } else {
-                const int c00 = nb * C::TILE_N + part * (C::TILE_N / 4);
+                constexpr int PC = C::TILE_N / 4;                 // 44 columns per warp: 11 groups of 4
+                const int c00 = nb * C::TILE_N + part * PC;
                 float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + c00;
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float acc[PC];
 #pragma unroll
-                for (int jj = 0; jj < C::TILE_N / 4; jj += 16) {
-                    float acc[16];
-                    tmem_ld16(tbase + part * (C::TILE_N / 4) + jj, acc);
-                    tmem_ld_wait();
-                    if (row < prm.rows) {
+                for (int jj = 0; jj < PC; jj += 4) tmem_ld4(tbase + part * PC + jj, acc + jj);
+                tmem_ld_wait();
+                if (row < prm.rows) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const int j = c00 + jj + i;
-                            float4 o = make_float4(acc[i] + prm.p1_b[j], acc[i + 1] + prm.p1_b[j + 1], acc[i + 2] + prm.p1_b[j + 2],
-                                                   acc[i + 3] + prm.p1_b[j + 3]);
-                            *reinterpret_cast<float4 *>(yrow + jj + i) = o;
+                    for (int jj = 0; jj < PC; jj += 4) {
+                        const int j = c00 + jj;
+                        if (j < ECORD_DIM_P1) {                   // the last block's tail columns do not exist
+                            const float4 b4 = *reinterpret_cast<const float4 *>(prm.p1_b + j);
+                            *reinterpret_cast<float4 *>(yrow + jj) =
+                                make_float4(acc[jj] + b4.x, acc[jj + 1] + b4.y, acc[jj + 2] + b4.z, acc[jj + 3] + b4.w);
                         }
                     }
                 }
@@ -691,17 +695,17 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t 
     CUtensorMap mA, mB;
     if ((rc = make_map(enc, &mA, p->th_bf16, Mp, H, BM))) return rc;
     const bool pair = use_pair(Mp);
-    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, pair ? 64 : 128))) return rc;
+    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, pair ? 88 : 176))) return rc;
     TcParams prm{};
     prm.p1_b = w->p1_b; prm.y1 = p->y1; prm.rows = p->rows; prm.rows_pad = Mp;
     if (pair) {
-        const int nblk2 = ECORD_DIM_P1 / 128, tiles2 = nblk2 * (Mp / (2 * BM));
+        const int nblk2 = 3, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
         ECORD_PDL_LAUNCH(k_gemm_tc2<1>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<1>(), st, mA, mB, mA, mA, mB, prm,
                          tiles2, nblk2);
         return 0;
     }
-    const int nblk = ECORD_DIM_P1 / 128, num_tiles = nblk * (Mp / BM);
+    const int nblk = 3, num_tiles = nblk * (Mp / BM);
     ECORD_PDL_LAUNCH(k_gemm_tc<1>, dim3(num_tiles < kNumSMs ? num_tiles : kNumSMs), dim3(kThreads), (size_t)tc_smem_bytes<1>(), st,
                      mA, mB, mA, mA, mB, prm, num_tiles, nblk);
     return 0;

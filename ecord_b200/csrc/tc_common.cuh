@@ -76,6 +76,13 @@ __host__ __device__ __forceinline__ float tf32_rn(float x) {
     union { float f; uint32_t u; } v; v.f = x; v.u = (v.u + 0x1000u) & 0xffffe000u; return v.f;
 #endif
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float *v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // MUFU.TANH (rel. error ~2^-11): the bf16 path rounds its outputs to 8 mantissa bits anyway
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
