@@ -3,8 +3,8 @@
 //   GRU  :  [M, 64+1024] x [1088, 3072]  fused with the GRU cell   (models/rnn_decoder.py:369-381 -> nn.GRUCell)
 //   PROJ :  [M, 1024]    x [1024, 512]   + bias                    (models/rnn_decoder.py:84-86, proj_rnn_to_gnn.1)
 //
-// Hand-written tcgen05 pipeline, one output tile per CTA:
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B) -> 4-stage smem ring, mbarrier complete_tx
+// Hand-written tcgen05 pipeline, persistent CTAs (or CTA pairs, cta_group::2 -- the default, see k_gemm_tc2 below):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B) -> 4-stage smem ring, mbarrier complete_tx; programmatic dependent launch: set-up overlaps the predecessor
 //   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
 //               (bf16 x bf16 -> fp32 accumulate in TMEM), tcgen05.commit releases smem stages / signals the epilogue
 //   warps 2..17 epilogue: tcgen05.ld (32 lanes x 16 columns at a time) -> registers -> fused math -> global;

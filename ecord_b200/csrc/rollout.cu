@@ -2,7 +2,7 @@
 //
 // Replaces the Python loop of DQNSolver.rollout (solvers/solver.py:316-362): per step the reference does
 // observe() on the host, H2D of [N,T,F], the torch model, D2H of the actions, the Cython step and a list
-// append of the scores.  Here one step is {policy_step, q_select, env_step} = 6 kernels (bf16 mode) enqueued
+// append of the scores.  Here one step is {policy_step, q_select, env_step} = 6 kernels (throughput mode: GRU, PROJ, tail, Q, finish, env) enqueued
 // back to back; `steps_per_graph` steps are captured once into a CUDA graph and replayed, so the host issues
 // one cudaGraphLaunch per k steps and never synchronises inside the rollout.  The step index lives in device
 // memory (step_counter): kernels read *step_counter + their unrolled offset, and the last node of each graph
@@ -74,7 +74,7 @@ int capture(ecord_rollout_plan *pl, int nsteps, cudaGraphExec_t *out) {
     ECORD_CUDA(cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeRelaxed));
     int rc = 0;
     const ecord_rollout_desc &d = pl->desc;
-    // ECORD_Q_FAST also fuses the next step's msg_in stage into the env-step kernel (u must be primed once with
+    // ECORD_Q_FAST / ECORD_Q_TC also fuse the next step's msg_in stage into the env-step kernel (u must be primed once with
     // ecord_policy_pre before the first step); ECORD_Q_EXACT keeps the literal kernel sequence.
     const int fused = d.q_mode != ECORD_Q_EXACT;
     for (int i = 0; i < nsteps && !rc; ++i) {
