@@ -146,6 +146,12 @@ extern "C" int ecord_rollout_plan_run(ecord_rollout_plan *pl, int32_t num_steps,
     return 0;
 }
 
+extern "C" int ecord_rollout_plan_reset(ecord_rollout_plan *pl) {
+    ECORD_RET_IF(!pl || !pl->exec_k, ECORD_E_PLAN);
+    pl->steps_enqueued = 0;
+    return 0;
+}
+
 extern "C" int ecord_rollout_plan_destroy(ecord_rollout_plan *pl) {
     if (!pl) return 0;
     if (pl->exec_k) cudaGraphExecDestroy(pl->exec_k);

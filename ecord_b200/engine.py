@@ -27,6 +27,18 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_ROLLOUT_STREAMS = {}
+
+
+def _rollout_stream(device):
+    """One long-lived side stream per device for all RolloutStates: torch's caching allocator keeps a pool per
+    stream, so a fresh stream per rollout would turn every allocation made under it into a cudaMalloc."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _ROLLOUT_STREAMS:
+        _ROLLOUT_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _ROLLOUT_STREAMS[key]
+
+
 def _on_stream(fn):
     """Run a RolloutState method on the state's own (non-default) stream.  CUDA graphs cannot be captured on
     the legacy default stream, so every kernel of a rollout is enqueued on `self.stream`; the caller's current
@@ -148,12 +160,13 @@ class RolloutState:
     tests and `log_stats`; `run()` executes whole steps through the CUDA-graph plan."""
 
     def __init__(self, dgraph, weights, num_tradj, gemm="bf16", compat=True, tau=0.0, seed=0,
-                 max_steps=0, log_scores=True, log_actions=True, steps_per_graph=16, dump_q=False, q_mode=None):
+                 max_steps=0, log_scores=True, log_actions=True, steps_per_graph=16, dump_q=False, q_mode=None,
+                 stream=None):
         self.lib = _lib.load()
         self.g, self.w = dgraph, weights
         dev = dgraph.device
         self.device = dev
-        self.stream = torch.cuda.Stream(device=dev)
+        self.stream = stream if stream is not None else _rollout_stream(dev)
         self.T = T = int(num_tradj)
         self.gemm = _GEMM_MODES[gemm]
         if self.gemm == GEMM_BF16 and weights.gru_w_bf16 is None:
@@ -230,6 +243,16 @@ class RolloutState:
         self.plan = None
         self.init_state_dev = None
         self.kernel_launches = 0
+        self.env_clock_extra = 0
+        self._best_out = torch.empty(M, **f32)
+
+    def reset(self):
+        """Make the state reusable for another rollout on the same graph batch: `env_init` re-initialises every
+        buffer a rollout reads before writing, the captured CUDA graphs stay valid."""
+        self.kernel_launches = 0
+        self.env_clock_extra = 0
+        if self.plan is not None:
+            check(self.lib.ecord_rollout_plan_reset(self.plan), "ecord_rollout_plan_reset")
 
     # ---- set-up -----------------------------------------------------------------------------
     @_on_stream
@@ -345,7 +368,7 @@ class RolloutState:
                   "ecord_env_rebase_clock")
             self.kernel_launches += 1
         elif not rebase:
-            self.env_clock_extra = getattr(self, "env_clock_extra", 0) + iters
+            self.env_clock_extra += iters
         if self.fused:      # the msg_in input of the next policy step depends on (best - score): refresh it
             check(self.lib.ecord_policy_pre(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c),
                                             C.byref(self.policy_c), _stream()), "ecord_policy_pre")
@@ -395,7 +418,12 @@ class RolloutState:
         N, G, T = self.g.N, self.g.G, self.T
         nf = torch.empty(N, T, 3, dtype=torch.float32, device=self.device) if nodes else None
         gf = torch.empty(G, T, 2, dtype=torch.float32, device=self.device)
-        bs = torch.empty(N, T, dtype=torch.float32, device=self.device)
+        if nodes:
+            bs = torch.empty(N, T, dtype=torch.float32, device=self.device)
+        else:                   # the end-of-rollout view: a cached buffer (consumed before the next export)
+            if getattr(self, "_bs_buf", None) is None:
+                self._bs_buf = torch.empty(N, T, dtype=torch.float32, device=self.device)
+            bs = self._bs_buf
         check(self.lib.ecord_env_export(C.byref(self.g.c), C.byref(self.env_c), self.steps_done, int(normalise),
                                         ptr(nf), ptr(gf), ptr(bs), _stream()), "ecord_env_export")
         return nf, gf, bs
@@ -418,8 +446,18 @@ class RolloutState:
         return self.score.view(self.g.G, self.T)
 
     @_on_stream
+    def score_log_host(self, num_steps):
+        """The first `num_steps` rows of the score log as a host tensor [S, G, T]: one D2H into a cached pinned
+        buffer, then a host copy (the caller owns the result)."""
+        S, G, T = int(num_steps), self.g.G, self.T
+        host = self.g.pinned_buffer((self.max_steps, self.M))
+        host[:S].copy_(self.score_log[:S], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host[:S].clone().view(S, G, T)
+
+    @_on_stream
     def best_from_log(self, num_steps):
-        out = torch.empty(self.M, dtype=torch.float32, device=self.device)
+        out = self._best_out
         check(self.lib.ecord_score_log_max(ptr(self.score_log), int(num_steps), self.M, ptr(out), _stream()),
               "ecord_score_log_max")
         return out.view(self.g.G, self.T)
@@ -439,8 +477,11 @@ class RolloutState:
             flat = self.plane_to_nt(plane.float())
         else:
             flat = self.export(nodes=False)[2]
-        # pad to [G, n_max, T] on the device (one index_copy), then a single D2H into a cached pinned buffer
-        pad = torch.full((G * self.g.n_max, T), -1.0, dtype=torch.float32, device=self.device)
+        # pad to [G, n_max, T] on the device (one index_copy into a cached buffer whose padding rows stay -1), then a
+        # single D2H into a cached pinned buffer
+        if getattr(self, "_pad", None) is None:
+            self._pad = torch.full((G * self.g.n_max, T), -1.0, dtype=torch.float32, device=self.device)
+        pad = self._pad
         pad.index_copy_(0, self.g.padded_row_index(), flat)
         host = self.g.pinned_buffer((G, self.g.n_max, T))
         host.copy_(pad.view(G, self.g.n_max, T), non_blocking=True)

@@ -78,11 +78,13 @@ class B200Solver:
         self.actor = _ActorShim(self)
         self._last_state = None
         self._graph_cache = (None, None)
+        self._state_cache = []
 
     # ---- weights ------------------------------------------------------------------------------
     def set_weights(self, state_dicts):
         self.state_dicts = check_state_dicts(state_dicts)
         self.weights = DeviceWeights(self.state_dicts, self.device, pack_bf16=True)
+        self._state_cache = []          # cached states hold pointers into the old weights
 
     def load(self, fname, quiet=False):
         """Ingest a reference checkpoint written by DQNSolver.save (solver.py:582-617)."""
@@ -125,6 +127,24 @@ class B200Solver:
         self._graph_cache = (tg, dg)
         return dg
 
+    def _rollout_state(self, dg, T, gemm, tau, S):
+        """Device state for a rollout.  States are kept (the two most recent) and re-initialised when the same graph
+        batch is rolled out again with the same shape -- test_solver's trajectory chunks (testing.py:174-189) and
+        repeated validation passes -- which saves the buffer allocations and the CUDA-graph capture."""
+        key = (id(dg), T, gemm, self.compat, tau, self.seed, self.steps_per_graph)
+        for i, (k, st) in enumerate(self._state_cache):
+            if k == key and st.g is dg and st.max_steps >= S:
+                self._state_cache.insert(0, self._state_cache.pop(i))
+                st.reset()
+                return st
+        st = RolloutState(dg, self.weights, T, gemm=gemm, compat=self.compat, tau=tau, seed=self.seed, max_steps=S,
+                          log_scores=True, log_actions=True, steps_per_graph=self.steps_per_graph, dump_q=False)
+        self._state_cache.insert(0, (key, st))
+        for _, old in self._state_cache[2:]:
+            old.close()
+        del self._state_cache[2:]
+        return st
+
     @torch.no_grad()
     def rollout(self, batch, num_tradj=1, num_steps=-1, log_stats=False, callbacks=None, use_epsilon=True,
                 use_network_initialisation=False, tau=None, max_time=None, pre_solve_with_greedy=False,
@@ -163,9 +183,7 @@ class B200Solver:
         T = init_state.shape[1]
 
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        state = RolloutState(dg, self.weights, T, gemm=gemm or self.gemm, compat=self.compat, tau=tau, seed=self.seed,
-                             max_steps=S, log_scores=True, log_actions=True, steps_per_graph=self.steps_per_graph,
-                             dump_q=False)
+        state = self._rollout_state(dg, T, gemm or self.gemm, tau, S)
         ev[0].record()
         state.gnn_embed()
         ev[1].record()
@@ -213,7 +231,7 @@ class B200Solver:
         t_setup = ev[1].elapsed_time(ev[2]) * 1e-3
         t_rollout = ev[2].elapsed_time(ev[3]) * 1e-3
 
-        scores = state.score_log[:S].view(S, G, T).cpu() if S > 0 else torch.zeros(0, G, T)
+        scores = state.score_log_host(S) if S > 0 else torch.zeros(0, G, T)
         init_score = init_score.cpu()
         best_step = state.best_step.view(G, T).cpu()
         log['t_init_emb'].append(torch.tensor([t_init_emb]))

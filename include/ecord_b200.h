@@ -319,6 +319,9 @@ int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *stream, ecor
 /* enqueue `num_steps` more steps on the plan's stream; asynchronous.  launches_out (optional, host)
  * receives the number of kernels enqueued. */
 int ecord_rollout_plan_run(ecord_rollout_plan *plan, int32_t num_steps, int64_t *launches_out);
+/* a new rollout on the same buffers (the caller has re-initialised the environment and zeroed step_counter):
+ * the plan's captured graphs stay valid, only its count of enqueued steps (log overrun check) restarts. */
+int ecord_rollout_plan_reset(ecord_rollout_plan *plan);
 int ecord_rollout_plan_destroy(ecord_rollout_plan *plan);
 
 /* ---- a11 (device part): best score per (g,t) over steps 1..S is env.best_score restricted to s>=1;

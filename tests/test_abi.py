@@ -45,6 +45,7 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.ecord_step_cy(*([None] * 11), 1, 1, 1, 1, 1) == -1
     assert lib.ecord_rollout_plan_create(None, None, None) == -1
     assert lib.ecord_rollout_plan_run(None, 1, None) == -6
+    assert lib.ecord_rollout_plan_reset(None) == -6
     assert lib.ecord_rollout_plan_destroy(None) == 0
     assert lib.ecord_gnn_workspace_bytes(0) == 0 and lib.ecord_gnn_workspace_bytes(100) >= 3 * 100 * 16 * 4
     assert lib.ecord_fold_q_host(None, None, None, None, None, None) == -1

@@ -132,6 +132,32 @@ def test_solver_log_contract_and_checkpoint_roundtrip(tmp_path):
     assert torch.equal(torch.stack(a["scores"]), torch.stack(b["scores"]))
 
 
+@pytest.mark.parametrize("gemm", ["fp32", "bf16"])
+def test_rollout_state_reuse_is_invisible(gemm):
+    """The solver keeps the device state of a graph batch and re-initialises it for the next trajectory chunk
+    (testing.py:174-189 calls rollout repeatedly on one batch): every call must equal a call on a fresh solver."""
+    graphs = synthetic_set("er", 40, 4, p=0.2)
+    sd = random_state_dicts(3)
+    batch = GraphBatcher()(graphs)
+    T, N = 6, batch.tg.num_nodes
+    inits = [np.random.RandomState(s).randint(0, 2, (N, T), dtype=np.int8) for s in (1, 2, 1)]
+    steps = [40, 24, 40]                       # the second call reuses the state with fewer steps than its logs hold
+    kw = dict(num_tradj=T, use_epsilon=False, tau=0)
+    reused = _solver(sd, gemm=gemm)
+    logs = [reused.rollout(batch, num_steps=S, init_state=i0, post_solve_with_greedy_from_best=(k == 1), **kw)
+            for k, (S, i0) in enumerate(zip(steps, inits))]
+    assert len(reused._state_cache) == 1
+    for k, (S, i0) in enumerate(zip(steps, inits)):
+        fresh = _solver(sd, gemm=gemm).rollout(batch, num_steps=S, init_state=i0,
+                                               post_solve_with_greedy_from_best=(k == 1), **kw)
+        assert len(logs[k]["scores"]) == len(fresh["scores"])
+        assert torch.equal(torch.stack(logs[k]["scores"]), torch.stack(fresh["scores"]))
+        assert torch.equal(logs[k]["best_state"], fresh["best_state"])
+        assert torch.equal(logs[k]["t_opt"] > 0, fresh["t_opt"] > 0)
+        assert torch.equal(logs[k]["best_score_by_tradj"], fresh["best_score_by_tradj"])
+    assert torch.equal(torch.stack(logs[0]["scores"]), torch.stack(logs[2]["scores"]))
+
+
 def test_unsupported_options_fail_loudly():
     sd = random_state_dicts(1)
     from ecord_b200.solver import B200Solver
