@@ -83,6 +83,45 @@ def test_loader_reads_reference_style_pickles(tmp_path):
     assert "2 graphs" in cfg.get_summary() and cfg.get_label() == "ER_4spin"
 
 
+def test_gset_mtx_loader_and_batcher(tmp_path):
+    """graphs/utils.py:36-52: a GSet .mtx file (+ cuts.pkl beside it) -> one sparse graph the batcher accepts, with
+    the reference's edge order (source ascending, neighbours ascending) and both directions of every edge."""
+    import scipy.io
+    import scipy.sparse as sp
+    from ecord_b200.graphs import load_gset_graph
+    d = tmp_path / "gset"
+    d.mkdir()
+    iu = np.array([0, 0, 1, 2, 3]); ju = np.array([2, 4, 3, 4, 4]); w = np.array([1, -1, 1, 1, -1], np.float32)
+    scipy.io.mmwrite(str(d / "G2.mtx"), sp.coo_matrix((w, (iu, ju)), shape=(5, 5)))     # upper triangle only, as GSet ships
+    with open(d / "cuts.pkl", "wb") as f:
+        pickle.dump([11624, 11620], f)
+    graphs, cuts = load_gset_graph(str(d / "G2"))
+    assert cuts == [11620] and len(graphs) == 1
+    graphs2, cuts2 = load_graph_from_file(str(d / "G2.mtx"), quiet=True)           # 'gset' in the path -> same loader
+    assert cuts2 == [11620]
+    tg = GraphBatcher()(graphs + graphs2).tg
+    assert tg.num_nodes == 10 and tg.num_edges == 20
+    src, dst, ww = tg.np_src[:10], tg.np_dst[:10], tg.np_w[:10]
+    assert np.all(np.diff(src) >= 0)
+    assert all(np.all(np.diff(dst[src == v]) > 0) for v in range(5))
+    assert sorted(zip(src.tolist(), dst.tolist(), ww.tolist())) == sorted(
+        [(int(a), int(b), float(c)) for a, b, c in zip(iu, ju, w)] + [(int(b), int(a), float(c)) for a, b, c in zip(iu, ju, w)])
+    np.testing.assert_array_equal(tg.np_src[10:] - 5, src)
+
+
+def test_dump_logs_roundtrip(tmp_path):
+    """experiments/validate.py:244-250 + experiments/utils/system.py:74-106: save_to_disk(fname, log, compressed=True)."""
+    from ecord_b200.io import load_from_disk, save_to_disk
+    log = {"scores": torch.arange(24.0).view(2, 3, 4), "t_step": np.array([0.1, 0.2]), "best_state": [torch.ones(2, 5, 3)],
+           "label": "ER_4spin"}
+    for compressed in (True, False):
+        out = save_to_disk(str(tmp_path / "ER_4spin_run1"), log, compressed=compressed)
+        assert os.path.exists(out) and os.path.splitext(out)[-1] in (".snappy", ".pbz2", ".pkl")
+        back = load_from_disk(str(tmp_path / "ER_4spin_run1"), compressed=compressed)
+        assert torch.equal(back["scores"], log["scores"]) and back["label"] == "ER_4spin"
+        assert torch.equal(back["best_state"][0], log["best_state"][0]) and back["t_step"].tolist() == [0.1, 0.2]
+
+
 def test_merge_log_semantics():
     """testing.py:120-143: list-of-tensor values stack on a new last dim; trajectory chunks concatenate on dim 1,
     graph chunks on dim 0; float lists add element-wise within a graph chunk and concatenate across graph chunks."""
