@@ -77,7 +77,7 @@ class Policy(C.Structure):
 
 class RolloutDesc(C.Structure):
     _fields_ = [("graph", C.POINTER(Graph)), ("env", C.POINTER(Env)), ("weights", C.POINTER(Weights)),
-                ("policy", C.POINTER(Policy)), ("gemm_mode", _i32), ("q_mode", _i32), ("compat", _i32), ("_pad0", _i32),
+                ("policy", C.POINTER(Policy)), ("gemm_mode", _i32), ("q_mode", _i32), ("compat", _i32), ("epsilon", _f32),
                 ("tau", _f32),
                 ("steps_per_graph", _i32), ("seed", _u64), ("step_counter", _vp), ("score_log", _vp),
                 ("action_log", _vp), ("max_steps", _i32), ("_pad", _i32)]
@@ -104,7 +104,7 @@ SYMBOLS = {
     "ecord_fold_q_host": (_i32, [_vp] * 6),
     "ecord_policy_step": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _i32, _i32, _vp]),
     "ecord_policy_pre": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _vp]),
-    "ecord_q_select": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _f32, _u64, _i32, _vp, _i32, _vp]),
+    "ecord_q_select": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _f32, _u64, _i32, _vp, _i32, _f32, _vp]),
     "ecord_rollout_plan_create": (_i32, [_P(RolloutDesc), _vp, _P(_vp)]),
     "ecord_rollout_plan_run": (_i32, [_vp, _i32, _P(_i64)]),
     "ecord_rollout_plan_reset": (_i32, [_vp]),
@@ -129,7 +129,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)   # AttributeError here = header/library drift
         fn.restype, fn.argtypes = res, args
-    if lib.ecord_version() != 1:
+    if lib.ecord_version() != 2:
         raise EcordError(f"ABI version mismatch: library reports {lib.ecord_version()}")
     for which, st in enumerate((Graph, Env, Weights, Policy, RolloutDesc)):
         if lib.ecord_abi_sizeof(which) != C.sizeof(st):

@@ -39,6 +39,17 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 __device__ __forceinline__ float uniform01_open(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
+// epsilon-greedy override (actors/ecord.py:171-180): with probability epsilon the unit's action becomes a uniformly random
+// vertex of its graph, floor(U * n_g).  One Philox draw per (unit, step); the stream differs from torch.rand, the
+// distribution is the reference's.
+__device__ __forceinline__ int eps_greedy(int a, float epsilon, uint64_t seed, int m, int steps_done, int n) {
+    if (epsilon <= 0.0f) return a;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)m, (uint32_t)steps_done, 0x45505347u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    if (uniform01_open(r.x) >= epsilon) return a;
+    return min((int)(((float)(r.y >> 8) * (1.0f / 16777216.0f)) * (float)n), n - 1);
+}
+
 // monotone float -> uint32 map (larger float <=> larger uint)
 __device__ __forceinline__ uint32_t f2ord(float f) {
     const uint32_t u = __float_as_uint(f);
@@ -113,7 +124,7 @@ __device__ __forceinline__ float q_row(const QSmem &S, const QConst &K, const fl
 __global__ void __launch_bounds__(256)
 k_q_select(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const __grid_constant__ QConst K,
            const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat,
-           const int32_t *__restrict__ forced) {
+           const int32_t *__restrict__ forced, float epsilon) {
     __shared__ QSmem S;
     const int m = blockIdx.x;
     const int T = e.num_tradj;
@@ -155,6 +166,7 @@ k_q_select(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const __
         k2 = block_max_key(k2, S.red);
         a = (int)(0xFFFFFFFFu - (uint32_t)(k2 & 0xFFFFFFFFull));
     }
+    a = eps_greedy(a, epsilon, seed, m, steps_done, n);
     if (forced) a = forced[m];
 
     // cache the embedding of the chosen vertex for the next GRU update (actors/_base.py:296-308).
@@ -310,7 +322,7 @@ k_q_fast(ecord_graph g, ecord_env e, ecord_policy p, const __grid_constant__ QCo
 // one warp per (g,t): decode the arg-max key, cache the chosen vertex's embedding, reset the key
 __global__ void __launch_bounds__(256)
 k_select_finish(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const int32_t *step_base, int step_off,
-                int compat, const int32_t *__restrict__ forced) {
+                int compat, const int32_t *__restrict__ forced, float epsilon, uint64_t seed) {
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     pdl_launch_dependents();
@@ -321,8 +333,9 @@ k_select_finish(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, con
     const int steps_done = (step_base ? *step_base : 0) + step_off;
     const unsigned long long key = p.keys[m];
     int a = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
-    if (forced) a = forced[m];
     const int lo = g.graph_ptr[gi];
+    a = eps_greedy(a, epsilon, seed, m, steps_done, g.graph_ptr[gi + 1] - lo);
+    if (forced) a = forced[m];
     const int j = compat ? a : lo + a;
     const int gj = g.node_graph[j];
     int nj;
@@ -403,14 +416,16 @@ int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights 
 int qtc_init_attrs();
 
 static int launch_select_finish(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                                const int32_t *step_base, int step_off, int compat, const int32_t *forced, cudaStream_t st) {
+                                const int32_t *step_base, int step_off, int compat, const int32_t *forced, float epsilon,
+                                uint64_t seed, cudaStream_t st) {
     ECORD_PDL_LAUNCH(k_select_finish, dim3(ceil_div((long long)p->rows * 32, 256)), dim3(256), (size_t)0, st, *g, *env, *w, *p,
-                     step_base, step_off, compat, forced);
+                     step_base, step_off, compat, forced, epsilon, seed);
     return 0;
 }
 
 static int launch_q_fast(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                         const int32_t *step_base, int step_off, int compat, const int32_t *forced, cudaStream_t st) {
+                         const int32_t *step_base, int step_off, int compat, const int32_t *forced, float epsilon,
+                         uint64_t seed, cudaStream_t st) {
     QConstFast K;
     memcpy(K.C0, w->q_fold + 384, 3 * Q * sizeof(float));          // centred C planes
     memcpy(K.gam, w->q_fold + 3 * Q, 3 * Q * sizeof(float));        // gamma | beta | w_o
@@ -425,23 +440,23 @@ static int launch_q_fast(const ecord_graph *g, const ecord_env *env, const ecord
     if (p->q) k_q_fast<true><<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
     else k_q_fast<false><<<dim3(g->num_qtiles, splits), QT, 0, st>>>(*g, *env, *p, K, w->q2_b, step_base, step_off, t_chunk);
     ECORD_LAUNCH_CHECK();
-    return launch_select_finish(g, env, w, p, step_base, step_off, compat, forced, st);
+    return launch_select_finish(g, env, w, p, step_base, step_off, compat, forced, epsilon, seed, st);
 }
 
 int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                     const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat, const int32_t *forced,
-                    int q_mode, cudaStream_t st) {
-    if (q_mode == ECORD_Q_FAST) return launch_q_fast(g, env, w, p, step_base, step_off, compat, forced, st);
+                    int q_mode, float epsilon, cudaStream_t st) {
+    if (q_mode == ECORD_Q_FAST) return launch_q_fast(g, env, w, p, step_base, step_off, compat, forced, epsilon, seed, st);
     if (q_mode == ECORD_Q_TC) {
         int rc = launch_q_tc(g, env, w, p, step_base, step_off, st);
         if (rc) return rc;
-        return launch_select_finish(g, env, w, p, step_base, step_off, compat, forced, st);
+        return launch_select_finish(g, env, w, p, step_base, step_off, compat, forced, epsilon, seed, st);
     }
     QConst K;
     static_assert(sizeof(QConst) == 6 * Q * sizeof(float), "QConst must be densely packed");
     memcpy(&K, w->q_fold, sizeof(QConst));      // q_fold is a HOST array (see ecord_weights)
     k_q_select<<<p->rows, q_block_size(g->n_max), 0, st>>>(*g, *env, *w, *p, K, step_base, step_off, tau, seed, compat,
-                                                           forced);
+                                                           forced, epsilon);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
@@ -463,15 +478,16 @@ int check_q_mode(const ecord_graph *g, const ecord_weights *w, const ecord_polic
 
 extern "C" int ecord_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                               int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
-                              int32_t q_mode, void *stream) {
+                              int32_t q_mode, float epsilon, void *stream) {
     ECORD_RET_IF(!g || !env || !w || !p, ECORD_E_NULL);
     ECORD_RET_IF(!p->A || !p->v || !p->node_B || !p->node_emb || !p->last_sel || !p->actions || !w->q_fold, ECORD_E_NULL);
     ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj || steps_done < 0, ECORD_E_SIZE);
-    ECORD_RET_IF(tau < 0.0f, ECORD_E_SIZE);
+    ECORD_RET_IF(tau < 0.0f || !(epsilon >= 0.0f && epsilon <= 1.0f), ECORD_E_SIZE);
     ECORD_RET_IF(tau > 0.0f && !p->q, ECORD_E_NULL);
     int rc = check_q_mode(g, w, p, q_mode, tau);
     if (rc) return rc;
-    return launch_q_select(g, env, w, p, nullptr, steps_done, tau, seed, compat, forced_actions, q_mode, as_stream(stream));
+    return launch_q_select(g, env, w, p, nullptr, steps_done, tau, seed, compat, forced_actions, q_mode, epsilon,
+                           as_stream(stream));
 }
 
 extern "C" int ecord_greedy_select(const ecord_graph *g, const ecord_env *env, float tau, uint64_t seed, int32_t step_no,

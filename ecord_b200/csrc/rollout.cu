@@ -21,7 +21,7 @@ int check_policy(const ecord_policy *p, int gemm_mode);
 int check_q_mode(const ecord_graph *g, const ecord_weights *w, const ecord_policy *p, int q_mode, float tau);
 int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                     const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat, const int32_t *forced,
-                    int q_mode, cudaStream_t st);
+                    int q_mode, float epsilon, cudaStream_t st);
 int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, const int32_t *step_base,
                     int step_off, float *score_log, int32_t *action_log, cudaStream_t st);
 
@@ -81,7 +81,7 @@ int capture(ecord_rollout_plan *pl, int nsteps, cudaGraphExec_t *out) {
         rc = launch_policy_step(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i, d.gemm_mode, fused,
                                 pl->stream);
         if (!rc) rc = launch_q_select(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i, d.tau, d.seed,
-                                      d.compat, nullptr, d.q_mode, pl->stream);
+                                      d.compat, nullptr, d.q_mode, d.epsilon, pl->stream);
         if (!rc && fused) rc = launch_env_step_fused(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i,
                                                      d.score_log, d.action_log, pl->stream);
         if (!rc && !fused) rc = launch_env_step(&pl->graph, &pl->env, pl->policy.actions, d.step_counter, i, d.score_log,
@@ -105,7 +105,7 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     ECORD_RET_IF(!desc->graph || !desc->env || !desc->weights || !desc->policy || !desc->step_counter, ECORD_E_NULL);
     ECORD_RET_IF(desc->gemm_mode != ECORD_GEMM_FP32 && desc->gemm_mode != ECORD_GEMM_BF16, ECORD_E_UNSUPPORTED);
     ECORD_RET_IF(desc->steps_per_graph <= 0 || desc->steps_per_graph > 256, ECORD_E_SIZE);
-    ECORD_RET_IF(desc->tau < 0.0f, ECORD_E_SIZE);
+    ECORD_RET_IF(desc->tau < 0.0f || !(desc->epsilon >= 0.0f && desc->epsilon <= 1.0f), ECORD_E_SIZE);
     ECORD_RET_IF((desc->score_log || desc->action_log) && desc->max_steps <= 0, ECORD_E_SIZE);
     int rc = check_policy(desc->policy, desc->gemm_mode);
     if (rc) return rc;

@@ -161,7 +161,7 @@ class RolloutState:
 
     def __init__(self, dgraph, weights, num_tradj, gemm="bf16", compat=True, tau=0.0, seed=0,
                  max_steps=0, log_scores=True, log_actions=True, steps_per_graph=16, dump_q=False, q_mode=None,
-                 stream=None):
+                 stream=None, epsilon=0.0):
         self.lib = _lib.load()
         self.g, self.w = dgraph, weights
         dev = dgraph.device
@@ -172,6 +172,9 @@ class RolloutState:
         if self.gemm == GEMM_BF16 and weights.gru_w_bf16 is None:
             raise ValueError("weights were created with pack_bf16=False")
         self.compat, self.tau, self.seed = bool(compat), float(tau), int(seed)
+        self.epsilon = float(epsilon)     # epsilon-greedy (actors/ecord.py:171-180); fixed for the life of the CUDA-graph plan
+        if not 0.0 <= self.epsilon <= 1.0:
+            raise ValueError("epsilon must lie in [0, 1]")
         # parity mode = (fp32 GEMM, exact Q); throughput mode = (bf16 tcgen05 GEMM, tensor-core Q).  tau > 0 needs exact Q.
         if q_mode is None:
             q_mode = "tc" if (gemm == "bf16" and self.tau == 0.0) else "exact"
@@ -304,7 +307,7 @@ class RolloutState:
             assert fa.numel() == self.M
         check(self.lib.ecord_q_select(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c), C.byref(self.policy_c),
                                       self.steps_done, self.tau, self.seed, int(self.compat), ptr(fa), self.q_mode,
-                                      _stream()), "ecord_q_select")
+                                      self.epsilon, _stream()), "ecord_q_select")
         self.kernel_launches += 1 if self.q_mode == Q_EXACT else 2
         self._fa = fa
 
@@ -383,7 +386,7 @@ class RolloutState:
     # ---- fused loop -------------------------------------------------------------------------
     def _make_plan(self):
         desc = _lib.RolloutDesc(C.pointer(self.g.c), C.pointer(self.env_c), C.pointer(self.w.c), C.pointer(self.policy_c),
-                                self.gemm, self.q_mode, int(self.compat), 0, self.tau, self.steps_per_graph, self.seed,
+                                self.gemm, self.q_mode, int(self.compat), self.epsilon, self.tau, self.steps_per_graph, self.seed,
                                 ptr(self.step_counter), ptr(self.score_log), ptr(self.action_log), self.max_steps, 0)
         out = C.c_void_p()
         check(self.lib.ecord_rollout_plan_create(C.byref(desc), _stream(), C.byref(out)), "ecord_rollout_plan_create")

@@ -127,18 +127,24 @@ class B200Solver:
         self._graph_cache = (tg, dg)
         return dg
 
-    def _rollout_state(self, dg, T, gemm, tau, S):
+    def get_epsilon(self):
+        """The reference's linear schedule over parameter steps (solver.py:184-186)."""
+        return self.initial_epsilon - (self.initial_epsilon - self.final_epsilon) * min(
+            1, self.num_param_steps / self.final_epsilon_step)
+
+    def _rollout_state(self, dg, T, gemm, tau, S, epsilon=0.0):
         """Device state for a rollout.  States are kept (the two most recent) and re-initialised when the same graph
         batch is rolled out again with the same shape -- test_solver's trajectory chunks (testing.py:174-189) and
         repeated validation passes -- which saves the buffer allocations and the CUDA-graph capture."""
-        key = (id(dg), T, gemm, self.compat, tau, self.seed, self.steps_per_graph)
+        key = (id(dg), T, gemm, self.compat, tau, self.seed, self.steps_per_graph, epsilon)
         for i, (k, st) in enumerate(self._state_cache):
             if k == key and st.g is dg and st.max_steps >= S:
                 self._state_cache.insert(0, self._state_cache.pop(i))
                 st.reset()
                 return st
         st = RolloutState(dg, self.weights, T, gemm=gemm, compat=self.compat, tau=tau, seed=self.seed, max_steps=S,
-                          log_scores=True, log_actions=True, steps_per_graph=self.steps_per_graph, dump_q=False)
+                          log_scores=True, log_actions=True, steps_per_graph=self.steps_per_graph, dump_q=False,
+                          epsilon=epsilon)
         self._state_cache.insert(0, (key, st))
         for _, old in self._state_cache[2:]:
             old.close()
@@ -152,7 +158,9 @@ class B200Solver:
         """Same contract as DQNSolver.rollout (solver.py:196-377) for the test-time path.
         Extra keywords: init_state (int8 [N, num_tradj]) pins the initial spins (the reference draws them
         from numpy's global RNG, tradjectories.py:64 -- reproduced here when init_state is None);
-        traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU sharding)."""
+        traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU sharding).
+        use_epsilon=True applies the epsilon-greedy exploration of actors/ecord.py:171-180 with epsilon =
+        get_epsilon() (solver.py:184-186,334), drawn on the device; validation passes use_epsilon=False."""
         if use_network_initialisation or callbacks:
             raise NotImplementedError("network initialisation / callbacks are not implemented by the B200 engine yet "
                                       "(SURVEY.md 8f)")
@@ -183,7 +191,9 @@ class B200Solver:
         T = init_state.shape[1]
 
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        state = self._rollout_state(dg, T, gemm or self.gemm, tau, S)
+        # solver.py:334: epsilon = get_epsilon() whenever use_epsilon is set (test_solver passes use_epsilon=False)
+        epsilon = float(self.get_epsilon()) if use_epsilon else 0.0
+        state = self._rollout_state(dg, T, gemm or self.gemm, tau, S, epsilon)
         ev[0].record()
         state.gnn_embed()
         ev[1].record()

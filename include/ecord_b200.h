@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ECORD_ABI_VERSION 1
+#define ECORD_ABI_VERSION 2
 
 /* error codes (<0) */
 #define ECORD_E_NULL      (-1)  /* required pointer is NULL */
@@ -288,10 +288,12 @@ int ecord_policy_pre(const ecord_graph *g, const ecord_env *env, const ecord_wei
  *      actors/ecord.py:12-19, Philox stream seeded by (seed, step_no)) selection, and the cache of the
  *      chosen vertex's embedding for the next step.  compat != 0 reproduces the reference's gather
  *      with the LOCAL index into the FLAT array (quirk A: ecord.py:167,183 -> _base.py:305-308).
- *      forced_actions (optional, [G*T] local ids) overrides the selection (teacher forcing). ---- */
+ *      forced_actions (optional, [G*T] local ids) overrides the selection (teacher forcing).
+ *      epsilon in [0,1]: epsilon-greedy (actors/ecord.py:171-180) -- with that probability a unit's action is replaced
+ *      by floor(U * n_g), U uniform (Philox stream seeded by (seed, unit, step_no)). ---- */
 int ecord_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                    int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
-                   int32_t q_mode /* ECORD_Q_*; tau > 0 requires ECORD_Q_EXACT */, void *stream);
+                   int32_t q_mode /* ECORD_Q_*; tau > 0 requires ECORD_Q_EXACT */, float epsilon, void *stream);
 
 /* ---- a10: the S-step loop as CUDA graphs of (policy_step, q_select, env_step); replaces the Python
  *      loop of DQNSolver.rollout (solvers/solver.py:316-362).  No host round trip per step. ---- */
@@ -303,7 +305,8 @@ typedef struct ecord_rollout_desc {
     int32_t  gemm_mode;       /* ECORD_GEMM_* */
     int32_t  q_mode;          /* ECORD_Q_* */
     int32_t  compat;          /* quirk A on/off */
-    int32_t  _pad0;
+    float    epsilon;         /* epsilon-greedy: probability of a uniformly random action per (g,t) and step
+                                 (actors/ecord.py:171-180); 0 = greedy / tau sampling only */
     float    tau;
     int32_t  steps_per_graph; /* steps unrolled into one CUDA graph (e.g. 16) */
     uint64_t seed;

@@ -275,6 +275,45 @@ def test_tau_sampling_is_distributionally_right():
     assert torch.equal(st.actions, st2.actions)     # same seed -> same draw (counter-based Philox)
 
 
+@pytest.mark.parametrize("gemm", ["fp32", "bf16"])
+def test_epsilon_greedy_is_distributionally_right(gemm):
+    """epsilon-greedy (actors/ecord.py:171-180): with probability epsilon a unit's action is floor(U * n_g), otherwise the
+    arg-max.  The reference draws from torch.rand, so the distribution is what can match: the fraction of overridden
+    units, uniformity of the random actions over each graph's own vertex range (ragged batch), determinism per seed --
+    in the exact selection kernel (fp32 mode) and in the tensor-core path's finish kernel (bf16 mode)."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    from ecord_b200.graphs import synthetic_set
+    sd = random_state_dicts(5, perturb_norms=True)
+    w = DeviceWeights(sd)
+    dg = DeviceGraph(GraphBatcher()(synthetic_set("er", 16, 1, p=0.4) + synthetic_set("er", 10, 1, p=0.4, seed0=3)).tg)
+    T = 4096
+
+    def first_actions(eps, seed=7):
+        st = RolloutState(dg, w, T, gemm=gemm, seed=seed, epsilon=eps)
+        st.gnn_embed()
+        st.env_init(np.zeros((dg.N, T), np.int8))
+        st.policy_step()
+        st.q_select()
+        return st.actions.view(dg.G, T).cpu().numpy()
+
+    greedy = first_actions(0.0)
+    assert (greedy == greedy[:, :1]).all()                 # identical states -> one arg-max per graph
+    full = first_actions(1.0)
+    for gi, n in enumerate((16, 10)):
+        counts = np.bincount(full[gi], minlength=n)
+        assert counts.shape[0] == n                          # never outside the graph's own vertices
+        chi2 = float(((counts - T / n) ** 2 / (T / n)).sum())
+        assert chi2 < (n - 1) + 6 * np.sqrt(2 * (n - 1)) + 10, (gi, chi2)
+    part = first_actions(0.25)
+    for gi, n in enumerate((16, 10)):
+        changed = float((part[gi] != greedy[gi, 0]).mean())
+        expect = 0.25 * (1 - 1 / n)
+        assert abs(changed - expect) < 5 * np.sqrt(expect * (1 - expect) / T), (gi, changed, expect)
+    assert np.array_equal(part, first_actions(0.25)) and not np.array_equal(part, first_actions(0.25, seed=8))
+    with pytest.raises(ValueError):
+        RolloutState(dg, w, 2, gemm=gemm, epsilon=1.5)
+
+
 def test_gemm_variants_agree_in_subprocesses():
     """The CTA-pair (cta_group::2) tcgen05 kernels, the single-CTA ones (ECORD_GEMM_PAIR=0) and plain launches
     (ECORD_PDL=0, no programmatic dependent launch) compute the same rollout: the switches are read once per process,

@@ -158,6 +158,53 @@ def test_rollout_state_reuse_is_invisible(gemm):
     assert torch.equal(torch.stack(logs[0]["scores"]), torch.stack(logs[2]["scores"]))
 
 
+def test_log_stats_matches_oracle_environment_replay():
+    """log_stats (solver.py:244-249,322-327): per-step `state` and `peeks` are the environment BEFORE the step's flip in
+    the padded [G, n_max, T] layout (fill -1 / -1e10), `actions` the local vertex ids.  Replaying the logged actions in
+    the oracle environment must reproduce every logged plane and score bit for bit (ragged batch, fp32 mode)."""
+    from util import oracle_batch
+    graphs = synthetic_set("er", 24, 2, p=0.3) + synthetic_set("er", 17, 2, p=0.3, seed0=5)
+    sd = random_state_dicts(2)
+    batch = GraphBatcher()(graphs)
+    T, S, N = 3, 12, batch.tg.num_nodes
+    init = np.random.RandomState(4).randint(0, 2, (N, T), dtype=np.int8)
+    log = _solver(sd, gemm="fp32").rollout(batch, num_tradj=T, num_steps=S, use_epsilon=False, tau=0, log_stats=True,
+                                           init_state=init)
+    ob = oracle_batch(graphs)
+    env = orc.EnvOracle(ob, T, init)
+    assert len(log["actions"]) == len(log["peeks"]) == len(log["state"]) == S
+    for s in range(S):
+        for gi in range(ob.G):
+            lo, hi = ob.ptr[gi], ob.ptr[gi + 1]
+            np.testing.assert_array_equal(log["state"][s][gi, :hi - lo].numpy(), env.node_features[lo:hi, :, 0])
+            np.testing.assert_array_equal(log["peeks"][s][gi, :hi - lo].numpy(), env.node_features[lo:hi, :, 1])
+            assert (log["state"][s][gi, hi - lo:] == -1).all() and (log["peeks"][s][gi, hi - lo:] == -1e10).all()
+        env.step(log["actions"][s].numpy())
+        np.testing.assert_array_equal(log["scores"][s].numpy(), env.scores)
+    np.testing.assert_array_equal(log["best_state"].numpy(), env.best_states_batched().numpy())
+
+
+def test_use_epsilon_follows_the_reference_schedule():
+    """solver.py:184-186,334: rollout(use_epsilon=True) explores with epsilon = get_epsilon() (linear in num_param_steps),
+    also outside training; a fresh solver therefore acts fully at random, one past final_epsilon_step mostly greedily."""
+    graphs = synthetic_set("er", 30, 2, p=0.3)
+    sd = random_state_dicts(1)
+    batch = GraphBatcher()(graphs)
+    T, S = 64, 20
+    init = np.random.RandomState(0).randint(0, 2, (batch.tg.num_nodes, T), dtype=np.int8)
+    solver = _solver(sd, gemm="fp32", final_epsilon=0.05, final_epsilon_step=100)
+    assert solver.get_epsilon() == 1.0
+    kw = dict(num_tradj=T, num_steps=S, tau=0, init_state=init, log_stats=True)
+    greedy = torch.stack(solver.rollout(batch, use_epsilon=False, **kw)["actions"])
+    rnd = torch.stack(solver.rollout(batch, use_epsilon=True, **kw)["actions"])
+    assert float((rnd != greedy).float().mean()) > 0.8                     # epsilon = 1: uniform random vertices
+    solver.num_param_steps = 1000
+    assert abs(solver.get_epsilon() - 0.05) < 1e-12
+    some = torch.stack(solver.rollout(batch, use_epsilon=True, **kw)["actions"])
+    first = float((some[0] != greedy[0]).float().mean())                  # step 0: same state in both runs
+    assert 0.0 < first < 0.2
+
+
 def test_unsupported_options_fail_loudly():
     sd = random_state_dicts(1)
     from ecord_b200.solver import B200Solver
