@@ -105,6 +105,7 @@ SYMBOLS = {
     "ecord_policy_step": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _i32, _i32, _vp]),
     "ecord_policy_pre": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _vp]),
     "ecord_q_select": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _f32, _u64, _i32, _vp, _i32, _f32, _vp]),
+    "ecord_node_init_sample": (_i32, [_P(Graph), _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _u64, _vp, _vp]),
     "ecord_rollout_plan_create": (_i32, [_P(RolloutDesc), _vp, _P(_vp)]),
     "ecord_rollout_plan_run": (_i32, [_vp, _i32, _P(_i64)]),
     "ecord_rollout_plan_reset": (_i32, [_vp]),

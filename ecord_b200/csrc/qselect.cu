@@ -490,6 +490,46 @@ extern "C" int ecord_q_select(const ecord_graph *g, const ecord_env *env, const 
                            as_stream(stream));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Network initialisation (solvers/solver.py:256-277, actors/_base.py:238-245, models/node_classifier.py): the initial
+// spins are drawn from Bernoulli(logits = heads[h](gnn_node_embeddings)), one Linear(16 -> 1) head per probability
+// map.  With more than one head the reference additionally re-draws each spin uniformly with probability epsilon
+// (the perturbation sits inside the multi-head branch, solver.py:268-273).  One thread per (vertex, trajectory);
+// output in the reference's [N][T] layout, the form ecord_env_init takes.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_node_init_sample(int N, int T, int t_off, const float *__restrict__ gnn_out, const float *__restrict__ head_w,
+                                   const float *__restrict__ head_b, int head, float perturb_eps, uint64_t seed,
+                                   int8_t *__restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * T) return;
+    const int v = (int)(idx / T), t = (int)(idx % T);
+    float logit = head_b[head];
+#pragma unroll
+    for (int k = 0; k < ECORD_DIM_GNN; ++k) logit = fmaf(gnn_out[(long long)v * ECORD_DIM_GNN + k], head_w[head * ECORD_DIM_GNN + k], logit);
+    const float prob = 1.0f / (1.0f + expf(-logit));
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)v, (uint32_t)(t + t_off), 0x494E4954u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    int s = uniform01_open(r.x) < prob ? 1 : 0;
+    if (perturb_eps > 0.0f && uniform01_open(r.y) < perturb_eps) s = (int)(r.z & 1u);
+    out[idx] = (int8_t)s;
+}
+}  // namespace
+
+extern "C" int ecord_node_init_sample(const ecord_graph *g, int32_t num_tradj, int32_t tradj_offset, const float *gnn_out, const float *head_w,
+                                      const float *head_b, int32_t num_heads, int32_t head, float perturb_epsilon,
+                                      uint64_t seed, int8_t *init_state_out, void *stream) {
+    ECORD_RET_IF(!g || !gnn_out || !head_w || !head_b || !init_state_out, ECORD_E_NULL);
+    ECORD_RET_IF(g->num_nodes <= 0 || num_tradj <= 0 || tradj_offset < 0 || num_heads <= 0 || head < 0 || head >= num_heads,
+                 ECORD_E_SIZE);
+    ECORD_RET_IF(!(perturb_epsilon >= 0.0f && perturb_epsilon <= 1.0f), ECORD_E_SIZE);
+    const long long NT = (long long)g->num_nodes * num_tradj;
+    k_node_init_sample<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(g->num_nodes, num_tradj, tradj_offset, gnn_out, head_w, head_b, head,
+                                                                        num_heads > 1 ? perturb_epsilon : 0.0f, seed,
+                                                                        init_state_out);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int ecord_greedy_select(const ecord_graph *g, const ecord_env *env, float tau, uint64_t seed, int32_t step_no,
                                    int32_t *actions, int32_t *at_local_min, void *stream) {
     ECORD_RET_IF(!g || !env || !actions, ECORD_E_NULL);

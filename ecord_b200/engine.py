@@ -272,7 +272,10 @@ class RolloutState:
     @_on_stream
     def env_init(self, init_state):
         """a2: init_state int8 [N,T] (host numpy / torch, reference layout)."""
-        s = torch.as_tensor(np.ascontiguousarray(np.asarray(init_state), dtype=np.int8))
+        if torch.is_tensor(init_state) and init_state.is_cuda:
+            s = init_state.to(torch.int8).contiguous()
+        else:
+            s = torch.as_tensor(np.ascontiguousarray(np.asarray(init_state), dtype=np.int8))
         if tuple(s.shape) != (self.g.N, self.T):
             raise AssertionError(f"init_state must have shape {(self.g.N, self.T)}.  Got {tuple(s.shape)}.")
         self.init_state_dev = s.to(self.device, non_blocking=False)
@@ -291,6 +294,19 @@ class RolloutState:
             check(self.lib.ecord_policy_pre(C.byref(self.g.c), C.byref(self.env_c), C.byref(self.w.c),
                                             C.byref(self.policy_c), _stream()), "ecord_policy_pre")
             self.kernel_launches += 1
+
+    @_on_stream
+    def network_init_state(self, head_w, head_b, head=0, perturb_epsilon=0.0, tradj_offset=0, draw=0):
+        """Initial spins drawn from the node classifier on the GNN embedding (use_network_initialisation,
+        solver.py:256-277); needs gnn_embed() first.  head_w [H,16], head_b [H] device tensors.  Returns int8 [N,T]
+        on the device, the form env_init takes.  `draw` numbers the call: each one is a fresh sample."""
+        out = torch.empty(self.g.N, self.T, dtype=torch.int8, device=self.device)
+        check(self.lib.ecord_node_init_sample(C.byref(self.g.c), self.T, int(tradj_offset), ptr(self.gnn_out), ptr(head_w), ptr(head_b),
+                                              int(head_w.shape[0]), int(head), float(perturb_epsilon),
+                                              (self.seed + 0x51ED270B + 0x9E3779B97F4A7C15 * int(draw)) & (2 ** 64 - 1), ptr(out),
+                                              _stream()), "ecord_node_init_sample")
+        self.kernel_launches += 1
+        return out
 
     # ---- step-wise API (tests, log_stats) -----------------------------------------------------
     @_on_stream

@@ -118,3 +118,23 @@ def state_dicts_from_checkpoint(checkpoint):
             raise KeyError(f"checkpoint has no '{key}' (canonical ECORD network expected)")
         sd[mod] = ck[key]
     return check_state_dicts(sd)
+
+
+def node_classifier_heads(sd):
+    """NodeClassifier (models/node_classifier.py:8-30: `heads.<i>.0` = Linear(16 -> 1), one per probability map) as
+    (weight [H,16], bias [H]) fp32 CPU tensors.  Accepts the module, its state_dict, or None (-> None)."""
+    if sd is None:
+        return None
+    if hasattr(sd, "state_dict"):
+        sd = sd.state_dict()
+    ws, bs = [], []
+    while f"heads.{len(ws)}.0.weight" in sd:
+        i = len(ws)
+        w = torch.as_tensor(sd[f"heads.{i}.0.weight"]).detach().to('cpu', torch.float32)
+        b = torch.as_tensor(sd[f"heads.{i}.0.bias"]).detach().to('cpu', torch.float32)
+        if tuple(w.shape) != (1, DIM_GNN) or tuple(b.shape) != (1,):
+            raise ValueError(f"node_classifier head {i}: expected Linear({DIM_GNN} -> 1)")
+        ws.append(w.view(-1)); bs.append(b.view(()))
+    if not ws:
+        raise KeyError("node_classifier state_dict has no 'heads.0.0.weight'")
+    return torch.stack(ws).contiguous(), torch.stack(bs).contiguous()

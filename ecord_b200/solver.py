@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .engine import DeviceGraph, DeviceWeights, RolloutState
-from .network import check_state_dicts, state_dicts_from_checkpoint
+from .network import check_state_dicts, node_classifier_heads, state_dicts_from_checkpoint
 from .observations import CANONICAL_GLOB_FEATURES, CANONICAL_NODE_FEATURES, check_canonical
 
 
@@ -57,8 +57,6 @@ class B200Solver:
                  gemm="bf16", compat=True, steps_per_graph=16, seed=0):
         if use_ecodqn or use_double_q_networks:
             raise NotImplementedError("only the single-Q ECORD actor (Actor_Q, actors/ecord.py:26) is implemented")
-        if node_classifier is not None:
-            raise NotImplementedError("network initialisation head is outside the canonical configuration")
         if node_encoder is None or add_glob_to_nodes or not add_glob_to_obs:
             raise NotImplementedError("canonical ECORD wiring expected: node_encoder set, add_glob_to_nodes=False, "
                                       "add_glob_to_obs=True (experiments/train.py:88-90)")
@@ -75,10 +73,12 @@ class B200Solver:
         self.num_env_steps = self.num_rollouts = self.num_param_steps = 0
         self.initial_epsilon, self.final_epsilon, self.final_epsilon_step = initial_epsilon, final_epsilon, final_epsilon_step
         self.set_weights({'gnn': _sd(gnn), 'rnn': _sd(rnn), 'gnn2rnn': _sd(gnn2rnn), 'node_encoder': _sd(node_encoder)})
+        self.set_node_classifier(node_classifier)
         self.actor = _ActorShim(self)
         self._last_state = None
         self._graph_cache = (None, None)
         self._state_cache = []
+        self._net_init_draws = 0
 
     # ---- weights ------------------------------------------------------------------------------
     def set_weights(self, state_dicts):
@@ -86,10 +86,19 @@ class B200Solver:
         self.weights = DeviceWeights(self.state_dicts, self.device, pack_bf16=True)
         self._state_cache = []          # cached states hold pointers into the old weights
 
+    def set_node_classifier(self, node_classifier):
+        """The optional per-vertex head that proposes initial spins (models/node_classifier.py; experiments/configs.py:
+        194-206): module, state_dict or None."""
+        heads = node_classifier_heads(node_classifier)
+        self.node_classifier = None if heads is None else tuple(t.to(self.device) for t in heads)
+
     def load(self, fname, quiet=False):
         """Ingest a reference checkpoint written by DQNSolver.save (solver.py:582-617)."""
         checkpoint = torch.load(fname, map_location="cpu", weights_only=False)
         self.set_weights(state_dicts_from_checkpoint(checkpoint))
+        ck = checkpoint.get('actor:checkpoint', checkpoint)
+        if 'node_classifier:state_dict' in ck:          # actors/ecord.py:250-251,269
+            self.set_node_classifier(ck['node_classifier:state_dict'])
         for k in ("num_env_steps", "num_rollouts", "num_param_steps", "initial_epsilon", "final_epsilon",
                   "final_epsilon_step"):
             if k in checkpoint:
@@ -101,7 +110,12 @@ class B200Solver:
         import os
         if os.path.splitext(fname)[-1] != '.pth':
             fname += '.pth'
-        ck = {'actor:checkpoint': {f'{m}:state_dict': sd for m, sd in self.state_dicts.items()},
+        actor_ck = {f'{m}:state_dict': sd for m, sd in self.state_dicts.items()}
+        if self.node_classifier is not None:            # actors/ecord.py:250-251
+            hw, hb = (t.cpu() for t in self.node_classifier)
+            actor_ck['node_classifier:state_dict'] = {k: v for i in range(hw.shape[0]) for k, v in
+                                                      ((f'heads.{i}.0.weight', hw[i:i + 1].clone()), (f'heads.{i}.0.bias', hb[i:i + 1].clone()))}
+        ck = {'actor:checkpoint': actor_ck,
               'num_env_steps': self.num_env_steps, 'num_rollouts': self.num_rollouts,
               'num_param_steps': self.num_param_steps, 'initial_epsilon': self.initial_epsilon,
               'final_epsilon': self.final_epsilon, 'final_epsilon_step': self.final_epsilon_step}
@@ -161,9 +175,8 @@ class B200Solver:
         traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU sharding).
         use_epsilon=True applies the epsilon-greedy exploration of actors/ecord.py:171-180 with epsilon =
         get_epsilon() (solver.py:184-186,334), drawn on the device; validation passes use_epsilon=False."""
-        if use_network_initialisation or callbacks:
-            raise NotImplementedError("network initialisation / callbacks are not implemented by the B200 engine yet "
-                                      "(SURVEY.md 8f)")
+        if callbacks:
+            raise NotImplementedError("training callbacks are not implemented by the B200 engine (SURVEY.md 8f rank 4)")
         tau = self.tau if tau is None else tau
         tau = 0.0 if tau is None else float(tau)
         log = defaultdict(list)
@@ -178,17 +191,23 @@ class B200Solver:
         else:
             S = int(num_steps)
 
-        if init_state is None:
-            init_state = np.random.randint(0, 2, (N, num_tradj), dtype=np.int8)   # tradjectories.py:64
+        # use_network_initialisation (solver.py:256-277): spins drawn from the node classifier on the GNN embedding; without
+        # such a head the reference falls back to the random default.  An explicit init_state (engine extra) wins.
+        from_network = bool(use_network_initialisation) and self.node_classifier is not None and init_state is None
+        if from_network:
+            T = num_tradj if traj_slice is None else traj_slice[1] - traj_slice[0]
         else:
-            if torch.is_tensor(init_state):
-                init_state = init_state.cpu().numpy()
-            assert init_state.shape == (N, num_tradj), \
-                f"init_state must have shape {(N, num_tradj)}.  Got {init_state.shape}."
-            init_state = np.asarray(init_state, dtype=np.int8)
-        if traj_slice is not None:
-            init_state = np.ascontiguousarray(init_state[:, traj_slice[0]:traj_slice[1]])
-        T = init_state.shape[1]
+            if init_state is None:
+                init_state = np.random.randint(0, 2, (N, num_tradj), dtype=np.int8)   # tradjectories.py:64
+            else:
+                if torch.is_tensor(init_state):
+                    init_state = init_state.cpu().numpy()
+                assert init_state.shape == (N, num_tradj), \
+                    f"init_state must have shape {(N, num_tradj)}.  Got {init_state.shape}."
+                init_state = np.asarray(init_state, dtype=np.int8)
+            if traj_slice is not None:
+                init_state = np.ascontiguousarray(init_state[:, traj_slice[0]:traj_slice[1]])
+            T = init_state.shape[1]
 
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         # solver.py:334: epsilon = get_epsilon() whenever use_epsilon is set (test_solver passes use_epsilon=False)
@@ -197,6 +216,12 @@ class B200Solver:
         ev[0].record()
         state.gnn_embed()
         ev[1].record()
+        if from_network:
+            hw, hb = self.node_classifier
+            head = int(np.random.randint(0, hw.shape[0]))           # solver.py:267: a random readout head
+            init_state = state.network_init_state(hw, hb, head, perturb_epsilon=epsilon,
+                                                  tradj_offset=0 if traj_slice is None else traj_slice[0],
+                                                  draw=self._net_init_draws)
         state.env_init(init_state)
         if pre_solve_with_greedy:                       # solver.py:294-295: greedy_solve(env, init_from_best=False)
             log['greedy_pre_steps'] = state.greedy_solve(init_from_best=False, rebase=True)
@@ -273,6 +298,7 @@ class B200Solver:
         log['t_tot'] = torch.tensor([t_init_emb + t_rollout])
         log['kernel_launches'] = state.kernel_launches
         self._last_state = state
+        self._net_init_draws += int(from_network)
         self.last_wall = time.time() - t_all
         return log
 

@@ -295,6 +295,17 @@ int ecord_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weigh
                    int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
                    int32_t q_mode /* ECORD_Q_*; tau > 0 requires ECORD_Q_EXACT */, float epsilon, void *stream);
 
+/* ---- network initialisation (rollout flag use_network_initialisation; solvers/solver.py:256-277,
+ *      actors/_base.py:238-245, models/node_classifier.py:8-30): init_state_out i8 [N][T] ~ Bernoulli(sigmoid(
+ *      head_w[head] . gnn_out[v] + head_b[head])), gnn_out = the GNN embedding BEFORE gnn2rnn (ecord_gnn_embed).
+ *      head_w f32 [num_heads][16], head_b f32 [num_heads] (device).  With num_heads > 1 every spin is re-drawn
+ *      uniformly with probability perturb_epsilon (solver.py:268-273); with one head the argument is ignored, as in
+ *      the reference.  The draw of (vertex v, trajectory t) depends on (seed, v, tradj_offset + t) only, so a
+ *      trajectory shard reproduces its columns of the unsharded draw.  The result feeds ecord_env_init. ---- */
+int ecord_node_init_sample(const ecord_graph *g, int32_t num_tradj, int32_t tradj_offset, const float *gnn_out, const float *head_w,
+                           const float *head_b, int32_t num_heads, int32_t head, float perturb_epsilon, uint64_t seed,
+                           int8_t *init_state_out, void *stream);
+
 /* ---- a10: the S-step loop as CUDA graphs of (policy_step, q_select, env_step); replaces the Python
  *      loop of DQNSolver.rollout (solvers/solver.py:316-362).  No host round trip per step. ---- */
 typedef struct ecord_rollout_desc {

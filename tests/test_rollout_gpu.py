@@ -205,6 +205,51 @@ def test_use_epsilon_follows_the_reference_schedule():
     assert 0.0 < first < 0.2
 
 
+def test_network_initialisation_samples_the_node_classifier(tmp_path):
+    """use_network_initialisation (solver.py:256-277): init spins ~ Bernoulli(sigmoid(head(gnn_embedding))).  The
+    reference samples with torch's RNG, so the per-vertex frequencies are what can match: they are checked against
+    sigmoid(W gnn_out + b) computed on the host from the (parity-tested) GNN embedding; a solver without the head falls
+    back to the random default, and the head survives a checkpoint round trip."""
+    graphs = synthetic_set("er", 20, 2, p=0.3)
+    sd = random_state_dicts(6, perturb_norms=True)
+    batch = GraphBatcher()(graphs)
+    gen = torch.Generator().manual_seed(0)
+    heads = {"heads.0.0.weight": torch.randn(1, 16, generator=gen) * 2, "heads.0.0.bias": torch.zeros(1),
+             "heads.1.0.weight": torch.randn(1, 16, generator=gen) * 2, "heads.1.0.bias": torch.randn(1, generator=gen)}
+    one = {k: v for k, v in heads.items() if k.startswith("heads.0")}
+    T = 4096
+    solver = _solver(sd, gemm="fp32", node_classifier=one)
+    log = solver.rollout(batch, num_tradj=T, num_steps=1, tau=0, use_epsilon=False, use_network_initialisation=True,
+                         log_stats=True)
+    state0 = torch.cat([log["state"][0][g, :20] for g in range(2)]).numpy()            # [N, T] spins before step 0
+    gnn_out = solver._last_state.gnn_out.cpu().double()
+    prob = torch.sigmoid(gnn_out @ one["heads.0.0.weight"].double().view(-1) + one["heads.0.0.bias"].double()).numpy()
+    freq = state0.mean(1)
+    assert np.all(np.abs(freq - prob) < 5 * np.sqrt(np.maximum(prob * (1 - prob), 1e-4) / T) + 1e-3), np.abs(freq - prob).max()
+    assert prob.max() - prob.min() > 0.05                      # the head is not trivially constant
+    # a second call is a fresh draw; the init score is the cut of the drawn spins
+    log_b = solver.rollout(batch, num_tradj=T, num_steps=1, tau=0, use_epsilon=False, use_network_initialisation=True,
+                           log_stats=True)
+    assert not torch.equal(log["state"][0], log_b["state"][0])
+    # two heads + use_epsilon: spins are re-drawn uniformly with probability epsilon (= 1 for a fresh solver)
+    two = _solver(sd, gemm="fp32", node_classifier=heads)
+    log2 = two.rollout(batch, num_tradj=T, num_steps=1, tau=0, use_epsilon=True, use_network_initialisation=True, log_stats=True)
+    s2 = torch.cat([log2["state"][0][g, :20] for g in range(2)]).numpy()
+    assert np.all(np.abs(s2.mean(1) - 0.5) < 5 * 0.5 / np.sqrt(T))
+    # no head -> the reference's fallback: random default initialisation
+    plain = _solver(sd, gemm="fp32")
+    np.random.seed(3)
+    a = plain.rollout(batch, num_tradj=8, num_steps=2, tau=0, use_epsilon=False, use_network_initialisation=True)
+    np.random.seed(3)
+    b = plain.rollout(batch, num_tradj=8, num_steps=2, tau=0, use_epsilon=False)
+    assert torch.equal(a["init_score"], b["init_score"])
+    # checkpoint round trip (actors/ecord.py:250-251,269)
+    f = two.save(str(tmp_path / "ck"))
+    other = _solver(random_state_dicts(9), gemm="fp32")
+    other.load(f, quiet=True)
+    assert other.node_classifier is not None and torch.equal(other.node_classifier[0].cpu(), two.node_classifier[0].cpu())
+
+
 def test_unsupported_options_fail_loudly():
     sd = random_state_dicts(1)
     from ecord_b200.solver import B200Solver
@@ -215,7 +260,7 @@ def test_unsupported_options_fail_loudly():
     solver = _solver(sd)
     batch = GraphBatcher()(synthetic_set("er", 10, 1, p=0.5))
     with pytest.raises(NotImplementedError):
-        solver.rollout(batch, num_tradj=2, num_steps=2, use_network_initialisation=True)
+        solver.rollout(batch, num_tradj=2, num_steps=2, callbacks=[(print, 1, None)])
 
 
 def test_full_size_er500_properties():
