@@ -344,11 +344,13 @@ def run_b200(args):
     solver = B200Solver(gnn=sd['gnn'], rnn=sd['rnn'], gnn2rnn=sd['gnn2rnn'], node_encoder=sd['node_encoder'],
                         device=dev, gemm=args.gemm, steps_per_graph=k)
     Ke = K
-    solver.rollout(batch, num_tradj=T, num_steps=min(Ke, 2 * k), tau=0, use_epsilon=False, init_state=init)   # warm
+    # warm-up call of the same shape: the solver keeps the device state of a graph batch (buffers, pinned staging, captured
+    # CUDA graphs) and re-initialises it on the next call, which is the steady state of test_solver's trajectory chunks
+    solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=init)
     pinned = torch.from_numpy(init).pin_memory()
     e2e_times = []
-    for _ in range(3):                  # median of three: a rollout allocates its state, and the caching allocator's
-        barrier()                       # occasional cudaMalloc / graph teardown shows up as a multi-ms outlier
+    for _ in range(3):                  # median of three calls
+        barrier()
         t0 = time.perf_counter()
         log = solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=pinned.numpy())
         sc = log['best_score_by_tradj'].to(dev)          # == torch.stack(log['scores'], -1).max(-1).values, reduced on the device
@@ -382,7 +384,7 @@ def run_b200(args):
                           "l2": "flushed (256 MB write) before every CUDA-graph launch of %d steps, outside the timed events" % k,
                           "weights": "random-init canonical ECORD network (seed 0)"},
                "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "note": "B200Solver.rollout incl. GNN, env init, H2D init states, D2H score log; median of 3 calls",
+                       "note": "B200Solver.rollout incl. GNN, env init, H2D init states, D2H score log and best states; median of 3 calls after one warm-up call of the same shape (device state of the batch reused)",
                        "calls_s": e2e_times, "device_s_last_call": e2e_dev},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
                "wall_s_timed_region": t_wall, "best_cut_mean": float(best.mean().item())}
