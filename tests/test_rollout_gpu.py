@@ -263,12 +263,19 @@ def test_unsupported_options_fail_loudly():
         solver.rollout(batch, num_tradj=2, num_steps=2, callbacks=[(print, 1, None)])
 
 
-def test_full_size_er500_properties():
-    """BASELINE configs[1] size (ER500, 50 graphs x 50 trajectories; steps truncated): size-independent properties."""
+@pytest.mark.parametrize("kind,n,G,T,S,gen", [
+    ("er", 500, 50, 50, 64, dict(p=0.15)),                                   # BASELINE configs[1]
+    ("ba", 500, 50, 50, 48, dict()),                                         # configs[2]: power-law degrees (dmax > 100)
+    ("er", 10000, 3, 128, 40, dict(avg_degree=10, signed=False)),            # configs[3]: ER10000 x 128 trajectories
+    ("er", 4000, 2, 128, 32, dict(avg_degree=40, signed=True)),              # configs[4]: GSet-shaped, degree 40, +-1
+], ids=["er500", "ba500", "er10000", "gset4000d40"])
+def test_full_size_properties(kind, n, G, T, S, gen):
+    """BASELINE config sizes (steps truncated): size-independent properties of the fused throughput-mode rollout --
+    the final score is the cut of the final spins, the peeks equal a from-scratch recomputation, the best score is the
+    maximum of the log, actions stay inside their graph, and the static counters equal the steps since the last flip."""
     from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
-    graphs = synthetic_set("er", 500, 50, p=0.15)
+    graphs = synthetic_set(kind, n, G, **gen)
     dg = DeviceGraph(GraphBatcher()(graphs).tg)
-    T, S = 50, 64
     st = RolloutState(dg, DeviceWeights(random_state_dicts(0)), T, gemm="bf16", max_steps=S)
     init = np.random.RandomState(1).randint(0, 2, (dg.N, T)).astype(np.int8)
     st.gnn_embed(); st.env_init(init); st.run(S)
@@ -281,12 +288,12 @@ def test_full_size_er500_properties():
     init_sc = orc.EnvOracle(ob, T, init).scores
     assert np.array_equal(np.maximum(log.max(0).values.cpu().numpy(), init_sc), st.best_score.view(dg.G, T).cpu().numpy())
     acts = st.action_log[:S].view(S, dg.G, T)
-    assert int(acts.min()) >= 0 and int(acts.max()) < 500
+    assert int(acts.min()) >= 0 and int(acts.max()) < n
     # static feature == steps since the vertex was last flipped
-    last = torch.zeros(dg.G, T, 500, dtype=torch.long)
+    last = torch.zeros(dg.G, T, n, dtype=torch.long)
     for s in range(S):
         last.scatter_(2, acts[s].cpu().long().unsqueeze(-1), s + 1)
-    static = nf[..., 2].cpu().view(dg.G, 500, T).permute(0, 2, 1)
+    static = nf[..., 2].cpu().view(dg.G, n, T).permute(0, 2, 1)
     assert torch.equal(static.long(), S - last)
 
 
