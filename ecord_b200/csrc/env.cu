@@ -10,6 +10,7 @@
 // the CSR row (coalesced col/w loads), the neighbour read-modify-writes scatter inside the unit's
 // contiguous row of the trajectory-major plane.  HBM/latency-bound: ~20 B per neighbour.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 // a2: initial peeks / scores (tradjectories.py:130-148), sequential per segment like segment_csr.
@@ -161,8 +162,9 @@ k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, co
     __shared__ float wb[64];
     msg_in_load(w.msg_w, w.msg_b, wt, wb);
     __syncthreads();
-    pdl_wait();                         // the chosen actions come from the selection kernel (no early trigger: the next
-                                        // kernel is the 148-CTA GRU, whose early residency only gets in the way)
+    pdl_wait();                         // the chosen actions come from the selection kernel (a no-op in a plain launch; no
+                                        // early trigger: the next kernel is the 148-CTA GRU, whose early residency only
+                                        // gets in the way)
     const int T = e.num_tradj;
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -342,8 +344,17 @@ int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *a
 int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                           const int32_t *step_base, int step_off, float *score_log, int32_t *action_log, cudaStream_t st) {
     const int GT = g->num_graphs * env->num_tradj;
-    ECORD_PDL_LAUNCH(k_env_step_fused, dim3(ceil_div((long long)GT * 32, 256)), dim3(256), (size_t)0, st, *g, *env, *w, *p, step_base, step_off, score_log,
-                                                                        action_log, GT);
+    // Large grids are launched plainly, small ones as programmatic dependents: letting 600+ small CTAs become resident
+    // while the Q kernel still runs costs more than their msg_in weight staging saves (ER500, 625 CTAs: 133.3 -> 131.7 us
+    // per step without the early launch), while a grid of about one CTA per SM gains (ER10000, 160 CTAs: 225.7 -> 223.5).
+    // Every other kernel of the chain gains from the early launch, 1.8 - 3.6 us each.
+    const int ctas = ceil_div((long long)GT * 32, 256);
+    static const int force = [] { const char *e = getenv("ECORD_ENV_PDL"); return e ? atoi(e) : -1; }();   // A/B: 0 plain, 1 PDL
+    if (force == 0 || (force < 0 && ctas > 2 * kNumSMs))
+        k_env_step_fused<<<dim3(ctas), dim3(256), 0, st>>>(*g, *env, *w, *p, step_base, step_off, score_log, action_log, GT);
+    else
+        ECORD_PDL_LAUNCH(k_env_step_fused, dim3(ctas), dim3(256), (size_t)0, st, *g, *env, *w, *p, step_base, step_off, score_log,
+                         action_log, GT);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
