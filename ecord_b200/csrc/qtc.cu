@@ -51,7 +51,8 @@ constexpr int kCtasPerSM = 4;         // 4 x 128 TMEM columns; shared memory and
 constexpr int A_BLK = QT * 32;        // bytes of one [128][16] fp16 operand block
 constexpr int B_BLK = QN * 32;        // bytes of one [80][16] block
 constexpr int kQtcThreads = 160;
-constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,88): the per-trajectory A operand R2 (16 fp16)
+constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,88) and [88,96): the per-trajectory A operand R2
+                                      // (16 fp16 = 8 columns), double-buffered by trajectory parity
 constexpr int kTmemCols = 128;
 
 constexpr int kRing = 8;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
@@ -255,7 +256,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
                 umma_f16(tmem_base, dA0, dB0, idesc, 0u);
                 umma_f16(tmem_base, dA1, dB0, idesc, 1u);
                 umma_f16(tmem_base, dA0, dB1, idesc, 1u);
-                umma_f16_ts(tmem_base, tmem_base + (uint32_t)kTmemA, dB2, idesc, 1u);
+                umma_f16_ts(tmem_base, tmem_base + (uint32_t)(kTmemA + 8 * (tt & 1)), dB2, idesc, 1u);
                 umma_commit(full0);
             }
             __syncwarp();
@@ -286,17 +287,25 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             const __half hz = __ushort_as_half((unsigned short)0), h1 = __ushort_as_half((unsigned short)0x3c00);   // 0, 1
             const __half f0h = (sp_c & 1) ? h1 : hz;
             const uint32_t w0 = pack_h2(f0h, f1h);
-            tmem_st8(trow + (uint32_t)kTmemA, w0, pack_h2(f2h, f1l), pack_h2(h1, h1), pack_h2(f2l, hz),
+            tmem_st8(trow + (uint32_t)(kTmemA + 8 * (tt & 1)), w0, pack_h2(f2h, f1l), pack_h2(h1, h1), pack_h2(f2l, hz),
                      w0, pack_h2(f2h, hz), 0u, 0u);
             tmem_st_wait();
+        };
+        // hand a trajectory to the tensor core: its R2 row is in tensor memory and the accumulator has been drained
+        auto hand_over = [&]() {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(ready0);
         };
         float f0, f1, f2, g0 = 0.f, g1 = 0.f, g2 = 0.f;
         prepare(0, f0, f1, f2);
+        hand_over();
         mbar_wait(setup_bar, 0);          // qa rows (bulk copy) are read by the epilogue
         for (int tt = 0; tt < nt; ++tt) {
+            // The R2 operand is double-buffered, so the next trajectory's row is written while the MMAs of this one run:
+            // the hand-off cycle of a CTA (accumulator read -> arrive -> control warp -> MMAs -> commit -> accumulator read)
+            // then contains only the accumulator read, not the feature preparation and its tcgen05.st round trip.
+            if (tt + 1 < nt) prepare(tt + 1, g0, g1, g2);
             mbar_wait(full0, (uint32_t)tt & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float gx[Q];
@@ -306,9 +315,9 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             tmem_ld16(trow + 48, gx + 48);
             const float d = tmem_ld1(trow + 64);
             tmem_ld_wait();
-            // accumulator drained, MMAs of trajectory tt complete (R2 free): hand trajectory tt+1 to the tensor core
-            // before the epilogue math, which its MMAs overlap
-            if (tt + 1 < nt) prepare(tt + 1, g0, g1, g2);
+            // accumulator drained, MMAs of trajectory tt complete: trajectory tt+1 goes to the tensor core before the
+            // epilogue math, which its MMAs overlap
+            if (tt + 1 < nt) hand_over();
             const float *sc = S.qa[tt];
             // |b' + Cc f|^2 = bb + 2 cb.f + f^T CC f
             float xx = fmaf(f0, fmaf(K.CC[0], f0, fmaf(2.0f * K.CC[1], f1, fmaf(2.0f * K.CC[2], f2, cb0))), bb);
