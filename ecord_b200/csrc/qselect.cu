@@ -26,19 +26,6 @@
 namespace {
 constexpr int Q = ECORD_DIM_Q;   // 64
 
-// ---- Philox4x32-10 (counter-based; stateless) for tau > 0 sampling ----
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-__device__ __forceinline__ float uniform01_open(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-
 // epsilon-greedy override (actors/ecord.py:171-180): with probability epsilon the unit's action becomes a uniformly random
 // vertex of its graph, floor(U * n_g).  One Philox draw per (unit, step); the stream differs from torch.rand, the
 // distribution is the reference's.
@@ -412,7 +399,7 @@ int q_kernels_per_step(int q_mode) { return q_mode == ECORD_Q_EXACT ? 1 : 2; }
 
 // qtc.cu
 int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                const int32_t *step_base, int step_off, cudaStream_t st);
+                const int32_t *step_base, int step_off, float tau, uint64_t seed, cudaStream_t st);
 int qtc_init_attrs();
 
 static int launch_select_finish(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
@@ -448,7 +435,7 @@ int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weig
                     int q_mode, float epsilon, cudaStream_t st) {
     if (q_mode == ECORD_Q_FAST) return launch_q_fast(g, env, w, p, step_base, step_off, compat, forced, epsilon, seed, st);
     if (q_mode == ECORD_Q_TC) {
-        int rc = launch_q_tc(g, env, w, p, step_base, step_off, st);
+        int rc = launch_q_tc(g, env, w, p, step_base, step_off, tau, seed, st);
         if (rc) return rc;
         return launch_select_finish(g, env, w, p, step_base, step_off, compat, forced, epsilon, seed, st);
     }
@@ -465,7 +452,7 @@ int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weig
 int check_q_mode(const ecord_graph *g, const ecord_weights *w, const ecord_policy *p, int q_mode, float tau) {
     ECORD_RET_IF(q_mode != ECORD_Q_EXACT && q_mode != ECORD_Q_FAST && q_mode != ECORD_Q_TC, ECORD_E_UNSUPPORTED);
     if (q_mode == ECORD_Q_EXACT) return 0;
-    ECORD_RET_IF(tau > 0.0f, ECORD_E_UNSUPPORTED);     // sampling needs the two-pass exact kernel
+    ECORD_RET_IF(tau > 0.0f && q_mode != ECORD_Q_TC, ECORD_E_UNSUPPORTED);     // sampling: exact (exponential race) or tensor-core (Gumbel-max) kernel
     ECORD_RET_IF(!p->keys, ECORD_E_NULL);
     ECORD_RET_IF(g->num_qtiles <= 0 || !g->qtile_graph || !g->qtile_v0, ECORD_E_NULL);
     if (q_mode == ECORD_Q_FAST) ECORD_RET_IF(!p->Ac || !p->LA || !p->node_Bc || !p->node_LB, ECORD_E_NULL);
@@ -483,7 +470,7 @@ extern "C" int ecord_q_select(const ecord_graph *g, const ecord_env *env, const 
     ECORD_RET_IF(!p->A || !p->v || !p->node_B || !p->node_emb || !p->last_sel || !p->actions || !w->q_fold, ECORD_E_NULL);
     ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj || steps_done < 0, ECORD_E_SIZE);
     ECORD_RET_IF(tau < 0.0f || !(epsilon >= 0.0f && epsilon <= 1.0f), ECORD_E_SIZE);
-    ECORD_RET_IF(tau > 0.0f && !p->q, ECORD_E_NULL);
+    ECORD_RET_IF(tau > 0.0f && q_mode == ECORD_Q_EXACT && !p->q, ECORD_E_NULL);     // the exact kernel's second pass re-reads q
     int rc = check_q_mode(g, w, p, q_mode, tau);
     if (rc) return rc;
     return launch_q_select(g, env, w, p, nullptr, steps_done, tau, seed, compat, forced_actions, q_mode, epsilon,

@@ -129,10 +129,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <bool DUMP_Q>
+// SAMPLE: tau > 0.  The reference's exponential race argmin_n -log(U_n) / exp((q_n - max q) / tau) (actors/ecord.py:12-19)
+// is the Gumbel-max trick in disguise: argmax_n q_n / tau - log(-log U_n), which needs no maximum first and therefore fits
+// this single pass.  U_n comes from the same Philox counter (vertex, unit, step; seed) as in the exact kernel, so both
+// kernels draw the same vertex wherever their Q-values agree to rounding.
+template <bool DUMP_Q, bool SAMPLE>
 __global__ void __launch_bounds__(kQtcThreads, kCtasPerSM)
 k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_tc, const __grid_constant__ QTcConst K,
-       const float *__restrict__ q2_b, const int32_t *step_base, int step_off, int t_chunk) {
+       const float *__restrict__ q2_b, const int32_t *step_base, int step_off, int t_chunk, float inv_tau, uint64_t seed) {
     extern __shared__ uint8_t smem_raw[];
     QTcSmem &S = *reinterpret_cast<QTcSmem *>(smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -346,8 +350,14 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
             const float dot = fmaf(0.505f, fmaf(lin, rstd, K.Wb), 0.495f * acc * rstd);
             const float q = (dot + bo) + sc[90];
             if (DUMP_Q) { if (valid) *q_ptr = q; q_ptr += n; }
+            float sel = q;
+            if (SAMPLE) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)(v0 + tid), (uint32_t)(gi * T + t_lo + tt), (uint32_t)steps_done,
+                                                         0x45434F52u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+                sel = fmaf(q, inv_tau, -__logf(-__logf(uniform01_open(r.x))));
+            }
             // arg-max: ordered-int max across the warp, lowest vertex among equals, one atomic per warp
-            const uint32_t u = __float_as_uint(q);
+            const uint32_t u = __float_as_uint(sel);
             const uint32_t ord = valid ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0u;
             const uint32_t mx = __reduce_max_sync(0xffffffffu, ord);
             const uint32_t bal = __ballot_sync(0xffffffffu, ord == mx);
@@ -371,8 +381,10 @@ constexpr int kQtcSmemBytes = 56 * 1024;
 
 int qtc_init_attrs() {
     // the dynamic request is padded so that at most four CTAs (4 x 128 TMEM columns) share an SM
-    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
-    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
+    ECORD_CUDA(cudaFuncSetAttribute(k_q_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQtcSmemBytes));
     return 0;
 }
 
@@ -392,7 +404,7 @@ static int qtc_t_chunk(int tiles, int T) {
 }
 
 int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                const int32_t *step_base, int step_off, cudaStream_t st) {
+                const int32_t *step_base, int step_off, float tau, uint64_t seed, cudaStream_t st) {
     static_assert(sizeof(QTcSmem) + 256 <= kQtcSmemBytes, "QTcSmem too large");
     QTcConst K;
     memcpy(K.bet, w->q_fold + 4 * Q, Q * sizeof(float));
@@ -402,11 +414,12 @@ int launch_q_tc(const ecord_graph *g, const ecord_env *env, const ecord_weights 
     const int T = env->num_tradj;
     const int t_chunk = qtc_t_chunk(g->num_qtiles, T);
     const dim3 grid(g->num_qtiles, ceil_div(T, t_chunk));
-    if (p->q)
-        ECORD_PDL_LAUNCH(k_q_tc<true>, grid, dim3(kQtcThreads), (size_t)kQtcSmemBytes, st, *g, *env, *p, (const float *)w->q_tc, K,
-                         w->q2_b, step_base, step_off, t_chunk);
-    else
-        ECORD_PDL_LAUNCH(k_q_tc<false>, grid, dim3(kQtcThreads), (size_t)kQtcSmemBytes, st, *g, *env, *p, (const float *)w->q_tc, K,
-                         w->q2_b, step_base, step_off, t_chunk);
+    const float inv_tau = tau > 0.0f ? 1.0f / tau : 0.0f;
+#define ECORD_QTC_LAUNCH(DQ, SM)                                                                                             \
+    ECORD_PDL_LAUNCH((k_q_tc<DQ, SM>), grid, dim3(kQtcThreads), (size_t)kQtcSmemBytes, st, *g, *env, *p, (const float *)w->q_tc, K, \
+                     w->q2_b, step_base, step_off, t_chunk, inv_tau, seed)
+    if (tau > 0.0f) { if (p->q) ECORD_QTC_LAUNCH(true, true); else ECORD_QTC_LAUNCH(false, true); }
+    else { if (p->q) ECORD_QTC_LAUNCH(true, false); else ECORD_QTC_LAUNCH(false, false); }
+#undef ECORD_QTC_LAUNCH
     return 0;
 }

@@ -110,7 +110,7 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     int rc = check_policy(desc->policy, desc->gemm_mode);
     if (rc) return rc;
     ECORD_RET_IF(desc->policy->rows != desc->graph->num_graphs * desc->env->num_tradj, ECORD_E_SIZE);
-    ECORD_RET_IF(desc->tau > 0.0f && !desc->policy->q, ECORD_E_NULL);
+    ECORD_RET_IF(desc->tau > 0.0f && desc->q_mode == ECORD_Q_EXACT && !desc->policy->q, ECORD_E_NULL);
     if ((rc = check_q_mode(desc->graph, desc->weights, desc->policy, desc->q_mode, desc->tau))) return rc;
     ECORD_RET_IF(!desc->weights->q_fold, ECORD_E_NULL);
     if (desc->gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!desc->weights->gru_w_bf16 || !desc->weights->p1_w_bf16, ECORD_E_NULL);

@@ -175,12 +175,13 @@ class RolloutState:
         self.epsilon = float(epsilon)     # epsilon-greedy (actors/ecord.py:171-180); fixed for the life of the CUDA-graph plan
         if not 0.0 <= self.epsilon <= 1.0:
             raise ValueError("epsilon must lie in [0, 1]")
-        # parity mode = (fp32 GEMM, exact Q); throughput mode = (bf16 tcgen05 GEMM, tensor-core Q).  tau > 0 needs exact Q.
+        # parity mode = (fp32 GEMM, exact Q); throughput mode = (bf16 tcgen05 GEMM, tensor-core Q).  tau > 0 (sampling) is
+        # implemented by the exact kernel (exponential race, two passes) and by the tensor-core kernel (Gumbel-max, one pass).
         if q_mode is None:
-            q_mode = "tc" if (gemm == "bf16" and self.tau == 0.0) else "exact"
+            q_mode = "tc" if gemm == "bf16" else "exact"
         self.q_mode = _Q_MODES[q_mode]
-        if self.q_mode != Q_EXACT and self.tau > 0:
-            raise ValueError("tau > 0 (sampling) requires q_mode='exact'")
+        if self.q_mode == Q_FAST and self.tau > 0:
+            raise ValueError("tau > 0 (sampling) requires q_mode='exact' or 'tc'")
         if self.q_mode == Q_TC and weights.q_tc is None:
             raise ValueError("weights were created with pack_bf16=False")
         self.fused = self.q_mode != Q_EXACT
@@ -215,7 +216,7 @@ class RolloutState:
         else:
             self.gates = torch.zeros(Mp, 6144, **f32)
             self.th = torch.zeros(Mp, 1024, **f32)
-        self.q = torch.zeros(N * T, **f32) if (dump_q or self.tau > 0) else None
+        self.q = torch.zeros(N * T, **f32) if (dump_q or (self.tau > 0 and self.q_mode == Q_EXACT)) else None
         self.gnn_out = torch.empty(N, 16, **f32)
         self.node_emb = torch.empty(N, 16, **f32)
         self.node_B = torch.empty(N, 64, **f32)

@@ -146,17 +146,18 @@ class B200Solver:
         return self.initial_epsilon - (self.initial_epsilon - self.final_epsilon) * min(
             1, self.num_param_steps / self.final_epsilon_step)
 
-    def _rollout_state(self, dg, T, gemm, tau, S, epsilon=0.0):
+    def _rollout_state(self, dg, T, gemm, tau, S, epsilon=0.0, seed=None):
         """Device state for a rollout.  States are kept (the two most recent) and re-initialised when the same graph
         batch is rolled out again with the same shape -- test_solver's trajectory chunks (testing.py:174-189) and
         repeated validation passes -- which saves the buffer allocations and the CUDA-graph capture."""
-        key = (id(dg), T, gemm, self.compat, tau, self.seed, self.steps_per_graph, epsilon)
+        seed = self.seed if seed is None else seed
+        key = (id(dg), T, gemm, self.compat, tau, seed, self.steps_per_graph, epsilon)
         for i, (k, st) in enumerate(self._state_cache):
             if k == key and st.g is dg and st.max_steps >= S:
                 self._state_cache.insert(0, self._state_cache.pop(i))
                 st.reset()
                 return st
-        st = RolloutState(dg, self.weights, T, gemm=gemm, compat=self.compat, tau=tau, seed=self.seed, max_steps=S,
+        st = RolloutState(dg, self.weights, T, gemm=gemm, compat=self.compat, tau=tau, seed=seed, max_steps=S,
                           log_scores=True, log_actions=True, steps_per_graph=self.steps_per_graph, dump_q=False,
                           epsilon=epsilon)
         self._state_cache.insert(0, (key, st))
@@ -212,7 +213,10 @@ class B200Solver:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         # solver.py:334: epsilon = get_epsilon() whenever use_epsilon is set (test_solver passes use_epsilon=False)
         epsilon = float(self.get_epsilon()) if use_epsilon else 0.0
-        state = self._rollout_state(dg, T, gemm or self.gemm, tau, S, epsilon)
+        # random streams (tau sampling, epsilon-greedy, greedy tie-breaks) are functions of (seed, unit, vertex, step): a
+        # trajectory shard gets its own seed so that the shards of one rollout do not repeat each other's draws
+        seed = self.seed if traj_slice is None else self.seed + 1000003 * int(traj_slice[0])
+        state = self._rollout_state(dg, T, gemm or self.gemm, tau, S, epsilon, seed)
         ev[0].record()
         state.gnn_embed()
         ev[1].record()

@@ -293,7 +293,8 @@ int ecord_policy_pre(const ecord_graph *g, const ecord_env *env, const ecord_wei
  *      by floor(U * n_g), U uniform (Philox stream seeded by (seed, unit, step_no)). ---- */
 int ecord_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                    int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
-                   int32_t q_mode /* ECORD_Q_*; tau > 0 requires ECORD_Q_EXACT */, float epsilon, void *stream);
+                   int32_t q_mode /* ECORD_Q_*; tau > 0: ECORD_Q_EXACT (exponential race, two passes) or ECORD_Q_TC
+                                      (Gumbel-max on the same Philox draws, one pass) */, float epsilon, void *stream);
 
 /* ---- network initialisation (rollout flag use_network_initialisation; solvers/solver.py:256-277,
  *      actors/_base.py:238-245, models/node_classifier.py:8-30): init_state_out i8 [N][T] ~ Bernoulli(sigmoid(

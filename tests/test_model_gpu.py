@@ -275,6 +275,46 @@ def test_tau_sampling_is_distributionally_right():
     assert torch.equal(st.actions, st2.actions)     # same seed -> same draw (counter-based Philox)
 
 
+def test_tau_sampling_in_the_tensor_core_kernel():
+    """tau > 0 in the fused throughput path (k_q_tc): Gumbel-max, argmax_n q_n / tau - log(-log U_n), is the exponential race
+    of actors/ecord.py:12-19 in one pass.  Checked two ways: chi-square of the empirical counts against softmax(q / tau),
+    and -- because both kernels read U_n from the same Philox counter -- vertex-for-vertex agreement with the exact
+    kernel's draw on the same state (up to near-ties of the race, where the 1e-6 differences between the two Q
+    evaluations decide)."""
+    from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
+    from ecord_b200.graphs import synthetic_set
+    sd = random_state_dicts(11, perturb_norms=True)
+    w = DeviceWeights(sd)
+    dg = DeviceGraph(GraphBatcher()(synthetic_set("er", 12, 1, p=0.4) + synthetic_set("er", 150, 1, p=0.1, seed0=2)).tg)
+    T, tau = 4096, 0.05
+
+    def draw(q_mode, seed=123):
+        st = RolloutState(dg, w, T, gemm="bf16", tau=tau, seed=seed, dump_q=True, q_mode=q_mode)
+        st.gnn_embed()
+        st.env_init(np.zeros((dg.N, T), np.int8))      # identical state in every trajectory -> identical q
+        st.policy_step()
+        st.q_select()
+        return st.actions.view(dg.G, T).cpu().numpy(), st.q_values().cpu()
+
+    a_tc, q_tc = draw("tc")
+    a_ex, q_ex = draw("exact")
+    assert float((q_tc - q_ex).abs().max() / q_ex.abs().max()) < 2e-5
+    assert (a_tc == a_ex).mean() > 0.995
+    q = q_tc[:12, 0].double()
+    pr = torch.softmax(q / tau, 0).numpy()
+    counts = np.bincount(a_tc[0], minlength=12)
+    chi2 = float((((counts - T * pr) ** 2) / np.maximum(T * pr, 1e-9))[pr * T > 5].sum())
+    dof = int((pr * T > 5).sum()) - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 10, (chi2, dof)
+    assert a_tc[1].min() >= 0 and a_tc[1].max() < 150 and len(np.unique(a_tc[1])) > 3
+    assert np.array_equal(a_tc, draw("tc")[0]) and not np.array_equal(a_tc, draw("tc", seed=124)[0])
+    # and through the fused loop
+    st = RolloutState(dg, w, 8, gemm="bf16", tau=tau, seed=5, max_steps=12)
+    st.gnn_embed(); st.env_init(np.zeros((dg.N, 8), np.int8)); st.run(12)
+    acts = st.action_log[:12].view(12, dg.G, 8).cpu().numpy()
+    assert acts[:, 0].max() < 12 and acts[:, 1].max() < 150 and len(np.unique(acts[:, 1])) > 8
+
+
 @pytest.mark.parametrize("gemm", ["fp32", "bf16"])
 def test_epsilon_greedy_is_distributionally_right(gemm):
     """epsilon-greedy (actors/ecord.py:171-180): with probability epsilon a unit's action is floor(U * n_g), otherwise the
