@@ -238,6 +238,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
 //   - tmem_empty lives in the leader and collects the 8 epilogue warps of both CTAs (remote mbarrier arrive)
 // =================================================================================================
 constexpr int kStages2 = 4;      // the pair kernel's stages are 28-32 KB (half of B per CTA): six fit in 192 KB
+constexpr int kHsPitch = 68;     // floats per row of the fp32 epilogue staging tile (64 + 4: 16-byte aligned rows, 4-way STS.128)
+constexpr int kBsPitch = 72;     // bf16 per row of the two bf16 staging tiles (64 + 8)
+constexpr int kStageTileBytes = BM * kHsPitch * 4 + 2 * BM * kBsPitch * 2;      // 34816 + 36864 bytes
 __device__ __forceinline__ bool elect_one() {          // one lane of the (converged) warp
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -289,6 +292,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     __shared__ __align__(16) float bias_s[2][4][64];       // GRU gate biases of the tile in flight (r, z combined; hn; in)
 
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *stage_gen = smem_raw + (tiles - smem_u32(smem_raw)) + kStages2 * STAGE_BYTES;      // epilogue staging tiles (GRU)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -393,56 +397,88 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
             const int row = m0 + q * 32 + lane;
             const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + ab * C::ACC_COLS;
             if (MODE == 0) {
-                const int j00 = nb * 64 + part * 16;
-                const float *hold = prm.hidden + ((size_t)cur * prm.rows_pad + row) * H + j00;
-                float *hnew = const_cast<float *>(prm.hidden) + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
-                __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
-                __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + j00;
-                float hv[16];                                 // old state, fetched while the MMAs run
-                if (row < prm.rows) {
+                // Global traffic of the epilogue goes through a shared-memory staging tile so that every LDG / STG covers
+                // whole 128-byte lines (a warp <-> 2 or 4 contiguous row pieces).  With lane <-> row (the TMEM layout) each
+                // 16-byte access of a warp hit 32 different lines and the L1 data pipe -- shared with the tensor core's
+                // operand reads and the TMA writes -- ran at 36 % on those wavefronts alone.
+                const int e = threadIdx.x - 64, ew = e >> 5;          // epilogue thread / warp index 0..511 / 0..15
+                const int rloc = q * 32 + lane;                        // row of the tile this thread owns in TMEM
+                float (*Hs)[kHsPitch] = reinterpret_cast<float (*)[kHsPitch]>(stage_gen);
+                __nv_bfloat16 (*Bs)[kBsPitch] = reinterpret_cast<__nv_bfloat16 (*)[kBsPitch]>(stage_gen + BM * kHsPitch * 4);
+                __nv_bfloat16 (*Ts)[kBsPitch] = Bs + BM;
+                const size_t cur_off = (size_t)cur * prm.rows_pad, nxt_off = (size_t)(1 - cur) * prm.rows_pad;
+                // (1) old state of the tile, coalesced: warp ew takes rows 8 ew .. 8 ew + 7, two 256-byte row pieces per instruction
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + i);
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m0 + r < prm.rows) v = *reinterpret_cast<const float4 *>(prm.hidden + (cur_off + m0 + r) * H + nb * 64 + 4 * c4);
+                    *reinterpret_cast<float4 *>(&Hs[r][4 * c4]) = v;
                 }
                 {   // this tile's 4 x 64 gate biases -> shared memory (read back as warp-uniform broadcasts)
-                    const int e = threadIdx.x - 64, gsel = e >> 6, j = nb * 64 + (e & 63);
+                    const int gsel = e >> 6, j = nb * 64 + (e & 63);
                     if (e < 256)
                         bias_s[ab][gsel][e & 63] = gsel == 0 ? prm.bih[j] + prm.bhh[j]
                                                  : gsel == 1 ? prm.bih[H + j] + prm.bhh[H + j]
                                                  : gsel == 2 ? prm.bhh[2 * H + j] : prm.bih[2 * H + j];
-                    asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");
                 }
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // staged state + biases visible
+                float hv[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(&Hs[rloc][part * 16 + i]);
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // every thread holds its values: Hs is free again
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int jj = 0; jj < ((prm.debug & 2) ? 0 : 16); jj += 16) {
-                    const int j0 = part * 16 + jj;
+                if (!(prm.debug & 2)) {
+                    const int j0 = part * 16;
                     float ar[16], az[16], ahn[16], ain[16];
                     tmem_ld16(tbase + j0, ar);
                     tmem_ld16(tbase + 64 + j0, az);
                     tmem_ld16(tbase + 128 + j0, ahn);
                     tmem_ld16(tbase + 192 + j0, ain);
                     tmem_ld_wait();
-                    if (row < prm.rows) {
-                        __align__(16) __nv_bfloat16 ob[16], ot[16];
+                    __align__(16) __nv_bfloat16 ob[16], ot[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int jl = part * 16 + jj + i;      // unit within the tile's 64
-                            const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
-                            const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
-                            const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
-                            const float hn = fmaf(hv[jj + i] - n, z, n);
-                            hv[jj + i] = hn;
-                            ob[i] = __float2bfloat16(hn);
-                            ot[i] = __float2bfloat16(tanh_fast(hn));
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        const int jl = part * 16 + i;           // unit within the tile's 64
+                        const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
+                        const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
+                        const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
+                        const float hn = fmaf(hv[i] - n, z, n);
+                        hv[i] = hn;
+                        ob[i] = __float2bfloat16(hn);
+                        ot[i] = __float2bfloat16(tanh_fast(hn));
+                    }
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(hnew + jj + i) = *reinterpret_cast<float4 *>(&hv[jj + i]);
-                        *reinterpret_cast<uint4 *>(hb + jj) = *reinterpret_cast<uint4 *>(&ob[0]);
-                        *reinterpret_cast<uint4 *>(hb + jj + 8) = *reinterpret_cast<uint4 *>(&ob[8]);
-                        *reinterpret_cast<uint4 *>(tb + jj) = *reinterpret_cast<uint4 *>(&ot[0]);
-                        *reinterpret_cast<uint4 *>(tb + jj + 8) = *reinterpret_cast<uint4 *>(&ot[8]);
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&Hs[rloc][part * 16 + i]) = *reinterpret_cast<float4 *>(&hv[i]);
+                    *reinterpret_cast<uint4 *>(&Bs[rloc][part * 16]) = *reinterpret_cast<uint4 *>(&ob[0]);
+                    *reinterpret_cast<uint4 *>(&Bs[rloc][part * 16 + 8]) = *reinterpret_cast<uint4 *>(&ob[8]);
+                    *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16]) = *reinterpret_cast<uint4 *>(&ot[0]);
+                    *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16 + 8]) = *reinterpret_cast<uint4 *>(&ot[8]);
+                }
+                // this warp has read its part of the accumulator: hand it back to the MMA issuer before the stores
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(ltempty0 + 8 * ab);
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // the three staged tiles are complete
+                // (2) coalesced stores: h' fp32 (two 256-byte row pieces per instruction), h' and tanh(h') bf16 (four 128-byte pieces)
+                float *hnew = const_cast<float *>(prm.hidden);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
+                    if (m0 + r < prm.rows)
+                        *reinterpret_cast<float4 *>(hnew + (nxt_off + m0 + r) * H + nb * 64 + 4 * c4) = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r = 8 * ew + 4 * i + (lane >> 3), c8 = lane & 7;
+                    if (m0 + r < prm.rows) {
+                        *reinterpret_cast<uint4 *>(prm.hidden_bf16 + (nxt_off + m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Bs[r][8 * c8]);
+                        *reinterpret_cast<uint4 *>(prm.th_bf16 + (size_t)(m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Ts[r][8 * c8]);
                     }
                 }
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // staging tiles are free for the next tile
+                continue;
             } else {
                 constexpr int PC = C::TILE_N / 4;                 // 44 columns per warp: 11 groups of 4
                 const int c00 = nb * C::TILE_N + part * PC;
@@ -485,7 +521,9 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
 template <int MODE>
 constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_ROWS * BK * 2) + 1024; }
 template <int MODE>
-constexpr int tc2_smem_bytes() { return kStages2 * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024; }
+constexpr int tc2_smem_bytes() {
+    return kStages2 * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024 + (MODE == 0 ? kStageTileBytes : 0);
+}
 // ECORD_GEMM_PAIR=0 selects the single-CTA kernels (A/B comparisons); rows_pad must be a multiple of 256 for the pair kernels
 static bool use_pair(int rows_pad) {
     static const int env = [] { const char *e = getenv("ECORD_GEMM_PAIR"); return e ? atoi(e) : 1; }();
