@@ -386,7 +386,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
             }
         }
     } else {
-        // ===================== epilogue (warps 2..9, both CTAs; identical to the single-CTA kernel) =====================
+        // ===================== epilogue (warps 2..17, both CTAs): the single-CTA kernel's math, global traffic staged =====================
         const int q = warp & 3;
         const int part = (warp - 2) >> 2;
         const uint32_t ltempty0 = mapa_u32(tempty0, 0);            // the leader's tmem_empty barriers
@@ -478,32 +478,41 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // staging tiles are free for the next tile
-                continue;
             } else {
+                // PROJ: bias added in registers, the tile staged in shared memory and stored with whole-line STGs (see above)
                 constexpr int PC = C::TILE_N / 4;                 // 44 columns per warp: 11 groups of 4
+                constexpr int kYsPitch = C::TILE_N + 4;           // 180 floats: 16-byte aligned rows, 4-way STS.128
+                const int e = threadIdx.x - 64;
+                const int rloc = q * 32 + lane;
+                float (*Ys)[kYsPitch] = reinterpret_cast<float (*)[kYsPitch]>(stage_gen);
                 const int c00 = nb * C::TILE_N + part * PC;
-                float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + c00;
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float acc[PC];
 #pragma unroll
                 for (int jj = 0; jj < PC; jj += 4) tmem_ld4(tbase + part * PC + jj, acc + jj);
                 tmem_ld_wait();
-                if (row < prm.rows) {
 #pragma unroll
-                    for (int jj = 0; jj < PC; jj += 4) {
-                        const int j = c00 + jj;
-                        if (j < ECORD_DIM_P1) {                   // the last block's tail columns do not exist
-                            const float4 b4 = *reinterpret_cast<const float4 *>(prm.p1_b + j);
-                            *reinterpret_cast<float4 *>(yrow + jj) =
-                                make_float4(acc[jj] + b4.x, acc[jj + 1] + b4.y, acc[jj + 2] + b4.z, acc[jj + 3] + b4.w);
-                        }
-                    }
+                for (int jj = 0; jj < PC; jj += 4) {
+                    const int j = c00 + jj;
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < ECORD_DIM_P1) b4 = *reinterpret_cast<const float4 *>(prm.p1_b + j);   // the last block's tail columns do not exist
+                    *reinterpret_cast<float4 *>(&Ys[rloc][part * PC + jj]) =
+                        make_float4(acc[jj] + b4.x, acc[jj + 1] + b4.y, acc[jj + 2] + b4.z, acc[jj + 3] + b4.w);
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(ltempty0 + 8 * ab);
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // the staged tile is complete
+                constexpr int kPieces = C::TILE_N / 4;            // float4 pieces per row
+                for (int idx = e; idx < BM * kPieces; idx += kThreads - 64) {
+                    const int r = idx / kPieces, c4 = idx - r * kPieces;
+                    const int col = nb * C::TILE_N + 4 * c4;
+                    if (m0 + r < prm.rows && col < ECORD_DIM_P1)
+                        *reinterpret_cast<float4 *>(prm.y1 + (size_t)(m0 + r) * ECORD_DIM_P1 + col) = *reinterpret_cast<const float4 *>(&Ys[r][4 * c4]);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // free for the next tile
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(ltempty0 + 8 * ab);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -522,7 +531,8 @@ template <int MODE>
 constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_ROWS * BK * 2) + 1024; }
 template <int MODE>
 constexpr int tc2_smem_bytes() {
-    return kStages2 * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024 + (MODE == 0 ? kStageTileBytes : 0);
+    return kStages2 * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024 +
+           (MODE == 0 ? kStageTileBytes : BM * (TcCfg<MODE>::TILE_N + 4) * 4);
 }
 // ECORD_GEMM_PAIR=0 selects the single-CTA kernels (A/B comparisons); rows_pad must be a multiple of 256 for the pair kernels
 static bool use_pair(int rows_pad) {
