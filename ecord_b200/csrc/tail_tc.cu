@@ -223,7 +223,11 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         // this part's Q channels: a_c, then everything that is linear in it
         float *Ao = p.A + (long long)m * QC;
         float *Aco = p.Ac ? p.Ac + (long long)m * QC : nullptr;
-        uint32_t *qw = p.qa ? reinterpret_cast<uint32_t *>(p.qa + (long long)m * ECORD_QA_STRIDE) : nullptr;
+        // the qa rows of the CTA are assembled in shared memory (behind the partial sums in the free A-operand tile) and leave as
+        // one contiguous block: word-by-word stores with lane <-> row cost 32 L1 wavefronts per instruction
+        constexpr int kQsPitch = ECORD_QA_STRIDE + 1;
+        uint32_t *qs_base = reinterpret_cast<uint32_t *>(S.act) + 24576;              // 96 KB into the 128 KB tile
+        uint32_t *qw = p.qa ? qs_base + rloc * kQsPitch : nullptr;
         const int nc = QC / nparts;
         for (int cc_ = 0; cc_ < nc; ++cc_) {
             const int c = part * nc + cc_;
@@ -245,7 +249,7 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
             if (qw) {
                 const float4 cc4 = *reinterpret_cast<const float4 *>(&S.cc[c * 4]);
                 const float ap = ac + cc4.w;
-                if (live) qw[c] = split_h2(w.qln_w[c] * ap);
+                qw[c] = split_h2(w.qln_w[c] * ap);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     const float4 g4 = *reinterpret_cast<const float4 *>(&S.wg[c * 16 + 4 * k4]);
@@ -298,6 +302,15 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         }
     }
     __syncthreads();
+    if (p.qa) {
+        const int nrows = min(R, p.rows - m0);
+        const uint32_t *qs = reinterpret_cast<const uint32_t *>(S.act) + 24576;
+        uint32_t *gq = reinterpret_cast<uint32_t *>(p.qa + (long long)m0 * ECORD_QA_STRIDE);
+        for (int idx = tid; idx < nrows * ECORD_QA_STRIDE; idx += kTtThreads) {
+            const int r = idx / ECORD_QA_STRIDE, k = idx - r * ECORD_QA_STRIDE;
+            gq[idx] = qs[r * (ECORD_QA_STRIDE + 1) + k];
+        }
+    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(32u) : "memory");
