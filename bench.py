@@ -328,6 +328,7 @@ def run_b200(args):
             b.record()
         b.synchronize()
         tp["env_step"] = a.elapsed_time(b) / reps
+        st.gnn_embed(); torch.cuda.synchronize()       # (its workspace allocation stays outside the timing)
         a.record()
         for _ in range(5):
             st.gnn_embed()
