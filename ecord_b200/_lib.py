@@ -14,7 +14,7 @@ GEMM_BF16 = 1
 Q_EXACT = 0
 Q_FAST = 1
 Q_TC = 2
-QTC_FLOATS = 4736
+QTC_FLOATS = 10160
 QA_STRIDE = 92
 QTILE = 128
 QFOLD_FLOATS = 588

@@ -637,6 +637,26 @@ __global__ void k_pack_qtc(ecord_weights w) {
 
 }  // namespace
 
+// Shared-memory image of the policy tail's constants (layout: ecord_weights.q_tc [4736, 10148)); runs after k_pack_qtc.
+__global__ void k_pack_tail(ecord_weights w) {
+    constexpr int P1 = ECORD_DIM_P1, ND = ECORD_DIM_NODE, QC = ECORD_DIM_Q;
+    float *img = w.q_tc + 4736;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P1) { img[i] = w.ln1_w[i]; img[P1 + i] = w.ln1_b[i]; }
+    if (i < ND * ND) img[2 * P1 + i] = w.v1_w[i];
+    if (i < QC * ND) img[2 * P1 + ND * ND + i] = w.q1_w[(i / ND) * QC + (i % ND)];
+    float *wg = img + 2 * P1 + ND * ND + QC * ND;
+    if (i < QC * 16) wg[i] = w.q_tc[1280 + i];
+    if (i < QC * 4) wg[QC * 16 + i] = w.q_tc[2304 + i];
+    float *colsum = wg + QC * 16 + QC * 4;
+    if (i <= ND) {                              // serial over the channels: the order the tail used to sum in
+        float s = 0.0f;
+        for (int c = 0; c < QC; ++c) s += i < ND ? w.q1_w[c * QC + i] : w.q1_b[c];
+        colsum[i] = s;
+    }
+    if (i > ND && i < ND + 4) colsum[i] = 0.0f;
+}
+
 extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
     ECORD_RET_IF(!w || !w->gru_w_bf16 || !w->p1_w_bf16 || !w->gru_whh || !w->gru_wih || !w->p1_w || !w->p2_w, ECORD_E_NULL);
     const long long n = (long long)3072 * H + (long long)4096 * 64 + (long long)512 * H + 32 * 512;
@@ -645,6 +665,9 @@ extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
     if (w->q_tc) {
         ECORD_RET_IF(!w->q1_w || !w->enc_w || !w->enc_b || !w->qln_w, ECORD_E_NULL);
         k_pack_qtc<<<1, ECORD_DIM_Q, 0, as_stream(stream)>>>(*w);
+        ECORD_LAUNCH_CHECK();
+        ECORD_RET_IF(!w->ln1_w || !w->ln1_b || !w->v1_w || !w->q1_b, ECORD_E_NULL);
+        k_pack_tail<<<ceil_div(ECORD_DIM_Q * ECORD_DIM_NODE, 256), 256, 0, as_stream(stream)>>>(*w);
         ECORD_LAUNCH_CHECK();
     }
     return 0;

@@ -27,6 +27,7 @@ constexpr int QC = ECORD_DIM_Q;      // 64
 constexpr int kTtThreads = 512;
 constexpr int A_SUB = BM * 128;      // bytes of one [128][64] bf16 sub-tile
 constexpr int W_SUB = ND * 128;      // bytes of one [32][64] bf16 sub-tile
+constexpr int kTailImgFloats = 2 * P1 + ND * ND + QC * ND + QC * 16 + QC * 4 + ND + 4;     // ecord_weights.q_tc [4736, ...)
 
 struct TailTcSmem {
     uint8_t act[8][A_SUB];           // 128 KB
@@ -36,10 +37,10 @@ struct TailTcSmem {
     float q1[QC * ND];               // Wq[:, :32]  [c][o]
     float wg[QC * 16];               // centred Wq[:,32:48] [c][k]
     float cc[QC * 4];                // centred C [c][0..2], bconst[c]
-    float colsum[ND + 1];            // sum_c Wq[c][o]; [32] = sum_c b_q[c]
+    float colsum[ND + 4];            // sum_c Wq[c][o]; [32] = sum_c b_q[c]; padded: ln1g .. colsum is one 16-byte-granular image
     float Ps[64][ND + 1], Ts[64][ND + 1];   // P and tanh(P) of the CTA's rows (padded: conflict-free row reads)
     float meanA[64];
-    uint64_t bar_w, bar_mma;
+    uint64_t bar_w, bar_mma, bar_c;
     uint32_t tmem_base;
 };
 
@@ -57,11 +58,19 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
     const int m0 = blockIdx.x * R;
     const uint32_t bar_w = smem_u32(&S.bar_w), bar_mma = smem_u32(&S.bar_mma);
 
+    const uint32_t bar_c = smem_u32(&S.bar_c);
+    const bool img = w.q_tc != nullptr;          // the constants come as one packed image (ecord_pack_weights) ...
     if (tid == 0) {
         mbar_init(bar_w, 1);
         mbar_init(bar_mma, 1);
+        mbar_init(bar_c, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tmap_prefetch(&mapW2);
+        if (img) {
+            mbar_expect_tx(bar_c, kTailImgFloats * 4);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(S.ln1g)), "l"(w.q_tc + 4736), "r"(kTailImgFloats * 4), "r"(bar_c) : "memory");
+        }
         mbar_expect_tx(bar_w, 8 * W_SUB);
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) tma_load_2d(smem_u32(S.w2[kb]), &mapW2, bar_w, kb * 64, 0);
@@ -71,20 +80,19 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < P1; i += kTtThreads) { S.ln1g[i] = w.ln1_w[i]; S.ln1b[i] = w.ln1_b[i]; }
-    for (int i = tid; i < ND * ND; i += kTtThreads) S.v1[i] = w.v1_w[i];
-    for (int i = tid; i < QC * ND; i += kTtThreads) S.q1[i] = w.q1_w[(i / ND) * QC + (i % ND)];
-    if (p.qa) {
-        for (int i = tid; i < QC * 16; i += kTtThreads) S.wg[i] = w.q_tc[1280 + i];
-        for (int i = tid; i < QC * 4; i += kTtThreads) S.cc[i] = w.q_tc[2304 + i];
-    }
-    if (tid <= ND) {
-        float s = 0.0f;
-        for (int c = 0; c < QC; ++c) s += tid < ND ? w.q1_w[c * QC + tid] : w.q1_b[c];
-        S.colsum[tid] = s;
+    if (!img) {                                  // ... or, without q_tc, are gathered by the threads
+        for (int i = tid; i < P1; i += kTtThreads) { S.ln1g[i] = w.ln1_w[i]; S.ln1b[i] = w.ln1_b[i]; }
+        for (int i = tid; i < ND * ND; i += kTtThreads) S.v1[i] = w.v1_w[i];
+        for (int i = tid; i < QC * ND; i += kTtThreads) S.q1[i] = w.q1_w[(i / ND) * QC + (i % ND)];
+        if (tid <= ND) {
+            float s = 0.0f;
+            for (int c = 0; c < QC; ++c) s += tid < ND ? w.q1_w[c * QC + tid] : w.q1_b[c];
+            S.colsum[tid] = s;
+        }
     }
     __syncthreads();
     pdl_launch_dependents();
+    if (img) mbar_wait(bar_c, 0);           // constants landed (async-proxy writes, made visible by the barrier's completion)
     pdl_wait();                             // y1 comes from the projection kernel
 
     // ---------------- phase 1: LN512 + LReLU -> bf16 A operand ----------------

@@ -125,6 +125,9 @@ typedef struct ecord_weights {
                               [2560,2816)  reserved
                               [2816,4736)  shared-memory image of the kernel's B operand: 3 swizzled [80][16] fp16 blocks
                                            (W1 hi | W1 lo | W2), 7680 bytes
+                              [4736,10148) shared-memory image of the policy tail's constants (one bulk copy per CTA):
+                                           LN512 gamma[512] | beta[512] | val_out.1 weight [32][32] | Wq[:, :32] as [64][32] |
+                                           Wg [64][16] | Cc,bconst [64][4] | column sums of Wq[:, :32] [32], sum(b_q), 3 pad
                             filled by ecord_pack_weights() */
     const float *q_fold; /* HOST f32 [ECORD_QFOLD_FLOATS] from ecord_fold_q_host():
                               [0,384)   C0|C1|C2 (C = Wq[:,48:64] @ W_enc, 64x3) | LN gamma | LN beta | w_o
@@ -133,7 +136,7 @@ typedef struct ecord_weights {
                               [580,586) Ccentred^T Ccentred (3x3 symmetric: 00 01 02 11 12 22); [586,588) unused
                             Passed to the Q kernels by value (constant bank), hence a host array. */
 #define ECORD_QFOLD_FLOATS 588
-#define ECORD_QTC_FLOATS 4736
+#define ECORD_QTC_FLOATS 10160
 #define ECORD_GRU_PACK_ELEMS (3072 * 1024 + 4096 * 64)
 #define ECORD_P1_PACK_ELEMS (512 * 1024 + 32 * 512)
 } ecord_weights;
