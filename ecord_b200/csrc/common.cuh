@@ -98,23 +98,28 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + e
 // u = LReLU(msg_in([last_sel (32); glob0; 0])) for one row, computed by one warp (lane holds last_sel[lane]).
 // wt = transposed msg_in weight in shared memory [34][64], wb = bias [64].  Outputs u[lane], u[lane+32].
 // (_ActorBase._update_internal_state, actors/_base.py:247-269; rnn_decoder.py:121-124)
+constexpr int kMsgPitch = 65;         // row pitch of the transposed msg_in weight in shared memory: 64 outputs + 1 (see msg_in_load)
+constexpr int kMsgWtFloats = 34 * kMsgPitch;
 __device__ __forceinline__ void msg_in_row(const float *wt, const float *wb, float x, float glob0, int lane, float &u0,
                                            float &u1) {
     float a0 = wb[lane], a1 = wb[lane + 32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
         const float xi = __shfl_sync(0xffffffffu, x, i);
-        a0 = fmaf(wt[i * 64 + lane], xi, a0);
-        a1 = fmaf(wt[i * 64 + lane + 32], xi, a1);
+        a0 = fmaf(wt[i * kMsgPitch + lane], xi, a0);
+        a1 = fmaf(wt[i * kMsgPitch + lane + 32], xi, a1);
     }
-    a0 = fmaf(wt[32 * 64 + lane], glob0, a0);     // + wt[33][.] * 0: the 2nd global feature is identically 0 (quirk C)
-    a1 = fmaf(wt[32 * 64 + lane + 32], glob0, a1);
+    a0 = fmaf(wt[32 * kMsgPitch + lane], glob0, a0);     // + wt[33][.] * 0: the 2nd global feature is identically 0 (quirk C)
+    a1 = fmaf(wt[32 * kMsgPitch + lane + 32], glob0, a1);
     u0 = lrelu(a0);
     u1 = lrelu(a1);
 }
+// msg_w [64][34] is read in memory order (whole lines per warp) and transposed on the way into shared memory; the pitch of
+// 65 makes both the transposing stores (lanes <-> consecutive inputs of one output row) and the row reads conflict-free.
+// (A gather in output order would touch 32 different lines per load instruction in every CTA's set-up.)
 __device__ __forceinline__ void msg_in_load(const float *__restrict__ msg_w, const float *__restrict__ msg_b, float *wt,
                                             float *wb) {
-    for (int i = threadIdx.x; i < 34 * 64; i += blockDim.x) wt[i] = msg_w[(i % 64) * 34 + (i / 64)];
+    for (int i = threadIdx.x; i < 34 * 64; i += blockDim.x) wt[(i % 34) * kMsgPitch + (i / 34)] = msg_w[i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) wb[i] = msg_b[i];
 }
 __device__ __forceinline__ void msg_in_store(const ecord_policy &p, int m, int lane, float u0, float u1) {

@@ -158,7 +158,7 @@ k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, cons
 __global__ void __launch_bounds__(256)
 k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const int32_t *step_base, int step_off,
                  float *score_log, int32_t *action_log, int log_stride) {
-    __shared__ float wt[34 * 64];
+    __shared__ float wt[kMsgWtFloats];
     __shared__ float wb[64];
     msg_in_load(w.msg_w, w.msg_b, wt, wb);
     __syncthreads();

@@ -38,7 +38,7 @@ constexpr int ND = ECORD_DIM_NODE;  // 32
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_policy_pre(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p) {
-    __shared__ float wt[34 * MSG];   // transposed msg_in weight: wt[i][o]
+    __shared__ float wt[kMsgWtFloats];   // transposed msg_in weight: wt[i][o], pitch kMsgPitch
     __shared__ float wb[MSG];
     msg_in_load(w.msg_w, w.msg_b, wt, wb);
     __syncthreads();
