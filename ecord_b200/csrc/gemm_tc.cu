@@ -745,6 +745,7 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     prm.bih = w->gru_bih; prm.bhh = w->gru_bhh;
     prm.rows = p->rows; prm.rows_pad = Mp; prm.step_base = step_base; prm.step_off = step_off;
     { static const int dbg = [] { const char *e = getenv("ECORD_TC_DEBUG"); return e ? atoi(e) : 0; }(); prm.debug = dbg; }
+    ECORD_RET_IF(prm.debug & 4, ECORD_E_UNSUPPORTED);      // the no-TMA diagnostic no longer terminates (it hung the GPU when tried)
     if (pair) {
         const int nblk2 = H / 64, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
