@@ -35,6 +35,11 @@ template <> struct TcCfg<0> { static constexpr int N_FIRST = 256, N_MAIN = 192, 
 // PROJ: 512 outputs as three column blocks of 176 (the last one runs 16 columns past the matrix: TMA zero-fills them, the
 // epilogue drops them): 3 x 20 pair tiles fit one wave of 74 clusters, where 4 x 20 tiles of 128 needed two
 template <> struct TcCfg<1> { static constexpr int N_FIRST = 0, N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
+// MODE 2 = PROJ when every CTA pair has at most ONE tile (the usual case: 3 x Mp/256 <= 74): the kernel is then a single
+// latency-bound pass over 16 k-chunks, so it runs seven stages deep and its epilogue staging tile reuses the stage memory
+// (all loads have landed and all MMAs have retired when the accumulator is complete).  Pair kernel only.
+template <> struct TcCfg<2> { static constexpr int N_FIRST = 0, N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
+template <int MODE> __host__ __device__ constexpr int stages2() { return MODE == 2 ? 7 : 4; }
 
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -284,23 +289,25 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS / 2 * BK * 2;      // per CTA: own A rows, half of B
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
+    constexpr int NST = stages2<MODE>();
     constexpr int TMEM_COLS = 2 * C::ACC_COLS;          // 512 for both modes
 
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kStages2 + 4];
+    __shared__ __align__(8) uint64_t bars[2 * NST + 4];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[2][4][64];       // GRU gate biases of the tile in flight (r, z combined; hn; in)
 
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t *stage_gen = smem_raw + (tiles - smem_u32(smem_raw)) + kStages2 * STAGE_BYTES;      // epilogue staging tiles (GRU)
+    // epilogue staging tiles: behind the stages, or (MODE 2: one tile per CTA) on top of them
+    uint8_t *stage_gen = smem_raw + (tiles - smem_u32(smem_raw)) + (MODE == 2 ? 0 : NST * STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages2]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * kStages2]), tempty0 = smem_u32(&bars[2 * kStages2 + 2]);
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NST]);
+    const uint32_t tfull0 = smem_u32(&bars[2 * NST]), tempty0 = smem_u32(&bars[2 * NST + 2]);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages2; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * (kThreads / 32 - 2)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -333,7 +340,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = (tile / nblk) * (2 * BM) + (int)rank * BM, nb = tile % nblk;
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
-                    const uint32_t s = it % kStages2, ph = (it / kStages2) & 1u;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);            // local: released by the leader's multicast commit
                     const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
                     const bool first = MODE == 0 && c == 0;
@@ -367,7 +374,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_d + ab * C::ACC_COLS;
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
-                    const uint32_t s = it % kStages2, ph = (it / kStages2) & 1u;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
@@ -531,8 +538,8 @@ template <int MODE>
 constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_ROWS * BK * 2) + 1024; }
 template <int MODE>
 constexpr int tc2_smem_bytes() {
-    return kStages2 * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024 +
-           (MODE == 0 ? kStageTileBytes : BM * (TcCfg<MODE>::TILE_N + 4) * 4);
+    return stages2<MODE>() * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024 +
+           (MODE == 0 ? kStageTileBytes : MODE == 1 ? BM * (TcCfg<MODE>::TILE_N + 4) * 4 : 0);
 }
 // ECORD_GEMM_PAIR=0 selects the single-CTA kernels (A/B comparisons); rows_pad must be a multiple of 256 for the pair kernels
 static bool use_pair(int rows_pad) {
@@ -721,6 +728,7 @@ int tc_init_attrs() {
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0>()));
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1>()));
+    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2>()));
     return 0;
 }
 
@@ -773,8 +781,12 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t 
     if (pair) {
         const int nblk2 = 3, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        ECORD_PDL_LAUNCH(k_gemm_tc2<1>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<1>(), st, mA, mB, mA, mA, mB, prm,
-                         tiles2, nblk2);
+        if (tiles2 <= clusters)          // one tile per CTA pair: deep pipeline, staging on top of the stages
+            ECORD_PDL_LAUNCH(k_gemm_tc2<2>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<2>(), st, mA, mB, mA, mA, mB, prm,
+                             tiles2, nblk2);
+        else
+            ECORD_PDL_LAUNCH(k_gemm_tc2<1>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<1>(), st, mA, mB, mA, mA, mB, prm,
+                             tiles2, nblk2);
         return 0;
     }
     const int nblk = 3, num_tiles = nblk * (Mp / BM);
