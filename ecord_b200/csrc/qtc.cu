@@ -14,7 +14,7 @@
 // the fp16 range, 65504).  A single low-precision product (tf32 or bf16) puts a fixed per-vertex bias of ~3e-4 on Q,
 // enough to change which vertex wins the arg-max and to degrade the rollout.  Logical operands:
 //     A operand rows (one per vertex, written by the vertex's own thread)
-//         R1 = node_emb[n] (16), hi block and lo block                shared memory, constant for the CTA
+//         R1 = node_emb[n] (16), hi block and lo block                TENSOR memory (tcgen05.st), written once per CTA
 //         R2 = [ f0 f1h f2h f1l 1 1 f2l 0 | f0 f1h f2h 0 0 0 0 0 ]    TENSOR memory (tcgen05.st), rewritten per trajectory
 //     B operand rows (one per output column), blocks W1 hi, W1 lo, W2
 //         c < 64 : W1 = gamma_c Wg[c][0..15];   W2 = [ C0h C1h C2h C1h ga'_hi ga'_lo C2h 0 | C0l C1l C2l 0 ... ]  (C = gamma_c Cc[c])
@@ -30,13 +30,15 @@
 // CTA = 4 row warps (thread i <-> vertex i of the tile <-> TMEM lane i) + 1 control warp (copies the per-trajectory
 // operand entries, issues tcgen05.mma / commit).  No CTA-wide barrier in the loop: the roles meet on mbarriers
 // (`ready`: R2 written + accumulator drained, 4 warp arrivals; `full`: tcgen05.commit).  A CTA owns 128 TMEM columns
-// (one accumulator + R2) so that FOUR CTAs share an SM: a row warp hands trajectory t+1 to the tensor core right
+// (accumulator [0,80), R2 double-buffered [80,96), R1 hi / lo [96,112)) so that FOUR CTAs share an SM: a row warp hands trajectory t+1 to the tensor core right
 // after reading the accumulator of t out of TMEM, its MMAs overlap the epilogue math of t, and the other CTAs'
 // warps cover what latency remains (the kernel is latency-, not issue-bound: see profiles/).
 // Shared-memory operand blocks are [rows][16 fp16] with 32-byte rows in the canonical K-major SWIZZLE_32B layout
-// (16-byte chunk index XOR bit 2 of the row; 8-row groups 256 B apart).  R2 lives in tensor memory because a
-// generic-proxy write to a shared-memory operand needs fence.proxy.async (a MEMBAR) before the MMA may read it,
-// and that fence would drain the row warps' prefetched global loads and arg-max atomics every trajectory.
+// (16-byte chunk index XOR bit 2 of the row; 8-row groups 256 B apart); only the B operand lives there.  R2 lives in tensor
+// memory because a generic-proxy write to a shared-memory operand needs fence.proxy.async (a MEMBAR) before the MMA may
+// read it, and that fence would drain the row warps' prefetched global loads and arg-max atomics every trajectory; R1
+// lives there because an A operand in TMEM costs no shared-memory read per MMA (12 of the 22 KB a trajectory used to pull
+// through the L1 data pipe).
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <string.h>
@@ -53,13 +55,13 @@ constexpr int B_BLK = QN * 32;        // bytes of one [80][16] block
 constexpr int kQtcThreads = 160;
 constexpr int kTmemA = QN;            // TMEM columns [0,80): accumulator; [80,88) and [88,96): the per-trajectory A operand R2
                                       // (16 fp16 = 8 columns), double-buffered by trajectory parity
+constexpr int kTmemR1 = QN + 16;      // TMEM columns [96,104): R1 hi, [104,112): R1 lo (node_emb of the tile's vertices, written once per CTA)
 constexpr int kTmemCols = 128;
 
 constexpr int kRing = 8;               // cp.async prefetch depth of the per-(vertex, trajectory) state, in trajectories
 constexpr int kImgBytes = 3 * B_BLK;   // packed image of the B operand: W1 hi | W1 lo | W2
 
 struct QTcSmem {
-    uint8_t R1[2][A_BLK];              // A operand (node_emb): hi | lo; constant for the CTA
     uint8_t W[3][B_BLK];               // B operand: W1 hi | W1 lo | W2
     float qa[kTcMaxT][QA];             // per-(g,t) rows of ecord_policy.qa
     int sp[kRing + 1][QT];             // state ring (cp.async), one slot per trajectory in flight
@@ -174,6 +176,7 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
     const bool valid = is_row && v0 + tid < n;
     const int v = is_row ? min(v0 + tid, n - 1) : 0;
     float bb = 0.f, cb0 = 0.f, cb1 = 0.f, cb2 = 0.f, lb = 0.f;
+    uint32_t r1h[8], r1l[8];
     // state row entries: element (t_lo, v); consecutive trajectories are n elements apart
     const long long base0 = (long long)lo * T + (long long)t_lo * n + v;
     const int *__restrict__ sp_ptr = e.sp + base0;          // next trajectory to fetch
@@ -187,28 +190,23 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
         for (int c4 = 0; c4 < 4; ++c4) x[c4] = ep[c4];
         const float4 q0 = qv[0];
         lb = qv[1].x;
-        // the vertex's R1 row: 16 fp16 hi values (32 bytes = two swizzled 16-byte chunks) and the 16 lo remainders
+        // the vertex's R1 row: 16 fp16 hi values and the 16 lo remainders, as eight 32-bit words each; they go to tensor memory
+        // (below, once the allocation is known): an A operand in TMEM costs no shared-memory read per MMA, and the L1 data
+        // pipe -- tensor-core operand reads + LSU wavefronts -- is this kernel's busiest unit (78 % before this change)
 #pragma unroll
         for (int c8 = 0; c8 < 2; ++c8) {
             const float e[8] = {x[2 * c8].x, x[2 * c8].y, x[2 * c8].z, x[2 * c8].w,
                                 x[2 * c8 + 1].x, x[2 * c8 + 1].y, x[2 * c8 + 1].z, x[2 * c8 + 1].w};
-            uint32_t wh[4], wl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 __half h0, l0, h1, l1;
                 split_h(e[2 * i], h0, l0);
                 split_h(e[2 * i + 1], h1, l1);
-                wh[i] = pack_h2(h0, h1);
-                wl[i] = pack_h2(l0, l1);
+                r1h[4 * c8 + i] = pack_h2(h0, h1);
+                r1l[4 * c8 + i] = pack_h2(l0, l1);
             }
-            *reinterpret_cast<uint4 *>(&S.R1[0][sw32(tid, 8 * c8)]) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-            *reinterpret_cast<uint4 *>(&S.R1[1][sw32(tid, 8 * c8)]) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
         bb = q0.x; cb0 = 2.0f * q0.y; cb1 = 2.0f * q0.z; cb2 = 2.0f * q0.w;
-        // R1 was written through the generic proxy: make it visible to the tensor core.  This fence is a MEMBAR, so
-        // it sits before the first cp.async; inside the trajectory loop the row warps touch no shared-memory operand
-        // (their per-trajectory operand R2 goes through tensor memory) and never fence.
-        fence_async_smem();
         pdl_wait();                     // the state planes and step counter belong to the step: predecessor kernels first
 #pragma unroll
         for (int j = 0; j < kRing; ++j) {
@@ -231,6 +229,11 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
     __syncthreads();                 // barrier inits, TMEM base, R1
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = S.tmem_base;
+    if (is_row) {        // R1 hi / lo rows -> tensor memory; published to the control warp by the first `ready` arrival
+        const uint32_t trow0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+        tmem_st8(trow0 + (uint32_t)kTmemR1, r1h[0], r1h[1], r1h[2], r1h[3], r1h[4], r1h[5], r1h[6], r1h[7]);
+        tmem_st8(trow0 + (uint32_t)(kTmemR1 + 8), r1l[0], r1l[1], r1l[2], r1l[3], r1l[4], r1l[5], r1l[6], r1l[7]);
+    }
 
     if (warp == 4) {
         // =============== control warp: per-trajectory B-operand entries, MMA issue ===============
@@ -241,7 +244,6 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
         uint8_t *Wb = S.W[0];
         const uint32_t dst_c0 = 2u * B_BLK + sw32(lane, 4), dst_c1 = 2u * B_BLK + sw32(lane + 32, 4);
         const uint32_t dst_r = (uint32_t)(lane >> 3) * B_BLK + sw32(Q, 2 * (lane & 7));
-        const uint64_t dA0 = umma_desc_sw32(smem_u32(S.R1[0])), dA1 = umma_desc_sw32(smem_u32(S.R1[1]));
         const uint64_t dB0 = umma_desc_sw32(smem_u32(S.W[0])), dB1 = umma_desc_sw32(smem_u32(S.W[1])),
                        dB2 = umma_desc_sw32(smem_u32(S.W[2]));
         for (int tt = 0; tt < nt; ++tt) {
@@ -257,9 +259,9 @@ k_q_tc(ecord_graph g, ecord_env e, ecord_policy p, const float *__restrict__ q_t
                 mbar_wait(ready0, (uint32_t)tt & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // x = (e_hi + e_lo)(W_hi + W_lo) ~ e_hi W_hi + e_lo W_hi + e_hi W_lo  (the lo.lo term is 2^-22 relative)
-                umma_f16(tmem_base, dA0, dB0, idesc, 0u);
-                umma_f16(tmem_base, dA1, dB0, idesc, 1u);
-                umma_f16(tmem_base, dA0, dB1, idesc, 1u);
+                umma_f16_ts(tmem_base, tmem_base + (uint32_t)kTmemR1, dB0, idesc, 0u);
+                umma_f16_ts(tmem_base, tmem_base + (uint32_t)(kTmemR1 + 8), dB0, idesc, 1u);
+                umma_f16_ts(tmem_base, tmem_base + (uint32_t)kTmemR1, dB1, idesc, 1u);
                 umma_f16_ts(tmem_base, tmem_base + (uint32_t)(kTmemA + 8 * (tt & 1)), dB2, idesc, 1u);
                 umma_commit(full0);
             }
