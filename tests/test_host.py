@@ -157,6 +157,29 @@ def test_weight_shapes_init_and_checkpoint_ingestion():
         check_state_dicts({**bad, "rnn": sd["rnn"]})
 
 
+def test_node_classifier_head_ingestion():
+    """models/node_classifier.py:8-30 (`heads.<i>.0` = Linear(16 -> 1)) -> stacked (weight [H,16], bias [H]); a module, a
+    state_dict or None are accepted, wrong shapes and empty dicts are rejected."""
+    from ecord_b200.network import node_classifier_heads
+    assert node_classifier_heads(None) is None
+    sd = {f"heads.{i}.0.weight": torch.full((1, 16), float(i + 1)) for i in range(3)}
+    sd.update({f"heads.{i}.0.bias": torch.tensor([0.5 * i]) for i in range(3)})
+    w, b = node_classifier_heads(sd)
+    assert w.shape == (3, 16) and b.shape == (3,) and w[2, 5] == 3.0 and b[1] == 0.5
+
+    class Heads(torch.nn.Module):            # the reference's module layout
+        def __init__(self):
+            super().__init__()
+            self.heads = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(16, 1)) for _ in range(2)])
+    m = Heads()
+    w2, b2 = node_classifier_heads(m)
+    assert w2.shape == (2, 16) and torch.equal(w2[1], m.heads[1][0].weight.detach().view(-1))
+    with pytest.raises(KeyError):
+        node_classifier_heads({})
+    with pytest.raises(ValueError):
+        node_classifier_heads({"heads.0.0.weight": torch.zeros(1, 8), "heads.0.0.bias": torch.zeros(1)})
+
+
 def test_shard_bounds_partition():
     for total, world in ((50, 8), (128, 8), (7, 2), (3, 4), (400, 1)):
         cuts = [shard_bounds(total, world, r) for r in range(world)]
