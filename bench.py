@@ -354,7 +354,7 @@ def run_b200(args):
                 "hbm_view": {"achieved_gbs": bytes_alg / (q_ms * 1e-3) / 1e9, "peak_gbs": hbm, "frac": bytes_alg / (q_ms * 1e-3) / 1e9 / hbm},
                 "policy_step_ms": tp["policy_step"],
                 "others": [
-                    {"kernel": "k_gemm_tc2<0> + k_gemm_tc2<1> + k_tail_tc (GRU, projection, tail; tcgen05 bf16)", "bound": "tensor",
+                    {"kernel": "k_gemm_tc2<0> + k_gemm_tc2<1|2> + k_tail_tc (GRU, projection, tail; tcgen05, %s)" % args.gemm, "bound": "tensor",
                      "ms_per_launch": tp["policy_step"], "unit": "TFLOP/s", "peak": tf_burst,
                      "achieved": (F_UNIT(0) * G * T) / (tp["policy_step"] * 1e-3) / 1e12,
                      "frac": (F_UNIT(0) * G * T) / (tp["policy_step"] * 1e-3) / 1e12 / tf_burst,
@@ -414,7 +414,9 @@ def run_b200(args):
                             f" + torch CPU model, {torch.get_num_threads()} threads)"}
         out = {"metric": "rollout steps/sec (graphs x tradj x steps)", "value": value, "unit": "steps/s", "n_gpus": world,
                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "bf16" if args.gemm == "bf16" else "f32", "data": "synthetic",
+               "vs_baseline": None,
+               "dtype": {"bf16x3": "bf16x3 (tcgen05 on bf16 hi/lo operand pairs, fp32 accumulate: fp32-grade)", "bf16": "bf16",
+                         "fp32": "f32"}[args.gemm], "data": "synthetic",
                "config": {"workload": desc, "graphs": G, "tradj_total": T_total, "units_per_step": G * T_total,
                           "parallelism": f"trajectory-sharded x{world}", "gemm": args.gemm,
                           "l2": "flushed (256 MB write) before every CUDA-graph launch of %d steps, outside the timed events" % k,
@@ -436,7 +438,9 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="er500", choices=sorted(WORKLOADS))
-    ap.add_argument("--gemm", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--gemm", default="bf16x3", choices=["bf16x3", "bf16", "fp32"],
+                    help="bf16x3 (default): tcgen05 GEMMs on bf16 hi/lo operand pairs, fp32-grade, passes the 99 %% best-cut "
+                         "tests; bf16: single bf16 products (fast mode, 2e-2 tolerance); fp32: CUDA-core SGEMM")
     ap.add_argument("--steps-per-graph", type=int, default=16)
     ap.add_argument("--cpu-graphs", type=int, default=10, help="graphs in the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=24, help="steps of the CPU baseline sample (b200 arm)")

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libecord_b200.so")
 
 GEMM_FP32 = 0
 GEMM_BF16 = 1
+GEMM_BF16X3 = 2
 Q_EXACT = 0
 Q_FAST = 1
 Q_TC = 2
@@ -18,8 +19,8 @@ QTC_FLOATS = 10160
 QA_STRIDE = 92
 QTILE = 128
 QFOLD_FLOATS = 588
-GRU_PACK_ELEMS = 3072 * 1024 + 4096 * 64
-P1_PACK_ELEMS = 512 * 1024 + 32 * 512
+GRU_PACK_ELEMS = 2 * (3072 * 1024 + 4096 * 64)
+P1_PACK_ELEMS = 2 * (512 * 1024 + 32 * 512)
 
 _vp, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 
@@ -32,11 +33,11 @@ class Graph(C.Structure):
     _fields_ = [("num_graphs", _i32), ("num_nodes", _i32), ("num_edges", _i32), ("n_max", _i32),
                 ("graph_ptr", _vp), ("node_graph", _vp), ("row_ptr", _vp), ("col", _vp), ("w", _vp),
                 ("graph_edge_ptr", _vp), ("in_ptr", _vp), ("in_src", _vp), ("in_w", _vp),
-                ("num_qtiles", _i32), ("_pad", _i32), ("qtile_graph", _vp), ("qtile_v0", _vp)]
+                ("num_qtiles", _i32), ("int_weights", _i32), ("qtile_graph", _vp), ("qtile_v0", _vp), ("graph_wsum", _vp)]
 
 
 class Env(C.Structure):
-    _fields_ = [("num_tradj", _i32), ("_pad", _i32), ("peek", _vp), ("sp", _vp), ("best_state", _vp),
+    _fields_ = [("num_tradj", _i32), ("true_snapshot", _i32), ("peek", _vp), ("sp", _vp), ("best_state", _vp),
                 ("score", _vp), ("best_score", _vp), ("best_step", _vp)]
 
 
@@ -72,7 +73,8 @@ class Policy(C.Structure):
     _fields_ = [("rows", _i32), ("rows_pad", _i32), ("hidden", _vp), ("hidden_bf16", _vp), ("th_bf16", _vp),
                 ("u_bf16", _vp), ("u", _vp), ("gates", _vp), ("th", _vp), ("y1", _vp), ("P", _vp), ("A", _vp),
                 ("v", _vp), ("last_sel", _vp), ("node_emb", _vp), ("node_B", _vp), ("actions", _vp), ("q", _vp),
-                ("Ac", _vp), ("LA", _vp), ("node_Bc", _vp), ("node_LB", _vp), ("keys", _vp), ("qa", _vp), ("node_qv", _vp)]
+                ("Ac", _vp), ("LA", _vp), ("node_Bc", _vp), ("node_LB", _vp), ("keys", _vp), ("qa", _vp), ("node_qv", _vp),
+                ("split", _i32), ("_pad", _i32)]
 
 
 class RolloutDesc(C.Structure):
@@ -130,7 +132,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)   # AttributeError here = header/library drift
         fn.restype, fn.argtypes = res, args
-    if lib.ecord_version() != 2:
+    if lib.ecord_version() != 3:
         raise EcordError(f"ABI version mismatch: library reports {lib.ecord_version()}")
     for which, st in enumerate((Graph, Env, Weights, Policy, RolloutDesc)):
         if lib.ecord_abi_sizeof(which) != C.sizeof(st):

@@ -127,7 +127,13 @@ __device__ __forceinline__ void msg_in_store(const ecord_policy &p, int m, int l
     p.u[(long long)m * 64 + lane + 32] = u1;
     if (p.u_bf16) {
         __nv_bfloat16 *ub = reinterpret_cast<__nv_bfloat16 *>(p.u_bf16);
-        ub[(long long)m * 64 + lane] = __float2bfloat16(u0);
-        ub[(long long)m * 64 + lane + 32] = __float2bfloat16(u1);
+        const __nv_bfloat16 h0 = __float2bfloat16(u0), h1 = __float2bfloat16(u1);
+        ub[(long long)m * 64 + lane] = h0;
+        ub[(long long)m * 64 + lane + 32] = h1;
+        if (p.split) {                  // ECORD_GEMM_BF16X3: the bf16 remainders, one plane ([rows_pad][64]) further
+            ub += (long long)p.rows_pad * 64;
+            ub[(long long)m * 64 + lane] = __float2bfloat16(u0 - __bfloat162float(h0));
+            ub[(long long)m * 64 + lane + 32] = __float2bfloat16(u1 - __bfloat162float(h1));
+        }
     }
 }

@@ -61,6 +61,32 @@ k_env_init_score(ecord_graph g, ecord_env e, const int8_t *__restrict__ s0) {
     }
 }
 
+// The same score from the peek plane k_env_init_peek has just written: with s = +-1 spins,
+//     cut = 1/2 sum_{(i,j) directed} w_ij [s_i != s_j] = 1/4 (sum_{directed} w_ij - sum_v peek_v),   peek_v = sum_j w_ij s_i s_j.
+// For integer-valued weights every partial sum is an integer below 2^24, so the result is exact in any order -- bit-equal
+// to the edge walk above -- and a unit reads its n_g contiguous peeks instead of walking all the edges of its graph
+// (ER500: 500 coalesced floats instead of 37 K scattered edge terms per unit; 848 us -> a few us per rollout).
+// graph_wsum[g] = sum of the graph's directed edge weights (host, exact); the edge walk stays for non-integer weights.
+__global__ void __launch_bounds__(256)
+k_env_init_score_peek(ecord_graph g, ecord_env e) {
+    const int T = e.num_tradj;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (m >= g.num_graphs * T) return;
+    const int gi = m / T, t = m % T;
+    int n;
+    const long long base = unit_base(g.graph_ptr, gi, t, T, n);
+    float acc = 0.0f;
+    for (int v = lane; v < n; v += 32) acc += e.peek[base + v];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float sc = 0.25f * (g.graph_wsum[gi] - acc);
+        e.score[m] = sc;
+        e.best_score[m] = sc;
+        e.best_step[m] = 0;
+    }
+}
+
 // Re-initialise spins, peeks and scores from given spins (init_state i8 [N][T]) or, with init_state == NULL, from the
 // best-state plane -- greedy_solve(init_from_best=True), solvers/solver.py:39-43: scores and node features are rebuilt
 // (static counters restart: last_flip_step = steps_done), best_score / best_state / best_step are NOT touched.
@@ -115,6 +141,15 @@ __global__ void k_env_rebase(ecord_graph g, ecord_env e, int by) {
 // ------------------------------------------------------------------------------------------------
 // a3: one step on the SoA state.  One warp per (g,t).
 // ------------------------------------------------------------------------------------------------
+// ecord_env.true_snapshot: on a new best score the unit's whole spin row is copied into the best-state plane, so that
+// plane is the configuration whose cut IS best_score.  (The reference records only the flipped vertex, quirk D --
+// _tradjectory_step_cy.pyx:142-146 -- which is what the flag's default, 0, reproduces bit for bit.)  Improvements become
+// rare after the first few hundred steps of a rollout, so the n_g-byte copy is paid seldom.
+__device__ __forceinline__ void snapshot_on_new_best(const ecord_env &e, long long base, int n, int new_best, int lane) {
+    new_best = __shfl_sync(0xffffffffu, new_best, 0);          // (also orders lane 0's flip before the row copy)
+    if (!new_best) return;
+    for (int v = lane; v < n; v += 32) e.best_state[base + v] = (uint8_t)(e.sp[base + v] & 1);
+}
 __global__ void __launch_bounds__(256)
 k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, const int32_t *step_base, int step_off,
            float *score_log, int32_t *action_log, int log_stride) {
@@ -140,10 +175,12 @@ k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, cons
         const float sw = fa * fn * g.w[k];
         e.peek[base + nb] = e.peek[base + nb] - 2.0f * sw;
     }
+    __syncwarp();                       // the lanes' reads of a's entries precede lane 0's rewrite of them
+    int new_best = 0;
     if (lane == 0) {
         const float sc = e.score[m] + pa;                      // 1. pyx:87
         e.score[m] = sc;
-        const bool new_best = sc > e.best_score[m];            // 2. pyx:90-93
+        new_best = sc > e.best_score[m];                       // 2. pyx:90-93
         if (new_best) { e.best_score[m] = sc; e.best_step[m] = step_no + 1; }
         e.peek[base + a] = -1.0f * pa;                         // 5(i). pyx:109
         e.sp[base + a] = ((step_no + 1) << 1) | (sa ^ 1);      // 7 + 9: flip, static = 0
@@ -151,6 +188,7 @@ k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, cons
         if (score_log) score_log[(long long)step_no * log_stride + m] = sc;
         if (action_log) action_log[(long long)step_no * log_stride + m] = a;
     }
+    if (e.true_snapshot) snapshot_on_new_best(e, base, n, new_best, lane);
 }
 
 // The same step fused with the NEXT step's msg_in stage (policy.cu k_policy_pre): the warp that just applied the
@@ -186,12 +224,14 @@ k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, co
         const float sw = fa * fn * g.w[k];
         e.peek[base + nb] = e.peek[base + nb] - 2.0f * sw;
     }
+    __syncwarp();                       // the lanes' reads of a's entries precede lane 0's rewrite of them
     float glob0 = 0.0f;
+    int new_best = 0;
     if (lane == 0) {
         const float sc = e.score[m] + pa;
         e.score[m] = sc;
         float best = e.best_score[m];
-        const bool new_best = sc > best;
+        new_best = sc > best;
         if (new_best) { best = sc; e.best_score[m] = sc; e.best_step[m] = step_no + 1; }
         e.peek[base + a] = -1.0f * pa;
         e.sp[base + a] = ((step_no + 1) << 1) | (sa ^ 1);
@@ -200,6 +240,7 @@ k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, co
         if (action_log) action_log[(long long)step_no * log_stride + m] = a;
         glob0 = (best - sc) / (float)n;                      // SCORE_FROM_BEST_NORM of the new observation
     }
+    if (e.true_snapshot) snapshot_on_new_best(e, base, n, new_best, lane);
     glob0 = __shfl_sync(0xffffffffu, glob0, 0);
     float u0, u1;
     msg_in_row(wt, wb, p.last_sel[(long long)m * ECORD_DIM_NODE + lane], glob0, lane, u0, u1);
@@ -275,6 +316,7 @@ k_stepcy(const int64_t *__restrict__ actions, float *scores, float *best_scores,
         NFA(v, ix.peek) = new_peek;
     }
     if (ix.ngr >= 0) dgreedy = warp_sum_int(dgreedy);
+    __syncwarp();                       // the lanes' reads of a's state precede lane 0's rewrite of it
     if (lane == 0) {
         const float sc = scores[m] + pa;
         scores[m] = sc;
@@ -327,7 +369,10 @@ extern "C" int ecord_env_init(const ecord_graph *g, const ecord_env *env, const 
     const int GT = g->num_graphs * env->num_tradj;
     k_env_init_peek<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state);
     ECORD_LAUNCH_CHECK();
-    k_env_init_score<<<ceil_div((long long)GT * 32, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state);
+    if (g->int_weights && g->graph_wsum)
+        k_env_init_score_peek<<<ceil_div((long long)GT * 32, 256), 256, 0, as_stream(stream)>>>(*g, *env);
+    else
+        k_env_init_score<<<ceil_div((long long)GT * 32, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state);
     ECORD_LAUNCH_CHECK();
     return 0;
 }

@@ -246,6 +246,16 @@ constexpr int kStages2 = 4;      // the pair kernel's stages are 28-32 KB (half 
 constexpr int kHsPitch = 68;     // floats per row of the fp32 epilogue staging tile (64 + 4: 16-byte aligned rows, 4-way STS.128)
 constexpr int kBsPitch = 72;     // bf16 per row of the two bf16 staging tiles (64 + 8)
 constexpr int kStageTileBytes = BM * kHsPitch * 4 + 2 * BM * kBsPitch * 2;      // 34816 + 36864 bytes
+// x ~ hi + lo, both bf16 (|x - hi - lo| <= 2^-17 |x|); four values -> packed hi words and lo words
+__device__ __forceinline__ void split_bf16x4(const float4 v, uint2 &hi, uint2 &lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16(v.x), h1 = __float2bfloat16(v.y), h2 = __float2bfloat16(v.z), h3 = __float2bfloat16(v.w);
+    const __nv_bfloat16 l0 = __float2bfloat16(v.x - __bfloat162float(h0)), l1 = __float2bfloat16(v.y - __bfloat162float(h1));
+    const __nv_bfloat16 l2 = __float2bfloat16(v.z - __bfloat162float(h2)), l3 = __float2bfloat16(v.w - __bfloat162float(h3));
+    hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+    lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+}
 __device__ __forceinline__ bool elect_one() {          // one lane of the (converged) warp
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -279,7 +289,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-template <int MODE>
+// NS = 1: bf16 operands (ECORD_GEMM_BF16).  NS = 3: every operand is a bf16 hi part plus a bf16 lo remainder
+// (x ~ hi + lo to 2^-17) and the three products hi.hi + lo.hi + hi.lo are accumulated (ECORD_GEMM_BF16X3): each k-chunk
+// is walked three times with the (A part, B part) pairs (hi, hi), (lo, hi), (hi, lo).  The lo parts live NS-1 "planes"
+// behind the hi parts in the same tensor maps (A: rows_pad rows further, B: the weight matrix's row count further).
+// The epilogue of NS = 3 uses the accurate sigmoid / tanh and writes h' and tanh(h') as hi / lo pairs: with it the
+// recurrent state tracks the reference's fp32 arithmetic to ~1e-6 instead of ~1e-3 (oracle/ablate_precision.py).
+template <int MODE, int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
            const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -288,7 +304,8 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     using C = TcCfg<MODE>;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS / 2 * BK * 2;      // per CTA: own A rows, half of B
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
+    constexpr int NCHUNK = NS * ((MODE == 0 ? 1 : 0) + H / BK);                 // (k-chunk, product) items per tile
+    constexpr int B_PLANE = MODE == 0 ? 3 * H : ECORD_DIM_P1;                   // rows between the hi and lo parts of B
     constexpr int NST = stages2<MODE>();
     constexpr int TMEM_COLS = 2 * C::ACC_COLS;          // 512 for both modes
 
@@ -343,20 +360,24 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);            // local: released by the leader's multicast commit
                     const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                    const bool first = MODE == 0 && c == 0;
+                    const int cl = c / NS, prod = c - cl * NS;     // k-chunk, product: (hi,hi) (lo,hi) (hi,lo)
+                    const bool first = MODE == 0 && cl == 0;
                     const int n_rows = first ? C::N_FIRST : C::N_MAIN;
+                    const int a_row = m0 + (prod == 1 ? prm.rows_pad : 0);
                     if (elect_one()) {
                         if (prm.debug & 4) {            // no TMA traffic: the leader completes the phase by itself
                             if (rank == 0) mbar_arrive_cta(full0 + 8 * s);
                         } else {
                             if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + n_rows / 2 * BK * 2));
                             if (first) {
-                                tma_load_2d_pair(a_dst, &mapU, lfull0 + 8 * s, 0, m0);
-                                tma_load_2d_pair(b_dst, &mapWu, lfull0 + 8 * s, 0, nb * n_rows + (int)rank * (n_rows / 2));
+                                tma_load_2d_pair(a_dst, &mapU, lfull0 + 8 * s, 0, a_row);
+                                tma_load_2d_pair(b_dst, &mapWu, lfull0 + 8 * s, 0,
+                                                 nb * n_rows + (int)rank * (n_rows / 2) + (prod == 2 ? 4 * H : 0));
                             } else {
-                                const int kc = (MODE == 0 ? c - 1 : c) * BK;
-                                tma_load_2d_pair(a_dst, mapA, lfull0 + 8 * s, kc, m0);
-                                tma_load_2d_pair(b_dst, &mapB, lfull0 + 8 * s, kc, nb * n_rows + (int)rank * (n_rows / 2));
+                                const int kc = (MODE == 0 ? cl - 1 : cl) * BK;
+                                tma_load_2d_pair(a_dst, mapA, lfull0 + 8 * s, kc, a_row);
+                                tma_load_2d_pair(b_dst, &mapB, lfull0 + 8 * s, kc,
+                                                 nb * n_rows + (int)rank * (n_rows / 2) + (prod == 2 ? B_PLANE : 0));
                             }
                         }
                     }
@@ -378,7 +399,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     mbar_wait(full0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
-                    const uint32_t idesc = (MODE == 0 && c == 0) ? umma_idesc(2 * BM, 256) : umma_idesc(2 * BM, C::N_MAIN);
+                    const uint32_t idesc = (MODE == 0 && c < NS) ? umma_idesc(2 * BM, 256) : umma_idesc(2 * BM, C::N_MAIN);
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -411,6 +432,9 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 const int e = threadIdx.x - 64, ew = e >> 5;          // epilogue thread / warp index 0..511 / 0..15
                 const int rloc = q * 32 + lane;                        // row of the tile this thread owns in TMEM
                 float (*Hs)[kHsPitch] = reinterpret_cast<float (*)[kHsPitch]>(stage_gen);
+                // NS = 1: bf16 images of h' and tanh(h') are staged; NS = 3: tanh(h') is staged in fp32 (second tile) and both
+                // are split into bf16 hi / lo pairs by the store pass
+                float (*Ths)[kHsPitch] = reinterpret_cast<float (*)[kHsPitch]>(stage_gen + BM * kHsPitch * 4);
                 __nv_bfloat16 (*Bs)[kBsPitch] = reinterpret_cast<__nv_bfloat16 (*)[kBsPitch]>(stage_gen + BM * kHsPitch * 4);
                 __nv_bfloat16 (*Ts)[kBsPitch] = Bs + BM;
                 const size_t cur_off = (size_t)cur * prm.rows_pad, nxt_off = (size_t)(1 - cur) * prm.rows_pad;
@@ -444,44 +468,88 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     tmem_ld16(tbase + 128 + j0, ahn);
                     tmem_ld16(tbase + 192 + j0, ain);
                     tmem_ld_wait();
-                    __align__(16) __nv_bfloat16 ob[16], ot[16];
+                    if (NS == 1) {
+                        __align__(16) __nv_bfloat16 ob[16], ot[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int jl = part * 16 + i;           // unit within the tile's 64
-                        const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
-                        const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
-                        const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
-                        const float hn = fmaf(hv[i] - n, z, n);
-                        hv[i] = hn;
-                        ob[i] = __float2bfloat16(hn);
-                        ot[i] = __float2bfloat16(tanh_fast(hn));
+                        for (int i = 0; i < 16; ++i) {
+                            const int jl = part * 16 + i;           // unit within the tile's 64
+                            const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
+                            const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
+                            const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
+                            const float hn = fmaf(hv[i] - n, z, n);
+                            hv[i] = hn;
+                            ob[i] = __float2bfloat16(hn);
+                            ot[i] = __float2bfloat16(tanh_fast(hn));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&Hs[rloc][part * 16 + i]) = *reinterpret_cast<float4 *>(&hv[i]);
+                        *reinterpret_cast<uint4 *>(&Bs[rloc][part * 16]) = *reinterpret_cast<uint4 *>(&ob[0]);
+                        *reinterpret_cast<uint4 *>(&Bs[rloc][part * 16 + 8]) = *reinterpret_cast<uint4 *>(&ob[8]);
+                        *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16]) = *reinterpret_cast<uint4 *>(&ot[0]);
+                        *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16 + 8]) = *reinterpret_cast<uint4 *>(&ot[8]);
+                    } else {
+                        float tv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int jl = part * 16 + i;
+                            const float r = sigmoidf_acc(ar[i] + bias_s[ab][0][jl]);
+                            const float z = sigmoidf_acc(az[i] + bias_s[ab][1][jl]);
+                            const float n = tanhf(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
+                            const float hn = fmaf(hv[i] - n, z, n);
+                            hv[i] = hn;
+                            tv[i] = tanhf(hn);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            *reinterpret_cast<float4 *>(&Hs[rloc][part * 16 + i]) = *reinterpret_cast<float4 *>(&hv[i]);
+                            *reinterpret_cast<float4 *>(&Ths[rloc][part * 16 + i]) = *reinterpret_cast<float4 *>(&tv[i]);
+                        }
                     }
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&Hs[rloc][part * 16 + i]) = *reinterpret_cast<float4 *>(&hv[i]);
-                    *reinterpret_cast<uint4 *>(&Bs[rloc][part * 16]) = *reinterpret_cast<uint4 *>(&ob[0]);
-                    *reinterpret_cast<uint4 *>(&Bs[rloc][part * 16 + 8]) = *reinterpret_cast<uint4 *>(&ob[8]);
-                    *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16]) = *reinterpret_cast<uint4 *>(&ot[0]);
-                    *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16 + 8]) = *reinterpret_cast<uint4 *>(&ot[8]);
                 }
                 // this warp has read its part of the accumulator: hand it back to the MMA issuer before the stores
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(ltempty0 + 8 * ab);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // the three staged tiles are complete
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // the staged tiles are complete
                 // (2) coalesced stores: h' fp32 (two 256-byte row pieces per instruction), h' and tanh(h') bf16 (four 128-byte pieces)
                 float *hnew = const_cast<float *>(prm.hidden);
+                if (NS == 1) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
-                    if (m0 + r < prm.rows)
-                        *reinterpret_cast<float4 *>(hnew + (nxt_off + m0 + r) * H + nb * 64 + 4 * c4) = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
-                }
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
+                        if (m0 + r < prm.rows)
+                            *reinterpret_cast<float4 *>(hnew + (nxt_off + m0 + r) * H + nb * 64 + 4 * c4) = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
+                    }
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int r = 8 * ew + 4 * i + (lane >> 3), c8 = lane & 7;
-                    if (m0 + r < prm.rows) {
-                        *reinterpret_cast<uint4 *>(prm.hidden_bf16 + (nxt_off + m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Bs[r][8 * c8]);
-                        *reinterpret_cast<uint4 *>(prm.th_bf16 + (size_t)(m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Ts[r][8 * c8]);
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = 8 * ew + 4 * i + (lane >> 3), c8 = lane & 7;
+                        if (m0 + r < prm.rows) {
+                            *reinterpret_cast<uint4 *>(prm.hidden_bf16 + (nxt_off + m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Bs[r][8 * c8]);
+                            *reinterpret_cast<uint4 *>(prm.th_bf16 + (size_t)(m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Ts[r][8 * c8]);
+                        }
+                    }
+                } else {
+                    // hidden_bf16 [parity][hi|lo][rows_pad][H], th_bf16 [hi|lo][rows_pad][H]: a thread splits four values, a
+                    // half-warp covers one 128-byte row piece of each of the four bf16 planes
+                    __nv_bfloat16 *hb_hi = prm.hidden_bf16 + (size_t)(1 - cur) * 2 * prm.rows_pad * H;
+                    __nv_bfloat16 *hb_lo = hb_hi + (size_t)prm.rows_pad * H;
+                    __nv_bfloat16 *tb_lo = prm.th_bf16 + (size_t)prm.rows_pad * H;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
+                        if (m0 + r < prm.rows) {
+                            const float4 hv4 = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
+                            const float4 tv4 = *reinterpret_cast<const float4 *>(&Ths[r][4 * c4]);
+                            const size_t o = (size_t)(m0 + r) * H + nb * 64 + 4 * c4;
+                            *reinterpret_cast<float4 *>(hnew + nxt_off * H + o) = hv4;
+                            uint2 hi, lo;
+                            split_bf16x4(hv4, hi, lo);
+                            *reinterpret_cast<uint2 *>(hb_hi + o) = hi;
+                            *reinterpret_cast<uint2 *>(hb_lo + o) = lo;
+                            split_bf16x4(tv4, hi, lo);
+                            *reinterpret_cast<uint2 *>(prm.th_bf16 + o) = hi;
+                            *reinterpret_cast<uint2 *>(tb_lo + o) = lo;
+                        }
                     }
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // staging tiles are free for the next tile
@@ -550,15 +618,23 @@ static bool use_pair(int rows_pad) {
 // ---------------------------------------------------------------------------------------------
 // weight packing (device): fp32 PyTorch layout -> bf16 tile-permuted, plus the folded encoder constants
 // ---------------------------------------------------------------------------------------------
+// bf16 hi part and bf16 lo remainder of x (x ~ hi + lo to 2^-17 relative)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16(x);
+    lo = __float2bfloat16(x - __bfloat162float(hi));
+}
 __global__ void k_pack_weights(ecord_weights w) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    __nv_bfloat16 *wh = reinterpret_cast<__nv_bfloat16 *>(w.gru_w_bf16);
-    __nv_bfloat16 *wu = wh + (size_t)3072 * H;
     const long long n_wh = (long long)3072 * H, n_wu = (long long)4096 * 64, n_p1 = (long long)512 * H, n_p2 = 32 * 512;
+    // layouts: gru_w_bf16 = [Wh hi | Wh lo | Wu hi | Wu lo], p1_w_bf16 = [W1 hi | W1 lo | W2 hi | W2 lo]
+    __nv_bfloat16 *wh = reinterpret_cast<__nv_bfloat16 *>(w.gru_w_bf16);
+    __nv_bfloat16 *wu = wh + 2 * n_wh;
+    __nv_bfloat16 *p1 = reinterpret_cast<__nv_bfloat16 *>(w.p1_w_bf16);
+    __nv_bfloat16 *p2 = p1 + 2 * n_p1;
     if (i < n_wh) {                               // Wh pack: row = jb*192 + gate*64 + jj  <-  W_hh[gate*1024 + jb*64 + jj]
         const int row = (int)(i / H), k = (int)(i % H);
         const int jb = row / 192, gate = (row % 192) / 64, jj = row % 64;
-        wh[i] = __float2bfloat16(w.gru_whh[(size_t)(gate * H + jb * 64 + jj) * H + k]);
+        split_bf16(w.gru_whh[(size_t)(gate * H + jb * 64 + jj) * H + k], wh[i], wh[n_wh + i]);
     } else if (i < n_wh + n_wu) {                 // Wu pack: row = jb*256 + slot*64 + jj; slots r, z, (zero), in
         const long long t = i - n_wh;
         const int row = (int)(t / 64), k = (int)(t % 64);
@@ -568,13 +644,13 @@ __global__ void k_pack_weights(ecord_weights w) {
             const int gate = slot == 3 ? 2 : slot;
             v = w.gru_wih[(size_t)(gate * H + jb * 64 + jj) * 64 + k];
         }
-        wu[t] = __float2bfloat16(v);
+        split_bf16(v, wu[t], wu[n_wu + t]);
     } else if (i < n_wh + n_wu + n_p1) {
         const long long t = i - n_wh - n_wu;
-        reinterpret_cast<__nv_bfloat16 *>(w.p1_w_bf16)[t] = __float2bfloat16(w.p1_w[t]);
+        split_bf16(w.p1_w[t], p1[t], p1[n_p1 + t]);
     } else if (i < n_wh + n_wu + n_p1 + n_p2) {   // proj_rnn_to_gnn.4 weight [32][512], behind W1
         const long long t = i - n_wh - n_wu - n_p1;
-        reinterpret_cast<__nv_bfloat16 *>(w.p1_w_bf16)[n_p1 + t] = __float2bfloat16(w.p2_w[t]);
+        split_bf16(w.p2_w[t], p2[t], p2[n_p2 + t]);
     }
 }
 
@@ -666,7 +742,7 @@ __global__ void k_pack_tail(ecord_weights w) {
 
 extern "C" int ecord_pack_weights(const ecord_weights *w, void *stream) {
     ECORD_RET_IF(!w || !w->gru_w_bf16 || !w->p1_w_bf16 || !w->gru_whh || !w->gru_wih || !w->p1_w || !w->p2_w, ECORD_E_NULL);
-    const long long n = (long long)3072 * H + (long long)4096 * 64 + (long long)512 * H + 32 * 512;
+    const long long n = (long long)3072 * H + (long long)4096 * 64 + (long long)512 * H + 32 * 512;      // one thread per weight: hi and lo
     k_pack_weights<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(*w);
     ECORD_LAUNCH_CHECK();
     if (w->q_tc) {
@@ -726,27 +802,33 @@ extern "C" int ecord_fold_q_host(const float *q1_w, const float *enc_w, const fl
 int tc_init_attrs() {
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<0>()));
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
-    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0>()));
-    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1>()));
-    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<0, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<2, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2>()));
     return 0;
 }
 
-int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, cudaStream_t st) {
+// split != 0: ECORD_GEMM_BF16X3 (bf16 hi / lo operands, three products; CTA-pair kernels only)
+int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, int split, cudaStream_t st) {
     PFN_encodeTiled enc;
     int rc = get_encoder(&enc);
     if (rc) return rc;
     const int Mp = p->rows_pad;
+    const int np = split ? 2 : 1;                                      // planes (hi [, lo]) the activation maps cover
     const __nv_bfloat16 *wh = reinterpret_cast<const __nv_bfloat16 *>(w->gru_w_bf16);
-    const __nv_bfloat16 *wu = wh + (size_t)3072 * H;
+    const __nv_bfloat16 *wu = wh + (size_t)2 * 3072 * H;
     const __nv_bfloat16 *hb = reinterpret_cast<const __nv_bfloat16 *>(p->hidden_bf16);
     CUtensorMap mU, mWu, mA0, mA1, mB;
-    if ((rc = make_map(enc, &mU, p->u_bf16, Mp, 64, BM))) return rc;
     const bool pair = use_pair(Mp);
-    if ((rc = make_map(enc, &mWu, wu, 4096, 64, pair ? 128 : 256))) return rc;
-    if ((rc = make_map(enc, &mA0, hb, Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mA1, hb + (size_t)Mp * H, Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mB, wh, 3072, H, pair ? 96 : 192))) return rc;
+    ECORD_RET_IF(split && !pair, ECORD_E_UNSUPPORTED);
+    if ((rc = make_map(enc, &mU, p->u_bf16, (uint64_t)np * Mp, 64, BM))) return rc;
+    if ((rc = make_map(enc, &mWu, wu, 2 * 4096, 64, pair ? 128 : 256))) return rc;
+    if ((rc = make_map(enc, &mA0, hb, (uint64_t)np * Mp, H, BM))) return rc;
+    if ((rc = make_map(enc, &mA1, hb + (size_t)np * Mp * H, (uint64_t)np * Mp, H, BM))) return rc;
+    if ((rc = make_map(enc, &mB, wh, 2 * 3072, H, pair ? 96 : 192))) return rc;
     TcParams prm{};
     prm.hidden = p->hidden; prm.hidden_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->hidden_bf16);
     prm.th_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->th_bf16);
@@ -757,8 +839,12 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     if (pair) {
         const int nblk2 = H / 64, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        ECORD_PDL_LAUNCH(k_gemm_tc2<0>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0>(), st, mU, mWu, mA0, mA1, mB, prm,
-                         tiles2, nblk2);
+        if (split)
+            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 3>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0>(), st, mU, mWu, mA0, mA1, mB,
+                             prm, tiles2, nblk2);
+        else
+            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 1>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0>(), st, mU, mWu, mA0, mA1, mB,
+                             prm, tiles2, nblk2);
         return 0;
     }
     const int nblk = H / 64, num_tiles = nblk * (Mp / BM);
@@ -767,26 +853,30 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     return 0;
 }
 
-int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st) {
+int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, int split, cudaStream_t st) {
     PFN_encodeTiled enc;
     int rc = get_encoder(&enc);
     if (rc) return rc;
     const int Mp = p->rows_pad;
     CUtensorMap mA, mB;
-    if ((rc = make_map(enc, &mA, p->th_bf16, Mp, H, BM))) return rc;
     const bool pair = use_pair(Mp);
-    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 512, H, pair ? 88 : 176))) return rc;
+    ECORD_RET_IF(split && !pair, ECORD_E_UNSUPPORTED);
+    if ((rc = make_map(enc, &mA, p->th_bf16, (uint64_t)(split ? 2 : 1) * Mp, H, BM))) return rc;
+    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 2 * 512, H, pair ? 88 : 176))) return rc;
     TcParams prm{};
     prm.p1_b = w->p1_b; prm.y1 = p->y1; prm.rows = p->rows; prm.rows_pad = Mp;
     if (pair) {
         const int nblk2 = 3, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        if (tiles2 <= clusters)          // one tile per CTA pair: deep pipeline, staging on top of the stages
-            ECORD_PDL_LAUNCH(k_gemm_tc2<2>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<2>(), st, mA, mB, mA, mA, mB, prm,
-                             tiles2, nblk2);
-        else
-            ECORD_PDL_LAUNCH(k_gemm_tc2<1>, dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<1>(), st, mA, mB, mA, mA, mB, prm,
-                             tiles2, nblk2);
+        const dim3 grid(2 * clusters), block(kThreads);
+#define ECORD_PROJ_LAUNCH(MODE, NS) \
+        ECORD_PDL_LAUNCH((k_gemm_tc2<MODE, NS>), grid, block, (size_t)tc2_smem_bytes<MODE>(), st, mA, mB, mA, mA, mB, prm, tiles2, nblk2)
+        if (tiles2 <= clusters) {        // one tile per CTA pair: deep pipeline, staging on top of the stages
+            if (split) ECORD_PROJ_LAUNCH(2, 3); else ECORD_PROJ_LAUNCH(2, 1);
+        } else {
+            if (split) ECORD_PROJ_LAUNCH(1, 3); else ECORD_PROJ_LAUNCH(1, 1);
+        }
+#undef ECORD_PROJ_LAUNCH
         return 0;
     }
     const int nblk = 3, num_tiles = nblk * (Mp / BM);

@@ -14,16 +14,18 @@
 // Rows are m = g*T + t (M = G*T of them), padded to a multiple of 128.
 // Two arithmetic paths for the two dense contractions ([M,1088]x[1088,3072] and [M,1024]x[1024,512]):
 //   ECORD_GEMM_FP32: CUDA-core FMA SGEMM below (parity mode),
-//   ECORD_GEMM_BF16: tcgen05/TMA kernels in gemm_tc.cu (throughput mode).
+//   ECORD_GEMM_BF16: tcgen05/TMA kernels in gemm_tc.cu, bf16 operands (fast mode, 2e-2 tolerance),
+//   ECORD_GEMM_BF16X3: the same kernels on bf16 hi / lo operand pairs, three products per k-chunk, exact gate functions
+//                      (fp32-grade: the default).
 #include "common.cuh"
 #include <cuda_fp16.h>
 
 // gemm_tc.cu
-int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, cudaStream_t st);
-int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st);
+int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, int split, cudaStream_t st);
+int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, int split, cudaStream_t st);
 int tc_init_attrs();
 // tail_tc.cu
-int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st);
+int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, int split, cudaStream_t st);
 int tail_tc_init_attrs();
 
 namespace {
@@ -342,11 +344,12 @@ int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_w
         k_sgemm_nt_bias<<<dim3(P1 / 64, Mp / 64), 256, 0, st>>>(p->th, p->th, nullptr, 0, w->p1_w, w->p1_b, p->y1, H, P1);
         ECORD_LAUNCH_CHECK();
     } else {
-        int rc = launch_gru_tc_ex(w, p, step_base, step_off, st);
+        const int split = gemm_mode == ECORD_GEMM_BF16X3;
+        int rc = launch_gru_tc_ex(w, p, step_base, step_off, split, st);
         if (rc) return rc;
-        rc = launch_proj1_tc(w, p, st);
+        rc = launch_proj1_tc(w, p, split, st);
         if (rc) return rc;
-        return launch_tail_tc(w, p, st);          // LN512 -> W2 on tcgen05 -> LN32, value head, Q-kernel operands
+        return launch_tail_tc(w, p, split, st);   // LN512 -> W2 on tcgen05 -> LN32, value head, Q-kernel operands
     }
     k_policy_tail<<<min(kNumSMs, ceil_div(M, kTailWarps)), kTailWarps * 32, sizeof(TailSmem), st>>>(*w, *p);
     ECORD_LAUNCH_CHECK();
@@ -368,6 +371,9 @@ int check_policy(const ecord_policy *p, int gemm_mode) {
     ECORD_RET_IF(!p->hidden || !p->u || !p->y1 || !p->P || !p->A || !p->v || !p->last_sel, ECORD_E_NULL);
     if (gemm_mode == ECORD_GEMM_FP32) ECORD_RET_IF(!p->gates || !p->th, ECORD_E_NULL);
     else ECORD_RET_IF(!p->hidden_bf16 || !p->th_bf16 || !p->u_bf16, ECORD_E_NULL);
+    // the hi / lo planes exist exactly in the split mode (msg_in writes the lo plane of u when p->split is set)
+    ECORD_RET_IF((gemm_mode == ECORD_GEMM_BF16X3) != (p->split != 0), ECORD_E_UNSUPPORTED);
+    ECORD_RET_IF(gemm_mode == ECORD_GEMM_BF16X3 && (p->rows_pad % 256) != 0, ECORD_E_SIZE);
     return 0;
 }
 
@@ -382,12 +388,12 @@ extern "C" int ecord_policy_pre(const ecord_graph *g, const ecord_env *env, cons
 extern "C" int ecord_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
                                  int32_t cur, int32_t gemm_mode, int32_t skip_pre, void *stream) {
     ECORD_RET_IF(!g || !env || !w, ECORD_E_NULL);
-    ECORD_RET_IF(gemm_mode != ECORD_GEMM_FP32 && gemm_mode != ECORD_GEMM_BF16, ECORD_E_UNSUPPORTED);
+    ECORD_RET_IF(gemm_mode != ECORD_GEMM_FP32 && gemm_mode != ECORD_GEMM_BF16 && gemm_mode != ECORD_GEMM_BF16X3, ECORD_E_UNSUPPORTED);
     ECORD_RET_IF(cur != 0 && cur != 1, ECORD_E_SIZE);
     int rc = check_policy(p, gemm_mode);
     if (rc) return rc;
     ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj, ECORD_E_SIZE);
-    if (gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!w->gru_w_bf16 || !w->p1_w_bf16, ECORD_E_NULL);
+    if (gemm_mode != ECORD_GEMM_FP32) ECORD_RET_IF(!w->gru_w_bf16 || !w->p1_w_bf16, ECORD_E_NULL);
     if ((rc = policy_init_attrs())) return rc;
     ECORD_RET_IF((p->Ac == nullptr) != (p->LA == nullptr), ECORD_E_NULL);
     ECORD_RET_IF(p->qa && !w->q_tc, ECORD_E_NULL);

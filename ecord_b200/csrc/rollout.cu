@@ -32,8 +32,8 @@ struct ecord_rollout_plan {
     ecord_policy policy;
     ecord_rollout_desc desc;
     cudaStream_t stream;
-    cudaGraphExec_t exec_k, exec_1;
-    int k;
+    cudaGraphExec_t exec_k, exec_rem;      // k steps; the most recent remainder length (rem_k steps), captured on demand
+    int k, rem_k;
     int kernels_per_step;
     int64_t steps_enqueued;
 };
@@ -103,7 +103,8 @@ int capture(ecord_rollout_plan *pl, int nsteps, cudaGraphExec_t *out) {
 extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *stream, ecord_rollout_plan **out) {
     ECORD_RET_IF(!desc || !out, ECORD_E_NULL);
     ECORD_RET_IF(!desc->graph || !desc->env || !desc->weights || !desc->policy || !desc->step_counter, ECORD_E_NULL);
-    ECORD_RET_IF(desc->gemm_mode != ECORD_GEMM_FP32 && desc->gemm_mode != ECORD_GEMM_BF16, ECORD_E_UNSUPPORTED);
+    ECORD_RET_IF(desc->gemm_mode != ECORD_GEMM_FP32 && desc->gemm_mode != ECORD_GEMM_BF16 && desc->gemm_mode != ECORD_GEMM_BF16X3,
+                 ECORD_E_UNSUPPORTED);
     ECORD_RET_IF(desc->steps_per_graph <= 0 || desc->steps_per_graph > 256, ECORD_E_SIZE);
     ECORD_RET_IF(desc->tau < 0.0f || !(desc->epsilon >= 0.0f && desc->epsilon <= 1.0f), ECORD_E_SIZE);
     ECORD_RET_IF((desc->score_log || desc->action_log) && desc->max_steps <= 0, ECORD_E_SIZE);
@@ -113,7 +114,7 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     ECORD_RET_IF(desc->tau > 0.0f && desc->q_mode == ECORD_Q_EXACT && !desc->policy->q, ECORD_E_NULL);
     if ((rc = check_q_mode(desc->graph, desc->weights, desc->policy, desc->q_mode, desc->tau))) return rc;
     ECORD_RET_IF(!desc->weights->q_fold, ECORD_E_NULL);
-    if (desc->gemm_mode == ECORD_GEMM_BF16) ECORD_RET_IF(!desc->weights->gru_w_bf16 || !desc->weights->p1_w_bf16, ECORD_E_NULL);
+    if (desc->gemm_mode != ECORD_GEMM_FP32) ECORD_RET_IF(!desc->weights->gru_w_bf16 || !desc->weights->p1_w_bf16, ECORD_E_NULL);
     if ((rc = policy_init_attrs())) return rc;
     ecord_rollout_plan *pl = new (std::nothrow) ecord_rollout_plan();
     ECORD_RET_IF(!pl, (int)cudaErrorMemoryAllocation);
@@ -124,10 +125,10 @@ extern "C" int ecord_rollout_plan_create(const ecord_rollout_desc *desc, void *s
     pl->k = desc->steps_per_graph;
     pl->kernels_per_step = policy_kernels_per_step(desc->gemm_mode, desc->q_mode != ECORD_Q_EXACT) +
                            q_kernels_per_step(desc->q_mode) + 1;
-    pl->exec_k = pl->exec_1 = nullptr;
+    pl->exec_k = pl->exec_rem = nullptr;
+    pl->rem_k = 0;
     pl->steps_enqueued = 0;
     rc = capture(pl, pl->k, &pl->exec_k);
-    if (!rc && pl->k > 1) rc = capture(pl, 1, &pl->exec_1);
     if (rc) { ecord_rollout_plan_destroy(pl); return rc; }
     *out = pl;
     return 0;
@@ -140,9 +141,19 @@ extern "C" int ecord_rollout_plan_run(ecord_rollout_plan *pl, int32_t num_steps,
         return ECORD_E_SIZE;   // would overrun the logs
     const int nk = num_steps / pl->k, rem = num_steps % pl->k;
     for (int i = 0; i < nk; ++i) ECORD_CUDA(cudaGraphLaunch(pl->exec_k, pl->stream));
-    for (int i = 0; i < rem; ++i) ECORD_CUDA(cudaGraphLaunch(pl->k > 1 ? pl->exec_1 : pl->exec_k, pl->stream));
+    if (rem) {
+        // the remainder runs as ONE graph of `rem` steps (captured on first use and kept while the length repeats): `rem`
+        // single-step graphs would pay a graph launch and lose the programmatic dependent launches across every step
+        if (pl->rem_k != rem) {
+            if (pl->exec_rem) { cudaGraphExecDestroy(pl->exec_rem); pl->exec_rem = nullptr; pl->rem_k = 0; }
+            int rc = capture(pl, rem, &pl->exec_rem);
+            if (rc) return rc;
+            pl->rem_k = rem;
+        }
+        ECORD_CUDA(cudaGraphLaunch(pl->exec_rem, pl->stream));
+    }
     pl->steps_enqueued += num_steps;
-    if (launches_out) *launches_out = (int64_t)num_steps * pl->kernels_per_step + nk + rem;
+    if (launches_out) *launches_out = (int64_t)num_steps * pl->kernels_per_step + nk + (rem ? 1 : 0);
     return 0;
 }
 
@@ -155,7 +166,7 @@ extern "C" int ecord_rollout_plan_reset(ecord_rollout_plan *pl) {
 extern "C" int ecord_rollout_plan_destroy(ecord_rollout_plan *pl) {
     if (!pl) return 0;
     if (pl->exec_k) cudaGraphExecDestroy(pl->exec_k);
-    if (pl->exec_1) cudaGraphExecDestroy(pl->exec_1);
+    if (pl->exec_rem) cudaGraphExecDestroy(pl->exec_rem);
     delete pl;
     return 0;
 }

@@ -29,17 +29,23 @@ constexpr int A_SUB = BM * 128;      // bytes of one [128][64] bf16 sub-tile
 constexpr int W_SUB = ND * 128;      // bytes of one [32][64] bf16 sub-tile
 constexpr int kTailImgFloats = 2 * P1 + ND * ND + QC * ND + QC * 16 + QC * 4 + ND + 4;     // ecord_weights.q_tc [4736, ...)
 
+struct TailTcPost {                  // written after the MMAs have completed: shares the memory of the W2 tiles
+    float Ps[64][ND + 1], Ts[64][ND + 1];   // P and tanh(P) of the CTA's rows (padded: conflict-free row reads)
+    float lo[64][ND + 1];            // NS = 3: accumulator rows 64.. (the lo-part products), handed to the rows' threads
+    float meanA[64];
+};
 struct TailTcSmem {
     uint8_t act[8][A_SUB];           // 128 KB
-    uint8_t w2[8][W_SUB];            // 32 KB
+    union {
+        uint8_t w2[2][8][W_SUB];     // 32 KB (hi) + 32 KB (lo, NS = 3)
+        TailTcPost post;
+    };
     float ln1g[P1], ln1b[P1];
     float v1[ND * ND];               // val_out.1 weight [j][o]
     float q1[QC * ND];               // Wq[:, :32]  [c][o]
     float wg[QC * 16];               // centred Wq[:,32:48] [c][k]
     float cc[QC * 4];                // centred C [c][0..2], bconst[c]
     float colsum[ND + 4];            // sum_c Wq[c][o]; [32] = sum_c b_q[c]; padded: ln1g .. colsum is one 16-byte-granular image
-    float Ps[64][ND + 1], Ts[64][ND + 1];   // P and tanh(P) of the CTA's rows (padded: conflict-free row reads)
-    float meanA[64];
     uint64_t bar_w, bar_mma, bar_c;
     uint32_t tmem_base;
 };
@@ -50,6 +56,11 @@ __device__ __forceinline__ uint32_t split_h2(float x) {     // fp16 (hi | lo << 
     return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
 }
 
+// NS = 1: bf16 A operand and weights (ECORD_GEMM_BF16).  NS = 3 (ECORD_GEMM_BF16X3): the LN512 output is split into a bf16 hi
+// part (A-operand rows 0..R-1) and its bf16 lo remainder (rows 64..64+R-1) of the SAME [128][512] operand, so one pass of
+// MMAs against W2 hi yields hi.hi in accumulator rows 0.. and lo.hi in rows 64.., and a second pass against W2 lo adds
+// hi.lo (and the negligible lo.lo); the two row halves are added through shared memory.  Exact tanh in the value head.
+template <int NS>
 __global__ void __launch_bounds__(kTtThreads, 1)
 k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_policy p, int R) {
     extern __shared__ uint8_t smem_raw[];
@@ -71,9 +82,13 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(S.ln1g)), "l"(w.q_tc + 4736), "r"(kTailImgFloats * 4), "r"(bar_c) : "memory");
         }
-        mbar_expect_tx(bar_w, 8 * W_SUB);
+        mbar_expect_tx(bar_w, (NS == 3 ? 2 : 1) * 8 * W_SUB);
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) tma_load_2d(smem_u32(S.w2[kb]), &mapW2, bar_w, kb * 64, 0);
+        for (int kb = 0; kb < 8; ++kb) tma_load_2d(smem_u32(S.w2[0][kb]), &mapW2, bar_w, kb * 64, 0);
+        if (NS == 3) {
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb) tma_load_2d(smem_u32(S.w2[1][kb]), &mapW2, bar_w, kb * 64, ND);
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(32u)
@@ -140,6 +155,12 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
                 const uint32_t off = (uint32_t)(r * 128 + (((((i & 63) >> 3) ^ (r & 7)) & 7) << 4) + (i & 7) * 2);
                 *reinterpret_cast<uint2 *>(&S.act[i >> 6][off]) =
                     make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+                if (NS == 3) {          // the remainders, as operand row r + 64 (same swizzle phase: 64 is a multiple of 8)
+                    const float2 f01 = __bfloat1622float2(lo), f23 = __bfloat1622float2(hi);
+                    const __nv_bfloat162 r01 = __floats2bfloat162_rn(y0 - f01.x, y1 - f01.y), r23 = __floats2bfloat162_rn(y2 - f23.x, y3 - f23.y);
+                    *reinterpret_cast<uint2 *>(&S.act[i >> 6][off + 64 * 128]) =
+                        make_uint2(*reinterpret_cast<const uint32_t *>(&r01), *reinterpret_cast<const uint32_t *>(&r23));
+                }
             }
         }
     }
@@ -155,16 +176,35 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         constexpr uint32_t idesc = umma_idesc(BM, ND);
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
-            const uint32_t a_src = smem_u32(S.act[kb]), b_src = smem_u32(S.w2[kb]);
+        for (int part = 0; part < (NS == 3 ? 2 : 1); ++part) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16(tmem_d, umma_desc(a_src + k * UMMA_K * 2), umma_desc(b_src + k * UMMA_K * 2), idesc, (kb | k) ? 1u : 0u);
+            for (int kb = 0; kb < 8; ++kb) {
+                const uint32_t a_src = smem_u32(S.act[kb]), b_src = smem_u32(S.w2[part][kb]);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_d, umma_desc(a_src + k * UMMA_K * 2), umma_desc(b_src + k * UMMA_K * 2), idesc, (part | kb | k) ? 1u : 0u);
+            }
         }
         umma_commit(bar_mma);
     }
 
     // ---------------- phase 3a: R threads read the accumulator (thread <-> row <-> TMEM lane), LN32, publish ----------------
+    TailTcPost &Z = S.post;              // (the W2 tiles are dead once bar_mma has completed)
+    if (NS == 3) {                       // accumulator rows 64 .. 64 + R - 1 hold the lo-part products of rows 0 .. R - 1
+        if (tid >= 64 && tid < 64 + R) {
+            mbar_wait(bar_mma, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float L[ND];
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+            tmem_ld16(taddr, L);
+            tmem_ld16(taddr + 16, L + 16);
+            tmem_ld_wait();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int o = 0; o < ND; ++o) Z.lo[tid - 64][o] = L[o];
+        }
+        __syncthreads();
+    }
     if (tid < R) {
         const int m = m0 + tid;
         mbar_wait(bar_mma, 0);
@@ -175,6 +215,10 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         tmem_ld16(taddr + 16, P + 16);
         tmem_ld_wait();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (NS == 3) {
+#pragma unroll
+            for (int o = 0; o < ND; ++o) P[o] += Z.lo[tid][o];
+        }
         float s = 0.0f;
 #pragma unroll
         for (int o = 0; o < ND; ++o) { P[o] += w.p2_b[o]; s += P[o]; }
@@ -187,12 +231,12 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
 #pragma unroll
         for (int o = 0; o < ND; ++o) {
             P[o] = lrelu(fmaf(P[o] * rstd, w.ln2_w[o], w.ln2_b[o]));
-            S.Ps[tid][o] = P[o];
-            S.Ts[tid][o] = tanh_fast(P[o]);                   // MUFU.TANH: this is the bf16-tolerance path
+            Z.Ps[tid][o] = P[o];
+            Z.Ts[tid][o] = NS == 3 ? tanhf(P[o]) : tanh_fast(P[o]);   // MUFU.TANH on the bf16-tolerance path only
             sa = fmaf(S.colsum[o], P[o], sa);
         }
         // mean over the 64 channels of A = Wq[:, :32] P + b_q, without forming A
-        S.meanA[tid] = sa * (1.0f / QC);
+        Z.meanA[tid] = sa * (1.0f / QC);
         if (m < p.rows) {
 #pragma unroll
             for (int o = 0; o < ND; o += 4)
@@ -209,8 +253,8 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         const bool live = m < p.rows;
         float P[ND], Tp[ND];
 #pragma unroll
-        for (int o = 0; o < ND; ++o) { P[o] = S.Ps[rloc][o]; Tp[o] = S.Ts[rloc][o]; }
-        const float meanA = S.meanA[rloc];
+        for (int o = 0; o < ND; ++o) { P[o] = Z.Ps[rloc][o]; Tp[o] = Z.Ts[rloc][o]; }
+        const float meanA = Z.meanA[rloc];
         float acc[22];                                        // Wg^T a' (16) | Cc^T a' (3) | |a'|^2 | LA | v   (partial sums)
 #pragma unroll
         for (int i = 0; i < 22; ++i) acc[i] = 0.0f;
@@ -327,19 +371,25 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
 }  // namespace
 
 int tail_tc_init_attrs() {
-    ECORD_CUDA(cudaFuncSetAttribute(k_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailTcSmem) + 1024));
+    ECORD_CUDA(cudaFuncSetAttribute(k_tail_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailTcSmem) + 1024));
+    ECORD_CUDA(cudaFuncSetAttribute(k_tail_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailTcSmem) + 1024));
     return 0;
 }
 
-int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, cudaStream_t st) {
+int launch_tail_tc(const ecord_weights *w, const ecord_policy *p, int split, cudaStream_t st) {
+    static_assert(sizeof(TailTcSmem) + 1024 <= 227 * 1024, "TailTcSmem too large");
     PFN_encodeTiled enc;
     int rc = get_encoder(&enc);
     if (rc) return rc;
     CUtensorMap mW2;
-    const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(w->p1_w_bf16) + (size_t)ECORD_DIM_P1 * H;
-    if ((rc = make_map(enc, &mW2, w2, ND, P1, ND))) return rc;
+    // p1_w_bf16 = [W1 hi | W1 lo | W2 hi | W2 lo]: the map covers W2 hi (rows 0..31) and W2 lo (rows 32..63)
+    const __nv_bfloat16 *w2 = reinterpret_cast<const __nv_bfloat16 *>(w->p1_w_bf16) + (size_t)2 * ECORD_DIM_P1 * H;
+    if ((rc = make_map(enc, &mW2, w2, 2 * ND, P1, ND))) return rc;
     // 32 rows per CTA while that stays within one wave of CTAs (one per SM: the A-operand tile is 128 KB), else 64
     const int R = ceil_div(p->rows, 32) <= kNumSMs ? 32 : 64;
-    ECORD_PDL_LAUNCH(k_tail_tc, dim3(ceil_div(p->rows, R)), dim3(kTtThreads), sizeof(TailTcSmem) + 1024, st, mW2, *w, *p, R);
+    if (split)
+        ECORD_PDL_LAUNCH(k_tail_tc<3>, dim3(ceil_div(p->rows, R)), dim3(kTtThreads), sizeof(TailTcSmem) + 1024, st, mW2, *w, *p, R);
+    else
+        ECORD_PDL_LAUNCH(k_tail_tc<1>, dim3(ceil_div(p->rows, R)), dim3(kTtThreads), sizeof(TailTcSmem) + 1024, st, mW2, *w, *p, R);
     return 0;
 }

@@ -81,6 +81,14 @@ class TgBatch:
         w = np.concatenate([e.w for e in els]).astype(np.float32)
         if np.any(np.diff(src) < 0):
             raise ValueError("edges must be grouped by ascending source vertex (reference edge order)")
+        # the env kernels update the neighbours of a flipped vertex in parallel: a self-loop or a repeated (src, dst) pair
+        # would make two lanes read-modify-write the same entry (the sequential reference has no such hazard)
+        if np.any(src == dst):
+            raise ValueError("self-loops are not supported (Max-Cut on simple graphs)")
+        if src.size:
+            key = src * np.int64(self.num_nodes) + dst
+            if np.unique(key).size != key.size:
+                raise ValueError("duplicate (src, dst) edges are not supported (Max-Cut on simple graphs)")
         self.np_src, self.np_dst, self.np_w = src, dst, w
         self.np_ptr = offs.astype(np.int64)
         self.np_edge_counts = np.asarray([len(e.w) for e in els], np.int64)

@@ -6,8 +6,8 @@ rank r runs trajectories [lo_r, hi_r) of the SAME graphs.  All ranks hold the wh
 tiny t=0 GNN redundantly, which keeps its batch-wide LayerNorm statistics identical to the single-GPU run
 (quirk B).  Initial spins are drawn once for the global [N, T] array and sliced, so results do not depend
 on the number of GPUs.  The only communication is at the END of the rollout:
-    all_reduce(MAX) of the per-graph best cut  f32[G]
-    all_gather of the per-trajectory best      f32[G, T_local]   (needed for scores_mean, testing.py:201-204)
+    one all_gather of the per-trajectory best  f32[G, T_local]   (needed for scores_mean, testing.py:201-204);
+    the per-graph best cut f32[G] is the maximum of the gathered values
 over NCCL (NVLink/NVSwitch) on GPUs, or gloo in the CPU tests.  Payloads are KBs.
 """
 import torch
@@ -28,19 +28,20 @@ def reduce_best(best_by_tradj_local, total_tradj, group=None):
         return best_by_tradj_local.max(-1).values, best_by_tradj_local
     world = dist.get_world_size(group)
     G = best_by_tradj_local.shape[0]
-    best = best_by_tradj_local.max(-1).values.contiguous()
-    dist.all_reduce(best, op=dist.ReduceOp.MAX, group=group)
-    # ragged split -> pad every shard to the largest, gather, then cut the padding out
+    # ONE collective: ragged split -> pad every shard to the largest, all_gather into one tensor, cut the padding out;
+    # the best cut is the maximum of the gathered values (an all_reduce(MAX) on top would be a second ~50 us launch)
     t_max = -(-int(total_tradj) // world)
     pad = torch.full((G, t_max), float("-inf"), dtype=best_by_tradj_local.dtype, device=best_by_tradj_local.device)
     pad[:, :best_by_tradj_local.shape[1]] = best_by_tradj_local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad.contiguous(), group=group)
+    gathered = torch.empty((world * G, t_max), dtype=pad.dtype, device=pad.device)      # shards concatenated along dim 0
+    dist.all_gather_into_tensor(gathered, pad.contiguous(), group=group)
+    gathered = gathered.view(world, G, t_max)
     cols = []
-    for r, p in enumerate(parts):
+    for r in range(world):
         lo, hi = shard_bounds(total_tradj, world, r)
-        cols.append(p[:, :hi - lo])
-    return best, torch.cat(cols, dim=1)
+        cols.append(gathered[r, :, :hi - lo])
+    by_all = torch.cat(cols, dim=1)
+    return by_all.max(-1).values, by_all
 
 
 def rollout_sharded(solver, batch, num_tradj, num_steps, init_state, tau=0.0, group=None):

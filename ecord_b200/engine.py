@@ -10,10 +10,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GEMM_BF16, GEMM_FP32, Q_EXACT, Q_FAST, Q_TC, check, ptr
+from ._lib import GEMM_BF16, GEMM_BF16X3, GEMM_FP32, Q_EXACT, Q_FAST, Q_TC, check, ptr
 from .network import check_state_dicts
 
-_GEMM_MODES = {"fp32": GEMM_FP32, "bf16": GEMM_BF16}
+# "bf16x3" (the default): tcgen05 GEMMs on bf16 hi/lo operand pairs, three products, exact gate functions -- fp32-grade
+# recurrent state on the tensor cores; "bf16": single bf16 products + MUFU.TANH (fast, 2e-2 tolerance); "fp32": CUDA-core SGEMM
+_GEMM_MODES = {"fp32": GEMM_FP32, "bf16": GEMM_BF16, "bf16x3": GEMM_BF16X3}
 _Q_MODES = {"exact": Q_EXACT, "fast": Q_FAST, "tc": Q_TC}
 
 
@@ -93,10 +95,17 @@ class DeviceGraph:
         starts = np.concatenate([[0], np.cumsum(tiles_per_graph)])[:-1]
         tv0 = ((np.arange(tg_ids.shape[0]) - np.repeat(starts, tiles_per_graph)) * _lib.QTILE).astype(np.int32)
         self.qtile_graph, self.qtile_v0 = up(tg_ids), up(tv0)
+        # per-graph sum of the directed edge weights (env init: cut = (sum w - sum peek) / 4, exact for integer weights)
+        w64 = w.astype(np.float64)
+        edge_graph = np.repeat(np.arange(G), tg.np_edge_counts)
+        wsum = np.bincount(edge_graph, weights=w64, minlength=G)
+        wabs = np.bincount(edge_graph, weights=np.abs(w64), minlength=G)
+        int_weights = int(bool(np.all(w64 == np.rint(w64)) and (wabs.max() if G else 0) < 2 ** 24))
+        self.graph_wsum = up(wsum.astype(np.float32))
         self.c = _lib.Graph(G, N, E, self.n_max, ptr(self.graph_ptr), ptr(self.node_graph), ptr(self.row_ptr),
                             ptr(self.col), ptr(self.w), ptr(self.graph_edge_ptr), ptr(self.in_ptr),
-                            ptr(self.in_src), ptr(self.in_w), int(tg_ids.shape[0]), 0, ptr(self.qtile_graph),
-                            ptr(self.qtile_v0))
+                            ptr(self.in_src), ptr(self.in_w), int(tg_ids.shape[0]), int_weights, ptr(self.qtile_graph),
+                            ptr(self.qtile_v0), ptr(self.graph_wsum))
 
     def padded_row_index(self):
         """int64 [N] on the device: row of vertex v in a [G * n_max, ...] padded array (graph * n_max + local id)."""
@@ -159,7 +168,7 @@ class RolloutState:
     Step-wise methods (`policy_step`, `q_select`, `env_step`) expose the individual kernels for parity
     tests and `log_stats`; `run()` executes whole steps through the CUDA-graph plan."""
 
-    def __init__(self, dgraph, weights, num_tradj, gemm="bf16", compat=True, tau=0.0, seed=0,
+    def __init__(self, dgraph, weights, num_tradj, gemm="bf16x3", compat=True, tau=0.0, seed=0,
                  max_steps=0, log_scores=True, log_actions=True, steps_per_graph=16, dump_q=False, q_mode=None,
                  stream=None, epsilon=0.0):
         self.lib = _lib.load()
@@ -169,7 +178,7 @@ class RolloutState:
         self.stream = stream if stream is not None else _rollout_stream(dev)
         self.T = T = int(num_tradj)
         self.gemm = _GEMM_MODES[gemm]
-        if self.gemm == GEMM_BF16 and weights.gru_w_bf16 is None:
+        if self.gemm != GEMM_FP32 and weights.gru_w_bf16 is None:
             raise ValueError("weights were created with pack_bf16=False")
         self.compat, self.tau, self.seed = bool(compat), float(tau), int(seed)
         self.epsilon = float(epsilon)     # epsilon-greedy (actors/ecord.py:171-180); fixed for the life of the CUDA-graph plan
@@ -178,7 +187,7 @@ class RolloutState:
         # parity mode = (fp32 GEMM, exact Q); throughput mode = (bf16 tcgen05 GEMM, tensor-core Q).  tau > 0 (sampling) is
         # implemented by the exact kernel (exponential race, two passes) and by the tensor-core kernel (Gumbel-max, one pass).
         if q_mode is None:
-            q_mode = "tc" if gemm == "bf16" else "exact"
+            q_mode = "tc" if gemm != "fp32" else "exact"
         self.q_mode = _Q_MODES[q_mode]
         if self.q_mode == Q_FAST and self.tau > 0:
             raise ValueError("tau > 0 (sampling) requires q_mode='exact' or 'tc'")
@@ -197,7 +206,8 @@ class RolloutState:
         self.score = torch.empty(M, **f32)
         self.best_score = torch.empty(M, **f32)
         self.best_step = torch.empty(M, dtype=torch.int32, device=dev)
-        self.env_c = _lib.Env(T, 0, ptr(self.peek), ptr(self.sp), ptr(self.best_state), ptr(self.score),
+        # compat=False also lifts quirk D: the best-state plane is a true snapshot (copied whole on every new best)
+        self.env_c = _lib.Env(T, int(not self.compat), ptr(self.peek), ptr(self.sp), ptr(self.best_state), ptr(self.score),
                               ptr(self.best_score), ptr(self.best_step))
         # policy
         self.hidden = torch.zeros(2, Mp, 1024, **f32)
@@ -209,10 +219,15 @@ class RolloutState:
         self.last_sel = torch.zeros(Mp, 32, **f32)
         self.actions = torch.zeros(M, dtype=torch.int32, device=dev)
         self.hidden_bf16 = self.th_bf16 = self.u_bf16 = self.gates = self.th = None
+        self.split = int(self.gemm == GEMM_BF16X3)
         if self.gemm == GEMM_BF16:
             self.hidden_bf16 = torch.zeros(2, Mp, 1024, dtype=torch.bfloat16, device=dev)
             self.th_bf16 = torch.zeros(Mp, 1024, dtype=torch.bfloat16, device=dev)
             self.u_bf16 = torch.zeros(Mp, 64, dtype=torch.bfloat16, device=dev)
+        elif self.gemm == GEMM_BF16X3:          # hi and lo planes (include/ecord_b200.h: ecord_policy)
+            self.hidden_bf16 = torch.zeros(2, 2, Mp, 1024, dtype=torch.bfloat16, device=dev)
+            self.th_bf16 = torch.zeros(2, Mp, 1024, dtype=torch.bfloat16, device=dev)
+            self.u_bf16 = torch.zeros(2, Mp, 64, dtype=torch.bfloat16, device=dev)
         else:
             self.gates = torch.zeros(Mp, 6144, **f32)
             self.th = torch.zeros(Mp, 1024, **f32)
@@ -235,7 +250,7 @@ class RolloutState:
                                     ptr(self.u), ptr(self.gates), ptr(self.th), ptr(self.y1), ptr(self.P), ptr(self.A),
                                     ptr(self.v), ptr(self.last_sel), ptr(self.node_emb), ptr(self.node_B),
                                     ptr(self.actions), ptr(self.q), ptr(self.Ac), ptr(self.LA), ptr(self.node_Bc),
-                                    ptr(self.node_LB), ptr(self.keys), ptr(self.qa), ptr(self.node_qv))
+                                    ptr(self.node_LB), ptr(self.keys), ptr(self.qa), ptr(self.node_qv), self.split, 0)
         # logs + step counter
         self.max_steps = int(max_steps)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -248,6 +263,7 @@ class RolloutState:
         self.init_state_dev = None
         self.kernel_launches = 0
         self.env_clock_extra = 0
+        self.greedy_steps = 0
         self._best_out = torch.empty(M, **f32)
 
     def reset(self):
@@ -255,6 +271,7 @@ class RolloutState:
         buffer a rollout reads before writing, the captured CUDA graphs stay valid."""
         self.kernel_launches = 0
         self.env_clock_extra = 0
+        self.greedy_steps = 0
         if self.plan is not None:
             check(self.lib.ecord_rollout_plan_reset(self.plan), "ecord_rollout_plan_reset")
 
@@ -383,6 +400,7 @@ class RolloutState:
             iters += 1
             select(clock + iters)
             done |= flags
+        self.greedy_steps += iters
         if rebase and iters:
             check(self.lib.ecord_env_rebase_clock(C.byref(self.g.c), C.byref(self.env_c), iters, _stream()),
                   "ecord_env_rebase_clock")
@@ -487,9 +505,16 @@ class RolloutState:
         """[G, n_max, T], -1 padded (tradjectories.py:324-328,378-385).  true_snapshot=False gives the
         reference's semantics (quirk D); True replays the action log up to each trajectory's best step."""
         N, G, T = self.g.N, self.g.G, self.T
-        if true_snapshot:
+        if true_snapshot and not self.compat:
+            # compat=False keeps the best-state plane as a true snapshot on the device (ecord_env.true_snapshot): greedy
+            # pre- / post-solve flips and rebased clocks are covered, nothing has to be replayed
+            flat = self.export(nodes=False)[2]
+        elif true_snapshot:
             if self.action_log is None or self.init_state_dev is None:
                 raise ValueError("true_snapshot needs log_actions=True")
+            if self.greedy_steps:
+                raise ValueError("greedy pre-/post-solve flips are not in the action log: use compat=False, which keeps a "
+                                 "true best-state snapshot on the device")
             plane = torch.empty(N * T, dtype=torch.uint8, device=self.device)
             check(self.lib.ecord_best_state_snapshot(C.byref(self.g.c), C.byref(self.env_c), ptr(self.init_state_dev),
                                                      ptr(self.action_log), min(self.steps_done, self.max_steps),

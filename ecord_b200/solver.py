@@ -54,7 +54,7 @@ class B200Solver:
                  default_actor_idx=None, tau=0, alpha=0, munch_lower_log_clip=-1,
                  initial_epsilon=1, final_epsilon=0.05, final_epsilon_step=1000, device=None,
                  # engine options (not in the reference)
-                 gemm="bf16", compat=True, steps_per_graph=16, seed=0):
+                 gemm="bf16x3", compat=True, steps_per_graph=16, seed=0):
         if use_ecodqn or use_double_q_networks:
             raise NotImplementedError("only the single-Q ECORD actor (Actor_Q, actors/ecord.py:26) is implemented")
         if node_encoder is None or add_glob_to_nodes or not add_glob_to_obs:
@@ -92,9 +92,11 @@ class B200Solver:
         heads = node_classifier_heads(node_classifier)
         self.node_classifier = None if heads is None else tuple(t.to(self.device) for t in heads)
 
-    def load(self, fname, quiet=False):
-        """Ingest a reference checkpoint written by DQNSolver.save (solver.py:582-617)."""
-        checkpoint = torch.load(fname, map_location="cpu", weights_only=False)
+    def load(self, fname, quiet=False, allow_pickle=False):
+        """Ingest a reference checkpoint written by DQNSolver.save (solver.py:582-617).  Such checkpoints hold only dicts,
+        OrderedDicts, tensors and numbers, so they are read with torch's restricted unpickler; allow_pickle=True opts into
+        the full one for legacy files that carry other objects (it executes code from the file: trusted sources only)."""
+        checkpoint = torch.load(fname, map_location="cpu", weights_only=not allow_pickle)
         self.set_weights(state_dicts_from_checkpoint(checkpoint))
         ck = checkpoint.get('actor:checkpoint', checkpoint)
         if 'node_classifier:state_dict' in ck:          # actors/ecord.py:250-251,269

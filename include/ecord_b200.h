@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ECORD_ABI_VERSION 2
+#define ECORD_ABI_VERSION 3
 
 /* error codes (<0) */
 #define ECORD_E_NULL      (-1)  /* required pointer is NULL */
@@ -57,6 +57,10 @@ extern "C" {
 /* GRU / projection arithmetic */
 #define ECORD_GEMM_FP32 0   /* CUDA-core fp32 FMA (parity mode; 1e-4 rel vs reference)            */
 #define ECORD_GEMM_BF16 1   /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM (2e-2 rel) */
+#define ECORD_GEMM_BF16X3 2 /* the same tcgen05 kernels with every operand split into a bf16 hi part and a bf16 lo remainder
+                               (x ~ hi + lo to 2^-17) and the products hi.hi + lo.hi + hi.lo accumulated in fp32, exact
+                               sigmoid / tanh in the GRU cell: fp32-grade recurrent state on the tensor cores (the engine's
+                               default; rows_pad must be a multiple of 256, ecord_policy.split = 1) */
 
 /* ---- graph batch: replaces GraphBatcher/Batch.tg (environment/data.py:53-83) + the CSR views
  *      Tradjectories builds (tradjectories.py:38-60).  All arrays read-only. ---- */
@@ -77,16 +81,18 @@ typedef struct ecord_graph {
     /* vertex tiles of ECORD_QTILE vertices for the fast Q kernel: tile i covers vertices
        [qtile_v0[i], qtile_v0[i] + ECORD_QTILE) (local ids, clipped to n_g) of graph qtile_graph[i] */
     int32_t num_qtiles;
-    int32_t _pad;
+    int32_t int_weights;           /* 1: every edge weight is an integer and sum |w| < 2^24 per graph (sums exact in any order) */
     const int32_t *qtile_graph;    /* [num_qtiles] */
     const int32_t *qtile_v0;       /* [num_qtiles] */
+    const float   *graph_wsum;     /* [G] sum of each graph's directed edge weights, or NULL (ecord_env_init then walks the edges) */
 } ecord_graph;
 #define ECORD_QTILE 128
 
 /* ---- environment state: replaces Tradjectories' arrays (tradjectories.py:78-116) ---- */
 typedef struct ecord_env {
     int32_t  num_tradj;            /* T */
-    int32_t  _pad;
+    int32_t  true_snapshot;        /* 0: best_state follows the reference (only the flipped vertex is recorded on a new best,
+                                      quirk D); 1: the whole spin row is copied on a new best, so cut(best_state) == best_score */
     float   *peek;                 /* [N*T] plane */
     int32_t *sp;                   /* [N*T] plane */
     uint8_t *best_state;           /* [N*T] plane */
@@ -114,10 +120,11 @@ typedef struct ecord_weights {
     const float *v1_w, *v1_b, *v2_w, *v2_b;        /* [32,32],[32],[1,32],[1] */
     const float *q1_w, *q1_b, *qln_w, *qln_b, *q2_w, *q2_b; /* [64,64],[64],[64],[64],[1,64],[1] */
     /* derived by ecord_pack_weights() into caller-allocated buffers */
-    void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [16][192][1024] (rows r|z|hn of each 64-unit block)
-                            followed by Wu pack [16][256][64] (rows r|z|0|in) -- tile order of the tcgen05 GRU kernel */
-    void  *p1_w_bf16;    /* bf16, ECORD_P1_PACK_ELEMS elements: proj_rnn_to_gnn.1 weight [512][1024] followed by
-                            proj_rnn_to_gnn.4 weight [32][512] */
+    void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [16][192][1024] (rows r|z|hn of each 64-unit block; tile
+                            order of the tcgen05 GRU kernel) as a hi plane (bf16(w)) and a lo plane (bf16(w - hi)), followed by
+                            the Wu pack [16][256][64] (rows r|z|0|in), hi plane and lo plane */
+    void  *p1_w_bf16;    /* bf16, ECORD_P1_PACK_ELEMS elements: proj_rnn_to_gnn.1 weight [512][1024] hi plane | lo plane, followed
+                            by proj_rnn_to_gnn.4 weight [32][512] hi plane | lo plane */
     float *q_tc;         /* f32 [ECORD_QTC_FLOATS] operands of the tensor-core Q kernel (ECORD_Q_TC), or NULL:
                               [0,1280)     reserved
                               [1280,2304)  Wg [64][16] = Wq[:,32:48] centred over the 64 channels (fp32)
@@ -137,8 +144,8 @@ typedef struct ecord_weights {
                             Passed to the Q kernels by value (constant bank), hence a host array. */
 #define ECORD_QFOLD_FLOATS 588
 #define ECORD_QTC_FLOATS 10160
-#define ECORD_GRU_PACK_ELEMS (3072 * 1024 + 4096 * 64)
-#define ECORD_P1_PACK_ELEMS (512 * 1024 + 32 * 512)
+#define ECORD_GRU_PACK_ELEMS (2 * (3072 * 1024 + 4096 * 64))
+#define ECORD_P1_PACK_ELEMS (2 * (512 * 1024 + 32 * 512))
 } ecord_weights;
 
 /* ---- per-rollout policy state and scratch (all caller-allocated) ---- */
@@ -147,9 +154,10 @@ typedef struct ecord_policy {
     int32_t  rows_pad;    /* M rounded up to a multiple of 128 (256 selects the CTA-pair tcgen05 GEMM kernels);
                              every [M][*] buffer below has rows_pad rows */
     float   *hidden;      /* [2][rows_pad][1024] double-buffered GRU state (fp32) */
-    void    *hidden_bf16; /* [2][rows_pad][1024] bf16 mirror (tcgen05 A operand) */
-    void    *th_bf16;     /* [rows_pad][1024] bf16 tanh(h) (projection A operand) */
-    void    *u_bf16;      /* [rows_pad][64] bf16 GRU input */
+    void    *hidden_bf16; /* [2][rows_pad][1024] bf16 mirror (tcgen05 A operand); split: [2][2][rows_pad][1024] = per state buffer
+                             a hi plane and a lo plane (bf16(h - hi)) */
+    void    *th_bf16;     /* [rows_pad][1024] bf16 tanh(h) (projection A operand); split: [2][rows_pad][1024] hi | lo */
+    void    *u_bf16;      /* [rows_pad][64] bf16 GRU input; split: [2][rows_pad][64] hi | lo */
     float   *u;           /* [rows_pad][64] GRU input  LReLU(msg_in([last_sel; glob])) */
     float   *gates;       /* [rows_pad][6144] fp32-mode scratch: gi | gh */
     float   *th;          /* [rows_pad][1024] fp32-mode tanh(h) */
@@ -175,6 +183,8 @@ typedef struct ecord_policy {
          node_qv[n] = [ |b'|^2 | Cc^T b' (3) | LB | 0 0 0 ],  b' = Wg node_emb[n]             written by ecord_gnn_embed */
     float   *qa;          /* [rows_pad][ECORD_QA_STRIDE] */
     float   *node_qv;     /* [N][8] */
+    int32_t  split;       /* 1: the bf16 buffers above carry hi and lo planes (ECORD_GEMM_BF16X3); 0 otherwise */
+    int32_t  _pad;
 } ecord_policy;
 
 /* Q-head evaluation */

@@ -15,6 +15,13 @@ Fixtures
                    Q-values / P / hidden slice / last_sel / actions / scores (ragged 6-graph batch)
   config1.npz      BASELINE config 1 (ER40 validation, 100 graphs, 80 steps, 50 tradj, batch 50):
                    scores_max / scores_mean / per-trajectory best / init scores
+  config2_er200.npz, config2_er500.npz, config3_ba500.npz
+                   BASELINE configs 2 and 3 at FULL length (num_steps = -4 -> 4*|V| steps, 50 tradj, greedy tau=0):
+                   the unmodified reference's test_solver on 10 graphs of testing/ER_200spin_p15_50graphs.pkl,
+                   5 synthesised ER500 graphs (SURVEY.md 8d recipe; the reference's file is not shipped) and 10 graphs
+                   of testing/BA_500spin_m4_50graphs.pkl: scores_max / scores_mean / per-trajectory best, best step and
+                   final score, and the chosen vertices of the first 8 trajectories at every step
+                   (python oracle/gen_golden.py full)
 """
 import os
 import pickle
@@ -271,11 +278,81 @@ def gen_config1():
     np.savez_compressed(os.path.join(GOLD, "config1.npz"), **out)
 
 
+# ------------------------------------------------------------------------------------------------
+def _to_nx(g):
+    """EdgeListGraph (ecord_b200.graphs.synthetic_set) -> networkx graph whose reference edge order
+    (GraphData.from_networkx: to_directed().edges) is the (src, dst)-sorted order of the edge list."""
+    import networkx as nx
+    G = nx.Graph()
+    G.add_nodes_from(range(g.n))
+    keep = g.src < g.dst
+    for i, j, w in zip(g.src[keep], g.dst[keep], g.w[keep]):
+        G.add_edge(int(i), int(j), weight=float(w))
+    return G
+
+
+def gen_fullsize(which=("er200", "er500", "ba500")):
+    """BASELINE configs 2-3 at the real rollout length, through the reference's own test_solver."""
+    from ecord_b200.graphs import synthetic_set
+    wseed, sseed, T, KEEP_T = 0, 4242, 50, 8
+    sd = random_state_dicts(wseed, perturb_norms=False)
+    for name in which:
+        if name == "er200":
+            graphs, _ = load("testing/ER_200spin_p15_50graphs"); graphs = graphs[:10]; out_name = "config2_er200.npz"
+        elif name == "ba500":
+            graphs, _ = load("testing/BA_500spin_m4_50graphs"); graphs = graphs[:10]; out_name = "config3_ba500.npz"
+        else:
+            graphs = [_to_nx(g) for g in synthetic_set("er", 500, 5, p=0.15, signed=True)]; out_name = "config2_er500.npz"
+        solver, gb = make_solver(sd)
+        acts = []
+        actor = solver.actor
+        orig = actor.action_select
+
+        def wrapped(obs, _orig=orig, _acts=acts, **kw):
+            ret = _orig(obs, **kw)
+            _acts.append(ret[0][:, :KEEP_T].clone())
+            return ret
+
+        actor.action_select = wrapped
+        cfg = TestGraphsConfig(graphs=graphs, opt_scores=None, num_steps=-4, tradj_per_graph=T, tau=0, max_time=None,
+                               graphs_bsz=len(graphs), tradj_bsz=T)
+        np.random.seed(sseed)
+        import time
+        t0 = time.time()
+        log = test_solver(solver, gb, cfg, verbose=False)
+        dt = time.time() - t0
+        scores = log['scores']                                   # [G,T,S]
+        by_tradj = scores.max(-1)
+        G, _, S = scores.shape
+        N = sum(g.number_of_nodes() for g in graphs)
+        init = np.random.RandomState(sseed).randint(0, 2, (N, T), dtype=np.int8)
+        # the init states the reference drew are reproduced by the line above: check through the initial score
+        ob = orc.build_batch(graphs)
+        env = orc.EnvOracle(ob, T, init)
+        assert np.array_equal(env.scores, log['init_score'].numpy()), "init states not reproduced"
+        actions = torch.stack(acts).numpy()                      # [S,G,KEEP_T] local ids
+        assert actions.shape == (S, G, KEEP_T)
+        out = pack_graphs(graphs)
+        out.update(dict(T=np.int32(T), S=np.int32(S), weight_seed=np.int32(wseed), state_seed=np.int32(sseed),
+                        scores_max=log['scores_max'].numpy(), scores_mean=log['scores_mean'].numpy(),
+                        scores_by_tradj=by_tradj.values.numpy().astype(np.int32),
+                        best_step_by_tradj=by_tradj.indices.numpy().astype(np.int32),
+                        init_score=log['init_score'].numpy().astype(np.int32),
+                        final_score=scores[..., -1].numpy().astype(np.int32),
+                        actions_first_tradj=actions.astype(np.int16)))
+        np.savez_compressed(os.path.join(GOLD, out_name), **out)
+        print(f"{out_name}: G={G} T={T} S={S}  reference run {dt:.0f}s ({G * T * S / dt:.0f} units/s)  "
+              f"scores_max={log['scores_max'].tolist()}", flush=True)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    gen_env_traces()
-    gen_model_trace()
-    gen_config1()
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        gen_fullsize(tuple(sys.argv[2:]) or ("er200", "er500", "ba500"))
+    else:
+        gen_env_traces()
+        gen_model_trace()
+        gen_config1()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")

@@ -31,7 +31,7 @@ def test_struct_mirrors_match(lib):
 
 
 def test_version_and_error_strings(lib):
-    assert lib.ecord_version() == 2
+    assert lib.ecord_version() == 3
     assert lib.ecord_error_string(0) == b"ok"
     for code in (-1, -2, -3, -4, -5, -6):
         assert lib.ecord_error_string(code).startswith(b"ECORD_E_")

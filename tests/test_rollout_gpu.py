@@ -88,7 +88,7 @@ def orc_single_vertex():
     return EdgeListGraph(1, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32))
 
 
-@pytest.mark.parametrize("gemm", ["fp32", "bf16"])
+@pytest.mark.parametrize("gemm", ["fp32", "bf16x3", "bf16"])
 def test_plan_equals_stepwise(gemm):
     from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
     graphs = synthetic_set("er", 60, 7, p=0.2)
@@ -129,22 +129,24 @@ def test_config1_best_cut_parity():
     assert np.allclose(log["apx_max"].numpy(), log["scores_max"].numpy() / z["opts"])
 
 
-def test_config1_best_cut_throughput_mode():
-    """The same config through the throughput path (tcgen05 bf16 GRU / projection / tail, fp16-split tensor-core Q):
-    bf16 rounding of the recurrent update can change a near-tie arg-max, so the bar here is agreement of the best cut
-    on >= 97% of the graphs (measured 99-100%) and of the per-graph mean-over-trajectories within 1%."""
+@pytest.mark.parametrize("gemm,bar", [("bf16x3", 0.99), ("bf16", 0.97)])
+def test_config1_best_cut_tensor_core_modes(gemm, bar):
+    """The same config through the tensor-core paths (tcgen05 GRU / projection / tail, fp16-split tensor-core Q).
+    "bf16x3" (the default and the benchmarked mode: bf16 hi / lo operand pairs, exact gate functions) is held to the
+    north_star bar of 99 %.  The opt-in fast mode "bf16" rounds the recurrent update to bf16, which can change a near-tie
+    arg-max: 97 % (measured 99-100 %).  Both: per-graph mean-over-trajectories within 1 %."""
     from ecord_b200.testing import TestGraphsConfig, test_solver
     z = load_gold("config1.npz")
     graphs = unpack_graphs(z)
     T, S, bsz = int(z["T"]), int(z["S"]), int(z["bsz"])
-    solver = _solver(random_state_dicts(int(z["weight_seed"])), gemm="bf16")
+    solver = _solver(random_state_dicts(int(z["weight_seed"])), gemm=gemm)
     cfg = TestGraphsConfig(graphs=graphs, opt_scores=torch.tensor(z["opts"]), num_steps=S, tradj_per_graph=T, tau=0,
                            graphs_bsz=bsz, tradj_bsz=T)
     np.random.seed(int(z["state_seed"]))
     log = test_solver(solver, GraphBatcher(), cfg)
     agree = float((log["scores_max"].numpy() == z["scores_max"]).mean())
-    print(f"throughput mode: best-cut agreement with the reference on {agree:.3f} of the graphs")
-    assert agree >= 0.97, f"best-cut agreement {agree:.3f}"
+    print(f"{gemm}: best-cut agreement with the reference on {agree:.3f} of the graphs")
+    assert agree >= bar, f"best-cut agreement {agree:.3f}"
     if "scores_mean" in z.files:
         rel = np.abs(log["scores_mean"].numpy() - z["scores_mean"]) / np.maximum(np.abs(z["scores_mean"]), 1.0)
         assert float(rel.mean()) < 0.01
@@ -179,7 +181,7 @@ def test_solver_log_contract_and_checkpoint_roundtrip(tmp_path):
     assert torch.equal(torch.stack(a["scores"]), torch.stack(b["scores"]))
 
 
-@pytest.mark.parametrize("gemm", ["fp32", "bf16"])
+@pytest.mark.parametrize("gemm", ["fp32", "bf16x3", "bf16"])
 def test_rollout_state_reuse_is_invisible(gemm):
     """The solver keeps the device state of a graph batch and re-initialises it for the next trajectory chunk
     (testing.py:174-189 calls rollout repeatedly on one batch): every call must equal a call on a fresh solver."""
@@ -323,7 +325,7 @@ def test_full_size_properties(kind, n, G, T, S, gen):
     from ecord_b200.engine import DeviceGraph, DeviceWeights, RolloutState
     graphs = synthetic_set(kind, n, G, **gen)
     dg = DeviceGraph(GraphBatcher()(graphs).tg)
-    st = RolloutState(dg, DeviceWeights(random_state_dicts(0)), T, gemm="bf16", max_steps=S)
+    st = RolloutState(dg, DeviceWeights(random_state_dicts(0)), T, gemm="bf16x3", max_steps=S)
     init = np.random.RandomState(1).randint(0, 2, (dg.N, T)).astype(np.int8)
     st.gnn_embed(); st.env_init(init); st.run(S)
     nf, gf, bs = st.export()
@@ -416,6 +418,30 @@ def test_greedy_tie_break_is_uniform_and_reaches_local_optima():
     fresh = orc.EnvOracle(orc.build_batch(graphs), T, nf[..., 0].cpu().numpy().astype(np.int8))
     assert np.array_equal(fresh.scores, st.scores().cpu().numpy())
     assert np.array_equal(fresh.node_features[..., 1], nf[..., 1].cpu().numpy())
+
+
+@pytest.mark.parametrize("pre,post", [(False, False), (True, False), (False, True), (True, True)])
+def test_true_best_state_snapshot_with_greedy_solves(pre, post):
+    """compat=False: log['best_state'] is the configuration whose cut IS the best score -- also when the rollout starts
+    from greedy-improved spins (pre-solve, rebased clock) and when the best is found by the post-solve's greedy flips,
+    neither of which is in the action log (the snapshot is kept on the device by the env step, ecord_env.true_snapshot)."""
+    graphs = synthetic_set("er", 50, 4, p=0.15) + synthetic_set("er", 23, 2, p=0.3, seed0=11)      # ragged
+    batch = GraphBatcher()(graphs)
+    T, S = 6, 30
+    init = np.random.RandomState(4).randint(0, 2, (batch.tg.num_nodes, T)).astype(np.int8)
+    solver = _solver(random_state_dicts(8), compat=False)
+    log = solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init,
+                         pre_solve_with_greedy=pre, post_solve_with_greedy_from_best=post)
+    st = solver._last_state
+    ob = orc.build_batch(graphs)
+    snap = log['best_state'].numpy()
+    assert (snap[4:, 23:] == -1).all()
+    flat = np.concatenate([snap[g, :ob.num_nodes_list[g]] for g in range(ob.G)]).astype(np.int8)
+    env = orc.EnvOracle(ob, T, flat)
+    best = st.best_score.view(ob.G, T).cpu().numpy()
+    assert np.array_equal(env.scores, best)
+    every = torch.stack(log['scores'] + [log['init_score']], -1).max(-1).values.numpy()
+    assert (best >= every).all()
 
 
 def test_rollout_with_greedy_pre_and_post_solve():
