@@ -39,7 +39,6 @@ template <> struct TcCfg<1> { static constexpr int N_FIRST = 0, N_MAIN = 176, B_
 // latency-bound pass over 16 k-chunks, so it runs seven stages deep and its epilogue staging tile reuses the stage memory
 // (all loads have landed and all MMAs have retired when the accumulator is complete).  Pair kernel only.
 template <> struct TcCfg<2> { static constexpr int N_FIRST = 0, N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
-template <int MODE> __host__ __device__ constexpr int stages2() { return MODE == 2 ? 7 : 4; }
 
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -290,11 +289,23 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 }
 
 // NS = 1: bf16 operands (ECORD_GEMM_BF16).  NS = 3: every operand is a bf16 hi part plus a bf16 lo remainder
-// (x ~ hi + lo to 2^-17) and the three products hi.hi + lo.hi + hi.lo are accumulated (ECORD_GEMM_BF16X3): each k-chunk
-// is walked three times with the (A part, B part) pairs (hi, hi), (lo, hi), (hi, lo).  The lo parts live NS-1 "planes"
-// behind the hi parts in the same tensor maps (A: rows_pad rows further, B: the weight matrix's row count further).
+// (x ~ hi + lo to 2^-17) and the three products hi.hi + lo.hi + hi.lo are accumulated (ECORD_GEMM_BF16X3).  A stage of
+// the NS = 3 pipeline holds all four operand tiles of a 32-element k-chunk -- A hi, A lo, B hi, B lo (64-byte rows,
+// SWIZZLE_64B) -- so each byte is fetched once from L2 for its two (hi parts) or one (lo parts) products: the kernel is
+// bound by the L2 -> SM path (three separate (A, B) fetches per k-chunk moved 914 MB per GRU launch at 9.2 TB/s, 75 % of
+// what the L2 slices deliver; this layout moves two thirds of that).  The lo parts live one "plane" behind the hi parts
+// in the same tensor maps (A: rows_pad rows further, B: the weight matrix's row count further).
 // The epilogue of NS = 3 uses the accurate sigmoid / tanh and writes h' and tanh(h') as hi / lo pairs: with it the
 // recurrent state tracks the reference's fp32 arithmetic to ~1e-6 instead of ~1e-3 (oracle/ablate_precision.py).
+template <int NS> __host__ __device__ constexpr int tc2_bk() { return NS == 3 ? 32 : 64; }      // bf16 elements per k-chunk
+template <int MODE, int NS> __host__ __device__ constexpr int tc2_stage_bytes() {
+    return (NS == 3 ? 2 : 1) * (BM + TcCfg<MODE>::B_ROWS / 2) * tc2_bk<NS>() * 2;              // per CTA: own A rows, half of B
+}
+template <int MODE, int NS> __host__ __device__ constexpr int stages2() { return MODE == 2 ? 7 : 4; }
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {      // K-major SWIZZLE_64B: 8-row groups 512 B apart
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
 template <int MODE, int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
@@ -302,11 +313,14 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
            const __grid_constant__ CUtensorMap mapB, TcParams prm, int num_tiles, int nblk) {
     // num_tiles = number of 256-row x TILE_N pair tiles; cluster c works on tiles c, c + #clusters, ...
     using C = TcCfg<MODE>;
-    constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS / 2 * BK * 2;      // per CTA: own A rows, half of B
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int NCHUNK = NS * ((MODE == 0 ? 1 : 0) + H / BK);                 // (k-chunk, product) items per tile
+    constexpr int BKK = tc2_bk<NS>(), ROWB = BKK * 2;                           // k-chunk width: elements, bytes per tile row
+    constexpr int PARTS = NS == 3 ? 2 : 1;                                      // operand tiles per side: hi [, lo]
+    constexpr int A_BYTES = BM * ROWB, B_BYTES = C::B_ROWS / 2 * ROWB;          // per CTA: own A rows, half of B
+    constexpr int STAGE_BYTES = tc2_stage_bytes<MODE, NS>();                    // [A hi][A lo][B hi][B lo]
+    constexpr int KCH_U = MODE == 0 ? ECORD_DIM_MSG / BKK : 0;                  // k-chunks of the GRU's input part (u, Wu)
+    constexpr int NCHUNK = KCH_U + H / BKK;
     constexpr int B_PLANE = MODE == 0 ? 3 * H : ECORD_DIM_P1;                   // rows between the hi and lo parts of B
-    constexpr int NST = stages2<MODE>();
+    constexpr int NST = stages2<MODE, NS>();
     constexpr int TMEM_COLS = 2 * C::ACC_COLS;          // 512 for both modes
 
     extern __shared__ uint8_t smem_raw[];
@@ -359,25 +373,25 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
                     const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);            // local: released by the leader's multicast commit
-                    const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                    const int cl = c / NS, prod = c - cl * NS;     // k-chunk, product: (hi,hi) (lo,hi) (hi,lo)
-                    const bool first = MODE == 0 && cl == 0;
+                    const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + PARTS * A_BYTES;
+                    const bool first = MODE == 0 && c < KCH_U;
                     const int n_rows = first ? C::N_FIRST : C::N_MAIN;
-                    const int a_row = m0 + (prod == 1 ? prm.rows_pad : 0);
+                    const int kc = (first ? c : c - KCH_U) * BKK;
+                    const int b_row = nb * n_rows + (int)rank * (n_rows / 2);
                     if (elect_one()) {
                         if (prm.debug & 4) {            // no TMA traffic: the leader completes the phase by itself
                             if (rank == 0) mbar_arrive_cta(full0 + 8 * s);
                         } else {
-                            if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * (A_BYTES + n_rows / 2 * BK * 2));
-                            if (first) {
-                                tma_load_2d_pair(a_dst, &mapU, lfull0 + 8 * s, 0, a_row);
-                                tma_load_2d_pair(b_dst, &mapWu, lfull0 + 8 * s, 0,
-                                                 nb * n_rows + (int)rank * (n_rows / 2) + (prod == 2 ? 4 * H : 0));
-                            } else {
-                                const int kc = (MODE == 0 ? cl - 1 : cl) * BK;
-                                tma_load_2d_pair(a_dst, mapA, lfull0 + 8 * s, kc, a_row);
-                                tma_load_2d_pair(b_dst, &mapB, lfull0 + 8 * s, kc,
-                                                 nb * n_rows + (int)rank * (n_rows / 2) + (prod == 2 ? B_PLANE : 0));
+                            if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * PARTS * (A_BYTES + n_rows / 2 * ROWB));
+#pragma unroll
+                            for (int part = 0; part < PARTS; ++part) {
+                                if (first) {
+                                    tma_load_2d_pair(a_dst + part * A_BYTES, &mapU, lfull0 + 8 * s, kc, m0 + part * prm.rows_pad);
+                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapWu, lfull0 + 8 * s, kc, b_row + part * 4 * H);
+                                } else {
+                                    tma_load_2d_pair(a_dst + part * A_BYTES, mapA, lfull0 + 8 * s, kc, m0 + part * prm.rows_pad);
+                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapB, lfull0 + 8 * s, kc, b_row + part * B_PLANE);
+                                }
                             }
                         }
                     }
@@ -398,13 +412,22 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                     const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
-                    const uint32_t idesc = (MODE == 0 && c < NS) ? umma_idesc(2 * BM, 256) : umma_idesc(2 * BM, C::N_MAIN);
+                    const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + PARTS * A_BYTES;
+                    const uint32_t idesc = (MODE == 0 && c < KCH_U) ? umma_idesc(2 * BM, 256) : umma_idesc(2 * BM, C::N_MAIN);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
-                            if (!(prm.debug & 1)) umma_bf16_pair(acc, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BKK / UMMA_K; ++k) {
+                            const uint32_t ko = k * UMMA_K * 2;
+                            if (prm.debug & 1) continue;
+                            if (NS == 1) {
+                                umma_bf16_pair(acc, umma_desc(a_src + ko), umma_desc(b_src + ko), idesc, (c > 0 || k > 0) ? 1u : 0u);
+                            } else {       // hi.hi + lo.hi + hi.lo
+                                const uint64_t ah = umma_desc_sw64(a_src + ko), al = umma_desc_sw64(a_src + A_BYTES + ko);
+                                const uint64_t bh = umma_desc_sw64(b_src + ko), bl = umma_desc_sw64(b_src + B_BYTES + ko);
+                                umma_bf16_pair(acc, ah, bh, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                                umma_bf16_pair(acc, al, bh, idesc, 1u);
+                                umma_bf16_pair(acc, ah, bl, idesc, 1u);
+                            }
                         }
                         umma_commit_pair(empty0 + 8 * s);         // frees the stage in both CTAs
                         if (c == NCHUNK - 1) umma_commit_pair(tfull0 + 8 * ab);            // accumulator complete, both CTAs
@@ -604,11 +627,13 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_ROWS * BK * 2) + 1024; }
-template <int MODE>
+template <int MODE, int NS>
 constexpr int tc2_smem_bytes() {
-    return stages2<MODE>() * (BM * BK * 2 + TcCfg<MODE>::B_ROWS / 2 * BK * 2) + 1024 +
+    return stages2<MODE, NS>() * tc2_stage_bytes<MODE, NS>() + 1024 +
            (MODE == 0 ? kStageTileBytes : MODE == 1 ? BM * (TcCfg<MODE>::TILE_N + 4) * 4 : 0);
 }
+static_assert(tc2_smem_bytes<0, 3>() <= 227 * 1024 && tc2_smem_bytes<1, 3>() <= 227 * 1024 && tc2_smem_bytes<2, 3>() <= 227 * 1024 &&
+              tc2_smem_bytes<2, 3>() - 1024 >= BM * (TcCfg<2>::TILE_N + 4) * 4, "shared-memory budget of the pair kernels");
 // ECORD_GEMM_PAIR=0 selects the single-CTA kernels (A/B comparisons); rows_pad must be a multiple of 256 for the pair kernels
 static bool use_pair(int rows_pad) {
     static const int env = [] { const char *e = getenv("ECORD_GEMM_PAIR"); return e ? atoi(e) : 1; }();
@@ -802,12 +827,12 @@ extern "C" int ecord_fold_q_host(const float *q1_w, const float *enc_w, const fl
 int tc_init_attrs() {
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<0>()));
     ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
-    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0>()));
-    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1>()));
-    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2>()));
-    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<0, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0>()));
-    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1>()));
-    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<2, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0, 1>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1, 1>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2, 1>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<0, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0, 3>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1, 3>()));
+    ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<2, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2, 3>()));
     return 0;
 }
 
@@ -824,11 +849,12 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     CUtensorMap mU, mWu, mA0, mA1, mB;
     const bool pair = use_pair(Mp);
     ECORD_RET_IF(split && !pair, ECORD_E_UNSUPPORTED);
-    if ((rc = make_map(enc, &mU, p->u_bf16, (uint64_t)np * Mp, 64, BM))) return rc;
-    if ((rc = make_map(enc, &mWu, wu, 2 * 4096, 64, pair ? 128 : 256))) return rc;
-    if ((rc = make_map(enc, &mA0, hb, (uint64_t)np * Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mA1, hb + (size_t)np * Mp * H, (uint64_t)np * Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mB, wh, 2 * 3072, H, pair ? 96 : 192))) return rc;
+    const uint32_t bc = split ? 32 : 64;                               // k-chunk width (tc2_bk)
+    if ((rc = make_map(enc, &mU, p->u_bf16, (uint64_t)np * Mp, 64, BM, bc))) return rc;
+    if ((rc = make_map(enc, &mWu, wu, 2 * 4096, 64, pair ? 128 : 256, bc))) return rc;
+    if ((rc = make_map(enc, &mA0, hb, (uint64_t)np * Mp, H, BM, bc))) return rc;
+    if ((rc = make_map(enc, &mA1, hb + (size_t)np * Mp * H, (uint64_t)np * Mp, H, BM, bc))) return rc;
+    if ((rc = make_map(enc, &mB, wh, 2 * 3072, H, pair ? 96 : 192, bc))) return rc;
     TcParams prm{};
     prm.hidden = p->hidden; prm.hidden_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->hidden_bf16);
     prm.th_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->th_bf16);
@@ -838,12 +864,13 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
     ECORD_RET_IF(prm.debug & 4, ECORD_E_UNSUPPORTED);      // the no-TMA diagnostic no longer terminates (it hung the GPU when tried)
     if (pair) {
         const int nblk2 = H / 64, tiles2 = nblk2 * (Mp / (2 * BM));
-        const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
+        int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
+        { const char *e = getenv("ECORD_TC_CLUSTERS"); if (e && atoi(e) > 0 && atoi(e) < clusters) clusters = atoi(e); }   // diagnostics
         if (split)
-            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 3>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0>(), st, mU, mWu, mA0, mA1, mB,
+            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 3>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0, 3>(), st, mU, mWu, mA0, mA1, mB,
                              prm, tiles2, nblk2);
         else
-            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 1>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0>(), st, mU, mWu, mA0, mA1, mB,
+            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 1>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0, 1>(), st, mU, mWu, mA0, mA1, mB,
                              prm, tiles2, nblk2);
         return 0;
     }
@@ -861,8 +888,8 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, int split, cu
     CUtensorMap mA, mB;
     const bool pair = use_pair(Mp);
     ECORD_RET_IF(split && !pair, ECORD_E_UNSUPPORTED);
-    if ((rc = make_map(enc, &mA, p->th_bf16, (uint64_t)(split ? 2 : 1) * Mp, H, BM))) return rc;
-    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 2 * 512, H, pair ? 88 : 176))) return rc;
+    if ((rc = make_map(enc, &mA, p->th_bf16, (uint64_t)(split ? 2 : 1) * Mp, H, BM, split ? 32 : 64))) return rc;
+    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 2 * 512, H, pair ? 88 : 176, split ? 32 : 64))) return rc;
     TcParams prm{};
     prm.p1_b = w->p1_b; prm.y1 = p->y1; prm.rows = p->rows; prm.rows_pad = Mp;
     if (pair) {
@@ -870,7 +897,7 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, int split, cu
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
         const dim3 grid(2 * clusters), block(kThreads);
 #define ECORD_PROJ_LAUNCH(MODE, NS) \
-        ECORD_PDL_LAUNCH((k_gemm_tc2<MODE, NS>), grid, block, (size_t)tc2_smem_bytes<MODE>(), st, mA, mB, mA, mA, mB, prm, tiles2, nblk2)
+        ECORD_PDL_LAUNCH((k_gemm_tc2<MODE, NS>), grid, block, (size_t)tc2_smem_bytes<MODE, NS>(), st, mA, mB, mA, mA, mB, prm, tiles2, nblk2)
         if (tiles2 <= clusters) {        // one tile per CTA pair: deep pipeline, staging on top of the stages
             if (split) ECORD_PROJ_LAUNCH(2, 3); else ECORD_PROJ_LAUNCH(2, 1);
         } else {

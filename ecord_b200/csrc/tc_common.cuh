@@ -117,15 +117,16 @@ int get_encoder(PFN_encodeTiled *out) {
     return 0;
 }
 
-// 2-D bf16 row-major [rows][cols], box = [box_rows][64 cols], 128-byte swizzle
-int make_map(PFN_encodeTiled enc, CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D bf16 row-major [rows][cols], box = [box_rows][box_cols]: 64 columns with the 128-byte swizzle, 32 with the 64-byte one
+int make_map(PFN_encodeTiled enc, CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+             uint32_t box_cols = BK) {
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : ECORD_E_DEVICE;
 }
 
