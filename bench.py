@@ -235,8 +235,14 @@ def run_b200(args):
 
     graphs, n, G, T, desc = make_graphs(args.workload)
     K, W = args.steps, max(args.warmup, 3)
-    T_total = T * world
+    if args.tradj:
+        T = args.tradj
+    strong = args.scaling == "strong"
+    # weak: every rank runs T more trajectories of the same graphs; strong: the config's T trajectories are split over the
+    # ranks (BASELINE config 4: "128 trajectories, sharded across 8xB200" -> 16 per GPU)
+    T_total = T if strong else T * world
     lo, hi = shard_bounds(T_total, world, rank)
+    T = hi - lo
     sd = random_state_dicts(0)
     batch = GraphBatcher()(graphs)
     avg_deg = batch.tg.num_edges / batch.tg.num_nodes
@@ -413,7 +419,7 @@ def run_b200(args):
                             f"({'compiled reference Cython step (oracle/_ref)' if have_ref else 'C restatement of the env step'}"
                             f" + torch CPU model, {torch.get_num_threads()} threads)"}
         out = {"metric": "rollout steps/sec (graphs x tradj x steps)", "value": value, "unit": "steps/s", "n_gpus": world,
-               "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+               "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling,
                "vs_baseline": None,
                "dtype": {"bf16x3": "bf16x3 (tcgen05 on bf16 hi/lo operand pairs, fp32 accumulate: fp32-grade)", "bf16": "bf16",
                          "fp32": "f32"}[args.gemm], "data": "synthetic",
@@ -442,6 +448,9 @@ if __name__ == "__main__":
                     help="bf16x3 (default): tcgen05 GEMMs on bf16 hi/lo operand pairs, fp32-grade, passes the 99 %% best-cut "
                          "tests; bf16: single bf16 products (fast mode, 2e-2 tolerance); fp32: CUDA-core SGEMM")
     ap.add_argument("--steps-per-graph", type=int, default=16)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = T more trajectories per rank (default); strong = the workload's T trajectories split over the ranks")
+    ap.add_argument("--tradj", type=int, default=0, help="override the workload's trajectories per graph (per GPU in weak scaling)")
     ap.add_argument("--cpu-graphs", type=int, default=10, help="graphs in the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=24, help="steps of the CPU baseline sample (b200 arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

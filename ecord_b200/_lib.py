@@ -82,7 +82,7 @@ class RolloutDesc(C.Structure):
                 ("policy", C.POINTER(Policy)), ("gemm_mode", _i32), ("q_mode", _i32), ("compat", _i32), ("epsilon", _f32),
                 ("tau", _f32),
                 ("steps_per_graph", _i32), ("seed", _u64), ("step_counter", _vp), ("score_log", _vp),
-                ("action_log", _vp), ("max_steps", _i32), ("_pad", _i32)]
+                ("action_log", _vp), ("max_steps", _i32), ("_pad", _i32), ("step_time_ns", _vp)]
 
 
 # every symbol include/ecord_b200.h declares: name -> (restype, argtypes)
@@ -114,6 +114,9 @@ SYMBOLS = {
     "ecord_rollout_plan_destroy": (_i32, [_vp]),
     "ecord_score_log_max": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "ecord_plane_to_nt": (_i32, [_P(Graph), _i32, _vp, _vp, _vp]),
+    "ecord_t_opt_steps": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "ecord_env_snapshot_padded": (_i32, [_P(Graph), _P(Env), _vp, _vp, _vp]),
+    "ecord_stamp_time": (_i32, [_vp, _vp]),
     "ecord_best_state_snapshot": (_i32, [_P(Graph), _P(Env), _vp, _vp, _i32, _vp, _vp]),
 }
 

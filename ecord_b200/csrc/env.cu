@@ -145,6 +145,11 @@ __global__ void k_env_rebase(ecord_graph g, ecord_env e, int by) {
 // plane is the configuration whose cut IS best_score.  (The reference records only the flipped vertex, quirk D --
 // _tradjectory_step_cy.pyx:142-146 -- which is what the flag's default, 0, reproduces bit for bit.)  Improvements become
 // rare after the first few hundred steps of a rollout, so the n_g-byte copy is paid seldom.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void snapshot_on_new_best(const ecord_env &e, long long base, int n, int new_best, int lane) {
     new_best = __shfl_sync(0xffffffffu, new_best, 0);          // (also orders lane 0's flip before the row copy)
     if (!new_best) return;
@@ -152,7 +157,7 @@ __device__ __forceinline__ void snapshot_on_new_best(const ecord_env &e, long lo
 }
 __global__ void __launch_bounds__(256)
 k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, const int32_t *step_base, int step_off,
-           float *score_log, int32_t *action_log, int log_stride) {
+           float *score_log, int32_t *action_log, int log_stride, unsigned long long *time_log) {
     const int T = e.num_tradj;
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -187,6 +192,7 @@ k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, cons
         if (new_best) e.best_state[base + a] = (uint8_t)(sa ^ 1);   // 8. pyx:142-146 (quirk D)
         if (score_log) score_log[(long long)step_no * log_stride + m] = sc;
         if (action_log) action_log[(long long)step_no * log_stride + m] = a;
+        if (time_log && m == 0) time_log[step_no] = globaltimer_ns();
     }
     if (e.true_snapshot) snapshot_on_new_best(e, base, n, new_best, lane);
 }
@@ -195,7 +201,7 @@ k_env_step(ecord_graph g, ecord_env e, const int32_t *__restrict__ actions, cons
 // flip holds everything that stage reads -- the new (best - score) and the cached embedding of the chosen vertex.
 __global__ void __launch_bounds__(256)
 k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, const int32_t *step_base, int step_off,
-                 float *score_log, int32_t *action_log, int log_stride) {
+                 float *score_log, int32_t *action_log, int log_stride, unsigned long long *time_log) {
     __shared__ float wt[kMsgWtFloats];
     __shared__ float wb[64];
     msg_in_load(w.msg_w, w.msg_b, wt, wb);
@@ -238,6 +244,7 @@ k_env_step_fused(ecord_graph g, ecord_env e, ecord_weights w, ecord_policy p, co
         if (new_best) e.best_state[base + a] = (uint8_t)(sa ^ 1);
         if (score_log) score_log[(long long)step_no * log_stride + m] = sc;
         if (action_log) action_log[(long long)step_no * log_stride + m] = a;
+        if (time_log && m == 0) time_log[step_no] = globaltimer_ns();     // device clock at the end of step `step_no` (t_step, t_opt)
         glob0 = (best - sc) / (float)n;                      // SCORE_FROM_BEST_NORM of the new observation
     }
     if (e.true_snapshot) snapshot_on_new_best(e, base, n, new_best, lane);
@@ -280,6 +287,26 @@ __global__ void k_env_export_glob(ecord_graph g, ecord_env e, int normalise, flo
     gf[m * 2 + 0] = d;
     gf[m * 2 + 1] = 0.0f;   // quirk C: PEEK_MAX* is never configured (tradjectories.py:294)
 }
+
+// log_stats view (solvers/solver.py:322-327): spins and peeks of every unit in the reference's padded layout
+// [G][n_max][T] (tradjectories.py:378-385 _flat2batch; padding -1 for the spins, -1e10 for the peeks).  One thread per
+// output element, T innermost: stores are coalesced, the plane reads (stride n_g) come out of L2.
+__global__ void k_env_snapshot_padded(ecord_graph g, ecord_env e, float *__restrict__ state_out, float *__restrict__ peek_out) {
+    const int T = e.num_tradj;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)g.num_graphs * g.n_max * T;
+    if (idx >= total) return;
+    const int t = (int)(idx % T);
+    const long long r = idx / T;
+    const int v = (int)(r % g.n_max), gi = (int)(r / g.n_max);
+    int n;
+    const long long base = unit_base(g.graph_ptr, gi, t, T, n);
+    float s = -1.0f, pk = -1e10f;
+    if (v < n) { s = (float)(e.sp[base + v] & 1); pk = e.peek[base + v]; }
+    if (state_out) state_out[idx] = s;
+    if (peek_out) peek_out[idx] = pk;
+}
+__global__ void k_stamp_time(unsigned long long *out) { *out = globaltimer_ns(); }
 
 // ------------------------------------------------------------------------------------------------
 // B3: step_cy() on the reference's own AoS layout with its full feature-index tables.
@@ -378,16 +405,17 @@ extern "C" int ecord_env_init(const ecord_graph *g, const ecord_env *env, const 
 }
 
 int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, const int32_t *step_base,
-                    int step_off, float *score_log, int32_t *action_log, cudaStream_t st) {
+                    int step_off, float *score_log, int32_t *action_log, unsigned long long *time_log, cudaStream_t st) {
     const int GT = g->num_graphs * env->num_tradj;
     k_env_step<<<ceil_div((long long)GT * 32, 256), 256, 0, st>>>(*g, *env, actions, step_base, step_off, score_log,
-                                                                  action_log, GT);
+                                                                  action_log, GT, time_log);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                          const int32_t *step_base, int step_off, float *score_log, int32_t *action_log, cudaStream_t st) {
+                          const int32_t *step_base, int step_off, float *score_log, int32_t *action_log,
+                          unsigned long long *time_log, cudaStream_t st) {
     const int GT = g->num_graphs * env->num_tradj;
     // Large grids are launched plainly, small ones as programmatic dependents: letting 600+ small CTAs become resident
     // while the Q kernel still runs costs more than their msg_in weight staging saves (ER500, 625 CTAs: 133.3 -> 131.7 us
@@ -396,10 +424,10 @@ int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecor
     const int ctas = ceil_div((long long)GT * 32, 256);
     static const int force = [] { const char *e = getenv("ECORD_ENV_PDL"); return e ? atoi(e) : -1; }();   // A/B: 0 plain, 1 PDL
     if (force == 0 || (force < 0 && ctas > 2 * kNumSMs))
-        k_env_step_fused<<<dim3(ctas), dim3(256), 0, st>>>(*g, *env, *w, *p, step_base, step_off, score_log, action_log, GT);
+        k_env_step_fused<<<dim3(ctas), dim3(256), 0, st>>>(*g, *env, *w, *p, step_base, step_off, score_log, action_log, GT, time_log);
     else
         ECORD_PDL_LAUNCH(k_env_step_fused, dim3(ctas), dim3(256), (size_t)0, st, *g, *env, *w, *p, step_base, step_off, score_log,
-                         action_log, GT);
+                         action_log, GT, time_log);
     ECORD_LAUNCH_CHECK();
     return 0;
 }
@@ -412,7 +440,7 @@ extern "C" int ecord_env_step_fused(const ecord_graph *g, const ecord_env *env, 
     ECORD_RET_IF(step_no < 0 || p->rows != g->num_graphs * env->num_tradj, ECORD_E_SIZE);
     const int GT = g->num_graphs * env->num_tradj;
     float *log0 = score_log ? score_log - (long long)step_no * GT : nullptr;
-    return launch_env_step_fused(g, env, w, p, nullptr, step_no, log0, nullptr, as_stream(stream));
+    return launch_env_step_fused(g, env, w, p, nullptr, step_no, log0, nullptr, nullptr, as_stream(stream));
 }
 
 extern "C" int ecord_env_reset_state(const ecord_graph *g, const ecord_env *env, const int8_t *init_state, int32_t steps_done,
@@ -447,7 +475,24 @@ extern "C" int ecord_env_step(const ecord_graph *g, const ecord_env *env, const 
     // score_log here is a single [G*T] row: bias the pointer so row `step_no` lands on it
     const int GT = g->num_graphs * env->num_tradj;
     float *log0 = score_log ? score_log - (long long)step_no * GT : nullptr;
-    return launch_env_step(g, env, actions, nullptr, step_no, log0, nullptr, as_stream(stream));
+    return launch_env_step(g, env, actions, nullptr, step_no, log0, nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int ecord_env_snapshot_padded(const ecord_graph *g, const ecord_env *env, float *state_out, float *peek_out, void *stream) {
+    int rc;
+    if ((rc = check_graph(g)) || (rc = check_env(env))) return rc;
+    ECORD_RET_IF(!state_out && !peek_out, ECORD_E_NULL);
+    const long long total = (long long)g->num_graphs * g->n_max * env->num_tradj;
+    k_env_snapshot_padded<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(*g, *env, state_out, peek_out);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ecord_stamp_time(uint64_t *out_ns, void *stream) {
+    ECORD_RET_IF(!out_ns, ECORD_E_NULL);
+    k_stamp_time<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long *>(out_ns));
+    ECORD_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int ecord_env_export(const ecord_graph *g, const ecord_env *env, int32_t steps_done, int32_t normalise,

@@ -15,7 +15,8 @@ int launch_policy_step(const ecord_graph *g, const ecord_env *env, const ecord_w
 int policy_kernels_per_step(int gemm_mode, int skip_pre);
 int q_kernels_per_step(int q_mode);
 int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecord_weights *w, const ecord_policy *p,
-                          const int32_t *step_base, int step_off, float *score_log, int32_t *action_log, cudaStream_t st);
+                          const int32_t *step_base, int step_off, float *score_log, int32_t *action_log,
+                          unsigned long long *time_log, cudaStream_t st);
 int policy_init_attrs();
 int check_policy(const ecord_policy *p, int gemm_mode);
 int check_q_mode(const ecord_graph *g, const ecord_weights *w, const ecord_policy *p, int q_mode, float tau);
@@ -23,7 +24,7 @@ int launch_q_select(const ecord_graph *g, const ecord_env *env, const ecord_weig
                     const int32_t *step_base, int step_off, float tau, uint64_t seed, int compat, const int32_t *forced,
                     int q_mode, float epsilon, cudaStream_t st);
 int launch_env_step(const ecord_graph *g, const ecord_env *env, const int32_t *actions, const int32_t *step_base,
-                    int step_off, float *score_log, int32_t *action_log, cudaStream_t st);
+                    int step_off, float *score_log, int32_t *action_log, unsigned long long *time_log, cudaStream_t st);
 
 struct ecord_rollout_plan {
     ecord_graph graph;
@@ -47,6 +48,24 @@ __global__ void k_score_log_max(const float *__restrict__ log, int S, int rows, 
     float best = -INFINITY;
     for (int s = 0; s < S; ++s) best = fmaxf(best, log[(long long)s * rows + m]);
     out[m] = best;
+}
+
+// log['t_opt'] of the reference (solvers/solver.py:241-242): the time of the LAST step at which a unit's score rose AND equals
+// its running best (initial score included) -- a best value that is lost and reached again counts again.  out[m] = that
+// step (1-based), 0 if the initial score was never improved on.
+__global__ void k_t_opt_steps(const float *__restrict__ log, const float *__restrict__ init_score, int S, int rows,
+                              int32_t *__restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= rows) return;
+    float prev = init_score[m], best = prev;
+    int last = 0;
+    for (int s = 0; s < S; ++s) {
+        const float sc = log[(long long)s * rows + m];
+        best = fmaxf(best, sc);
+        if (sc > prev && sc == best) last = s + 1;
+        prev = sc;
+    }
+    out[m] = last;
 }
 
 __global__ void k_snapshot_init(ecord_graph g, int T, const int8_t *__restrict__ s0, uint8_t *__restrict__ out) {
@@ -83,9 +102,9 @@ int capture(ecord_rollout_plan *pl, int nsteps, cudaGraphExec_t *out) {
         if (!rc) rc = launch_q_select(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i, d.tau, d.seed,
                                       d.compat, nullptr, d.q_mode, d.epsilon, pl->stream);
         if (!rc && fused) rc = launch_env_step_fused(&pl->graph, &pl->env, &pl->weights, &pl->policy, d.step_counter, i,
-                                                     d.score_log, d.action_log, pl->stream);
+                                                     d.score_log, d.action_log, (unsigned long long *)d.step_time_ns, pl->stream);
         if (!rc && !fused) rc = launch_env_step(&pl->graph, &pl->env, pl->policy.actions, d.step_counter, i, d.score_log,
-                                                d.action_log, pl->stream);
+                                                d.action_log, (unsigned long long *)d.step_time_ns, pl->stream);
     }
     if (!rc) {
         k_advance<<<1, 1, 0, pl->stream>>>(d.step_counter, nsteps);
@@ -175,6 +194,15 @@ extern "C" int ecord_score_log_max(const float *score_log, int32_t num_steps, in
     ECORD_RET_IF(!score_log || !out_best, ECORD_E_NULL);
     ECORD_RET_IF(num_steps <= 0 || rows <= 0, ECORD_E_SIZE);
     k_score_log_max<<<ceil_div(rows, 128), 128, 0, as_stream(stream)>>>(score_log, num_steps, rows, out_best);
+    ECORD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int ecord_t_opt_steps(const float *score_log, const float *init_score, int32_t num_steps, int32_t rows,
+                                 int32_t *out_steps, void *stream) {
+    ECORD_RET_IF(!score_log || !init_score || !out_steps, ECORD_E_NULL);
+    ECORD_RET_IF(num_steps < 0 || rows <= 0, ECORD_E_SIZE);
+    k_t_opt_steps<<<ceil_div(rows, 128), 128, 0, as_stream(stream)>>>(score_log, init_score, num_steps, rows, out_steps);
     ECORD_LAUNCH_CHECK();
     return 0;
 }

@@ -104,6 +104,35 @@ class TgBatch:
     def num_edges(self):
         return self.np_src.shape[0]
 
+    @classmethod
+    def from_reference_batch(cls, tg):
+        """A batch collated by the REFERENCE's own GraphBatcher (a torch_geometric `Batch`: edge_index i64[2,E] with
+        cumulative vertex offsets, edge_attr [E,1], ptr i64[G+1]; environment/data.py:53-69) -> TgBatch.  This is what lets
+        `ecord.validate.testing.test_solver` drive the engine with the reference's own batcher."""
+        ptr = np.asarray(tg.ptr.cpu().numpy(), np.int64)
+        ei = np.asarray(tg.edge_index.cpu().numpy(), np.int64)
+        w = np.asarray(tg.edge_attr.detach().cpu().numpy(), np.float32).reshape(-1)
+        gid = np.searchsorted(ptr, ei[0], side="right") - 1          # graph of every edge (by its source vertex)
+        els = []
+        for g in range(len(ptr) - 1):
+            m = gid == g
+            els.append(EdgeListGraph(int(ptr[g + 1] - ptr[g]), ei[0][m] - ptr[g], ei[1][m] - ptr[g], w[m]))
+        return cls(els)
+
+
+def as_tg_batch(tg):
+    """TgBatch as is; a torch_geometric-style batch (the reference's) converted once and cached on the object."""
+    if isinstance(tg, TgBatch):
+        return tg
+    cached = getattr(tg, "_ecord_b200_tg", None)
+    if cached is None:
+        cached = TgBatch.from_reference_batch(tg)
+        try:
+            tg._ecord_b200_tg = cached
+        except Exception:
+            pass
+    return cached
+
 
 def get_batch_info(batch, num_nodes_list):
     """`get_batch_info` of the reference (data.py:85-94)."""

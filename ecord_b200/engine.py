@@ -257,6 +257,9 @@ class RolloutState:
         self.score_log = torch.empty(max(self.max_steps, 1), M, **f32) if log_scores and max_steps > 0 else None
         self.action_log = (torch.empty(max(self.max_steps, 1), M, dtype=torch.int32, device=dev)
                            if log_actions and max_steps > 0 else None)
+        # device clock (%globaltimer, ns) at the end of every step: per-step t_step / t_opt / max_time without host syncs
+        self.step_time = torch.zeros(max(self.max_steps, 1), dtype=torch.int64, device=dev) if max_steps > 0 else None
+        self.time_base = torch.zeros(1, dtype=torch.int64, device=dev)
         self.steps_per_graph = int(steps_per_graph)
         self.steps_done = 0
         self.plan = None
@@ -422,7 +425,8 @@ class RolloutState:
     def _make_plan(self):
         desc = _lib.RolloutDesc(C.pointer(self.g.c), C.pointer(self.env_c), C.pointer(self.w.c), C.pointer(self.policy_c),
                                 self.gemm, self.q_mode, int(self.compat), self.epsilon, self.tau, self.steps_per_graph, self.seed,
-                                ptr(self.step_counter), ptr(self.score_log), ptr(self.action_log), self.max_steps, 0)
+                                ptr(self.step_counter), ptr(self.score_log), ptr(self.action_log), self.max_steps, 0,
+                                ptr(self.step_time))
         out = C.c_void_p()
         check(self.lib.ecord_rollout_plan_create(C.byref(desc), _stream(), C.byref(out)), "ecord_rollout_plan_create")
         self.plan = out
@@ -436,6 +440,92 @@ class RolloutState:
         check(self.lib.ecord_rollout_plan_run(self.plan, int(num_steps), C.byref(n)), "ecord_rollout_plan_run")
         self.kernel_launches += n.value
         self.steps_done += int(num_steps)
+
+    @_on_stream
+    def stamp_time_base(self):
+        """Sample the device clock on the rollout stream: the origin of `step_time` (call right before the first run())."""
+        check(self.lib.ecord_stamp_time(ptr(self.time_base), _stream()), "ecord_stamp_time")
+
+    def step_times_host(self, num_steps):
+        """Seconds each of the first `num_steps` steps took (device clock; the first one counts from the time base)."""
+        S = int(num_steps)
+        if S <= 0:
+            return torch.zeros(0, dtype=torch.float64)
+        t = torch.cat([self.time_base, self.step_time[:S]]).cpu().double()
+        return (t[1:] - t[:-1]) * 1e-9
+
+    @_on_stream
+    def t_opt_steps(self, num_steps, init_score):
+        """Per unit, the last step (1-based) at which the score rose to its running best (0: never) -- what the reference's
+        log['t_opt'] marks (solver.py:241-242)."""
+        out = torch.empty(self.M, dtype=torch.int32, device=self.device)
+        check(self.lib.ecord_t_opt_steps(ptr(self.score_log), ptr(init_score.contiguous().view(-1)), int(num_steps), self.M,
+                                         ptr(out), _stream()), "ecord_t_opt_steps")
+        return out.view(self.g.G, self.T)
+
+    # ---- log_stats (SURVEY.md 8f rank 3; solvers/solver.py:244-249,322-327) ----------------------------------------
+    @_on_stream
+    def clone_env(self):
+        """A copy of the environment planes as they are now (the spins / peeks the rollout starts from, after any greedy
+        pre-solve): the base from which replay_stats() reconstructs the per-step views."""
+        t = dict(peek=self.peek.clone(), sp=self.sp.clone(), best_state=self.best_state.clone(), score=self.score.clone(),
+                 best_score=self.best_score.clone(), best_step=self.best_step.clone())
+        c = _lib.Env(self.T, 0, ptr(t['peek']), ptr(t['sp']), ptr(t['best_state']), ptr(t['score']), ptr(t['best_score']),
+                     ptr(t['best_step']))
+        return t, c, self.steps_done
+
+    def replay_stats(self, base, num_steps, chunk=8):
+        """Per-step `peeks` and `state` of a finished rollout in the reference's layout (f32 [G, n_max, T] on the host,
+        padding -1e10 / -1): yields (step, peeks, state) for step = 0 .. num_steps - 1, each the view BEFORE that step's flip,
+        exactly what DQNSolver.rollout appends with log_stats=True.
+
+        The rollout itself ran through the CUDA-graph plan with no host round trip; here the action log is replayed onto a
+        copy of the initial environment (one snapshot kernel + one env-step kernel per step, no policy kernels), `chunk`
+        steps at a time into one of two device buffers whose device->host copy into pinned memory runs on a side stream
+        while the next chunk is being replayed.  The reference copies both arrays to the host every step inside its loop."""
+        tensors, env_c, step0 = base
+        G, nmax, T = self.g.G, self.g.n_max, self.T
+        S = int(num_steps)
+        chunk = max(1, min(int(chunk), S)) if S else 1
+        dev_buf = [torch.empty(chunk, 2, G, nmax, T, dtype=torch.float32, device=self.device) for _ in range(2)]
+        host_buf = [torch.empty(chunk, 2, G, nmax, T, dtype=torch.float32).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=self.device)
+        done = [torch.cuda.Event() for _ in range(2)]          # D2H of buffer i complete
+        filled = [torch.cuda.Event() for _ in range(2)]        # replay of buffer i complete
+        pending = []                                           # (buffer, first step, count)
+
+        def drain(entry):
+            b, s0, cnt = entry
+            done[b].synchronize()
+            for i in range(cnt):
+                yield s0 + i, host_buf[b][i, 1].clone(), host_buf[b][i, 0].clone()
+
+        st_ptr = C.c_void_p(self.stream.cuda_stream)
+
+        def enqueue(c0, b, cnt):          # replay `cnt` steps into device buffer b, then its D2H on the side stream
+            for i in range(cnt):
+                s = c0 + i
+                check(self.lib.ecord_env_snapshot_padded(C.byref(self.g.c), C.byref(env_c), ptr(dev_buf[b][i, 0]),
+                                                         ptr(dev_buf[b][i, 1]), st_ptr), "ecord_env_snapshot_padded")
+                check(self.lib.ecord_env_step(C.byref(self.g.c), C.byref(env_c), ptr(self.action_log[s]), step0 + s, None,
+                                              st_ptr), "ecord_env_step")
+            filled[b].record(self.stream)
+            copy_stream.wait_event(filled[b])
+            with torch.cuda.stream(copy_stream):
+                host_buf[b][:cnt].copy_(dev_buf[b][:cnt], non_blocking=True)
+                done[b].record(copy_stream)
+            self.kernel_launches += 2 * cnt
+
+        for c0 in range(0, S, chunk):
+            b = (c0 // chunk) & 1
+            cnt = min(chunk, S - c0)
+            if len(pending) == 2:         # buffer b still belongs to the copy issued two chunks ago: hand its steps out first
+                yield from drain(pending.pop(0))
+            enqueue(c0, b, cnt)
+            pending.append((b, c0, cnt))
+        for entry in pending:
+            yield from drain(entry)
+        del tensors
 
     def close(self):
         if self.plan is not None:

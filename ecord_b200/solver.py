@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .data import as_tg_batch
 from .engine import DeviceGraph, DeviceWeights, RolloutState
 from .network import check_state_dicts, node_classifier_heads, state_dicts_from_checkpoint
 from .observations import CANONICAL_GLOB_FEATURES, CANONICAL_NODE_FEATURES, check_canonical
@@ -139,7 +140,7 @@ class B200Solver:
         tg = batch.tg
         if self._graph_cache[0] is tg:
             return self._graph_cache[1]
-        dg = DeviceGraph(tg, self.device)
+        dg = DeviceGraph(as_tg_batch(tg), self.device)     # our TgBatch, or the reference batcher's torch_geometric Batch
         self._graph_cache = (tg, dg)
         return dg
 
@@ -230,41 +231,39 @@ class B200Solver:
                                                   draw=self._net_init_draws)
         state.env_init(init_state)
         if pre_solve_with_greedy:                       # solver.py:294-295: greedy_solve(env, init_from_best=False)
-            log['greedy_pre_steps'] = state.greedy_solve(init_from_best=False, rebase=True)
-        init_score = state.scores().clone()
+            log['greedy_pre_steps'] = [state.greedy_solve(init_from_best=False, rebase=True)]
+        init_score_dev = state.scores().clone()
+        init_score = init_score_dev
         ev[2].record()
 
         per_step = defaultdict(list)
-        if log_stats:
-            # per-step peeks / states need the [G, n_max, T] views each step -> step-wise path
-            for _ in range(S):
-                nf, _, _ = state.export()
-                per_step['peeks'].append(self._flat2batch(dg, nf[..., 1].cpu(), -1e10))
-                per_step['state'].append(self._flat2batch(dg, nf[..., 0].cpu(), -1))
-                state.step()
-                per_step['actions'].append(state.actions.view(G, T).cpu().long())
-        elif max_time is None:
+        stats_base = state.clone_env() if log_stats else None      # the spins / peeks the rollout starts from
+        state.stamp_time_base()
+        if max_time is None:
             state.run(S)
         else:
-            # solver.py:318-320: stop once the accumulated time (embedding + steps) reaches max_time.  The fused loop is
-            # checked between CUDA-graph launches, i.e. with a granularity of `steps_per_graph` steps (the reference
-            # checks every step).
+            # solver.py:318-320: stop before a step once the accumulated time (embedding + steps) has reached max_time.  The
+            # time is the device clock stamped at the end of every step.  While a whole CUDA graph of k steps fits into the
+            # remaining budget (at the measured pace) it is launched; close to the limit the loop goes step by step, so the
+            # rollout ends at the same step granularity as the reference's.
             ev[1].synchronize()
             t_used = ev[0].elapsed_time(ev[1]) * 1e-3
-            done_steps = 0
+            done_steps, dt_est = 0, None
             while done_steps < S:
                 if t_used >= max_time:
                     print(f"Max time exceeded, terminating optimisation after {done_steps} steps.")
                     break
-                c = min(self.steps_per_graph, S - done_steps)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); state.run(c); e1.record(); e1.synchronize()
-                t_used += e0.elapsed_time(e1) * 1e-3
+                k = self.steps_per_graph
+                c = min(k, S - done_steps) if (dt_est is not None and t_used + (k + 1) * dt_est < max_time) else 1
+                state.run(c)
+                dts = state.step_times_host(done_steps + c)     # (synchronises on the stream)
+                t_used = ev[0].elapsed_time(ev[1]) * 1e-3 + float(dts.sum())
                 done_steps += c
+                dt_est = float(dts[-min(len(dts), 8):].mean())
             S = done_steps
         post_scores = None
         if post_solve_with_greedy_from_best:            # solver.py:367-371: greedy from the best states + one more log entry
-            log['greedy_post_steps'] = state.greedy_solve(init_from_best=True)
+            log['greedy_post_steps'] = [state.greedy_solve(init_from_best=True)]
             post_scores = state.scores().clone()
         ev[3].record()
         ev[3].synchronize()
@@ -272,22 +271,35 @@ class B200Solver:
         t_setup = ev[1].elapsed_time(ev[2]) * 1e-3
         t_rollout = ev[2].elapsed_time(ev[3]) * 1e-3
 
+        if log_stats:
+            # per-step peeks / spins (before each flip) and actions, reconstructed from the device-side action log after the
+            # rollout has run at full speed: see RolloutState.replay_stats
+            acts = state.action_log[:S].view(S, G, T).cpu().long() if S else torch.zeros(0, G, T, dtype=torch.long)
+            for s_, pk, stt in state.replay_stats(stats_base, S):
+                per_step['peeks'].append(pk)
+                per_step['state'].append(stt)
+                per_step['actions'].append(acts[s_])
         scores = state.score_log_host(S) if S > 0 else torch.zeros(0, G, T)
         init_score = init_score.cpu()
-        best_step = state.best_step.view(G, T).cpu()
         log['t_init_emb'].append(torch.tensor([t_init_emb]))
         log['t_setup'].append(torch.tensor([t_setup]))
         log['init_score'] = init_score
-        dt = t_rollout / max(S, 1)
-        # t_opt: time at which each trajectory reached its best score (solver.py:241-242), from the step index
-        log['t_opt'] = t_init_emb + best_step.float() * dt
+        # per-step times from the device clock; t_opt (solver.py:241-242): accumulated time (embedding + steps) at the last
+        # step where a trajectory's score rose to its running best; trajectories that never improve keep t_init_emb
+        dts = state.step_times_host(S)
+        cum = t_init_emb + torch.cumsum(dts, 0)
+        if S > 0:
+            opt_step = state.t_opt_steps(S, init_score_dev).cpu().long()
+            log['t_opt'] = torch.where(opt_step > 0, cum[(opt_step - 1).clamp(min=0)], torch.full_like(cum[:1], t_init_emb)).float()
+        else:
+            log['t_opt'] = torch.full((G, T), t_init_emb)
         prev = init_score
         for s in range(S):
             log['scores'].append(scores[s])
             log['scores0'].append(prev)
             prev = scores[s]
-            log['t_step'].append(dt)
-            log['t_inf'].append(dt)
+            log['t_step'].append(float(dts[s]))
+            log['t_inf'].append(float(dts[s]))
         if post_scores is not None:                     # log_step(env, -ones, ...) of solver.py:369-371
             log['scores'].append(post_scores.cpu())
             if log_stats:
@@ -302,7 +314,8 @@ class B200Solver:
         log['best_state'] = state.best_states_batched(true_snapshot=not self.compat)
         log['t_rollout'] = torch.tensor([t_rollout])
         log['t_tot'] = torch.tensor([t_init_emb + t_rollout])
-        log['kernel_launches'] = state.kernel_launches
+        # engine extras are lists / tensors too, so that the reference's merge_log (testing.py:120-143) accepts the log as it is
+        log['kernel_launches'] = [state.kernel_launches]
         self._last_state = state
         self._net_init_draws += int(from_network)
         self.last_wall = time.time() - t_all

@@ -340,6 +340,8 @@ typedef struct ecord_rollout_desc {
     int32_t *action_log;      /* device i32 [max_steps][G*T] or NULL */
     int32_t  max_steps;       /* capacity of the logs */
     int32_t  _pad;
+    uint64_t *step_time_ns;   /* device u64 [max_steps] or NULL: %globaltimer (ns) when step s has been applied -- the per-step
+                                 timings DQNSolver.rollout logs as t_step and uses for t_opt / max_time (solver.py:241,318-341) */
 } ecord_rollout_desc;
 
 typedef struct ecord_rollout_plan ecord_rollout_plan;   /* opaque */
@@ -356,6 +358,16 @@ int ecord_rollout_plan_destroy(ecord_rollout_plan *plan);
  *      since best_score also covers the initial score, the log-based maximum is provided:
  *      out_best[g*T+t] = max_s score_log[s][g*T+t]  (validate/testing.py:201). ---- */
 int ecord_score_log_max(const float *score_log, int32_t num_steps, int32_t rows, float *out_best, void *stream);
+
+/* log['t_opt'] (solver.py:241-242): out_steps[g*T+t] = the last step (1-based) at which the unit's score rose and equals its
+ * running best (init_score included); 0 if the initial score was never improved on. */
+int ecord_t_opt_steps(const float *score_log, const float *init_score, int32_t num_steps, int32_t rows,
+                      int32_t *out_steps, void *stream);
+/* ---- log_stats views (solver.py:322-327; tradjectories.py:378-385): spins and peeks of the current state in the reference's
+ *      padded layout f32 [G][n_max][T] (padding -1 / -1e10).  Either output may be NULL. ---- */
+int ecord_env_snapshot_padded(const ecord_graph *g, const ecord_env *env, float *state_out, float *peek_out, void *stream);
+/* one %globaltimer sample (ns) on the stream: the time base of ecord_rollout_desc.step_time_ns */
+int ecord_stamp_time(uint64_t *out_ns, void *stream);
 
 /* ---- layout helper: trajectory-major plane f32 [N*T] -> the reference's [N][T] ---- */
 int ecord_plane_to_nt(const ecord_graph *g, int32_t num_tradj, const float *plane, float *out, void *stream);
