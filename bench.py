@@ -301,85 +301,123 @@ def run_b200(args):
     units = G * T_total * K
     value = units / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel: the tensor-core Q kernel (ecord_q_select = k_q_tc + the 5 us k_select_finish),
-    #      timed alone with CUDA events (torch's current stream is ordered around the state's own stream), L2 flushed
-    #      before every launch.  Algorithmic work per launch: 8416 FLOP and 12 B per (vertex, trajectory). ----
+    # ---- roofline: every kernel of the step timed ALONE with CUDA events on the rollout stream (L2 flushed before every
+    #      launch), the dominant one reported as `roofline`, the rest under `others`.  Algorithmic work:
+    #        GRU   2 x M x (64 + 1024) x 3072 FLOP       PROJ  2 x M x 1024 x 512 FLOP      tail  2 x M x (512 x 32 + 32 x 32 + 32) FLOP
+    #        Q     8416 FLOP and 12 B per (vertex, trajectory) row                          env   (20 d + 76) B per unit
+    #      literal FLOPs of the reference's fp32 model: the bf16x3 mode executes three tensor-core products for each of them. ----
     roof = None
     if rank == 0:
-        reps = 30
-        st.q_select(); torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tot = 0.0
-        for _ in range(reps):
-            flush.fill_(1)
-            a.record(); st.q_select(); b.record(); b.synchronize()
-            tot += a.elapsed_time(b)
-        q_ms = tot / reps
-        tp = {}
-        for nm, fn in (("policy_step", st.policy_step),):
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record(); b.synchronize()
-            tp[nm] = a.elapsed_time(b) / reps
-        # env step (HBM / latency bound: (20 d + 76) B per unit) and the t=0 GNN embedding (CSR gathers:
-        # 4 layers x E x 16 floats read + N x 16 x 3 floats of state per layer), each timed alone
         import ctypes as C
-        torch.cuda.synchronize()
-        with torch.cuda.stream(st.stream):              # the C entry point directly: the step-wise Python wrapper adds torch ops
-            a.record()
-            for _ in range(reps):
-                st.lib.ecord_env_step_fused(C.byref(st.g.c), C.byref(st.env_c), C.byref(st.w.c), C.byref(st.policy_c),
-                                            int(st.steps_done), None, C.c_void_p(st.stream.cuda_stream))
-            b.record()
-        b.synchronize()
-        tp["env_step"] = a.elapsed_time(b) / reps
+        reps = 20
+        hbm, tf_burst, tf_sus, which = peaks()
+        M = G * T
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic_tab = json.load(f).get(args.workload, {})
+        except Exception:
+            traffic_tab = {}
+
+        def timed(fn, n=reps):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tot = 0.0
+            for _ in range(n):
+                flush.fill_(1)
+                st.stream.wait_stream(torch.cuda.current_stream())     # the flush has finished before the kernel starts
+                with torch.cuda.stream(st.stream):
+                    a.record(); fn(); b.record()
+                b.synchronize()
+                tot += a.elapsed_time(b)
+            return tot / n
+
+        sp = C.c_void_p(st.stream.cuda_stream)
+
+        def policy_part(mask):
+            def run():
+                os.environ["ECORD_POLICY_MASK"] = str(mask)
+                st.lib.ecord_policy_step(C.byref(st.g.c), C.byref(st.env_c), C.byref(st.w.c), C.byref(st.policy_c), int(st.steps_done & 1),
+                                         int(st.gemm), int(st.fused), sp)
+                os.environ.pop("ECORD_POLICY_MASK", None)
+            return run
+
+        def q_part():
+            st.lib.ecord_q_select(C.byref(st.g.c), C.byref(st.env_c), C.byref(st.w.c), C.byref(st.policy_c), int(st.steps_done),
+                                  C.c_float(st.tau), C.c_uint64(st.seed), int(st.compat), None, int(st.q_mode), C.c_float(st.epsilon), sp)
+
+        def env_part():
+            st.lib.ecord_env_step_fused(C.byref(st.g.c), C.byref(st.env_c), C.byref(st.w.c), C.byref(st.policy_c), int(st.steps_done), None, sp)
+
+        tms = {}
+        if st.gemm != 0:
+            tms["gru"], tms["proj"], tms["tail"] = timed(policy_part(1)), timed(policy_part(2)), timed(policy_part(4))
+        else:
+            tms["policy_fp32"] = timed(policy_part(7))
+        tms["q"] = timed(q_part)
+        tms["env"] = timed(env_part)
         st.gnn_embed(); torch.cuda.synchronize()       # (its workspace allocation stays outside the timing)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(5):
             st.gnn_embed()
         b.record(); b.synchronize()
-        tp["gnn_embed"] = a.elapsed_time(b) / 5
-        hbm, tf_burst, tf_sus, which = peaks()
+        tms["gnn"] = a.elapsed_time(b) / 5
         rows = float(dg.N) * T
-        flops = 8416.0 * rows                           # literal mlp_out + encoder FLOPs per launch
-        bytes_alg = 12.0 * rows                         # (state, peek, static) fp32 per (vertex, trajectory)
-        ach = flops / (q_ms * 1e-3) / 1e12
-        traffic = None
-        try:                                            # dram bytes per launch of this kernel from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload, {}).get("k_q_tc")
-        except Exception:
-            traffic = None
-        qname = {"tc": "k_q_tc (tcgen05 kind::f16) + k_select_finish", "fast": "k_q_fast + k_select_finish",
-                 "exact": "k_q_select"}[{2: "tc", 1: "fast", 0: "exact"}[st.q_mode]]
-        roof = {"kernel": qname, "bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s",
-                "frac": ach / tf_burst, "traffic": traffic, "peak_source": which + " (bf16 burst; kernel timed alone)",
-                "algorithmic": {"flops_per_row": 8416, "bytes_per_row": 12, "rows_per_launch": rows},
-                "ms_per_launch": q_ms, "launch_share_of_step": q_ms / (ms / K),
-                "hbm_view": {"achieved_gbs": bytes_alg / (q_ms * 1e-3) / 1e9, "peak_gbs": hbm, "frac": bytes_alg / (q_ms * 1e-3) / 1e9 / hbm},
-                "policy_step_ms": tp["policy_step"],
-                "others": [
-                    {"kernel": "k_gemm_tc2<0> + k_gemm_tc2<1|2> + k_tail_tc (GRU, projection, tail; tcgen05, %s)" % args.gemm, "bound": "tensor",
-                     "ms_per_launch": tp["policy_step"], "unit": "TFLOP/s", "peak": tf_burst,
-                     "achieved": (F_UNIT(0) * G * T) / (tp["policy_step"] * 1e-3) / 1e12,
-                     "frac": (F_UNIT(0) * G * T) / (tp["policy_step"] * 1e-3) / 1e12 / tf_burst,
-                     "algorithmic": {"flops_per_unit": F_UNIT(0), "units_per_launch": G * T}},
-                    {"kernel": "k_env_step_fused (flip + neighbour deltas + next msg_in)", "bound": "hbm",
-                     "ms_per_launch": tp["env_step"], "unit": "GB/s", "peak": hbm,
-                     "achieved": (20.0 * avg_deg + 76.0) * G * T / (tp["env_step"] * 1e-3) / 1e9,
-                     "frac": (20.0 * avg_deg + 76.0) * G * T / (tp["env_step"] * 1e-3) / 1e9 / hbm,
-                     "algorithmic": {"bytes_per_unit": 20.0 * avg_deg + 76.0, "units_per_launch": G * T},
-                     "note": "scattered 4-byte accesses behind four dependent loads: latency-, not bandwidth-bound"},
-                    {"kernel": "gnn.cu (t=0 embedding: 4 message-passing layers, once per rollout)", "bound": "hbm",
-                     "ms_per_launch": tp["gnn_embed"], "unit": "GB/s", "peak": hbm,
-                     "achieved": 4.0 * (dg.E * 16 * 4 + dg.E * 8 + dg.N * 16 * 4 * 3) / (tp["gnn_embed"] * 1e-3) / 1e9,
-                     "frac": 4.0 * (dg.E * 16 * 4 + dg.E * 8 + dg.N * 16 * 4 * 3) / (tp["gnn_embed"] * 1e-3) / 1e9 / hbm,
-                     "algorithmic": {"bytes_per_layer": dg.E * 16 * 4 + dg.E * 8 + dg.N * 16 * 4 * 3, "layers": 4},
-                     "note": "sequential per-row accumulation reproduces the reference's summation order; 16 small kernels"}],
-                "whole_step": {"flops_per_unit": F_UNIT(n), "bytes_per_unit": B_UNIT(n, avg_deg),
-                               "tensor_bound_units_s": tf_sus * 1e12 / F_UNIT(n), "hbm_bound_units_s": hbm * 1e9 / B_UNIT(n, avg_deg),
-                               "frac_of_binding_bound": (value / world) / min(tf_sus * 1e12 / F_UNIT(n), hbm * 1e9 / B_UNIT(n, avg_deg))}}
+        gm = args.gemm
+        ns = "3" if gm == "bf16x3" else "1"
+
+        def entry(kernel, bound, ms, work, unit_work, traffic_key=None, note=None, extra=None):
+            peak = tf_burst if bound == "tensor" else hbm
+            ach = work / (ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+            e = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                 "frac": ach / peak, "traffic": traffic_tab.get(traffic_key) if traffic_key else None, "ms_per_launch": ms,
+                 "launch_share_of_step": ms / (ms_total / K), "algorithmic": unit_work,
+                 "peak_source": which + (" (bf16 burst; kernel timed alone)" if bound == "tensor" else " (copy bandwidth)")}
+            if note:
+                e["note"] = note
+            if extra:
+                e.update(extra)
+            return e
+
+        ms_total = ms
+        ents = []
+        if "gru" in tms:
+            ents.append(entry(f"k_gemm_tc2<0,{ns}> (GRU cell: tcgen05 cta_group::2, {gm})", "tensor", tms["gru"], 2.0 * M * 1088 * 3072,
+                              {"flops_per_unit": 2 * 1088 * 3072, "units_per_launch": M, "tensor_products_per_literal_flop": int(ns)},
+                              f"k_gemm_tc2<0, {ns}>",
+                              "literal fp32-model FLOPs; bf16x3 issues 3 MMAs per literal product (hi.hi + lo.hi + hi.lo), so the tensor pipe "
+                              "does 3x this work" if ns == "3" else None))
+            ents.append(entry(f"k_gemm_tc2<1|2,{ns}> (projection 1024->512)", "tensor", tms["proj"], 2.0 * M * 1024 * 512,
+                              {"flops_per_unit": 2 * 1024 * 512, "units_per_launch": M}, f"k_gemm_tc2<2, {ns}>"))
+            ents.append(entry("k_tail_tc (LN512, 512->32 on tcgen05, LN32, value head, Q operands)", "tensor", tms["tail"],
+                              2.0 * M * (512 * 32 + 32 * 32 + 32 + 32 * 64), {"flops_per_unit": 2 * (512 * 32 + 32 * 32 + 32 + 32 * 64), "units_per_launch": M},
+                              "k_tail_tc", "latency chain per CTA, not a throughput kernel"))
+        else:
+            ents.append(entry("k_sgemm_nt_bias x3 + k_gru_gates + k_policy_tail (fp32 CUDA-core policy step)", "tensor", tms["policy_fp32"],
+                              float(F_UNIT(0)) * M, {"flops_per_unit": F_UNIT(0), "units_per_launch": M}))
+        qname = {2: "k_q_tc (tcgen05 kind::f16, fp16 hi/lo) + k_select_finish", 1: "k_q_fast + k_select_finish", 0: "k_q_select"}[st.q_mode]
+        ents.append(entry(qname, "tensor", tms["q"], 8416.0 * rows, {"flops_per_row": 8416, "bytes_per_row": 12, "rows_per_launch": rows}, "k_q_tc",
+                          extra={"hbm_view": {"achieved_gbs": 12.0 * rows / (tms["q"] * 1e-3) / 1e9, "peak_gbs": hbm,
+                                              "frac": 12.0 * rows / (tms["q"] * 1e-3) / 1e9 / hbm}}))
+        ents.append(entry("k_env_step_fused (flip + neighbour deltas + next msg_in)", "hbm", tms["env"], (20.0 * avg_deg + 76.0) * M,
+                          {"bytes_per_unit": 20.0 * avg_deg + 76.0, "units_per_launch": M}, "k_env_step_fused",
+                          "latency-bound: four dependent loads (action -> CSR row -> neighbour entries -> write); the DRAM traffic ncu "
+                          "counts is sector-granular (32 B per scattered 4-byte access)"))
+        # t=0 GNN: compulsory HBM bytes per layer = E x 8 (incoming src + weight) + N x 192 (x, y, state in / out); the E x 64 B of
+        # gathers hit the L2-resident y[N,16] and are not HBM traffic
+        gnn_bytes = 4.0 * (dg.E * 8 + dg.N * 192)
+        ents.append(entry("gnn.cu (t=0 embedding: 4 message-passing layers, once per ROLLOUT, not per step)", "hbm", tms["gnn"], gnn_bytes,
+                          {"bytes_per_layer": dg.E * 8 + dg.N * 192, "layers": 4}, "k_gnn_update",
+                          "sequential per-vertex accumulation reproduces the reference's summation order; gathers are L2 hits"))
+        step_kernels = [e for e in ents if not e["kernel"].startswith("gnn.cu")]
+        dom = max(step_kernels, key=lambda e: e["ms_per_launch"])
+        roof = dict(dom)
+        roof["others"] = [e for e in ents if e is not dom]
+        roof["kernel_ms_sum"] = sum(e["ms_per_launch"] for e in step_kernels)
+        roof["whole_step"] = {"flops_per_unit": F_UNIT(n), "bytes_per_unit": B_UNIT(n, avg_deg),
+                              "tensor_bound_units_s": tf_sus * 1e12 / F_UNIT(n), "hbm_bound_units_s": hbm * 1e9 / B_UNIT(n, avg_deg),
+                              "frac_of_binding_bound": (value / world) / min(tf_sus * 1e12 / F_UNIT(n), hbm * 1e9 / B_UNIT(n, avg_deg)),
+                              "note": "literal fp32-model FLOPs over the sustained bf16 peak"}
     st.close()
 
     # ---- e2e: the public API with host buffers (H2D of inputs, D2H of the score log inside the timed region) ----

@@ -366,6 +366,8 @@ class RolloutState:
             check(self.lib.ecord_env_step(C.byref(self.g.c), C.byref(self.env_c), ptr(a), self.steps_done, ptr(row),
                                           _stream()), "ecord_env_step")
         self.kernel_launches += 1
+        if self.step_time is not None and self.steps_done < self.max_steps:      # the plan's env kernel stamps this itself
+            check(self.lib.ecord_stamp_time(C.c_void_p(self.step_time.data_ptr() + 8 * self.steps_done), _stream()), "ecord_stamp_time")
         self.steps_done += 1
         self.step_counter.fill_(self.steps_done)
 

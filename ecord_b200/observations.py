@@ -55,3 +55,51 @@ def check_canonical(node_features, global_features):
             "the B200 rollout engine implements the canonical ECORD observation set "
             f"{_names(CANONICAL_NODE_FEATURES)} / {_names(CANONICAL_GLOB_FEATURES)}; got "
             f"{_names(node_features)} / {_names(global_features)}")
+
+
+# ---- what a training-time rollout hands to its callbacks -------------------------------------
+# Field-for-field mirrors of the reference's EnvObservation (environment/environment.py:12-38) and ActorState
+# (solvers/actors/_base.py:24-47), so that a replay-buffer callback written for DQNSolver.rollout reads them unchanged.
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+
+def _to(obj, names, device):
+    for n in names:
+        v = getattr(obj, n)
+        if torch.is_tensor(v):
+            setattr(obj, n, v.to(device))
+    return obj
+
+
+@dataclass
+class EnvObservation:
+    node_features: torch.Tensor              # [num_nodes, num_tradj, 3] normalised (STATE, PEEK_NORM, STEPS_STATIC_CLIP)
+    glob_features: torch.Tensor              # [num_graphs, num_tradj, 2] (SCORE_FROM_BEST_NORM, 0)
+    edge_index: Optional[torch.Tensor]       # None: the canonical actor does not read the graph structure per step
+    edge_attr: Optional[torch.Tensor]
+    batch_idx: torch.Tensor                  # [num_nodes]
+    batch_ptr: torch.Tensor                  # [num_graphs + 1]
+    degree: Optional[torch.Tensor]
+    num_tradj: int
+
+    def to(self, device):
+        return _to(self, ("node_features", "glob_features", "edge_index", "edge_attr", "batch_idx", "batch_ptr", "degree"), device)
+
+
+@dataclass
+class ActorState:
+    hidden_embeddings: torch.Tensor          # [num_graphs, num_tradj, 1024] GRU state BEFORE the step
+    init_node_embeddings: torch.Tensor       # [num_nodes, num_tradj, 16] gnn2rnn(gnn(x)), the same for every trajectory
+    last_selected_node_embeddings: Optional[torch.Tensor] = None    # [num_graphs, num_tradj, 32]
+    cell_embeddings: Optional[torch.Tensor] = None
+    graph_embeddings: Optional[torch.Tensor] = None
+
+    def to(self, *args, **kwargs):
+        for n in ("hidden_embeddings", "init_node_embeddings", "last_selected_node_embeddings", "cell_embeddings", "graph_embeddings"):
+            v = getattr(self, n)
+            if v is not None:
+                setattr(self, n, v.to(*args, **kwargs))
+        return self

@@ -23,7 +23,7 @@ from . import _lib
 from .data import as_tg_batch
 from .engine import DeviceGraph, DeviceWeights, RolloutState
 from .network import check_state_dicts, node_classifier_heads, state_dicts_from_checkpoint
-from .observations import CANONICAL_GLOB_FEATURES, CANONICAL_NODE_FEATURES, check_canonical
+from .observations import (CANONICAL_GLOB_FEATURES, CANONICAL_NODE_FEATURES, ActorState, EnvObservation, check_canonical)
 
 
 def _sd(x):
@@ -71,6 +71,7 @@ class B200Solver:
         self.node_features, self.global_features = node_features, global_features
         self.is_training = False
         self.trainable = False
+        self.intermediate_reward, self.revisit_reward = intermediate_reward, revisit_reward
         self.num_env_steps = self.num_rollouts = self.num_param_steps = 0
         self.initial_epsilon, self.final_epsilon, self.final_epsilon_step = initial_epsilon, final_epsilon, final_epsilon_step
         self.set_weights({'gnn': _sd(gnn), 'rnn': _sd(rnn), 'gnn2rnn': _sd(gnn2rnn), 'node_encoder': _sd(node_encoder)})
@@ -126,14 +127,19 @@ class B200Solver:
         return fname
 
     def train(self):
-        raise NotImplementedError("the B200 engine is inference-only (test-time rollout)")
+        """Training-mode ROLLOUTS (data collection for the reference's Trainer, trainer.py:279-289): rollout() then computes
+        rewards, keeps the step / rollout counters and feeds the callbacks (solver.py:329-365).  The engine holds no
+        optimiser: gradient steps stay with the reference's torch modules, whose weights come back through set_weights()."""
+        if self.intermediate_reward != 0 or self.revisit_reward != 0:
+            raise NotImplementedError("intermediate / revisit rewards (environment.py:116-139; the ECO-DQN training setting) are "
+                                      "not implemented: canonical ECORD trains with both at 0 (experiments/train.py:104-105)")
+        self.is_training = True
 
     def test(self):
         self.is_training = False
 
     def set_training(self, is_training):
-        if is_training:
-            self.train()
+        self.train() if is_training else self.test()
 
     # ---- rollout (seam B1) ---------------------------------------------------------------------
     def _device_graph(self, batch):
@@ -179,8 +185,6 @@ class B200Solver:
         traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU sharding).
         use_epsilon=True applies the epsilon-greedy exploration of actors/ecord.py:171-180 with epsilon =
         get_epsilon() (solver.py:184-186,334), drawn on the device; validation passes use_epsilon=False."""
-        if callbacks:
-            raise NotImplementedError("training callbacks are not implemented by the B200 engine (SURVEY.md 8f rank 4)")
         tau = self.tau if tau is None else tau
         tau = 0.0 if tau is None else float(tau)
         log = defaultdict(list)
@@ -239,7 +243,9 @@ class B200Solver:
         per_step = defaultdict(list)
         stats_base = state.clone_env() if log_stats else None      # the spins / peeks the rollout starts from
         state.stamp_time_base()
-        if max_time is None:
+        if self.is_training:
+            S = self._training_rollout(state, dg, S, num_steps, callbacks, max_time, t_used0=None)
+        elif max_time is None:
             state.run(S)
         else:
             # solver.py:318-320: stop before a step once the accumulated time (embedding + steps) has reached max_time.  The
@@ -320,6 +326,50 @@ class B200Solver:
         self._net_init_draws += int(from_network)
         self.last_wall = time.time() - t_all
         return log
+
+    def _training_rollout(self, state, dg, S, num_steps, callbacks, max_time, t_used0=None):
+        """The training-time loop of DQNSolver.rollout (solver.py:316-365), step by step: before each step the actor state
+        (GRU state, cached embedding) and the observation are snapshotted for the callbacks, after it the reward
+            r = max(score_new - best_before, 0) / n_g          (environment.py:113-141 with the extra rewards at 0)
+        is formed on the device; `done` marks the graphs whose own step budget (|num_steps| * n_g) has been used up.
+        Callbacks are (fn, env_step_freq, param_step_freq) triples called as fn(solver, actor_state=, obs=, action=, reward=,
+        done=, t_step=), exactly as Trainer registers them."""
+        G, T, N = dg.G, state.T, dg.N
+        dev = self.device
+        n_nodes = torch.as_tensor(dg.num_nodes_list, dtype=torch.float32, device=dev).view(G, 1)
+        per_graph_steps = (torch.as_tensor(dg.num_nodes_list, dtype=torch.long) * abs(int(num_steps))) if num_steps < 0 \
+            else torch.full((G,), int(num_steps), dtype=torch.long)
+        batch_idx = torch.as_tensor(dg.tg.batch, device=dev) if not torch.is_tensor(dg.tg.batch) else dg.tg.batch.to(dev)
+        batch_ptr = torch.as_tensor(dg.tg.np_ptr, device=dev)
+        done = torch.zeros(G, T, device=dev)
+        want_cb = bool(callbacks)
+        init_emb = state.node_emb.unsqueeze(1).expand(N, T, 16) if want_cb else None
+        t = 0
+        for t in range(S):
+            if max_time is not None and t > 0 and float(state.step_times_host(t).sum()) >= max_time:
+                print(f"Max time exceeded, terminating optimisation after {t} steps.")
+                return t
+            actor_state = obs = None
+            if want_cb:
+                actor_state = ActorState(hidden_embeddings=state.hidden_state().clone(), init_node_embeddings=init_emb,
+                                         last_selected_node_embeddings=state.last_sel[:state.M].view(G, T, 32).clone())
+                nf, gf, _ = state.export(normalise=True)
+                obs = EnvObservation(node_features=nf, glob_features=gf, edge_index=None, edge_attr=None, batch_idx=batch_idx,
+                                     batch_ptr=batch_ptr, degree=None, num_tradj=T)
+            best_before = state.best_score.view(G, T).clone()
+            state.step()
+            reward = (state.score.view(G, T) - best_before).clamp(min=0) / n_nodes
+            actions = state.actions.view(G, T).long().clone()
+            self.num_env_steps += 1
+            done[(per_graph_steps == t + 1).to(dev)] = 1
+            if want_cb:
+                for fn, env_step_freq, param_step_freq in callbacks:
+                    if env_step_freq is not None and self.num_env_steps % env_step_freq == 0:
+                        fn(self, actor_state=actor_state, obs=obs, action=actions, reward=reward, done=done, t_step=t)
+                    if param_step_freq is not None and self.num_param_steps % param_step_freq == 0:
+                        fn(self, actor_state=actor_state, obs=obs, action=actions, reward=reward, done=done, t_step=t)
+        self.num_rollouts += G * T
+        return S
 
     @staticmethod
     def _flat2batch(dg, arr, fill):

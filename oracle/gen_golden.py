@@ -345,10 +345,58 @@ def gen_fullsize(which=("er200", "er500", "ba500")):
               f"scores_max={log['scores_max'].tolist()}", flush=True)
 
 
+def gen_train_trace():
+    """Training-time data collection: the unmodified reference's DQNSolver.rollout in TRAINING mode
+    (solver.train(); solver.py:329-356) with a recording callback -- what Trainer's replay buffer receives every step:
+    actor_state (GRU state and cached embedding BEFORE the step), obs (normalised features BEFORE the step), action,
+    reward (environment.py:113-141 with intermediate_reward = revisit_reward = 0, the canonical ECORD setting) and done.
+    Greedy (use_epsilon=False) so that the actions are reproducible without torch's RNG stream."""
+    er40, _ = load("validation/ER_40spin_p15_100graphs")
+    ba20, _ = load("validation/BA_20spin_m4_100graphs")
+    ba60, _ = load("testing/BA_60spin_m4_50graphs")
+    graphs = [er40[30], ba20[7], ba60[4], er40[31]]
+    T, wseed, sseed = 3, 11, 777
+    sd = random_state_dicts(wseed, perturb_norms=True)
+    solver, gb = make_solver(sd)
+    solver.train()
+    batch = gb(graphs)
+    rec = {k: [] for k in ("hidden", "last_sel", "node_feat", "glob_feat", "action", "reward", "done", "t_step")}
+
+    def cb(slv, actor_state, obs, action, reward, done, t_step):
+        rec["hidden"].append(actor_state.hidden_embeddings.clone())
+        rec["last_sel"].append(actor_state.last_selected_node_embeddings.clone())
+        rec["node_feat"].append(obs.node_features.clone())
+        rec["glob_feat"].append(obs.glob_features.clone())
+        rec["action"].append(action.clone())
+        rec["reward"].append(reward.clone())
+        rec["done"].append(done.clone())
+        rec["t_step"].append(t_step)
+
+    np.random.seed(sseed)
+    steps0 = solver.num_env_steps
+    log = solver.rollout(batch, num_tradj=T, num_steps=-1, callbacks=[(cb, 1, None)], use_epsilon=False, tau=0)
+    S = len(rec["action"])
+    N = sum(g.shape[0] if isinstance(g, np.ndarray) else g.number_of_nodes() for g in graphs)
+    init = np.random.RandomState(sseed).randint(0, 2, (N, T), dtype=np.int8)
+    out = pack_graphs(graphs)
+    out.update(dict(T=np.int32(T), S=np.int32(S), weight_seed=np.int32(wseed), init_state=init,
+                    num_env_steps=np.int32(solver.num_env_steps - steps0), num_rollouts=np.int32(solver.num_rollouts),
+                    hidden_slice=torch.stack(rec["hidden"])[..., ::16].numpy(), last_sel=torch.stack(rec["last_sel"]).numpy(),
+                    node_feat=torch.stack(rec["node_feat"]).numpy(), glob_feat=torch.stack(rec["glob_feat"]).numpy(),
+                    action=torch.stack(rec["action"]).numpy().astype(np.int16), reward=torch.stack(rec["reward"]).numpy(),
+                    done=torch.stack(rec["done"]).numpy(), t_step=np.asarray(rec["t_step"], np.int32),
+                    scores=torch.stack(log["scores"]).numpy(), init_score=log["init_score"].numpy()))
+    np.savez_compressed(os.path.join(GOLD, "train_trace.npz"), **out)
+    print(f"train_trace.npz: G={len(graphs)} T={T} S={S} (num_steps=-1 -> |V| per graph, loop to the max), "
+          f"reward sum {float(torch.stack(rec['reward']).sum()):.4f}, done at the end {torch.stack(rec['done'])[-1].sum().item()}")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    if len(sys.argv) > 1 and sys.argv[1] == "full":
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        gen_train_trace()
+    elif len(sys.argv) > 1 and sys.argv[1] == "full":
         gen_fullsize(tuple(sys.argv[2:]) or ("er200", "er500", "ba500"))
     else:
         gen_env_traces()

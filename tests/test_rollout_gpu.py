@@ -306,10 +306,18 @@ def test_unsupported_options_fail_loudly():
     with pytest.raises(NotImplementedError):
         B200Solver(gnn=sd['gnn'], rnn=sd['rnn'], gnn2rnn=sd['gnn2rnn'], node_encoder=sd['node_encoder'],
                    node_features=[NodeObservation.STATE, NodeObservation.PEEK])
+    with pytest.raises(NotImplementedError):           # the ECO-DQN actor and the double-Q actor are outside the hot path
+        _solver(sd, use_ecodqn=True)
+    with pytest.raises(NotImplementedError):
+        _solver(sd, use_double_q_networks=True)
+    with pytest.raises(NotImplementedError):           # extra rewards of the ECO-DQN training setting (environment.py:116-139)
+        _solver(sd, intermediate_reward=1 / 40).train()
+    # in test mode the reference ignores callbacks (solver.py:348: `if callbacks is not None and self.is_training`)
     solver = _solver(sd)
     batch = GraphBatcher()(synthetic_set("er", 10, 1, p=0.5))
-    with pytest.raises(NotImplementedError):
-        solver.rollout(batch, num_tradj=2, num_steps=2, callbacks=[(print, 1, None)])
+    calls = []
+    solver.rollout(batch, num_tradj=2, num_steps=2, callbacks=[(lambda *a, **k: calls.append(1), 1, None)], use_epsilon=False)
+    assert calls == []
 
 
 @pytest.mark.parametrize("kind,n,G,T,S,gen", [
@@ -506,3 +514,50 @@ def test_max_time_stops_the_rollout_at_step_granularity():
     assert len(log['t_step']) == n and log['best_score_by_tradj'].shape == (20, T)
     full = solver.rollout(batch, num_tradj=T, num_steps=n, tau=0, use_epsilon=False, init_state=init)
     assert torch.equal(torch.stack(full['scores']), torch.stack(log['scores']))     # same steps as an un-timed rollout
+
+
+def test_training_mode_rollout_feeds_callbacks_like_the_reference():
+    """DQNSolver.rollout in TRAINING mode (solver.py:329-365) -- per step the callbacks get the actor
+    state and observation BEFORE the step, the action, the reward (environment.py:113-141) and the done flags.  Fixture:
+    the unmodified reference with a recording callback (oracle/gen_golden.py train -> train_trace.npz), greedy so that the
+    actions are reproducible; fp32-grade modes must reproduce actions, rewards and dones exactly and the tensors to 1e-4."""
+    from util import rel_err
+    z = load_gold("train_trace.npz")
+    graphs = unpack_graphs(z)
+    T, S = int(z["T"]), int(z["S"])
+    batch = GraphBatcher()(graphs)
+    for gemm in ("bf16x3", "fp32"):
+        solver = _solver(random_state_dicts(int(z["weight_seed"]), perturb_norms=True), gemm=gemm)
+        solver.train()
+        assert solver.is_training
+        rec = {k: [] for k in ("hidden", "last_sel", "node_feat", "glob_feat", "action", "reward", "done", "t_step")}
+
+        def cb(slv, actor_state, obs, action, reward, done, t_step):
+            assert slv is solver and obs.num_tradj == T and actor_state.init_node_embeddings.shape == (batch.tg.num_nodes, T, 16)
+            rec["hidden"].append(actor_state.hidden_embeddings.cpu())
+            rec["last_sel"].append(actor_state.last_selected_node_embeddings.cpu())
+            rec["node_feat"].append(obs.node_features.cpu()); rec["glob_feat"].append(obs.glob_features.cpu())
+            rec["action"].append(action.cpu()); rec["reward"].append(reward.cpu()); rec["done"].append(done.cpu().clone())
+            rec["t_step"].append(t_step)
+
+        log = solver.rollout(batch, num_tradj=T, num_steps=-1, callbacks=[(cb, 1, None)], use_epsilon=False, tau=0,
+                             init_state=z["init_state"])
+        assert len(rec["action"]) == S and rec["t_step"] == list(range(S))
+        assert solver.num_env_steps == int(z["num_env_steps"]) and solver.num_rollouts == int(z["num_rollouts"])
+        assert np.array_equal(torch.stack(rec["action"]).numpy(), z["action"].astype(np.int64)), gemm
+        assert np.array_equal(torch.stack(rec["reward"]).numpy(), z["reward"]), gemm
+        assert np.array_equal(torch.stack(rec["done"]).numpy(), z["done"]), gemm
+        assert np.array_equal(torch.stack(rec["node_feat"]).numpy(), z["node_feat"]), gemm
+        assert np.array_equal(torch.stack(rec["glob_feat"]).numpy(), z["glob_feat"]), gemm
+        assert rel_err(torch.stack(rec["hidden"]).numpy()[..., ::16], z["hidden_slice"]) < 1e-4
+        assert rel_err(torch.stack(rec["last_sel"]).numpy(), z["last_sel"]) < 1e-5
+        assert np.array_equal(torch.stack(log["scores"]).numpy(), z["scores"])
+        assert len(log["t_step"]) == S and all(t > 0 for t in log["t_step"])
+        # callbacks on every 4th environment step only
+        calls = []
+        solver.num_env_steps = 0
+        solver.rollout(batch, num_tradj=T, num_steps=10, callbacks=[(lambda slv, **kw: calls.append(kw["t_step"]), 4, None)],
+                       use_epsilon=False, tau=0, init_state=z["init_state"])
+        assert calls == [3, 7]
+        solver.test()
+        assert not solver.is_training
