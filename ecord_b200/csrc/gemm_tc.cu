@@ -280,6 +280,22 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t a_desc,
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// collector variants: the A operand of an MMA marked `fill` stays in the tensor core's collector buffer and the next MMA marked
+// `lastuse` takes it from there instead of reading shared memory again (SASS: UTCHMMA ... .A_KEEP / .A_REUSE).  The split kernels
+// read A hi for two products per k-step: one 4 KB shared-memory read less per three MMAs on the L1 / shared-memory data pipe,
+// which (TMA fills + operand reads) is what bounds them.
+__device__ __forceinline__ void umma_bf16_pair_keep(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair_reuse(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` in both CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -301,7 +317,9 @@ template <int NS> __host__ __device__ constexpr int tc2_bk() { return NS == 3 ? 
 template <int MODE, int NS> __host__ __device__ constexpr int tc2_stage_bytes() {
     return (NS == 3 ? 2 : 1) * (BM + TcCfg<MODE>::B_ROWS / 2) * tc2_bk<NS>() * 2;              // per CTA: own A rows, half of B
 }
-template <int MODE, int NS> __host__ __device__ constexpr int stages2() { return MODE == 2 ? 7 : 4; }
+// pipeline depth: the GRU split kernel needs its bytes in flight (TMA latency x 45 B/clk of ingest per SM): three stages cost
+// 10 us per launch against four; its epilogue stages one fp32 tile only (tanh is taken in the store pass), which pays for a fifth
+template <int MODE, int NS> __host__ __device__ constexpr int stages2() { return MODE == 2 ? 7 : (MODE == 0 && NS == 3) ? 5 : 4; }
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {      // K-major SWIZZLE_64B: 8-row groups 512 B apart
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
@@ -424,9 +442,14 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                             } else {       // hi.hi + lo.hi + hi.lo
                                 const uint64_t ah = umma_desc_sw64(a_src + ko), al = umma_desc_sw64(a_src + A_BYTES + ko);
                                 const uint64_t bh = umma_desc_sw64(b_src + ko), bl = umma_desc_sw64(b_src + B_BYTES + ko);
-                                umma_bf16_pair(acc, ah, bh, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                                if (prm.debug & 16) {          // A/B switch: no collector reuse
+                                    umma_bf16_pair(acc, ah, bh, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                                    umma_bf16_pair(acc, ah, bl, idesc, 1u);
+                                } else {
+                                    umma_bf16_pair_keep(acc, ah, bh, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                                    umma_bf16_pair_reuse(acc, ah, bl, idesc, 1u);
+                                }
                                 umma_bf16_pair(acc, al, bh, idesc, 1u);
-                                umma_bf16_pair(acc, ah, bl, idesc, 1u);
                             }
                         }
                         umma_commit_pair(empty0 + 8 * s);         // frees the stage in both CTAs
@@ -455,9 +478,8 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 const int e = threadIdx.x - 64, ew = e >> 5;          // epilogue thread / warp index 0..511 / 0..15
                 const int rloc = q * 32 + lane;                        // row of the tile this thread owns in TMEM
                 float (*Hs)[kHsPitch] = reinterpret_cast<float (*)[kHsPitch]>(stage_gen);
-                // NS = 1: bf16 images of h' and tanh(h') are staged; NS = 3: tanh(h') is staged in fp32 (second tile) and both
-                // are split into bf16 hi / lo pairs by the store pass
-                float (*Ths)[kHsPitch] = reinterpret_cast<float (*)[kHsPitch]>(stage_gen + BM * kHsPitch * 4);
+                // NS = 1: bf16 images of h' and tanh(h') are staged as well; NS = 3: only h' (fp32) is staged, the store pass takes
+                // tanh(h') and splits both into bf16 hi / lo pairs
                 __nv_bfloat16 (*Bs)[kBsPitch] = reinterpret_cast<__nv_bfloat16 (*)[kBsPitch]>(stage_gen + BM * kHsPitch * 4);
                 __nv_bfloat16 (*Ts)[kBsPitch] = Bs + BM;
                 const size_t cur_off = (size_t)cur * prm.rows_pad, nxt_off = (size_t)(1 - cur) * prm.rows_pad;
@@ -511,22 +533,17 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                         *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16]) = *reinterpret_cast<uint4 *>(&ot[0]);
                         *reinterpret_cast<uint4 *>(&Ts[rloc][part * 16 + 8]) = *reinterpret_cast<uint4 *>(&ot[8]);
                     } else {
-                        float tv[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int jl = part * 16 + i;
                             const float r = sigmoidf_acc(ar[i] + bias_s[ab][0][jl]);
                             const float z = sigmoidf_acc(az[i] + bias_s[ab][1][jl]);
                             const float n = tanhf(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
-                            const float hn = fmaf(hv[i] - n, z, n);
-                            hv[i] = hn;
-                            tv[i] = tanhf(hn);
+                            hv[i] = fmaf(hv[i] - n, z, n);
                         }
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
+                        for (int i = 0; i < 16; i += 4)
                             *reinterpret_cast<float4 *>(&Hs[rloc][part * 16 + i]) = *reinterpret_cast<float4 *>(&hv[i]);
-                            *reinterpret_cast<float4 *>(&Ths[rloc][part * 16 + i]) = *reinterpret_cast<float4 *>(&tv[i]);
-                        }
                     }
                 }
                 // this warp has read its part of the accumulator: hand it back to the MMA issuer before the stores
@@ -562,7 +579,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                         const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
                         if (m0 + r < prm.rows) {
                             const float4 hv4 = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
-                            const float4 tv4 = *reinterpret_cast<const float4 *>(&Ths[r][4 * c4]);
+                            const float4 tv4 = make_float4(tanhf(hv4.x), tanhf(hv4.y), tanhf(hv4.z), tanhf(hv4.w));   // projection input
                             const size_t o = (size_t)(m0 + r) * H + nb * 64 + 4 * c4;
                             *reinterpret_cast<float4 *>(hnew + nxt_off * H + o) = hv4;
                             uint2 hi, lo;
@@ -630,7 +647,7 @@ constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_R
 template <int MODE, int NS>
 constexpr int tc2_smem_bytes() {
     return stages2<MODE, NS>() * tc2_stage_bytes<MODE, NS>() + 1024 +
-           (MODE == 0 ? kStageTileBytes : MODE == 1 ? BM * (TcCfg<MODE>::TILE_N + 4) * 4 : 0);
+           (MODE == 0 ? (NS == 3 ? BM * kHsPitch * 4 : kStageTileBytes) : MODE == 1 ? BM * (TcCfg<MODE>::TILE_N + 4) * 4 : 0);
 }
 static_assert(tc2_smem_bytes<0, 3>() <= 227 * 1024 && tc2_smem_bytes<1, 3>() <= 227 * 1024 && tc2_smem_bytes<2, 3>() <= 227 * 1024 &&
               tc2_smem_bytes<2, 3>() - 1024 >= BM * (TcCfg<2>::TILE_N + 4) * 4, "shared-memory budget of the pair kernels");
