@@ -93,6 +93,11 @@ SYMBOLS = {
     "ecord_abi_sizeof": (_i64, [_i32]),
     "ecord_step_cy": (_i32, [_vp] * 11 + [_i32] * 5),
     "ecord_step_cy_device": (_i32, [_vp] * 11 + [_i32] * 6 + [_vp]),
+    "ecord_step_cy_ctx_create": (_i32, [_i32] * 5 + [_vp] * 3 + [_P(_vp)]),
+    "ecord_step_cy_ctx_upload": (_i32, [_vp] * 6),
+    "ecord_step_cy_ctx_step": (_i32, [_vp] * 5),
+    "ecord_step_cy_ctx_download": (_i32, [_vp] * 6),
+    "ecord_step_cy_ctx_destroy": (_i32, [_vp]),
     "ecord_env_init": (_i32, [_P(Graph), _P(Env), _vp, _vp]),
     "ecord_env_step": (_i32, [_P(Graph), _P(Env), _vp, _i32, _vp, _vp]),
     "ecord_env_step_fused": (_i32, [_P(Graph), _P(Env), _P(Weights), _P(Policy), _i32, _vp, _vp]),

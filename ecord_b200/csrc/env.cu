@@ -11,6 +11,7 @@
 // contiguous row of the trajectory-major plane.  HBM/latency-bound: ~20 B per neighbour.
 #include "common.cuh"
 #include <stdlib.h>
+#include <new>
 
 // ------------------------------------------------------------------------------------------------
 // a2: initial peeks / scores (tradjectories.py:130-148), sequential per segment like segment_csr.
@@ -581,4 +582,94 @@ extern "C" int ecord_step_cy(const int64_t *actions, float *scores, float *best_
     if (!rc) rc = (int)cudaStreamSynchronize(st);
     cudaFree(d);
     return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// B3 with a cached arena: ecord_step_cy() pays a cudaMalloc / cudaFree and a full H2D + D2H of every array per call
+// (about 2 x the state size over PCIe per step: the price of keeping the reference's host-side Tradjectories untouched).
+// A caller that can keep the state on the device between steps creates a context once per Tradjectories object (graph
+// uploaded once, arena allocated once), uploads the arrays after __init__, then per step ships only the actions
+// (G*T*8 bytes) and optionally reads the scores back; download() materialises the host arrays when they are needed.
+// ------------------------------------------------------------------------------------------------
+struct ecord_step_cy_ctx {
+    int N, G, T, Fn, Fg, E;
+    char *arena;
+    size_t o_act, o_sc, o_bs, o_bst, o_nf, o_gf, o_e, o_w, o_p, bytes;
+    cudaStream_t stream;
+};
+
+extern "C" int ecord_step_cy_ctx_create(int32_t N, int32_t G, int32_t T, int32_t Fn, int32_t Fg, const int32_t *edges_by_node,
+                                        const float *edge_attrs, const int32_t *edge_ptr, ecord_step_cy_ctx **out) {
+    ECORD_RET_IF(!edge_ptr || !out, ECORD_E_NULL);
+    ECORD_RET_IF(N <= 0 || G <= 0 || T <= 0 || Fn <= 0 || Fg < 0, ECORD_E_SIZE);
+    const int E = edge_ptr[N];
+    ECORD_RET_IF(E < 0, ECORD_E_SIZE);
+    ECORD_RET_IF(E > 0 && (!edges_by_node || !edge_attrs), ECORD_E_NULL);
+    ecord_step_cy_ctx *c = new (std::nothrow) ecord_step_cy_ctx();
+    ECORD_RET_IF(!c, (int)cudaErrorMemoryAllocation);
+    c->N = N; c->G = G; c->T = T; c->Fn = Fn; c->Fg = Fg; c->E = E; c->arena = nullptr; c->stream = nullptr;
+    const size_t GT = (size_t)G * T, NT = (size_t)N * T;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    c->o_act = carve(GT * 8); c->o_sc = carve(GT * 4); c->o_bs = carve(GT * 4); c->o_bst = carve(NT * 4);
+    c->o_nf = carve(NT * Fn * 4); c->o_gf = carve(GT * (Fg > 0 ? Fg : 1) * 4); c->o_e = carve((size_t)E * 8 + 8);
+    c->o_w = carve((size_t)E * 4 + 4); c->o_p = carve((size_t)(N + 1) * 4);
+    c->bytes = off;
+    cudaError_t e = cudaMalloc(&c->arena, off);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && E) e = cudaMemcpyAsync(c->arena + c->o_e, edges_by_node, (size_t)E * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && E) e = cudaMemcpyAsync(c->arena + c->o_w, edge_attrs, (size_t)E * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->arena + c->o_p, edge_ptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { if (c->arena) cudaFree(c->arena); if (c->stream) cudaStreamDestroy(c->stream); delete c; return (int)e; }
+    *out = c;
+    return 0;
+}
+
+static int ctx_copy(ecord_step_cy_ctx *c, float *scores, float *best_scores, float *best_states, float *node_features,
+                    float *global_features, bool up) {
+    ECORD_RET_IF(!c, ECORD_E_PLAN);
+    const size_t GT = (size_t)c->G * c->T, NT = (size_t)c->N * c->T;
+    struct { float *host; size_t off, bytes; } parts[5] = {{scores, c->o_sc, GT * 4}, {best_scores, c->o_bs, GT * 4},
+        {best_states, c->o_bst, NT * 4}, {node_features, c->o_nf, NT * c->Fn * 4}, {global_features, c->o_gf, GT * c->Fg * 4}};
+    for (auto &p : parts) {
+        if (!p.host || !p.bytes) continue;
+        if (up) ECORD_CUDA(cudaMemcpyAsync(c->arena + p.off, p.host, p.bytes, cudaMemcpyHostToDevice, c->stream));
+        else ECORD_CUDA(cudaMemcpyAsync(p.host, c->arena + p.off, p.bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    ECORD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int ecord_step_cy_ctx_upload(ecord_step_cy_ctx *c, const float *scores, const float *best_scores, const float *best_states,
+                                        const float *node_features, const float *global_features) {
+    return ctx_copy(c, const_cast<float *>(scores), const_cast<float *>(best_scores), const_cast<float *>(best_states),
+                    const_cast<float *>(node_features), const_cast<float *>(global_features), true);
+}
+extern "C" int ecord_step_cy_ctx_download(ecord_step_cy_ctx *c, float *scores, float *best_scores, float *best_states,
+                                          float *node_features, float *global_features) {
+    return ctx_copy(c, scores, best_scores, best_states, node_features, global_features, false);
+}
+extern "C" int ecord_step_cy_ctx_step(ecord_step_cy_ctx *c, const int64_t *actions, const int32_t *nidx, const int32_t *gidx,
+                                      float *scores_out) {
+    ECORD_RET_IF(!c, ECORD_E_PLAN);
+    ECORD_RET_IF(!actions || !nidx || !gidx, ECORD_E_NULL);
+    const size_t GT = (size_t)c->G * c->T;
+    ECORD_CUDA(cudaMemcpyAsync(c->arena + c->o_act, actions, GT * 8, cudaMemcpyHostToDevice, c->stream));
+    char *d = c->arena;
+    int rc = ecord_step_cy_device((const int64_t *)(d + c->o_act), (float *)(d + c->o_sc), (float *)(d + c->o_bs), (float *)(d + c->o_bst),
+                                  (float *)(d + c->o_nf), c->Fg > 0 ? (float *)(d + c->o_gf) : nullptr, nidx, gidx,
+                                  (const int32_t *)(d + c->o_e), (const float *)(d + c->o_w), (const int32_t *)(d + c->o_p), c->N, c->G,
+                                  c->T, c->Fn, c->Fg, c->E, c->stream);
+    if (rc) return rc;
+    if (scores_out) ECORD_CUDA(cudaMemcpyAsync(scores_out, d + c->o_sc, GT * 4, cudaMemcpyDeviceToHost, c->stream));
+    ECORD_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int ecord_step_cy_ctx_destroy(ecord_step_cy_ctx *c) {
+    if (!c) return 0;
+    if (c->arena) cudaFree(c->arena);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
 }

@@ -231,6 +231,23 @@ int ecord_step_cy_device(const int64_t *actions, float *scores, float *best_scor
                          int32_t num_nodes, int32_t num_graphs, int32_t num_tradj,
                          int32_t num_node_features, int32_t num_glob_features, int32_t num_edges, void *stream);
 
+/* B3 with a cached arena: ecord_step_cy() allocates, uploads every array, steps, downloads every array and frees on EVERY
+ * call (~2 x the state size over PCIe per step).  A context keeps the graph and the state on the device: create once per
+ * Tradjectories object (the CSR arrays are host buffers, uploaded once), upload the arrays after __init__ (any pointer may be
+ * NULL = skip), then per step only the actions [G][T] i64 go up and, optionally, the scores [G][T] come back; download()
+ * materialises the host arrays (any pointer may be NULL).  Same kernel, same bit-exact results as ecord_step_cy. */
+typedef struct ecord_step_cy_ctx ecord_step_cy_ctx;   /* opaque */
+int ecord_step_cy_ctx_create(int32_t num_nodes, int32_t num_graphs, int32_t num_tradj, int32_t num_node_features,
+                             int32_t num_glob_features, const int32_t *edges_by_node, const float *edge_attrs_by_node,
+                             const int32_t *edge_by_node_ptr, ecord_step_cy_ctx **out);
+int ecord_step_cy_ctx_upload(ecord_step_cy_ctx *ctx, const float *scores, const float *best_scores, const float *best_states,
+                             const float *node_features, const float *global_features);
+int ecord_step_cy_ctx_step(ecord_step_cy_ctx *ctx, const int64_t *actions, const int32_t *node_feature_idxs,
+                           const int32_t *glob_feature_idxs, float *scores_out /* host [G][T] or NULL */);
+int ecord_step_cy_ctx_download(ecord_step_cy_ctx *ctx, float *scores, float *best_scores, float *best_states,
+                               float *node_features, float *global_features);
+int ecord_step_cy_ctx_destroy(ecord_step_cy_ctx *ctx);
+
 /* ---- a2: initial scores / peeks from spin states; replaces Tradjectories.__init__ +
  *      _calc_scores_and_peeks (tradjectories.py:62-116,130-148).
  *      init_state: i8 [N][T] (reference layout), values in {0,1}. ---- */

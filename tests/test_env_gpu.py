@@ -47,6 +47,39 @@ def test_step_cy_dropin_is_bit_exact(lib, name):
     assert np.array_equal(bst, z[name + "/best_states"])
 
 
+@pytest.mark.parametrize("name", ["canon", "allfeat", "ragged"])
+def test_step_cy_cached_arena_is_bit_exact(lib, name):
+    """Seam B3 with the state kept on the device (ecord_step_cy_ctx_*): graph and arrays uploaded once, per step only the
+    actions go up and the scores come back; the arrays downloaded at the end equal the reference's, bit for bit."""
+    import ctypes as C
+    import time
+    z = load_gold("env_traces.npz")
+    ob = orc.build_batch(unpack_graphs(z, name + "/"))
+    T = int(z[name + "/T"])
+    nf, gf = z[name + "/init_node_features"].copy(), z[name + "/init_glob_features"].copy()
+    sc = z[name + "/init_scores"].copy()
+    bsc, bst = sc.copy(), z[name + "/init_state"].astype(np.float32).copy()
+    nidx, gidx = z[name + "/node_idx"].astype(np.int32), z[name + "/glob_idx"].astype(np.int32)
+    acts = z[name + "/actions"].astype(np.int64)
+    ctx = C.c_void_p()
+    assert lib.ecord_step_cy_ctx_create(ob.N, ob.G, T, nf.shape[-1], gf.shape[-1], _p(ob.edges_by_node), _p(ob.edge_w),
+                                        _p(ob.edge_ptr), C.byref(ctx)) == 0
+    assert lib.ecord_step_cy_ctx_upload(ctx, _p(sc), _p(bsc), _p(bst), _p(nf), _p(gf)) == 0
+    out = np.empty_like(sc)
+    t0 = time.perf_counter()
+    for s in range(acts.shape[0]):
+        a = np.ascontiguousarray(acts[s] + ob.ptr[:-1, None])
+        assert lib.ecord_step_cy_ctx_step(ctx, _p(a), _p(nidx), _p(gidx), _p(out)) == 0
+        assert np.array_equal(out, z[name + "/score_log"][s]), s
+    dt = (time.perf_counter() - t0) / acts.shape[0]
+    assert lib.ecord_step_cy_ctx_download(ctx, _p(sc), _p(bsc), _p(bst), _p(nf), _p(gf)) == 0
+    assert lib.ecord_step_cy_ctx_destroy(ctx) == 0
+    assert np.array_equal(nf, z[name + "/node_features"]) and np.array_equal(gf, z[name + "/glob_features"])
+    assert np.array_equal(bsc, z[name + "/best_scores"]) and np.array_equal(bst, z[name + "/best_states"])
+    assert np.array_equal(sc, z[name + "/score_log"][-1])
+    print(f"{name}: {dt * 1e6:.0f} us per cached-arena step (host call incl. actions H2D, scores D2H)")
+
+
 def test_step_cy_rejects_bad_tables(lib):
     a = np.zeros((1, 1), np.int64)
     f = np.zeros(4, np.float32)
