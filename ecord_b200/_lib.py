@@ -133,10 +133,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise EcordError(f"{LIB_PATH} not found: build it with `python -m ecord_b200.build` "
+    path = os.environ.get("ECORD_B200_LIB") or LIB_PATH      # diagnostics: a variant build of the same library (build.py -D...)
+    if not os.path.exists(path):
+        raise EcordError(f"{path} not found: build it with `python -m ecord_b200.build` "
                          "(there is no CPU / PyTorch fallback for the rollout path)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)   # AttributeError here = header/library drift
         fn.restype, fn.argtypes = res, args

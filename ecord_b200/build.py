@@ -30,15 +30,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: diagnostic variants (e.g. -DECORD_GRU_STAGES=6) built next to the product library and selected at run
+    time with ECORD_B200_LIB=<path> (see _lib.py)."""
+    if not force and not needs_build() and not defines and out is None:
         return LIB
     nvcc = _nvcc()
     objs = []
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + [f"-D{d}" for d in defines]
+    tag = ("_" + "_".join(d.replace("=", "") for d in defines)) if defines else ""
     for src in SOURCES:
-        obj = os.path.join(HERE, "_build", src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "_build", src.replace(".cu", tag + ".o"))
         cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
@@ -48,10 +51,13 @@ def build(force=False, verbose=False):
         with open(obj + ".ptxas.txt", "w") as f:
             f.write(r.stderr)
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    lib = out or LIB
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

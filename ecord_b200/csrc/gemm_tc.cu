@@ -242,6 +242,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUte
 //   - tmem_empty lives in the leader and collects the 8 epilogue warps of both CTAs (remote mbarrier arrive)
 // =================================================================================================
 constexpr int kStages2 = 4;      // the pair kernel's stages are 28-32 KB (half of B per CTA): six fit in 192 KB
+// kProducers TMA warps (warp 0 and, for kProducers > 1, the warps behind the epilogue; producer j takes the ring iterations
+// j, j + kProducers, ...).  A lone thread issuing every stage of a ring of tensor copies sustains 24-26 B/clk/SM with 64-byte
+// box rows and 31-34 B/clk/SM with 128-byte rows however deep the ring is, where two threads taking whole stages in turn reach
+// 52-55 and 72 B/clk/SM (tools/microbench/tma_ingest2d.cu, measured on the B200).  In THESE kernels a second producer changes
+// nothing (split GRU 97.2 vs 99 us): with the MMAs switched off the ring already moves 609 MB per launch in 50 us = 12.2 TB/s,
+// the L2 -> SM delivery limit of the chip, whatever the ring depth (3, 4, 5 stages: 49.7 / 50.2 / 50.0 us) -- so one it is.
+constexpr int kProducers = 1;
+constexpr int kEpiThreads = kThreads - 64;                    // 16 epilogue warps
+constexpr int kThreads2 = kThreads + 32 * (kProducers - 1);   // + the extra producer warps
 constexpr int kHsPitch = 68;     // floats per row of the fp32 epilogue staging tile (64 + 4: 16-byte aligned rows, 4-way STS.128)
 constexpr int kBsPitch = 72;     // bf16 per row of the two bf16 staging tiles (64 + 8)
 constexpr int kStageTileBytes = BM * kHsPitch * 4 + 2 * BM * kBsPitch * 2;      // 34816 + 36864 bytes
@@ -319,13 +328,16 @@ template <int MODE, int NS> __host__ __device__ constexpr int tc2_stage_bytes() 
 }
 // pipeline depth: the GRU split kernel needs its bytes in flight (TMA latency x 45 B/clk of ingest per SM): three stages cost
 // 10 us per launch against four; its epilogue stages one fp32 tile only (tanh is taken in the store pass), which pays for a fifth
-template <int MODE, int NS> __host__ __device__ constexpr int stages2() { return MODE == 2 ? 7 : (MODE == 0 && NS == 3) ? 5 : 4; }
+#ifndef ECORD_GRU_STAGES
+#define ECORD_GRU_STAGES 5
+#endif
+template <int MODE, int NS> __host__ __device__ constexpr int stages2() { return MODE == 2 ? 7 : (MODE == 0 && NS == 3) ? ECORD_GRU_STAGES : 4; }
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {      // K-major SWIZZLE_64B: 8-row groups 512 B apart
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
 template <int MODE, int NS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
            const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapB, TcParams prm, int num_tiles, int nblk) {
@@ -357,7 +369,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     const uint32_t tfull0 = smem_u32(&bars[2 * NST]), tempty0 = smem_u32(&bars[2 * NST + 2]);
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * (kThreads / 32 - 2)); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 2 * (kEpiThreads / 32)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -375,8 +387,8 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
     pdl_wait();                             // everything below reads / writes step data
     const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
 
-    if (warp == 0) {
-        // ===================== TMA producer (both CTAs) =====================
+    if (warp == 0 || warp >= kThreads / 32) {
+        // ===================== TMA producers (both CTAs): warp 0 and the warps behind the epilogue =====================
         // the whole warp walks the loop converged (uniform registers, no divergence bookkeeping); one elected lane issues
         {
             const CUtensorMap *mapA = (MODE == 0) ? (cur ? &mapA1 : &mapA0) : &mapA0;
@@ -385,10 +397,12 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
             }
             const uint32_t lfull0 = mapa_u32(full0, 0);            // the leader's full barriers
+            const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - kThreads / 32 + 1);     // this producer's turn in the ring
             uint32_t it = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = (tile / nblk) * (2 * BM) + (int)rank * BM, nb = tile % nblk;
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
+                    if (it % kProducers != me) continue;
                     const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);            // local: released by the leader's multicast commit
                     const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + PARTS * A_BYTES;
@@ -400,15 +414,19 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                         if (prm.debug & 4) {            // no TMA traffic: the leader completes the phase by itself
                             if (rank == 0) mbar_arrive_cta(full0 + 8 * s);
                         } else {
-                            if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * PARTS * (A_BYTES + n_rows / 2 * ROWB));
+                            // diagnostics: 32 = hi planes only (half the bytes), 64 = every cluster fetches tile (0, 0) (hot lines)
+                            const int parts = (prm.debug & 32) ? 1 : PARTS;
+                            const int m0d = (prm.debug & 64) ? (int)rank * BM : m0, b_rowd = (prm.debug & 64) ? (int)rank * (n_rows / 2) : b_row;
+                            if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * parts * (A_BYTES + n_rows / 2 * ROWB));
 #pragma unroll
                             for (int part = 0; part < PARTS; ++part) {
+                                if (part >= parts) break;
                                 if (first) {
-                                    tma_load_2d_pair(a_dst + part * A_BYTES, &mapU, lfull0 + 8 * s, kc, m0 + part * prm.rows_pad);
-                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapWu, lfull0 + 8 * s, kc, b_row + part * 4 * H);
+                                    tma_load_2d_pair(a_dst + part * A_BYTES, &mapU, lfull0 + 8 * s, kc, m0d + part * prm.rows_pad);
+                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapWu, lfull0 + 8 * s, kc, b_rowd + part * 4 * H);
                                 } else {
-                                    tma_load_2d_pair(a_dst + part * A_BYTES, mapA, lfull0 + 8 * s, kc, m0 + part * prm.rows_pad);
-                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapB, lfull0 + 8 * s, kc, b_row + part * B_PLANE);
+                                    tma_load_2d_pair(a_dst + part * A_BYTES, mapA, lfull0 + 8 * s, kc, m0d + part * prm.rows_pad);
+                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapB, lfull0 + 8 * s, kc, b_rowd + part * B_PLANE);
                                 }
                             }
                         }
@@ -488,7 +506,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 for (int i = 0; i < 4; ++i) {
                     const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m0 + r < prm.rows) v = *reinterpret_cast<const float4 *>(prm.hidden + (cur_off + m0 + r) * H + nb * 64 + 4 * c4);
+                    if (m0 + r < prm.rows && !(prm.debug & 128)) v = *reinterpret_cast<const float4 *>(prm.hidden + (cur_off + m0 + r) * H + nb * 64 + 4 * c4);
                     *reinterpret_cast<float4 *>(&Hs[r][4 * c4]) = v;
                 }
                 {   // this tile's 4 x 64 gate biases -> shared memory (read back as warp-uniform broadcasts)
@@ -498,11 +516,11 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                                                  : gsel == 1 ? prm.bih[H + j] + prm.bhh[H + j]
                                                  : gsel == 2 ? prm.bhh[2 * H + j] : prm.bih[2 * H + j];
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // staged state + biases visible
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // staged state + biases visible
                 float hv[16];
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(&Hs[rloc][part * 16 + i]);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // every thread holds its values: Hs is free again
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // every thread holds its values: Hs is free again
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (!(prm.debug & 2)) {
@@ -550,7 +568,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(ltempty0 + 8 * ab);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // the staged tiles are complete
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // the staged tiles are complete
                 // (2) coalesced stores: h' fp32 (two 256-byte row pieces per instruction), h' and tanh(h') bf16 (four 128-byte pieces)
                 float *hnew = const_cast<float *>(prm.hidden);
                 if (NS == 1) {
@@ -577,7 +595,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
-                        if (m0 + r < prm.rows) {
+                        if (m0 + r < prm.rows && !(prm.debug & 128)) {
                             const float4 hv4 = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
                             const float4 tv4 = make_float4(tanhf(hv4.x), tanhf(hv4.y), tanhf(hv4.z), tanhf(hv4.w));   // projection input
                             const size_t o = (size_t)(m0 + r) * H + nb * 64 + 4 * c4;
@@ -592,7 +610,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                         }
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // staging tiles are free for the next tile
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // staging tiles are free for the next tile
             } else {
                 // PROJ: bias added in registers, the tile staged in shared memory and stored with whole-line STGs (see above)
                 constexpr int PC = C::TILE_N / 4;                 // 44 columns per warp: 11 groups of 4
@@ -618,15 +636,15 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(ltempty0 + 8 * ab);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // the staged tile is complete
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // the staged tile is complete
                 constexpr int kPieces = C::TILE_N / 4;            // float4 pieces per row
-                for (int idx = e; idx < BM * kPieces; idx += kThreads - 64) {
+                for (int idx = e; idx < BM * kPieces; idx += kEpiThreads) {
                     const int r = idx / kPieces, c4 = idx - r * kPieces;
                     const int col = nb * C::TILE_N + 4 * c4;
                     if (m0 + r < prm.rows && col < ECORD_DIM_P1)
                         *reinterpret_cast<float4 *>(prm.y1 + (size_t)(m0 + r) * ECORD_DIM_P1 + col) = *reinterpret_cast<const float4 *>(&Ys[r][4 * c4]);
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");     // free for the next tile
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // free for the next tile
             }
         }
     }
@@ -884,10 +902,10 @@ int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_
         int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
         { const char *e = getenv("ECORD_TC_CLUSTERS"); if (e && atoi(e) > 0 && atoi(e) < clusters) clusters = atoi(e); }   // diagnostics
         if (split)
-            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 3>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0, 3>(), st, mU, mWu, mA0, mA1, mB,
+            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 3>), dim3(2 * clusters), dim3(kThreads2), (size_t)tc2_smem_bytes<0, 3>(), st, mU, mWu, mA0, mA1, mB,
                              prm, tiles2, nblk2);
         else
-            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 1>), dim3(2 * clusters), dim3(kThreads), (size_t)tc2_smem_bytes<0, 1>(), st, mU, mWu, mA0, mA1, mB,
+            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 1>), dim3(2 * clusters), dim3(kThreads2), (size_t)tc2_smem_bytes<0, 1>(), st, mU, mWu, mA0, mA1, mB,
                              prm, tiles2, nblk2);
         return 0;
     }
@@ -912,7 +930,7 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, int split, cu
     if (pair) {
         const int nblk2 = 3, tiles2 = nblk2 * (Mp / (2 * BM));
         const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        const dim3 grid(2 * clusters), block(kThreads);
+        const dim3 grid(2 * clusters), block(kThreads2);
 #define ECORD_PROJ_LAUNCH(MODE, NS) \
         ECORD_PDL_LAUNCH((k_gemm_tc2<MODE, NS>), grid, block, (size_t)tc2_smem_bytes<MODE, NS>(), st, mA, mB, mA, mA, mB, prm, tiles2, nblk2)
         if (tiles2 <= clusters) {        // one tile per CTA pair: deep pipeline, staging on top of the stages

@@ -577,13 +577,13 @@ class RolloutState:
 
     @_on_stream
     def score_log_host(self, num_steps):
-        """The first `num_steps` rows of the score log as a host tensor [S, G, T]: one D2H into a cached pinned
-        buffer, then a host copy (the caller owns the result)."""
+        """The first `num_steps` rows of the score log as a host tensor [S, G, T]: one D2H into a page-locked tensor
+        owned by the caller."""
         S, G, T = int(num_steps), self.g.G, self.T
-        host = self.g.pinned_buffer((self.max_steps, self.M))
-        host[:S].copy_(self.score_log[:S], non_blocking=True)
+        host = torch.empty((S, self.M), dtype=torch.float32, pin_memory=True)
+        host.copy_(self.score_log[:S], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return host[:S].clone().view(S, G, T)
+        return host.view(S, G, T)
 
     @_on_stream
     def best_from_log(self, num_steps):
@@ -593,9 +593,10 @@ class RolloutState:
         return out.view(self.g.G, self.T)
 
     @_on_stream
-    def best_states_batched(self, true_snapshot=False):
-        """[G, n_max, T], -1 padded (tradjectories.py:324-328,378-385).  true_snapshot=False gives the
-        reference's semantics (quirk D); True replays the action log up to each trajectory's best step."""
+    def best_states_device(self, true_snapshot=False):
+        """[G, n_max, T] f32 on the device, -1 padded (tradjectories.py:324-328,378-385).  true_snapshot=False gives the
+        reference's semantics (quirk D); True replays the action log up to each trajectory's best step.  The result is a
+        cached buffer: consume (copy) it before the next call."""
         N, G, T = self.g.N, self.g.G, self.T
         if true_snapshot and not self.compat:
             # compat=False keeps the best-state plane as a true snapshot on the device (ecord_env.true_snapshot): greedy
@@ -614,13 +615,19 @@ class RolloutState:
             flat = self.plane_to_nt(plane.float())
         else:
             flat = self.export(nodes=False)[2]
-        # pad to [G, n_max, T] on the device (one index_copy into a cached buffer whose padding rows stay -1), then a
-        # single D2H into a cached pinned buffer
+        if G * self.g.n_max == N:          # equal-sized graphs: [N, T] is [G, n_max, T] already
+            return flat.view(G, self.g.n_max, T)
+        # ragged batch: pad on the device (one index_copy into a cached buffer whose padding rows stay -1)
         if getattr(self, "_pad", None) is None:
             self._pad = torch.full((G * self.g.n_max, T), -1.0, dtype=torch.float32, device=self.device)
         pad = self._pad
         pad.index_copy_(0, self.g.padded_row_index(), flat)
-        host = self.g.pinned_buffer((G, self.g.n_max, T))
-        host.copy_(pad.view(G, self.g.n_max, T), non_blocking=True)
+        return pad.view(G, self.g.n_max, T)
+
+    def best_states_batched(self, true_snapshot=False):
+        """best_states_device() on the host (a page-locked tensor owned by the caller)."""
+        dev = self.best_states_device(true_snapshot)
+        host = torch.empty(dev.shape, dtype=dev.dtype, pin_memory=True)
+        host.copy_(dev, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return host.clone()
+        return host
