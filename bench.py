@@ -253,6 +253,10 @@ def run_b200(args):
     weights = DeviceWeights(sd, dev)
     dg = DeviceGraph(batch.tg, dev)
     k = args.steps_per_graph
+    if K % k and K <= 2 * k:
+        # short runs (the driver's --steps 20): equal chunks instead of one full graph plus a short remainder whose cold start
+        # would be amortised over a handful of steps only
+        k = -(-K // -(-K // k))
     st = RolloutState(dg, weights, T, gemm=args.gemm, compat=True, max_steps=W + K + k, steps_per_graph=k)
     st.gnn_embed()
     st.env_init(init)
@@ -319,17 +323,23 @@ def run_b200(args):
             traffic_tab = {}
 
         def timed(fn, n=reps):
+            """Mean duration of one launch, L2 flushed before each.  The events and the kernel are enqueued while a ~150 us
+            spin kernel still runs ahead of them on the rollout stream, so that the host's launch path (ctypes call, tensor-map
+            encoding) is not inside the event pair; the median-of-n guards against a stray long launch."""
             fn(); torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            tot = 0.0
+            ts = []
             for _ in range(n):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 flush.fill_(1)
                 st.stream.wait_stream(torch.cuda.current_stream())     # the flush has finished before the kernel starts
                 with torch.cuda.stream(st.stream):
+                    torch.cuda._sleep(300000)
                     a.record(); fn(); b.record()
                 b.synchronize()
-                tot += a.elapsed_time(b)
-            return tot / n
+                ts.append(a.elapsed_time(b))
+            ts.sort()
+            mid = ts[len(ts) // 4: len(ts) - len(ts) // 4]          # interquartile mean
+            return sum(mid) / len(mid)
 
         sp = C.c_void_p(st.stream.cuda_stream)
 
@@ -426,8 +436,10 @@ def run_b200(args):
     Ke = K
     # warm-up call of the same shape: the solver keeps the device state of a graph batch (buffers, pinned staging, captured
     # CUDA graphs) and re-initialises it on the next call, which is the steady state of test_solver's trajectory chunks
-    solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=init)
     pinned = torch.from_numpy(init).pin_memory()
+    log = None
+    for _ in range(3):                  # (three of them: the page-locked result buffers of a live log plus the next call's)
+        log = solver.rollout(batch, num_tradj=T, num_steps=Ke, tau=0, use_epsilon=False, init_state=pinned.numpy())
     e2e_times = []
     for _ in range(3):                  # median of three calls
         barrier()
@@ -466,7 +478,7 @@ def run_b200(args):
                           "l2": "flushed (256 MB write) before every CUDA-graph launch of %d steps, outside the timed events" % k,
                           "weights": "random-init canonical ECORD network (seed 0)"},
                "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "note": "B200Solver.rollout incl. GNN, env init, H2D init states, D2H score log and best states; median of 3 calls after one warm-up call of the same shape (device state of the batch reused)",
+                       "note": "B200Solver.rollout incl. GNN, env init, H2D init states, D2H score log and best states; median of 3 calls after three warm-up calls of the same shape (device state of the batch and the page-locked result buffers reused)",
                        "calls_s": e2e_times, "device_s_last_call": e2e_dev},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
                "wall_s_timed_region": t_wall, "best_cut_mean": float(best.mean().item())}

@@ -8,12 +8,16 @@
 // LN is PyG's LayerNorm(affine=False) called without `batch` (gnn_embedder.py:178,194,199): statistics
 // over ALL vertices of ALL graphs in the batch (quirk B):  (x - mean) / (std_pop + 1e-5).
 //
-// Shape of the work: N x 16 activations, E edge messages of 16 channels; one-off per rollout and tiny
-// next to the S-step loop, so the design goal is exactness of summation order (incoming edges are
-// accumulated sequentially in global edge order, as scatter_add does on the CPU), not peak bandwidth:
-// one thread per vertex gathers its incoming CSR row (16 consecutive floats per neighbour = one
-// 64-byte segment), weights staged once per block in shared memory.  Batch-wide LN sums are
-// block-reduced and accumulated in fp64 atomics.
+// Shape of the work: N x 16 activations, E edge messages of 16 channels; one-off per rollout.  Exactness of the summation
+// order comes first (incoming edges are accumulated sequentially in global edge order, as scatter_add does on the CPU), so
+// the aggregation is parallel over vertices and CHANNELS, never over the edges of a vertex:
+//   k_gnn_aggregate  sixteen lanes per vertex (lane <-> channel): a half-warp reads 16 (src, w) pairs with one coalesced
+//                    load each, issues the 16 neighbour-row loads (64 contiguous bytes per neighbour, L2 hits) back to back
+//                    and only then runs the 16 dependent adds -- the round-1 kernel (one thread per vertex, in_src -> row
+//                    address -> 4 x LDG.128 -> adds, every edge two serial L2 round trips) took 84 us per layer at ER500
+//   k_gnn_update     one thread per vertex: receive layer + GRUCell (3.3 K FMA, weights staged once per block)
+//   k_gnn_ln_send    batch-wide LayerNorm of the previous layer fused with the send layer; k_gnn_finish normalises on read
+// Batch-wide LN sums are block-reduced and accumulated in fp64 atomics.
 #include "common.cuh"
 
 namespace {
@@ -61,31 +65,36 @@ __global__ void k_gnn_embed0(int N, const float *__restrict__ ew, const float *_
     block_accumulate(s, ss, acc);
 }
 
-// x <- (x - mean) / (std_pop + eps), batch-wide
-__global__ void k_gnn_ln(int N, float *x, const double *acc) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)N * D) return;
+// batch-wide LayerNorm statistics from the fp64 sums: x <- (x - mean) / (std_pop + eps)
+struct LnStat { float mean, denom; };
+__device__ __forceinline__ LnStat ln_stat(int N, const double *acc) {
     const double cnt = (double)N * D;
     const double mean = acc[0] / cnt;
     double var = acc[1] / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float meanf = (float)mean, stdf = (float)sqrt(var);
-    const float c = x[i] - meanf;
-    x[i] = c / (stdf + kLnEps);
+    LnStat s;
+    s.mean = (float)mean;
+    s.denom = (float)sqrt(var) + kLnEps;
+    return s;
 }
 
-// y = LReLU(W_s x + b_s)
-__global__ void k_gnn_send(int N, const float *__restrict__ x, const float *__restrict__ sw, const float *__restrict__ sb,
-                           float *y) {
+// x <- LN(x) (in place), y = LReLU(W_s x + b_s)
+__global__ void k_gnn_ln_send(int N, float *x, const double *acc, const float *__restrict__ sw, const float *__restrict__ sb,
+                              float *y) {
     __shared__ float w[D * D], b[D];
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) w[i] = sw[i];
     if (threadIdx.x < D) b[threadIdx.x] = sb[threadIdx.x];
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N) return;
+    const LnStat st = ln_stat(N, acc);
     float xi[D];
 #pragma unroll
     for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(&xi[c]) = *reinterpret_cast<const float4 *>(&x[(long long)v * D + c]);
+#pragma unroll
+    for (int c = 0; c < D; ++c) xi[c] = (xi[c] - st.mean) / st.denom;
+#pragma unroll
+    for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(&x[(long long)v * D + c]) = *reinterpret_cast<float4 *>(&xi[c]);
 #pragma unroll
     for (int o = 0; o < D; ++o) {
         float a = b[o];
@@ -95,8 +104,38 @@ __global__ void k_gnn_send(int N, const float *__restrict__ x, const float *__re
     }
 }
 
-// aggregate + receive + GRUCell; writes the pre-LN x_new and accumulates the LN sums
-__global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const float *__restrict__ y,
+// m_i = mean_{j -> i} w_ji y_j.  Sixteen lanes per vertex, lane <-> channel; the edges of a vertex stay in global edge order
+// and every channel's sum is sequential (product rounded separately, as the reference's `y[row] * edge_attr` then scatter_add).
+__global__ void __launch_bounds__(128)
+k_gnn_aggregate(ecord_graph g, const float *__restrict__ y, float *__restrict__ msg) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = (int)(gt >> 4), c = (int)(gt & 15);
+    const int vv = min(v, g.num_nodes - 1);
+    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);          // this vertex's half-warp
+    const int k0 = g.in_ptr[vv], k1 = g.in_ptr[vv + 1];
+    float acc = 0.0f;
+    for (int kb = k0; kb < k1; kb += 16) {                         // (trip count uniform within the half-warp)
+        const int kk = kb + c;
+        const int s = kk < k1 ? g.in_src[kk] : 0;
+        const float wv = kk < k1 ? g.in_w[kk] : 0.0f;
+        const int cnt = min(16, k1 - kb);
+        float yv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int sj = __shfl_sync(mask, s, j, 16);
+            yv[j] = j < cnt ? y[(long long)sj * D + c] : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float wj = __shfl_sync(mask, wv, j, 16);
+            if (j < cnt) acc = __fadd_rn(acc, __fmul_rn(yv[j], wj));
+        }
+    }
+    if (v < g.num_nodes) msg[(long long)v * D + c] = acc / (float)max(k1 - k0, 1);    // scatter_mean: count clamped to >= 1
+}
+
+// receive + GRUCell on [msg ; x]; writes the pre-LN x_new and accumulates the LN sums
+__global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const float *__restrict__ msg,
                              float *xn, double *acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GnnSmem &S = *reinterpret_cast<GnnSmem *>(smem_raw);
@@ -111,24 +150,10 @@ __global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__res
     if (v < g.num_nodes) {
         float in[2 * D];   // [msg ; x]
 #pragma unroll
-        for (int c = 0; c < D; ++c) in[c] = 0.0f;
-        const int k0 = g.in_ptr[v], k1 = g.in_ptr[v + 1];
-        for (int k = k0; k < k1; ++k) {             // sequential, global edge order (scatter_add on CPU)
-            const float wk = g.in_w[k];
-            const float *yj = y + (long long)g.in_src[k] * D;
-#pragma unroll
-            for (int c = 0; c < D; c += 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(yj + c);
-                // product rounded separately, as the reference's `y[row] * edge_attr` then scatter_add does
-                in[c + 0] = __fadd_rn(in[c + 0], __fmul_rn(t.x, wk)); in[c + 1] = __fadd_rn(in[c + 1], __fmul_rn(t.y, wk));
-                in[c + 2] = __fadd_rn(in[c + 2], __fmul_rn(t.z, wk)); in[c + 3] = __fadd_rn(in[c + 3], __fmul_rn(t.w, wk));
-            }
+        for (int c = 0; c < D; c += 4) {
+            *reinterpret_cast<float4 *>(&in[c]) = *reinterpret_cast<const float4 *>(&msg[(long long)v * D + c]);
+            *reinterpret_cast<float4 *>(&in[D + c]) = *reinterpret_cast<const float4 *>(&x[(long long)v * D + c]);
         }
-        const float cnt = (float)max(k1 - k0, 1);    // scatter_mean: count clamped to >= 1
-#pragma unroll
-        for (int c = 0; c < D; ++c) in[c] = in[c] / cnt;
-#pragma unroll
-        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(&in[D + c]) = *reinterpret_cast<const float4 *>(&x[(long long)v * D + c]);
         float r[2 * D];    // LReLU(W_r [msg;x] + b_r)
 #pragma unroll
         for (int o = 0; o < 2 * D; ++o) {
@@ -163,7 +188,8 @@ __global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__res
 }
 
 // node_emb = W_g x + b_g ; node_B = Wq[:,32:48] node_emb + Wq[:,48:64] b_enc
-__global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ x, float *gnn_out, float *node_emb,
+// (x is the last layer's pre-LN output: the batch-wide LayerNorm is applied on read)
+__global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ x, const double *acc, float *gnn_out, float *node_emb,
                              float *node_B, float *node_Bc, float *node_LB, float *node_qv) {
     __shared__ float gw[D * D], gb[D], qb[ECORD_DIM_Q * D], qd[ECORD_DIM_Q];
     for (int i = threadIdx.x; i < D * D; i += blockDim.x) gw[i] = wt.g2r_w[i];
@@ -177,9 +203,13 @@ __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ 
     __syncthreads();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N) return;
+    const LnStat st = ln_stat(N, acc);
     float xi[D], e[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) { xi[c] = x[(long long)v * D + c]; if (gnn_out) gnn_out[(long long)v * D + c] = xi[c]; }
+    for (int c = 0; c < D; ++c) {
+        xi[c] = (x[(long long)v * D + c] - st.mean) / st.denom;
+        if (gnn_out) gnn_out[(long long)v * D + c] = xi[c];
+    }
 #pragma unroll
     for (int o = 0; o < D; ++o) {
         float a = gb[o];
@@ -228,7 +258,7 @@ __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ 
 
 extern "C" size_t ecord_gnn_workspace_bytes(int32_t N) {
     if (N <= 0) return 0;
-    return (size_t)3 * N * D * sizeof(float) + 256 + 16 * sizeof(double);
+    return (size_t)4 * N * D * sizeof(float) + 256 + 16 * sizeof(double);
 }
 
 extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
@@ -244,24 +274,23 @@ extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, flo
     float *x = reinterpret_cast<float *>(workspace);
     float *y = x + (size_t)N * D;
     float *xn = y + (size_t)N * D;
-    double *acc = reinterpret_cast<double *>(((uintptr_t)(xn + (size_t)N * D) + 255) & ~(uintptr_t)255);
+    double *acc = reinterpret_cast<double *>(((uintptr_t)(xn + (size_t)2 * N * D) + 255) & ~(uintptr_t)255);
     ECORD_CUDA(cudaMemsetAsync(acc, 0, 16 * sizeof(double), st));
     const int TB = 128, nb = ceil_div(N, TB);
     k_gnn_embed0<<<nb, TB, 0, st>>>(N, w->gnn_embed_w, w->gnn_embed_b, x, acc);
     ECORD_LAUNCH_CHECK();
-    k_gnn_ln<<<ceil_div((long long)N * D, 256), 256, 0, st>>>(N, x, acc);
-    ECORD_LAUNCH_CHECK();
     float *cur = x, *nxt = xn;
+    float *msg = xn + (size_t)N * D;                          // fourth N x 16 array of the workspace
     for (int l = 0; l < 4; ++l) {   // num_layers is hard-coded to 4 by experiments/configs.py:99
-        k_gnn_send<<<nb, TB, 0, st>>>(N, cur, w->gnn_snd_w, w->gnn_snd_b, y);
+        k_gnn_ln_send<<<nb, TB, 0, st>>>(N, cur, acc + 2 * l, w->gnn_snd_w, w->gnn_snd_b, y);
         ECORD_LAUNCH_CHECK();
-        k_gnn_update<<<nb, TB, sizeof(GnnSmem), st>>>(*g, *w, cur, y, nxt, acc + 2 * (l + 1));
+        k_gnn_aggregate<<<ceil_div((long long)N * D, 128), 128, 0, st>>>(*g, y, msg);
         ECORD_LAUNCH_CHECK();
-        k_gnn_ln<<<ceil_div((long long)N * D, 256), 256, 0, st>>>(N, nxt, acc + 2 * (l + 1));
+        k_gnn_update<<<nb, TB, sizeof(GnnSmem), st>>>(*g, *w, cur, msg, nxt, acc + 2 * (l + 1));
         ECORD_LAUNCH_CHECK();
         float *t = cur; cur = nxt; nxt = t;
     }
-    k_gnn_finish<<<nb, TB, 0, st>>>(N, *w, cur, gnn_out, node_emb, node_B, node_Bc, node_LB, node_qv);
+    k_gnn_finish<<<nb, TB, 0, st>>>(N, *w, cur, acc + 8, gnn_out, node_emb, node_B, node_Bc, node_LB, node_qv);
     ECORD_LAUNCH_CHECK();
     return 0;
 }

@@ -104,6 +104,21 @@ class TgBatch:
     def num_edges(self):
         return self.np_src.shape[0]
 
+    def select(self, graph_ids):
+        """A new batch made of the given graphs of this one, in the given order (graph sharding, dist.py)."""
+        ptr, epos = self.np_ptr, np.concatenate([[0], np.cumsum(self.np_edge_counts)])
+        els = []
+        for g in graph_ids:
+            e0, e1 = int(epos[g]), int(epos[g + 1])
+            els.append(EdgeListGraph(int(ptr[g + 1] - ptr[g]), self.np_src[e0:e1] - ptr[g], self.np_dst[e0:e1] - ptr[g],
+                                     self.np_w[e0:e1]))
+        return TgBatch(els)
+
+    def vertex_index(self, graph_ids):
+        """int64 [n]: the vertices of the given graphs (in that order) as indices into this batch."""
+        ptr = self.np_ptr
+        return np.concatenate([np.arange(ptr[g], ptr[g + 1]) for g in graph_ids]) if len(graph_ids) else np.zeros(0, np.int64)
+
     @classmethod
     def from_reference_batch(cls, tg):
         """A batch collated by the REFERENCE's own GraphBatcher (a torch_geometric `Batch`: edge_index i64[2,E] with

@@ -5,7 +5,9 @@ Every (graph, trajectory) unit is independent for all S steps (GRU state per (g,
 rank r runs trajectories [lo_r, hi_r) of the SAME graphs.  All ranks hold the whole batch's CSR and run the
 tiny t=0 GNN redundantly, which keeps its batch-wide LayerNorm statistics identical to the single-GPU run
 (quirk B).  Initial spins are drawn once for the global [N, T] array and sliced, so results do not depend
-on the number of GPUs.  The only communication is at the END of the rollout:
+on the number of GPUs.  (Graph sharding -- `rollout_graph_sharded`: every rank rolls out all trajectories of a contiguous
+range of graphs, for sets of many small graphs -- is the other axis; see graph_shard() for what quirk A asks of it.)
+The only communication is at the END of the rollout:
     one all_gather of the per-trajectory best  f32[G, T_local]   (needed for scores_mean, testing.py:201-204);
     the per-graph best cut f32[G] is the maximum of the gathered values
 over NCCL (NVLink/NVSwitch) on GPUs, or gloo in the CPU tests.  Payloads are KBs.
@@ -42,6 +44,77 @@ def reduce_best(best_by_tradj_local, total_tradj, group=None):
         cols.append(gathered[r, :, :hi - lo])
     by_all = torch.cat(cols, dim=1)
     return by_all.max(-1).values, by_all
+
+
+def graph_shard(num_nodes_list, world_size, rank, compat=True):
+    """Graph sharding: (subset, own) -- `own` = the contiguous, balanced range of graphs whose results this rank reports,
+    `subset` = the graphs it has to roll out for that, in order.
+
+    With quirk A on (compat, the reference's behaviour: actors/ecord.py:183-193 gathers the cached embedding of the chosen
+    vertex with its LOCAL index used as a batch-wide one) a unit of graph g reads the state of vertex a < n_g of the BATCH,
+    i.e. of the leading graphs that cover vertex indices [0, n_g).  Those graphs evolve on their own (their quirk-A reads
+    stay inside the same prefix), so a rank reproduces the single-GPU rollout of its graphs exactly by rolling the prefix
+    out as well, in front of its own graphs, and dropping the prefix's results.  compat=False needs no prefix."""
+    n = [int(x) for x in num_nodes_list]
+    lo, hi = shard_bounds(len(n), world_size, rank)
+    own = list(range(lo, hi))
+    if not own:
+        return [], []
+    prefix = []
+    if compat:
+        need, covered, g = max(n[lo:hi]), 0, 0
+        while covered < need:
+            prefix.append(g)
+            covered += n[g]
+            g += 1
+    subset = prefix + [g for g in own if g not in set(prefix)]
+    return subset, own
+
+
+def gather_graph_shards(local, num_graphs, group=None):
+    """local: f32 [G_own, ...] rows of this rank's own graphs (contiguous, balanced split).  Returns [num_graphs, ...] on
+    every rank: ONE all_gather of shards padded to the largest."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    g_max = -(-int(num_graphs) // world)
+    pad = torch.zeros((g_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * g_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    out = out.view((world, g_max) + tuple(local.shape[1:]))
+    rows = []
+    for r in range(world):
+        lo, hi = shard_bounds(num_graphs, world, r)
+        rows.append(out[r, :hi - lo])
+    return torch.cat(rows, dim=0)
+
+
+def rollout_graph_sharded(solver, batch, num_tradj, num_steps, init_state, tau=0.0, group=None, world_size=None, rank=None):
+    """Run this rank's GRAPH shard of a rollout (all trajectories of a contiguous range of graphs; for many-small-graph sets,
+    where a trajectory shard would leave too few rows per GPU) and gather the per-graph results.  `init_state` is the GLOBAL
+    int8 [N, num_tradj] array.  world_size / rank override the process group's (single-process checks)."""
+    if world_size is None:
+        world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    tg = batch.tg
+    n_list = tg.num_nodes_list if hasattr(tg, "num_nodes_list") else (tg.ptr[1:] - tg.ptr[:-1]).tolist()
+    G = len(n_list)
+    subset, own = graph_shard(n_list, world_size, rank, compat=solver.compat)
+    if not own:
+        by_tradj = torch.zeros(0, num_tradj, device=solver.device)
+        log = {}
+    else:
+        log = solver.rollout(batch, num_tradj=num_tradj, num_steps=num_steps, tau=tau, use_epsilon=False,
+                             init_state=init_state, graph_subset=subset)
+        keep = torch.as_tensor([subset.index(g) for g in own])
+        by_tradj = log['best_score_by_tradj'][keep].to(solver.device)
+        log['graph_subset'], log['graphs_own'] = [subset], [own]
+    by_all = gather_graph_shards(by_tradj, G, group)
+    log['scores_max'] = by_all.max(-1).values.cpu()
+    log['scores_mean'] = by_all.mean(-1).cpu()
+    log['scores_by_tradj'] = by_all.cpu()
+    return log
 
 
 def rollout_sharded(solver, batch, num_tradj, num_steps, init_state, tau=0.0, group=None):

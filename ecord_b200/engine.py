@@ -287,8 +287,28 @@ class RolloutState:
                                        ptr(self.node_B), ptr(self.node_Bc), ptr(self.node_LB), ptr(self.node_qv), ptr(ws),
                                        _stream()),
               "ecord_gnn_embed")
-        self.kernel_launches += 16
+        self.kernel_launches += 14
         self._ws = ws
+
+    @_on_stream
+    def gnn_embed_from(self, full_graph, vertex_index):
+        """t=0 embedding of a SUB-batch (graph sharding, dist.py): the GNN runs over `full_graph` (the DeviceGraph of the whole
+        batch, whose batch-wide LayerNorm statistics the reference's embedding depends on -- quirk B) and the rows of this
+        state's vertices (`vertex_index` i64 [N_sub] on the device, indices into the full batch) are gathered."""
+        fg = full_graph
+        f32 = dict(dtype=torch.float32, device=self.device)
+        full = dict(gnn_out=torch.empty(fg.N, 16, **f32), node_emb=torch.empty(fg.N, 16, **f32), node_B=torch.empty(fg.N, 64, **f32),
+                    node_Bc=torch.empty(fg.N, 64, **f32) if self.node_Bc is not None else None,
+                    node_LB=torch.empty(fg.N, **f32) if self.node_LB is not None else None,
+                    node_qv=torch.empty(fg.N, 8, **f32) if self.node_qv is not None else None)
+        ws = torch.empty(self.lib.ecord_gnn_workspace_bytes(fg.N), dtype=torch.uint8, device=self.device)
+        check(self.lib.ecord_gnn_embed(C.byref(fg.c), C.byref(self.w.c), ptr(full['gnn_out']), ptr(full['node_emb']),
+                                       ptr(full['node_B']), ptr(full['node_Bc']), ptr(full['node_LB']), ptr(full['node_qv']),
+                                       ptr(ws), _stream()), "ecord_gnn_embed")
+        self.kernel_launches += 14
+        for name, src in full.items():
+            if src is not None:
+                torch.index_select(src, 0, vertex_index, out=getattr(self, name))
 
     @_on_stream
     def env_init(self, init_state):

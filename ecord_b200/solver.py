@@ -79,6 +79,7 @@ class B200Solver:
         self.actor = _ActorShim(self)
         self._last_state = None
         self._graph_cache = (None, None)
+        self._subgraph_cache = {}
         self._state_cache = []
         self._net_init_draws = 0
 
@@ -148,7 +149,19 @@ class B200Solver:
             return self._graph_cache[1]
         dg = DeviceGraph(as_tg_batch(tg), self.device)     # our TgBatch, or the reference batcher's torch_geometric Batch
         self._graph_cache = (tg, dg)
+        self._subgraph_cache = {}
         return dg
+
+    def _device_subgraph(self, batch, graph_subset):
+        """(DeviceGraph of the sub-batch, its vertices as indices into the full batch: numpy and device)."""
+        key = tuple(int(g) for g in graph_subset)
+        hit = self._subgraph_cache.get(key)
+        if hit is None:
+            tg = as_tg_batch(batch.tg)
+            vidx = tg.vertex_index(key)
+            hit = (DeviceGraph(tg.select(key), self.device), vidx, torch.from_numpy(vidx).to(self.device))
+            self._subgraph_cache = {key: hit}
+        return hit
 
     def get_epsilon(self):
         """The reference's linear schedule over parameter steps (solver.py:184-186)."""
@@ -178,11 +191,15 @@ class B200Solver:
     @torch.no_grad()
     def rollout(self, batch, num_tradj=1, num_steps=-1, log_stats=False, callbacks=None, use_epsilon=True,
                 use_network_initialisation=False, tau=None, max_time=None, pre_solve_with_greedy=False,
-                post_solve_with_greedy_from_best=False, init_state=None, gemm=None, traj_slice=None):
+                post_solve_with_greedy_from_best=False, init_state=None, gemm=None, traj_slice=None, graph_subset=None):
         """Same contract as DQNSolver.rollout (solver.py:196-377) for the test-time path.
         Extra keywords: init_state (int8 [N, num_tradj]) pins the initial spins (the reference draws them
         from numpy's global RNG, tradjectories.py:64 -- reproduced here when init_state is None);
-        traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU sharding).
+        traj_slice=(lo, hi) runs only trajectories lo..hi of that initial state (multi-GPU trajectory sharding);
+        graph_subset=[g0, g1, ...] rolls out only those graphs of the batch, in that order (multi-GPU graph sharding,
+        dist.py): the t=0 GNN still runs over the WHOLE batch, because its LayerNorm statistics are batch-wide (quirk B), and
+        init_state stays the [N, num_tradj] array of the whole batch; every [G, ...] entry of the log then has one row per
+        graph of the subset.
         use_epsilon=True applies the epsilon-greedy exploration of actors/ecord.py:171-180 with epsilon =
         get_epsilon() (solver.py:184-186,334), drawn on the device; validation passes use_epsilon=False."""
         tau = self.tau if tau is None else tau
@@ -193,9 +210,14 @@ class B200Solver:
         N, G = dg.N, dg.G
         num_graphs = len(batch.info.num_nodes) if batch.info is not None else G
         assert num_graphs == G
+        dg_full, sub_vidx = dg, None
+        if graph_subset is not None:
+            if use_network_initialisation and self.node_classifier is not None and init_state is None:
+                raise NotImplementedError("graph_subset with use_network_initialisation: pass init_state")
+            dg, sub_vidx_np, sub_vidx = self._device_subgraph(batch, graph_subset)
 
         if num_steps < 0:
-            S = int(abs(num_steps) * int(np.max(dg.num_nodes_list)))   # loop runs to the max (solver.py:306-316)
+            S = int(abs(num_steps) * int(np.max(dg_full.num_nodes_list)))   # loop runs to the max (solver.py:306-316)
         else:
             S = int(num_steps)
 
@@ -215,6 +237,9 @@ class B200Solver:
                 init_state = np.asarray(init_state, dtype=np.int8)
             if traj_slice is not None:
                 init_state = np.ascontiguousarray(init_state[:, traj_slice[0]:traj_slice[1]])
+            if sub_vidx is not None:
+                init_state = np.ascontiguousarray(init_state[sub_vidx_np])
+                N, G = dg.N, dg.G
             T = init_state.shape[1]
 
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -225,7 +250,10 @@ class B200Solver:
         seed = self.seed if traj_slice is None else self.seed + 1000003 * int(traj_slice[0])
         state = self._rollout_state(dg, T, gemm or self.gemm, tau, S, epsilon, seed)
         ev[0].record()
-        state.gnn_embed()
+        if sub_vidx is None:
+            state.gnn_embed()
+        else:
+            state.gnn_embed_from(dg_full, sub_vidx)
         ev[1].record()
         if from_network:
             hw, hb = self.node_classifier

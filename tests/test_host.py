@@ -189,6 +189,42 @@ def test_shard_bounds_partition():
         assert max(sizes) - min(sizes) <= 1
 
 
+def test_graph_shard_covers_quirk_a_prefix():
+    """Graph sharding (dist.graph_shard): own ranges partition the graphs; with quirk A the subset starts with the leading
+    graphs that cover vertex indices [0, max n of the own graphs), so that local-as-global indices resolve as in the full batch."""
+    from ecord_b200.dist import graph_shard
+    for sizes, world in (([500] * 100, 8), ([40, 30, 50, 20, 60, 10], 3), ([10, 100, 20], 3), ([5, 5], 4)):
+        owned = []
+        ptr = np.concatenate([[0], np.cumsum(sizes)])
+        for r in range(world):
+            subset, own = graph_shard(sizes, world, r, compat=True)
+            owned += own
+            if not own:
+                assert subset == []
+                continue
+            k = 0
+            while k < len(subset) and subset[k] == k:
+                k += 1                                         # leading graphs 0..k-1 are in place
+            assert ptr[k] >= max(sizes[g] for g in own)
+            assert [g for g in subset if g in own] == own and len(set(subset)) == len(subset)
+            assert graph_shard(sizes, world, r, compat=False) == (own, own)
+        assert owned == list(range(len(sizes)))
+
+
+def test_tg_batch_select_roundtrip():
+    rs = np.random.RandomState(3)
+    graphs = []
+    for n in (7, 4, 9, 5):
+        a = np.triu((rs.rand(n, n) < 0.5) * rs.choice([-1.0, 1.0], (n, n)), 1)
+        graphs.append(a + a.T)
+    tg = GraphBatcher()(graphs).tg
+    sub = tg.select([0, 2, 3])
+    ref = GraphBatcher()([graphs[0], graphs[2], graphs[3]]).tg
+    assert np.array_equal(sub.np_src, ref.np_src) and np.array_equal(sub.np_dst, ref.np_dst) and np.array_equal(sub.np_w, ref.np_w)
+    assert np.array_equal(sub.np_ptr, ref.np_ptr)
+    assert np.array_equal(tg.vertex_index([2, 0]), np.concatenate([np.arange(11, 20), np.arange(0, 7)]))
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, sys.argv[1])
@@ -202,6 +238,9 @@ lo, hi = shard_bounds(T, 2, rank)
 best, by_all = reduce_best(full[:, lo:hi].contiguous(), T)
 assert torch.equal(by_all, full), (rank, by_all)
 assert torch.equal(best, full.max(-1).values)
+from ecord_b200.dist import gather_graph_shards
+glo, ghi = shard_bounds(G, 2, rank)                  # graph sharding: 3 + 2 graphs
+assert torch.equal(gather_graph_shards(full[glo:ghi].contiguous(), G), full)
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''

@@ -561,3 +561,37 @@ def test_training_mode_rollout_feeds_callbacks_like_the_reference():
         assert calls == [3, 7]
         solver.test()
         assert not solver.is_training
+
+
+@pytest.mark.parametrize("gemm,compat,ragged", [("bf16x3", True, False), ("bf16x3", True, True), ("fp32", True, True),
+                                                ("bf16x3", False, True)])
+def test_graph_sharding_reproduces_the_full_batch_rollout(gemm, compat, ragged):
+    """SURVEY.md 8e, graph axis (dist.rollout_graph_sharded): every simulated rank rolls out its own graphs (behind the
+    quirk-A prefix) with the GNN embedding of the WHOLE batch (quirk B: batch-wide LayerNorm statistics); the per-trajectory
+    scores of every step, the best cuts and the best states of its own graphs must equal the single-GPU rollout bit for bit,
+    for 1, 2, 3 and 5 ranks."""
+    from ecord_b200.dist import graph_shard, rollout_graph_sharded
+    sd = random_state_dicts(5, perturb_norms=True)
+    ns = [40, 27, 64, 33, 50, 21, 45] if ragged else [36] * 7
+    graphs = [g for n in ns for g in synthetic_set("er", n, 1, seed0=n, p=0.2, signed=True)]
+    batch = GraphBatcher()(graphs)
+    T, S = 6, 40
+    init = np.random.RandomState(7).randint(0, 2, (batch.tg.num_nodes, T), dtype=np.int8)
+    solver = _solver(sd, gemm=gemm, compat=compat)
+    full = solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init)
+    full_scores = torch.stack(full['scores'], -1)                     # [G, T, S]
+    for world in (1, 2, 3, 5):
+        seen = []
+        for rank in range(world):
+            subset, own = graph_shard(ns, world, rank, compat=compat)
+            if not own:
+                continue
+            log = rollout_graph_sharded(solver, batch, T, S, init, world_size=world, rank=rank)
+            keep = [subset.index(g) for g in own]
+            part = torch.stack(log['scores'], -1)[keep]
+            assert torch.equal(part, full_scores[own]), (world, rank)
+            assert torch.equal(log['best_score_by_tradj'][keep], full['best_score_by_tradj'][own])
+            for k, g in zip(keep, own):
+                assert torch.equal(log['best_state'][k, :ns[g]], full['best_state'][g, :ns[g]]), (world, rank, g)
+            seen += own
+        assert seen == list(range(len(ns)))
