@@ -395,6 +395,9 @@ extern "C" int ecord_env_init(const ecord_graph *g, const ecord_env *env, const 
     ECORD_RET_IF(!init_state, ECORD_E_NULL);
     const long long NT = (long long)g->num_nodes * env->num_tradj;
     const int GT = g->num_graphs * env->num_tradj;
+    // (a variant transposed through shared memory -- spins read with trajectories innermost, planes written with vertices
+    // innermost -- was measured SLOWER, 228 against 154 us at ER500: the kernel is bound by the E x T edge loop, which wants
+    // every (vertex, trajectory) pair on its own thread, not by its scattered 4-byte plane stores)
     k_env_init_peek<<<ceil_div(NT, 256), 256, 0, as_stream(stream)>>>(*g, *env, init_state);
     ECORD_LAUNCH_CHECK();
     if (g->int_weights && g->graph_wsum)

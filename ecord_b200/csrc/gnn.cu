@@ -10,12 +10,9 @@
 //
 // Shape of the work: N x 16 activations, E edge messages of 16 channels; one-off per rollout.  Exactness of the summation
 // order comes first (incoming edges are accumulated sequentially in global edge order, as scatter_add does on the CPU), so
-// the aggregation is parallel over vertices and CHANNELS, never over the edges of a vertex:
-//   k_gnn_aggregate  sixteen lanes per vertex (lane <-> channel): a half-warp reads 16 (src, w) pairs with one coalesced
-//                    load each, issues the 16 neighbour-row loads (64 contiguous bytes per neighbour, L2 hits) back to back
-//                    and only then runs the 16 dependent adds -- the round-1 kernel (one thread per vertex, in_src -> row
-//                    address -> 4 x LDG.128 -> adds, every edge two serial L2 round trips) took 84 us per layer at ER500
-//   k_gnn_update     one thread per vertex: receive layer + GRUCell (3.3 K FMA, weights staged once per block)
+// the aggregation is parallel over vertices, never over the edges of a vertex:
+//   k_gnn_update     one thread per vertex: gather of the incoming y rows (staged through shared memory per graph where
+//                    they fit, see the kernel), receive layer + GRUCell (3.3 K FMA, weights staged once per block)
 //   k_gnn_ln_send    batch-wide LayerNorm of the previous layer fused with the send layer; k_gnn_finish normalises on read
 // Batch-wide LN sums are block-reduced and accumulated in fp64 atomics.
 #include "common.cuh"
@@ -104,56 +101,92 @@ __global__ void k_gnn_ln_send(int N, float *x, const double *acc, const float *_
     }
 }
 
-// m_i = mean_{j -> i} w_ji y_j.  Sixteen lanes per vertex, lane <-> channel; the edges of a vertex stay in global edge order
-// and every channel's sum is sequential (product rounded separately, as the reference's `y[row] * edge_attr` then scatter_add).
+// aggregate + receive + GRUCell; writes the pre-LN x_new and accumulates the LN sums.  One thread per vertex: the sixteen
+// channels of a message are one thread's registers, so an edge costs 4 vector loads + 32 arithmetic instructions per THREAD
+// (a lane-per-channel layout spends a shuffle pair and a load instruction per edge and half-warp: measured slower).
+//   STAGE = true : block <-> one 128-vertex tile of a graph (the Q kernels' tiling).  Every edge's source lies in the
+//                  destination's own graph, so the block first copies its graph's y rows -- n_g x 64 B, coalesced -- into
+//                  shared memory and gathers from there: the CSR gather/scatter SpMM staged through shared memory.  The
+//                  per-edge chain in_src -> row address -> row loads is then one L1-resident load plus shared-memory
+//                  latency instead of two serial L2 round trips (84 us per layer at ER500 in round 1).
+//   STAGE = false: graphs whose rows do not fit (ER10000: 640 KB): block <-> 128 consecutive vertices, rows gathered from
+//                  L2, four edges' loads in flight.
+// The sums run over a vertex's incoming edges in global edge order either way (scatter_add on the CPU).
+template <bool STAGE>
 __global__ void __launch_bounds__(128)
-k_gnn_aggregate(ecord_graph g, const float *__restrict__ y, float *__restrict__ msg) {
-    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = (int)(gt >> 4), c = (int)(gt & 15);
-    const int vv = min(v, g.num_nodes - 1);
-    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);          // this vertex's half-warp
-    const int k0 = g.in_ptr[vv], k1 = g.in_ptr[vv + 1];
-    float acc = 0.0f;
-    for (int kb = k0; kb < k1; kb += 16) {                         // (trip count uniform within the half-warp)
-        const int kk = kb + c;
-        const int s = kk < k1 ? g.in_src[kk] : 0;
-        const float wv = kk < k1 ? g.in_w[kk] : 0.0f;
-        const int cnt = min(16, k1 - kb);
-        float yv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int sj = __shfl_sync(mask, s, j, 16);
-            yv[j] = j < cnt ? y[(long long)sj * D + c] : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float wj = __shfl_sync(mask, wv, j, 16);
-            if (j < cnt) acc = __fadd_rn(acc, __fmul_rn(yv[j], wj));
-        }
-    }
-    if (v < g.num_nodes) msg[(long long)v * D + c] = acc / (float)max(k1 - k0, 1);    // scatter_mean: count clamped to >= 1
-}
-
-// receive + GRUCell on [msg ; x]; writes the pre-LN x_new and accumulates the LN sums
-__global__ void k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const float *__restrict__ msg,
-                             float *xn, double *acc) {
+k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const float *__restrict__ y, float *xn, double *acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GnnSmem &S = *reinterpret_cast<GnnSmem *>(smem_raw);
+    float *ys = reinterpret_cast<float *>(smem_raw + sizeof(GnnSmem));      // STAGE: [n_g][16]
     for (int i = threadIdx.x; i < 2 * D * 2 * D; i += blockDim.x) S.rec_w[i] = wt.gnn_rec_w[i];
     for (int i = threadIdx.x; i < 3 * D * 2 * D; i += blockDim.x) S.wih[i] = wt.gnn_wih[i];
     for (int i = threadIdx.x; i < 3 * D * D; i += blockDim.x) S.whh[i] = wt.gnn_whh[i];
     for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) { S.bih[i] = wt.gnn_bih[i]; S.bhh[i] = wt.gnn_bhh[i]; }
     for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) S.rec_b[i] = wt.gnn_rec_b[i];
+    int v, lo = 0;
+    bool live;
+    if (STAGE) {
+        const int tile = blockIdx.x;
+        const int gi = g.qtile_graph[tile];
+        lo = g.graph_ptr[gi];
+        const int n = g.graph_ptr[gi + 1] - lo;
+        const float4 *src = reinterpret_cast<const float4 *>(y + (long long)lo * D);
+        float4 *dst = reinterpret_cast<float4 *>(ys);
+        for (int i = threadIdx.x; i < n * (D / 4); i += blockDim.x) dst[i] = src[i];
+        const int vl = g.qtile_v0[tile] + threadIdx.x;
+        live = vl < n;
+        v = lo + vl;
+    } else {
+        v = blockIdx.x * blockDim.x + threadIdx.x;
+        live = v < g.num_nodes;
+    }
     __syncthreads();
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.0, ss = 0.0;
-    if (v < g.num_nodes) {
+    if (live) {
         float in[2 * D];   // [msg ; x]
 #pragma unroll
-        for (int c = 0; c < D; c += 4) {
-            *reinterpret_cast<float4 *>(&in[c]) = *reinterpret_cast<const float4 *>(&msg[(long long)v * D + c]);
-            *reinterpret_cast<float4 *>(&in[D + c]) = *reinterpret_cast<const float4 *>(&x[(long long)v * D + c]);
+        for (int c = 0; c < D; ++c) in[c] = 0.0f;
+        const int k0 = g.in_ptr[v], k1 = g.in_ptr[v + 1];
+        auto add_row = [&](const float4 *yj, float wk) {
+#pragma unroll
+            for (int c4 = 0; c4 < D / 4; ++c4) {
+                const float4 t = yj[c4];
+                const int c = 4 * c4;
+                // product rounded separately, as the reference's `y[row] * edge_attr` then scatter_add does
+                in[c + 0] = __fadd_rn(in[c + 0], __fmul_rn(t.x, wk)); in[c + 1] = __fadd_rn(in[c + 1], __fmul_rn(t.y, wk));
+                in[c + 2] = __fadd_rn(in[c + 2], __fmul_rn(t.z, wk)); in[c + 3] = __fadd_rn(in[c + 3], __fmul_rn(t.w, wk));
+            }
+        };
+        if (STAGE) {
+            int k = k0;
+            for (; k + 2 <= k1; k += 2) {               // sequential, global edge order; the next edge's indices are in flight
+                const int s0 = g.in_src[k] - lo, s1 = g.in_src[k + 1] - lo;
+                const float w0 = g.in_w[k], w1 = g.in_w[k + 1];
+                add_row(reinterpret_cast<const float4 *>(ys + s0 * D), w0);
+                add_row(reinterpret_cast<const float4 *>(ys + s1 * D), w1);
+            }
+            if (k < k1) add_row(reinterpret_cast<const float4 *>(ys + (g.in_src[k] - lo) * D), g.in_w[k]);
+        } else {
+            int k = k0;
+            for (; k + 4 <= k1; k += 4) {               // four edges' row loads in flight, sums in edge order
+                const float *y0 = y + (long long)g.in_src[k] * D, *y1 = y + (long long)g.in_src[k + 1] * D;
+                const float *y2 = y + (long long)g.in_src[k + 2] * D, *y3 = y + (long long)g.in_src[k + 3] * D;
+                const float w0 = g.in_w[k], w1 = g.in_w[k + 1], w2 = g.in_w[k + 2], w3 = g.in_w[k + 3];
+                float4 r[4][D / 4];
+#pragma unroll
+                for (int c4 = 0; c4 < D / 4; ++c4) {
+                    r[0][c4] = reinterpret_cast<const float4 *>(y0)[c4]; r[1][c4] = reinterpret_cast<const float4 *>(y1)[c4];
+                    r[2][c4] = reinterpret_cast<const float4 *>(y2)[c4]; r[3][c4] = reinterpret_cast<const float4 *>(y3)[c4];
+                }
+                add_row(r[0], w0); add_row(r[1], w1); add_row(r[2], w2); add_row(r[3], w3);
+            }
+            for (; k < k1; ++k) add_row(reinterpret_cast<const float4 *>(y + (long long)g.in_src[k] * D), g.in_w[k]);
         }
+        const float cnt = (float)max(k1 - k0, 1);    // scatter_mean: count clamped to >= 1
+#pragma unroll
+        for (int c = 0; c < D; ++c) in[c] = in[c] / cnt;
+#pragma unroll
+        for (int c = 0; c < D; c += 4) *reinterpret_cast<float4 *>(&in[D + c]) = *reinterpret_cast<const float4 *>(&x[(long long)v * D + c]);
         float r[2 * D];    // LReLU(W_r [msg;x] + b_r)
 #pragma unroll
         for (int o = 0; o < 2 * D; ++o) {
@@ -219,12 +252,14 @@ __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ 
         node_emb[(long long)v * D + o] = a;
     }
     float bsum = 0.0f;
-    for (int c = 0; c < ECORD_DIM_Q; ++c) {
-        float a = qd[c];
+    if (node_B) {      // exact / fast Q kernels only (the tensor-core kernel works from node_emb and node_qv)
+        for (int c = 0; c < ECORD_DIM_Q; ++c) {
+            float a = qd[c];
 #pragma unroll
-        for (int i = 0; i < D; ++i) a = fmaf(qb[c * D + i], e[i], a);
-        node_B[(long long)v * ECORD_DIM_Q + c] = a;
-        bsum += a;
+            for (int i = 0; i < D; ++i) a = fmaf(qb[c * D + i], e[i], a);
+            node_B[(long long)v * ECORD_DIM_Q + c] = a;
+            bsum += a;
+        }
     }
     if (node_Bc) {     // fast Q kernel operands: B - mean_c(B) and its projection on w_o * gamma
         const float mean = bsum * (1.0f / ECORD_DIM_Q);
@@ -258,14 +293,15 @@ __global__ void k_gnn_finish(int N, ecord_weights wt, const float *__restrict__ 
 
 extern "C" size_t ecord_gnn_workspace_bytes(int32_t N) {
     if (N <= 0) return 0;
-    return (size_t)4 * N * D * sizeof(float) + 256 + 16 * sizeof(double);
+    return (size_t)3 * N * D * sizeof(float) + 256 + 16 * sizeof(double);
 }
 
 extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
                                float *node_Bc, float *node_LB, float *node_qv, void *workspace, void *stream) {
     ECORD_RET_IF((node_Bc == nullptr) != (node_LB == nullptr), ECORD_E_NULL);
     ECORD_RET_IF(node_qv && (!w || !w->q_tc), ECORD_E_NULL);
-    ECORD_RET_IF(!g || !w || !node_emb || !node_B || !workspace, ECORD_E_NULL);
+    ECORD_RET_IF(!g || !w || !node_emb || !workspace, ECORD_E_NULL);
+    ECORD_RET_IF(!node_B && (node_Bc || !node_qv), ECORD_E_NULL);      // node_B may be omitted for the tensor-core Q kernel only
     ECORD_RET_IF(g->num_nodes <= 0, ECORD_E_SIZE);
     ECORD_RET_IF(!g->in_ptr || (g->num_edges > 0 && (!g->in_src || !g->in_w)), ECORD_E_NULL);
     ECORD_RET_IF(((uintptr_t)workspace & 15) != 0, ECORD_E_ALIGN);
@@ -274,19 +310,24 @@ extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, flo
     float *x = reinterpret_cast<float *>(workspace);
     float *y = x + (size_t)N * D;
     float *xn = y + (size_t)N * D;
-    double *acc = reinterpret_cast<double *>(((uintptr_t)(xn + (size_t)2 * N * D) + 255) & ~(uintptr_t)255);
+    double *acc = reinterpret_cast<double *>(((uintptr_t)(xn + (size_t)N * D) + 255) & ~(uintptr_t)255);
     ECORD_CUDA(cudaMemsetAsync(acc, 0, 16 * sizeof(double), st));
     const int TB = 128, nb = ceil_div(N, TB);
     k_gnn_embed0<<<nb, TB, 0, st>>>(N, w->gnn_embed_w, w->gnn_embed_b, x, acc);
     ECORD_LAUNCH_CHECK();
+    // shared-memory staging of a graph's y rows: needs the vertex tiling and rows that fit beside a few co-resident CTAs
+    static const int smem_cap = [] {
+        cudaFuncSetAttribute(k_gnn_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GnnSmem) + 64 * 1024);
+        return 64 * 1024;
+    }();
+    static_assert(ECORD_QTILE == 128, "k_gnn_update<true>: one thread per vertex of a tile");
+    const bool stage = g->num_qtiles > 0 && g->qtile_graph && g->qtile_v0 && (size_t)g->n_max * D * sizeof(float) <= (size_t)smem_cap;
     float *cur = x, *nxt = xn;
-    float *msg = xn + (size_t)N * D;                          // fourth N x 16 array of the workspace
     for (int l = 0; l < 4; ++l) {   // num_layers is hard-coded to 4 by experiments/configs.py:99
         k_gnn_ln_send<<<nb, TB, 0, st>>>(N, cur, acc + 2 * l, w->gnn_snd_w, w->gnn_snd_b, y);
         ECORD_LAUNCH_CHECK();
-        k_gnn_aggregate<<<ceil_div((long long)N * D, 128), 128, 0, st>>>(*g, y, msg);
-        ECORD_LAUNCH_CHECK();
-        k_gnn_update<<<nb, TB, sizeof(GnnSmem), st>>>(*g, *w, cur, msg, nxt, acc + 2 * (l + 1));
+        if (stage) k_gnn_update<true><<<g->num_qtiles, TB, sizeof(GnnSmem) + (size_t)g->n_max * D * sizeof(float), st>>>(*g, *w, cur, y, nxt, acc + 2 * (l + 1));
+        else k_gnn_update<false><<<nb, TB, sizeof(GnnSmem), st>>>(*g, *w, cur, y, nxt, acc + 2 * (l + 1));
         ECORD_LAUNCH_CHECK();
         float *t = cur; cur = nxt; nxt = t;
     }

@@ -467,7 +467,8 @@ extern "C" int ecord_q_select(const ecord_graph *g, const ecord_env *env, const 
                               int32_t steps_done, float tau, uint64_t seed, int32_t compat, const int32_t *forced_actions,
                               int32_t q_mode, float epsilon, void *stream) {
     ECORD_RET_IF(!g || !env || !w || !p, ECORD_E_NULL);
-    ECORD_RET_IF(!p->A || !p->v || !p->node_B || !p->node_emb || !p->last_sel || !p->actions || !w->q_fold, ECORD_E_NULL);
+    ECORD_RET_IF(!p->A || !p->v || !p->node_emb || !p->last_sel || !p->actions || !w->q_fold, ECORD_E_NULL);
+    ECORD_RET_IF(!p->node_B && q_mode != ECORD_Q_TC, ECORD_E_NULL);
     ECORD_RET_IF(p->rows != g->num_graphs * env->num_tradj || steps_done < 0, ECORD_E_SIZE);
     ECORD_RET_IF(tau < 0.0f || !(epsilon >= 0.0f && epsilon <= 1.0f), ECORD_E_SIZE);
     ECORD_RET_IF(tau > 0.0f && q_mode == ECORD_Q_EXACT && !p->q, ECORD_E_NULL);     // the exact kernel's second pass re-reads q

@@ -234,7 +234,7 @@ class RolloutState:
         self.q = torch.zeros(N * T, **f32) if (dump_q or (self.tau > 0 and self.q_mode == Q_EXACT)) else None
         self.gnn_out = torch.empty(N, 16, **f32)
         self.node_emb = torch.empty(N, 16, **f32)
-        self.node_B = torch.empty(N, 64, **f32)
+        self.node_B = torch.empty(N, 64, **f32) if self.q_mode != Q_TC else None      # read by the exact / fast Q kernels only
         self.Ac = self.LA = self.node_Bc = self.node_LB = self.keys = self.qa = self.node_qv = None
         if self.q_mode == Q_FAST:
             self.Ac = torch.zeros(Mp, 64, **f32)
@@ -287,7 +287,7 @@ class RolloutState:
                                        ptr(self.node_B), ptr(self.node_Bc), ptr(self.node_LB), ptr(self.node_qv), ptr(ws),
                                        _stream()),
               "ecord_gnn_embed")
-        self.kernel_launches += 14
+        self.kernel_launches += 10
         self._ws = ws
 
     @_on_stream
@@ -297,7 +297,7 @@ class RolloutState:
         state's vertices (`vertex_index` i64 [N_sub] on the device, indices into the full batch) are gathered."""
         fg = full_graph
         f32 = dict(dtype=torch.float32, device=self.device)
-        full = dict(gnn_out=torch.empty(fg.N, 16, **f32), node_emb=torch.empty(fg.N, 16, **f32), node_B=torch.empty(fg.N, 64, **f32),
+        full = dict(gnn_out=torch.empty(fg.N, 16, **f32), node_emb=torch.empty(fg.N, 16, **f32), node_B=torch.empty(fg.N, 64, **f32) if self.node_B is not None else None,
                     node_Bc=torch.empty(fg.N, 64, **f32) if self.node_Bc is not None else None,
                     node_LB=torch.empty(fg.N, **f32) if self.node_LB is not None else None,
                     node_qv=torch.empty(fg.N, 8, **f32) if self.node_qv is not None else None)
@@ -305,7 +305,7 @@ class RolloutState:
         check(self.lib.ecord_gnn_embed(C.byref(fg.c), C.byref(self.w.c), ptr(full['gnn_out']), ptr(full['node_emb']),
                                        ptr(full['node_B']), ptr(full['node_Bc']), ptr(full['node_LB']), ptr(full['node_qv']),
                                        ptr(ws), _stream()), "ecord_gnn_embed")
-        self.kernel_launches += 14
+        self.kernel_launches += 10
         for name, src in full.items():
             if src is not None:
                 torch.index_select(src, 0, vertex_index, out=getattr(self, name))

@@ -292,7 +292,8 @@ int ecord_env_export(const ecord_graph *g, const ecord_env *env, int32_t steps_d
  *      GNN2RNN (actors/_base.py:185-237, gnn_embedder.py:133-149,182-199, gnn_to_rnn.py:16-18),
  *      one pass (the reference's 10 extra timing passes, gnn_embedder.py:201-217, are dropped).
  *      LayerNorm statistics are batch-wide (quirk B).  gnn_out, node_emb: f32 [N][16];
- *      node_B: f32 [N][64] (see ecord_policy).  workspace: ecord_gnn_workspace_bytes(N) bytes. ---- */
+ *      node_B: f32 [N][64] (see ecord_policy; may be NULL when only the tensor-core Q kernel, which works from node_emb and
+ *      node_qv, will run).  workspace: ecord_gnn_workspace_bytes(N) bytes. ---- */
 size_t ecord_gnn_workspace_bytes(int32_t num_nodes);
 int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, float *gnn_out, float *node_emb, float *node_B,
                     float *node_Bc /* [N][64] or NULL */, float *node_LB /* [N] or NULL */,
