@@ -3,233 +3,57 @@
 //   GRU  :  [M, 64+1024] x [1088, 3072]  fused with the GRU cell   (models/rnn_decoder.py:369-381 -> nn.GRUCell)
 //   PROJ :  [M, 1024]    x [1024, 512]   + bias                    (models/rnn_decoder.py:84-86, proj_rnn_to_gnn.1)
 //
-// Hand-written tcgen05 pipeline, persistent CTAs (or CTA pairs, cta_group::2 -- the default, see k_gemm_tc2 below):
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B) -> 4-stage smem ring, mbarrier complete_tx; programmatic dependent launch: set-up overlaps the predecessor
-//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
-//               (bf16 x bf16 -> fp32 accumulate in TMEM), tcgen05.commit releases smem stages / signals the epilogue
+// Hand-written tcgen05 pipeline on CTA pairs (cta_group::2, k_gemm_tc2 below), persistent:
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d -> shared-memory ring, mbarrier complete_tx; programmatic dependent
+//               launch: set-up overlaps the predecessor
+//   warp 1      TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma.cta_group::2.kind::f16
+//               (bf16 x bf16 -> fp32 accumulate in TMEM), tcgen05.commit releases stages / signals the epilogue
 //   warps 2..17 epilogue: tcgen05.ld (32 lanes x 16 columns at a time) -> registers -> fused math -> global;
 //               warp w reads TMEM lanes 32*(w%4).., the four warps of a lane quarter split the tile's columns
 //
-// GRU tile = 128 rows x 64 hidden units.  The weight rows of one 64-unit block are packed (ecord_pack_weights)
-// as [r | z | hn | in] so ONE accumulator [128 x 256] holds all four gate pre-activations of the block:
-//   k-chunk 0      : A = u[128 x 64],        B = [W_ir; W_iz; 0; W_in] (256 x 64)   -> N = 256, initialises all columns
-//   k-chunks 1..16 : A = h[128 x 64 chunk],  B = [W_hr; W_hz; W_hn]    (192 x 64)   -> N = 192, accumulates cols 0..191
+// GRU tile = 256 rows (128 per CTA) x W hidden units, W = 64, 32 or 16.  The weights are packed (ecord_pack_weights) in
+// 16-unit sub-blocks so that a tile of k = W/16 sub-blocks is a CONTIGUOUS row range of each packed matrix:
+//   Wh      [64 sub-blocks][r16 | z16 | hn16][1024]      48 rows per sub-block
+//   Wu_main [64 sub-blocks][r16 | z16 | 0  ][64]         48 rows per sub-block (the zero rows initialise the hn columns)
+//   Wu_in   [1024][64]                                    W_in: 16 rows per sub-block
+// and ONE accumulator [128 x 64k] holds all four gate pre-activations of the tile:
+//   columns [48 j, 48 j + 48): r | z | hn of sub-block j;   columns [48 k + 16 j, +16): in of sub-block j
+//   u-chunks : A = u,          B = Wu_main rows (N = 48k, initialises) and Wu_in rows (N = 16k, a second MMA)
+//   h-chunks : A = h chunk,    B = Wh rows (N = 48k), accumulates
 // so gi_n and gh_n stay separate (n = tanh(gi_n + r * gh_n)) at no extra MMA work, and the epilogue applies the
-// cell per element:  h' = (h - n) * z + n.  It writes h' (fp32, the recurrent state), h' (bf16, next step's A
-// operand) and tanh(h') (bf16, PROJ's A operand).  h is double-buffered: buffer (s & 1) holds the state after s steps.
+// cell per element:  h' = (h - n) * z + n.  h is double-buffered: buffer (s & 1) holds the state after s steps.
+// Why three widths: a launch is 16 x Mp/256 tiles of 64 units on 74 CTA pairs, and the last wave of such tiles is mostly
+// empty (ER500: 320 tiles = 4.32 waves; ER10000: 80 tiles = 1.08 waves; 16 trajectories per GPU: 16 tiles on 74 pairs).
+// The leftover tiles are therefore cut into 32- or 16-unit ones (launch_gru_tc_ex picks the width that minimises the
+// makespan) -- the results do not depend on the width: every output element sees the same k-chunks in the same order.
 
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
-// MODE 0 = GRU : tile = 128 rows x 64 hidden units; k-chunk 0 (N=256) from (u, Wu), then 16 chunks (N=192) from
-//                (h[cur], Wh); accumulator = 256 TMEM columns, two accumulators = all 512 columns
-// MODE 1 = PROJ: tile = 128 rows x 176 outputs; 16 chunks (N=176) from (th, W1); accumulator = 176 of 256 columns
+// MODE 0 = GRU : see above; accumulator = 256 TMEM columns (W = 64), two accumulators = all 512 columns
+// MODE 1 = PROJ: tile = 256 rows x 176 outputs; 16 chunks (N=176) from (th, W1); accumulator = 176 of 256 columns
 //
-// Persistent: grid = min(#tiles, #SMs); CTA b works on tiles b, b + grid, ...  The accumulator is double-buffered in
-// TMEM (tmem_full / tmem_empty barriers), so the epilogue of tile i (TMEM -> registers -> GRU cell -> global) runs
-// while TMA + MMA already work on tile i+1; the epilogue warps prefetch the old hidden state before they wait.
+// Persistent: grid = min(#tiles, #SMs); the accumulator is double-buffered in TMEM (tmem_full / tmem_empty barriers), so the
+// epilogue of tile i (TMEM -> registers -> GRU cell -> global) runs while TMA + MMA already work on tile i+1.
 template <int MODE> struct TcCfg;
-template <> struct TcCfg<0> { static constexpr int N_FIRST = 256, N_MAIN = 192, B_ROWS = 256, ACC_COLS = 256, TILE_N = 64; };
+template <> struct TcCfg<0> { static constexpr int N_MAIN = 192, B_ROWS = 256, ACC_COLS = 256, TILE_N = 64; };
 // PROJ: 512 outputs as three column blocks of 176 (the last one runs 16 columns past the matrix: TMA zero-fills them, the
 // epilogue drops them): 3 x 20 pair tiles fit one wave of 74 clusters, where 4 x 20 tiles of 128 needed two
-template <> struct TcCfg<1> { static constexpr int N_FIRST = 0, N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
+template <> struct TcCfg<1> { static constexpr int N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
 // MODE 2 = PROJ when every CTA pair has at most ONE tile (the usual case: 3 x Mp/256 <= 74): the kernel is then a single
 // latency-bound pass over 16 k-chunks, so it runs seven stages deep and its epilogue staging tile reuses the stage memory
-// (all loads have landed and all MMAs have retired when the accumulator is complete).  Pair kernel only.
-template <> struct TcCfg<2> { static constexpr int N_FIRST = 0, N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
+// (all loads have landed and all MMAs have retired when the accumulator is complete).
+template <> struct TcCfg<2> { static constexpr int N_MAIN = 176, B_ROWS = 176, ACC_COLS = 256, TILE_N = 176; };
 
 __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
-          const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-          const __grid_constant__ CUtensorMap mapB, TcParams prm, int num_tiles, int nblk) {
-    using C = TcCfg<MODE>;
-    constexpr int A_BYTES = BM * BK * 2, B_BYTES = C::B_ROWS * BK * 2;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int NCHUNK = (MODE == 0 ? 1 : 0) + H / BK;
-    constexpr int TMEM_COLS = 2 * C::ACC_COLS;          // 512 for both modes
-
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * kStages + 4];
-    __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) float bias_s[2][4][64];       // GRU gate biases of the tile in flight (r, z combined; hn; in)
-
-    const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B atoms need 1024-byte alignment
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]);
-    const uint32_t tfull0 = smem_u32(&bars[2 * kStages]), tempty0 = smem_u32(&bars[2 * kStages + 2]);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kThreads / 32 - 2); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                     "r"((uint32_t)TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_smem;
-    pdl_launch_dependents();
-    pdl_wait();                             // everything below reads / writes step data
-    const int cur = ((prm.step_base ? *prm.step_base : 0) + prm.step_off) & 1;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            const CUtensorMap *mapA = (MODE == 0) ? (cur ? &mapA1 : &mapA0) : &mapA0;
-            tmap_prefetch(mapA); tmap_prefetch(&mapB);
-            if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / nblk) * BM, nb = tile % nblk;
-                for (int c = 0; c < NCHUNK; ++c, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                    if (MODE == 0 && c == 0) {
-                        mbar_expect_tx(full0 + 8 * s, A_BYTES + C::N_FIRST * BK * 2);
-                        tma_load_2d(a_dst, &mapU, full0 + 8 * s, 0, m0);
-                        tma_load_2d(b_dst, &mapWu, full0 + 8 * s, 0, nb * C::N_FIRST);
-                    } else {
-                        const int kc = (MODE == 0 ? c - 1 : c) * BK;
-                        mbar_expect_tx(full0 + 8 * s, A_BYTES + C::N_MAIN * BK * 2);
-                        tma_load_2d(a_dst, mapA, full0 + 8 * s, kc, m0);
-                        tma_load_2d(b_dst, &mapB, full0 + 8 * s, kc, nb * C::N_MAIN);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-                const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
-                mbar_wait(tempty0 + 8 * ab, aph ^ 1u);            // the epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_d + ab * C::ACC_COLS;
-                for (int c = 0; c < NCHUNK; ++c, ++it) {
-                    const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
-                    mbar_wait(full0 + 8 * s, ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + A_BYTES;
-                    const uint32_t idesc = (MODE == 0 && c == 0) ? umma_idesc(BM, 256) : umma_idesc(BM, C::N_MAIN);
-#pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t ad = umma_desc(a_src + k * UMMA_K * 2), bd = umma_desc(b_src + k * UMMA_K * 2);
-                        umma_bf16(acc, ad, bd, idesc, (c > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(empty0 + 8 * s);              // frees the smem stage once these MMAs retire
-                }
-                umma_commit(tfull0 + 8 * ab);                 // accumulator complete
-            }
-        }
-    } else {
-        // ===================== epilogue (warps 2..9) =====================
-        const int q = warp & 3;                           // TMEM lane quarter this warp may access
-        const int part = (warp - 2) >> 2;                 // which quarter of the tile's output columns
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int m0 = (tile / nblk) * BM, nb = tile % nblk;
-            const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
-            const int row = m0 + q * 32 + lane;
-            const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + ab * C::ACC_COLS;
-            if (MODE == 0) {
-                const int j00 = nb * 64 + part * 16;          // first hidden unit of this thread
-                const float *hold = prm.hidden + ((size_t)cur * prm.rows_pad + row) * H + j00;
-                float *hnew = const_cast<float *>(prm.hidden) + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
-                __nv_bfloat16 *hb = prm.hidden_bf16 + ((size_t)(1 - cur) * prm.rows_pad + row) * H + j00;
-                __nv_bfloat16 *tb = prm.th_bf16 + (size_t)row * H + j00;
-                float hv[16];                                 // old state, fetched while the MMAs run
-                if (row < prm.rows) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(&hv[i]) = *reinterpret_cast<const float4 *>(hold + i);
-                }
-                {   // this tile's 4 x 64 gate biases -> shared memory (read back as warp-uniform broadcasts)
-                    const int e = threadIdx.x - 64, gsel = e >> 6, j = nb * 64 + (e & 63);
-                    if (e < 256)
-                        bias_s[ab][gsel][e & 63] = gsel == 0 ? prm.bih[j] + prm.bhh[j]
-                                                 : gsel == 1 ? prm.bih[H + j] + prm.bhh[H + j]
-                                                 : gsel == 2 ? prm.bhh[2 * H + j] : prm.bih[2 * H + j];
-                    asm volatile("bar.sync 1, %0;" ::"n"(kThreads - 64) : "memory");
-                }
-                mbar_wait(tfull0 + 8 * ab, aph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int jj = 0; jj < 16; jj += 16) {
-                    const int j0 = part * 16 + jj;
-                    float ar[16], az[16], ahn[16], ain[16];
-                    tmem_ld16(tbase + j0, ar);
-                    tmem_ld16(tbase + 64 + j0, az);
-                    tmem_ld16(tbase + 128 + j0, ahn);
-                    tmem_ld16(tbase + 192 + j0, ain);
-                    tmem_ld_wait();
-                    if (row < prm.rows) {
-                        __align__(16) __nv_bfloat16 ob[16], ot[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int jl = part * 16 + jj + i;      // unit within the tile's 64
-                            const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
-                            const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
-                            const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
-                            const float hn = fmaf(hv[jj + i] - n, z, n);
-                            hv[jj + i] = hn;
-                            ob[i] = __float2bfloat16(hn);
-                            ot[i] = __float2bfloat16(tanh_fast(hn));
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(hnew + jj + i) = *reinterpret_cast<float4 *>(&hv[jj + i]);
-                        *reinterpret_cast<uint4 *>(hb + jj) = *reinterpret_cast<uint4 *>(&ob[0]);
-                        *reinterpret_cast<uint4 *>(hb + jj + 8) = *reinterpret_cast<uint4 *>(&ob[8]);
-                        *reinterpret_cast<uint4 *>(tb + jj) = *reinterpret_cast<uint4 *>(&ot[0]);
-                        *reinterpret_cast<uint4 *>(tb + jj + 8) = *reinterpret_cast<uint4 *>(&ot[8]);
-                    }
-                }
-            } else {
-                constexpr int PC = C::TILE_N / 4;                 // 44 columns per warp: 11 groups of 4
-                const int c00 = nb * C::TILE_N + part * PC;
-                float *yrow = prm.y1 + (size_t)row * ECORD_DIM_P1 + c00;
-                mbar_wait(tfull0 + 8 * ab, aph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                float acc[PC];
-#pragma unroll
-                for (int jj = 0; jj < PC; jj += 4) tmem_ld4(tbase + part * PC + jj, acc + jj);
-                tmem_ld_wait();
-                if (row < prm.rows) {
-#pragma unroll
-                    for (int jj = 0; jj < PC; jj += 4) {
-                        const int j = c00 + jj;
-                        if (j < ECORD_DIM_P1) {                   // the last block's tail columns do not exist
-                            const float4 b4 = *reinterpret_cast<const float4 *>(prm.p1_b + j);
-                            *reinterpret_cast<float4 *>(yrow + jj) =
-                                make_float4(acc[jj] + b4.x, acc[jj + 1] + b4.y, acc[jj + 2] + b4.z, acc[jj + 3] + b4.w);
-                        }
-                    }
-                }
-            }
-            // this warp has read its part of the accumulator: hand it back to the MMA issuer
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cta(tempty0 + 8 * ab);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TMEM_COLS) : "memory");
-    }
-}
+// tensor maps of a launch, passed as one __grid_constant__ block.  GRU: u, a0 / a1 (h of either parity), and per tile width
+// (index 0: 64 units, 1: the narrow width of this launch) b = Wh, wum = Wu_main, wui = Wu_in.  PROJ: a0 = tanh(h), b[0] = W1.
+struct TcMaps { CUtensorMap u, a0, a1, b[2], wum[2], wui[2]; };
 
 // =================================================================================================
 // CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster (= the two SMs of a TPC) work on a 256-row tile.
@@ -289,22 +113,8 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t a_desc,
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
-// collector variants: the A operand of an MMA marked `fill` stays in the tensor core's collector buffer and the next MMA marked
-// `lastuse` takes it from there instead of reading shared memory again (SASS: UTCHMMA ... .A_KEEP / .A_REUSE).  The split kernels
-// read A hi for two products per k-step: one 4 KB shared-memory read less per three MMAs on the L1 / shared-memory data pipe,
-// which (TMA fills + operand reads) is what bounds them.
-__device__ __forceinline__ void umma_bf16_pair_keep(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair_reuse(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
+// (collector hints -- .collector::a::fill / ::lastuse on the two MMAs that share A hi -- changed neither the kernel's time nor its
+// shared-memory operand wavefronts, 7.37 M per launch with and without: measured and dropped)
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {      // arrives on `bar` in both CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -336,12 +146,41 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {      //
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
 }
 
+// tile i of cluster `cluster_id`.  PROJ: pair tiles cluster_id + i * num_clusters of 256 rows x TILE_N columns.  GRU: first
+// prm.sched_full rounds of 64-unit tiles, then the leftover 64-unit tiles cut into prm.sched_kn-sub-block ones
+// (prm.sched_narrow of them), both dealt round-robin; nb = first 16-unit sub-block, k = sub-blocks (4, 2 or 1).
+template <int MODE>
+__device__ __forceinline__ bool tc2_tile(int i, int cluster_id, int num_clusters, int num_tiles, int nblk, const TcParams &prm,
+                                         int &m0_pair, int &nb, int &k) {
+    if (MODE == 0) {
+        int id;
+        k = 4;
+        if (i < prm.sched_full) {
+            id = cluster_id + i * num_clusters;
+            nb = (id & 15) * 4;
+        } else {
+            const int j = cluster_id + (i - prm.sched_full) * num_clusters;
+            if (j >= prm.sched_narrow) return false;
+            k = prm.sched_kn;
+            const int per = 4 / k;
+            id = prm.sched_full * num_clusters + j / per;
+            nb = (id & 15) * 4 + (j % per) * k;
+        }
+        m0_pair = (id >> 4) * (2 * BM);
+        return true;
+    }
+    const int tile = cluster_id + i * num_clusters;
+    if (tile >= num_tiles) return false;
+    m0_pair = (tile / nblk) * (2 * BM);
+    nb = tile % nblk;
+    k = 0;
+    return true;
+}
+
 template <int MODE, int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
-k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapWu,
-           const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-           const __grid_constant__ CUtensorMap mapB, TcParams prm, int num_tiles, int nblk) {
-    // num_tiles = number of 256-row x TILE_N pair tiles; cluster c works on tiles c, c + #clusters, ...
+k_gemm_tc2(const __grid_constant__ TcMaps maps, TcParams prm, int num_tiles, int nblk) {
+    // num_tiles = number of 256-row x TILE_N pair tiles (PROJ); the GRU's tiles come from prm.sched_* (tc2_tile)
     using C = TcCfg<MODE>;
     constexpr int BKK = tc2_bk<NS>(), ROWB = BKK * 2;                           // k-chunk width: elements, bytes per tile row
     constexpr int PARTS = NS == 3 ? 2 : 1;                                      // operand tiles per side: hi [, lo]
@@ -391,43 +230,44 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
         // ===================== TMA producers (both CTAs): warp 0 and the warps behind the epilogue =====================
         // the whole warp walks the loop converged (uniform registers, no divergence bookkeeping); one elected lane issues
         {
-            const CUtensorMap *mapA = (MODE == 0) ? (cur ? &mapA1 : &mapA0) : &mapA0;
+            const CUtensorMap *mapA = (MODE == 0) ? (cur ? &maps.a1 : &maps.a0) : &maps.a0;
             if (lane == 0) {
-                tmap_prefetch(mapA); tmap_prefetch(&mapB);
-                if (MODE == 0) { tmap_prefetch(&mapU); tmap_prefetch(&mapWu); }
+                tmap_prefetch(mapA); tmap_prefetch(&maps.b[0]);
+                if (MODE == 0) { tmap_prefetch(&maps.u); tmap_prefetch(&maps.wum[0]); tmap_prefetch(&maps.wui[0]); }
             }
             const uint32_t lfull0 = mapa_u32(full0, 0);            // the leader's full barriers
             const uint32_t me = warp == 0 ? 0u : (uint32_t)(warp - kThreads / 32 + 1);     // this producer's turn in the ring
             uint32_t it = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m0 = (tile / nblk) * (2 * BM) + (int)rank * BM, nb = tile % nblk;
+            int m0p, nb, kw;
+            for (int ti = 0; tc2_tile<MODE>(ti, cluster_id, num_clusters, num_tiles, nblk, prm, m0p, nb, kw); ++ti) {
+                const int m0 = m0p + (int)rank * BM;
+                const int wsel = kw == 4 ? 0 : 1;                              // which set of weight maps (box heights)
+                const int n_main = MODE == 0 ? 24 * kw : C::N_MAIN / 2;        // B rows this CTA fetches per plane (half of the MMA's N)
+                const int n_in = 8 * kw;                                       // GRU u-chunks: its half of the W_in rows
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
                     if (it % kProducers != me) continue;
                     const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);            // local: released by the leader's multicast commit
                     const uint32_t a_dst = tiles + s * STAGE_BYTES, b_dst = a_dst + PARTS * A_BYTES;
                     const bool first = MODE == 0 && c < KCH_U;
-                    const int n_rows = first ? C::N_FIRST : C::N_MAIN;
                     const int kc = (first ? c : c - KCH_U) * BKK;
-                    const int b_row = nb * n_rows + (int)rank * (n_rows / 2);
+                    const int b_row = MODE == 0 ? nb * 48 + (int)rank * n_main : nb * C::N_MAIN + (int)rank * n_main;
                     if (elect_one()) {
-                        if (prm.debug & 4) {            // no TMA traffic: the leader completes the phase by itself
-                            if (rank == 0) mbar_arrive_cta(full0 + 8 * s);
-                        } else {
-                            // diagnostics: 32 = hi planes only (half the bytes), 64 = every cluster fetches tile (0, 0) (hot lines)
-                            const int parts = (prm.debug & 32) ? 1 : PARTS;
-                            const int m0d = (prm.debug & 64) ? (int)rank * BM : m0, b_rowd = (prm.debug & 64) ? (int)rank * (n_rows / 2) : b_row;
-                            if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * parts * (A_BYTES + n_rows / 2 * ROWB));
+                        // diagnostics: 32 = hi planes only (half the bytes), 64 = every cluster fetches tile (0, 0) (hot lines)
+                        const int parts = (prm.debug & 32) ? 1 : PARTS;
+                        const int m0d = (prm.debug & 64) ? (int)rank * BM : m0, b_rowd = (prm.debug & 64) ? (int)rank * n_main : b_row;
+                        if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * parts * (A_BYTES + (n_main + (first ? n_in : 0)) * ROWB));
 #pragma unroll
-                            for (int part = 0; part < PARTS; ++part) {
-                                if (part >= parts) break;
-                                if (first) {
-                                    tma_load_2d_pair(a_dst + part * A_BYTES, &mapU, lfull0 + 8 * s, kc, m0d + part * prm.rows_pad);
-                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapWu, lfull0 + 8 * s, kc, b_rowd + part * 4 * H);
-                                } else {
-                                    tma_load_2d_pair(a_dst + part * A_BYTES, mapA, lfull0 + 8 * s, kc, m0d + part * prm.rows_pad);
-                                    tma_load_2d_pair(b_dst + part * B_BYTES, &mapB, lfull0 + 8 * s, kc, b_rowd + part * B_PLANE);
-                                }
+                        for (int part = 0; part < PARTS; ++part) {
+                            if (part >= parts) break;
+                            if (first) {
+                                tma_load_2d_pair(a_dst + part * A_BYTES, &maps.u, lfull0 + 8 * s, kc, m0d + part * prm.rows_pad);
+                                tma_load_2d_pair(b_dst + part * B_BYTES, &maps.wum[wsel], lfull0 + 8 * s, kc, b_rowd + part * B_PLANE);
+                                tma_load_2d_pair(b_dst + part * B_BYTES + n_main * ROWB, &maps.wui[wsel], lfull0 + 8 * s, kc,
+                                                 nb * 16 + (int)rank * n_in + part * H);
+                            } else {
+                                tma_load_2d_pair(a_dst + part * A_BYTES, mapA, lfull0 + 8 * s, kc, m0d + part * prm.rows_pad);
+                                tma_load_2d_pair(b_dst + part * B_BYTES, &maps.b[wsel], lfull0 + 8 * s, kc, b_rowd + part * B_PLANE);
                             }
                         }
                     }
@@ -439,35 +279,42 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
         // ===================== MMA issuer (leader CTA only) =====================
         if (rank == 0) {                    // converged warp, elected lane issues (see the producer)
             uint32_t it = 0, lt = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+            int m0p, nb, kw;
+            for (int ti = 0; tc2_tile<MODE>(ti, cluster_id, num_clusters, num_tiles, nblk, prm, m0p, nb, kw); ++ti, ++lt) {
                 const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * ab, aph ^ 1u);            // both CTAs' epilogues have drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_d + ab * C::ACC_COLS;
+                const uint32_t idesc = umma_idesc(2 * BM, MODE == 0 ? 48 * kw : C::N_MAIN);
+                // GRU u-chunks: the W_in rows (N = 16 kw) sit behind this CTA's Wu_main rows and feed accumulator columns 48 kw ..
+                const uint32_t idesc_in = umma_idesc(2 * BM, 16 * kw), acc_in = acc + 48 * kw, in_off = 24 * kw * ROWB;
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
                     const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_src = tiles + s * STAGE_BYTES, b_src = a_src + PARTS * A_BYTES;
-                    const uint32_t idesc = (MODE == 0 && c < KCH_U) ? umma_idesc(2 * BM, 256) : umma_idesc(2 * BM, C::N_MAIN);
+                    const bool first = MODE == 0 && c < KCH_U;
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BKK / UMMA_K; ++k) {
                             const uint32_t ko = k * UMMA_K * 2;
+                            const uint32_t fresh = (c > 0 || k > 0) ? 1u : 0u;
                             if (prm.debug & 1) continue;
                             if (NS == 1) {
-                                umma_bf16_pair(acc, umma_desc(a_src + ko), umma_desc(b_src + ko), idesc, (c > 0 || k > 0) ? 1u : 0u);
-                            } else {       // hi.hi + lo.hi + hi.lo
+                                umma_bf16_pair(acc, umma_desc(a_src + ko), umma_desc(b_src + ko), idesc, fresh);
+                                if (first) umma_bf16_pair(acc_in, umma_desc(a_src + ko), umma_desc(b_src + in_off + ko), idesc_in, fresh);
+                            } else {       // hi.hi + hi.lo + lo.hi
                                 const uint64_t ah = umma_desc_sw64(a_src + ko), al = umma_desc_sw64(a_src + A_BYTES + ko);
                                 const uint64_t bh = umma_desc_sw64(b_src + ko), bl = umma_desc_sw64(b_src + B_BYTES + ko);
-                                if (prm.debug & 16) {          // A/B switch: no collector reuse
-                                    umma_bf16_pair(acc, ah, bh, idesc, (c > 0 || k > 0) ? 1u : 0u);
-                                    umma_bf16_pair(acc, ah, bl, idesc, 1u);
-                                } else {
-                                    umma_bf16_pair_keep(acc, ah, bh, idesc, (c > 0 || k > 0) ? 1u : 0u);
-                                    umma_bf16_pair_reuse(acc, ah, bl, idesc, 1u);
-                                }
+                                umma_bf16_pair(acc, ah, bh, idesc, fresh);
+                                umma_bf16_pair(acc, ah, bl, idesc, 1u);
                                 umma_bf16_pair(acc, al, bh, idesc, 1u);
+                                if (first) {
+                                    const uint64_t ih = umma_desc_sw64(b_src + in_off + ko), il = umma_desc_sw64(b_src + B_BYTES + in_off + ko);
+                                    umma_bf16_pair(acc_in, ah, ih, idesc_in, fresh);
+                                    umma_bf16_pair(acc_in, ah, il, idesc_in, 1u);
+                                    umma_bf16_pair(acc_in, al, ih, idesc_in, 1u);
+                                }
                             }
                         }
                         umma_commit_pair(empty0 + 8 * s);         // frees the stage in both CTAs
@@ -483,8 +330,9 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
         const int part = (warp - 2) >> 2;
         const uint32_t ltempty0 = mapa_u32(tempty0, 0);            // the leader's tmem_empty barriers
         uint32_t lt = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
-            const int m0 = (tile / nblk) * (2 * BM) + (int)rank * BM, nb = tile % nblk;
+        int m0p, nb, kw;
+        for (int ti = 0; tc2_tile<MODE>(ti, cluster_id, num_clusters, num_tiles, nblk, prm, m0p, nb, kw); ++ti, ++lt) {
+            const int m0 = m0p + (int)rank * BM;
             const uint32_t ab = lt & 1u, aph = (lt >> 1) & 1u;
             const int row = m0 + q * 32 + lane;
             const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16) + ab * C::ACC_COLS;
@@ -493,8 +341,12 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 // whole 128-byte lines (a warp <-> 2 or 4 contiguous row pieces).  With lane <-> row (the TMEM layout) each
                 // 16-byte access of a warp hit 32 different lines and the L1 data pipe -- shared with the tensor core's
                 // operand reads and the TMA writes -- ran at 36 % on those wavefronts alone.
+                // A tile is kw sub-blocks of 16 units (kw = 4, 2 or 1): epilogue part p owns sub-block p (parts >= kw idle
+                // through the math but keep the barrier protocol), the staging tile uses its first 16 kw columns.
                 const int e = threadIdx.x - 64, ew = e >> 5;          // epilogue thread / warp index 0..511 / 0..15
                 const int rloc = q * 32 + lane;                        // row of the tile this thread owns in TMEM
+                const int unit0 = nb * 16, tw = kw * 16;               // first hidden unit and width of the tile
+                const bool active = part < kw;
                 float (*Hs)[kHsPitch] = reinterpret_cast<float (*)[kHsPitch]>(stage_gen);
                 // NS = 1: bf16 images of h' and tanh(h') are staged as well; NS = 3: only h' (fp32) is staged, the store pass takes
                 // tanh(h') and splits both into bf16 hi / lo pairs
@@ -506,12 +358,13 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 for (int i = 0; i < 4; ++i) {
                     const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m0 + r < prm.rows && !(prm.debug & 128)) v = *reinterpret_cast<const float4 *>(prm.hidden + (cur_off + m0 + r) * H + nb * 64 + 4 * c4);
+                    if (m0 + r < prm.rows && 4 * c4 < tw && !(prm.debug & 128))
+                        v = *reinterpret_cast<const float4 *>(prm.hidden + (cur_off + m0 + r) * H + unit0 + 4 * c4);
                     *reinterpret_cast<float4 *>(&Hs[r][4 * c4]) = v;
                 }
-                {   // this tile's 4 x 64 gate biases -> shared memory (read back as warp-uniform broadcasts)
-                    const int gsel = e >> 6, j = nb * 64 + (e & 63);
-                    if (e < 256)
+                {   // this tile's 4 x 16 kw gate biases -> shared memory (read back as warp-uniform broadcasts)
+                    const int gsel = e >> 6, j = unit0 + (e & 63);
+                    if (e < 256 && (e & 63) < tw)
                         bias_s[ab][gsel][e & 63] = gsel == 0 ? prm.bih[j] + prm.bhh[j]
                                                  : gsel == 1 ? prm.bih[H + j] + prm.bhh[H + j]
                                                  : gsel == 2 ? prm.bhh[2 * H + j] : prm.bih[2 * H + j];
@@ -523,19 +376,19 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");     // every thread holds its values: Hs is free again
                 mbar_wait(tfull0 + 8 * ab, aph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (!(prm.debug & 2)) {
-                    const int j0 = part * 16;
+                if (active && !(prm.debug & 2)) {
+                    // accumulator columns: r | z | hn of sub-block `part` at 48 part, its `in` columns behind all main columns
                     float ar[16], az[16], ahn[16], ain[16];
-                    tmem_ld16(tbase + j0, ar);
-                    tmem_ld16(tbase + 64 + j0, az);
-                    tmem_ld16(tbase + 128 + j0, ahn);
-                    tmem_ld16(tbase + 192 + j0, ain);
+                    tmem_ld16(tbase + 48 * part, ar);
+                    tmem_ld16(tbase + 48 * part + 16, az);
+                    tmem_ld16(tbase + 48 * part + 32, ahn);
+                    tmem_ld16(tbase + 48 * kw + 16 * part, ain);
                     tmem_ld_wait();
                     if (NS == 1) {
                         __align__(16) __nv_bfloat16 ob[16], ot[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const int jl = part * 16 + i;           // unit within the tile's 64
+                            const int jl = part * 16 + i;           // unit within the tile
                             const float r = sigmoid_fast(ar[i] + bias_s[ab][0][jl]);
                             const float z = sigmoid_fast(az[i] + bias_s[ab][1][jl]);
                             const float n = tanh_fast(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
@@ -575,15 +428,15 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
-                        if (m0 + r < prm.rows)
-                            *reinterpret_cast<float4 *>(hnew + (nxt_off + m0 + r) * H + nb * 64 + 4 * c4) = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
+                        if (m0 + r < prm.rows && 4 * c4 < tw)
+                            *reinterpret_cast<float4 *>(hnew + (nxt_off + m0 + r) * H + unit0 + 4 * c4) = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
                     }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int r = 8 * ew + 4 * i + (lane >> 3), c8 = lane & 7;
-                        if (m0 + r < prm.rows) {
-                            *reinterpret_cast<uint4 *>(prm.hidden_bf16 + (nxt_off + m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Bs[r][8 * c8]);
-                            *reinterpret_cast<uint4 *>(prm.th_bf16 + (size_t)(m0 + r) * H + nb * 64 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Ts[r][8 * c8]);
+                        if (m0 + r < prm.rows && 8 * c8 < tw) {
+                            *reinterpret_cast<uint4 *>(prm.hidden_bf16 + (nxt_off + m0 + r) * H + unit0 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Bs[r][8 * c8]);
+                            *reinterpret_cast<uint4 *>(prm.th_bf16 + (size_t)(m0 + r) * H + unit0 + 8 * c8) = *reinterpret_cast<const uint4 *>(&Ts[r][8 * c8]);
                         }
                     }
                 } else {
@@ -595,10 +448,10 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
-                        if (m0 + r < prm.rows && !(prm.debug & 128)) {
+                        if (m0 + r < prm.rows && 4 * c4 < tw && !(prm.debug & 128)) {
                             const float4 hv4 = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
                             const float4 tv4 = make_float4(tanhf(hv4.x), tanhf(hv4.y), tanhf(hv4.z), tanhf(hv4.w));   // projection input
-                            const size_t o = (size_t)(m0 + r) * H + nb * 64 + 4 * c4;
+                            const size_t o = (size_t)(m0 + r) * H + unit0 + 4 * c4;
                             *reinterpret_cast<float4 *>(hnew + nxt_off * H + o) = hv4;
                             uint2 hi, lo;
                             split_bf16x4(hv4, hi, lo);
@@ -660,8 +513,6 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
-constexpr int tc_smem_bytes() { return kStages * (BM * BK * 2 + TcCfg<MODE>::B_ROWS * BK * 2) + 1024; }
 template <int MODE, int NS>
 constexpr int tc2_smem_bytes() {
     return stages2<MODE, NS>() * tc2_stage_bytes<MODE, NS>() + 1024 +
@@ -669,11 +520,6 @@ constexpr int tc2_smem_bytes() {
 }
 static_assert(tc2_smem_bytes<0, 3>() <= 227 * 1024 && tc2_smem_bytes<1, 3>() <= 227 * 1024 && tc2_smem_bytes<2, 3>() <= 227 * 1024 &&
               tc2_smem_bytes<2, 3>() - 1024 >= BM * (TcCfg<2>::TILE_N + 4) * 4, "shared-memory budget of the pair kernels");
-// ECORD_GEMM_PAIR=0 selects the single-CTA kernels (A/B comparisons); rows_pad must be a multiple of 256 for the pair kernels
-static bool use_pair(int rows_pad) {
-    static const int env = [] { const char *e = getenv("ECORD_GEMM_PAIR"); return e ? atoi(e) : 1; }();
-    return env != 0 && (rows_pad % (2 * BM)) == 0;
-}
 
 // ---------------------------------------------------------------------------------------------
 // weight packing (device): fp32 PyTorch layout -> bf16 tile-permuted, plus the folded encoder constants
@@ -686,25 +532,31 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
 __global__ void k_pack_weights(ecord_weights w) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long n_wh = (long long)3072 * H, n_wu = (long long)4096 * 64, n_p1 = (long long)512 * H, n_p2 = 32 * 512;
-    // layouts: gru_w_bf16 = [Wh hi | Wh lo | Wu hi | Wu lo], p1_w_bf16 = [W1 hi | W1 lo | W2 hi | W2 lo]
+    // layouts: gru_w_bf16 = [Wh hi | Wh lo | Wu_main hi | Wu_main lo | Wu_in hi | Wu_in lo], p1_w_bf16 = [W1 hi | W1 lo | W2 hi | W2 lo]
     __nv_bfloat16 *wh = reinterpret_cast<__nv_bfloat16 *>(w.gru_w_bf16);
     __nv_bfloat16 *wu = wh + 2 * n_wh;
     __nv_bfloat16 *p1 = reinterpret_cast<__nv_bfloat16 *>(w.p1_w_bf16);
     __nv_bfloat16 *p2 = p1 + 2 * n_p1;
-    if (i < n_wh) {                               // Wh pack: row = jb*192 + gate*64 + jj  <-  W_hh[gate*1024 + jb*64 + jj]
+    if (i < n_wh) {                               // Wh pack: row = sb*48 + gate*16 + jj  <-  W_hh[gate*1024 + sb*16 + jj]
         const int row = (int)(i / H), k = (int)(i % H);
-        const int jb = row / 192, gate = (row % 192) / 64, jj = row % 64;
-        split_bf16(w.gru_whh[(size_t)(gate * H + jb * 64 + jj) * H + k], wh[i], wh[n_wh + i]);
-    } else if (i < n_wh + n_wu) {                 // Wu pack: row = jb*256 + slot*64 + jj; slots r, z, (zero), in
-        const long long t = i - n_wh;
-        const int row = (int)(t / 64), k = (int)(t % 64);
-        const int jb = row / 256, slot = (row % 256) / 64, jj = row % 64;
+        const int sb = row / 48, gate = (row % 48) / 16, jj = row % 16;
+        split_bf16(w.gru_whh[(size_t)(gate * H + sb * 16 + jj) * H + k], wh[i], wh[n_wh + i]);
+    } else if (i < n_wh + n_wu) {                 // Wu_main pack [3072][64]: row = sb*48 + slot*16 + jj, slots r, z, (zero);
+        const long long t = i - n_wh;             // then Wu_in [1024][64]: row = unit  <-  W_ih[2*1024 + unit]
+        const long long n_main = (long long)3 * H * 64;
         float v = 0.0f;
-        if (slot != 2) {
-            const int gate = slot == 3 ? 2 : slot;
-            v = w.gru_wih[(size_t)(gate * H + jb * 64 + jj) * 64 + k];
+        __nv_bfloat16 *hi_p, *lo_p;
+        if (t < n_main) {
+            const int row = (int)(t / 64), k = (int)(t % 64);
+            const int sb = row / 48, slot = (row % 48) / 16, jj = row % 16;
+            if (slot != 2) v = w.gru_wih[(size_t)(slot * H + sb * 16 + jj) * 64 + k];
+            hi_p = wu + t; lo_p = wu + n_main + t;
+        } else {
+            const long long q = t - n_main;
+            v = w.gru_wih[(size_t)(2 * H + (int)(q / 64)) * 64 + (int)(q % 64)];
+            hi_p = wu + 2 * n_main + q; lo_p = wu + 2 * n_main + (long long)H * 64 + q;
         }
-        split_bf16(v, wu[t], wu[n_wu + t]);
+        split_bf16(v, *hi_p, *lo_p);
     } else if (i < n_wh + n_wu + n_p1) {
         const long long t = i - n_wh - n_wu;
         split_bf16(w.p1_w[t], p1[t], p1[n_p1 + t]);
@@ -860,8 +712,6 @@ extern "C" int ecord_fold_q_host(const float *q1_w, const float *enc_w, const fl
 }
 
 int tc_init_attrs() {
-    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<0>()));
-    ECORD_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<1>()));
     ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<0, 1>()));
     ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<1, 1>()));
     ECORD_CUDA(cudaFuncSetAttribute((k_gemm_tc2<2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, tc2_smem_bytes<2, 1>()));
@@ -871,47 +721,67 @@ int tc_init_attrs() {
     return 0;
 }
 
+// The GRU's tile schedule (tc2_tile): `full` rounds of 64-unit tiles over the clusters, then the leftover 64-unit tiles cut
+// into kn-sub-block ones.  kn minimises the makespan under relative tile costs of 1 / 0.85 / 0.7: a narrow tile fetches the
+// same A bytes as a 64-unit one (22 and 19 KB per k-chunk and SM against 28), and operand delivery, not the MMAs, bounds the
+// kernel, so halving the width saves far less than half the time.  ECORD_GRU_NARROW = 4 | 2 | 1 forces the width (A/B tests).
+struct GruSched { int clusters, full, kn, narrow; };
+static GruSched gru_schedule(int tiles64) {
+    static const int forced = [] { const char *e = getenv("ECORD_GRU_NARROW"); return e ? atoi(e) : 0; }();
+    const int pairs = kNumSMs / 2;
+    GruSched best{};
+    double best_cost = 1e30;
+    for (int kn = 4; kn >= 1; kn >>= 1) {
+        if (forced && kn != forced) continue;
+        const int per = 4 / kn;
+        const double cost = kn == 4 ? 1.0 : kn == 2 ? 0.85 : 0.7;
+        GruSched s;
+        s.kn = kn;
+        if (tiles64 >= pairs) { s.clusters = pairs; s.full = tiles64 / pairs; s.narrow = (tiles64 % pairs) * per; }
+        else { s.full = 0; s.narrow = tiles64 * per; s.clusters = s.narrow < pairs ? s.narrow : pairs; }
+        const double make = s.full + ceil_div(s.narrow, s.clusters) * cost;
+        if (make < best_cost - 1e-9) { best_cost = make; best = s; }
+    }
+    return best;
+}
+
 // split != 0: ECORD_GEMM_BF16X3 (bf16 hi / lo operands, three products; CTA-pair kernels only)
 int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, int split, cudaStream_t st) {
     PFN_encodeTiled enc;
     int rc = get_encoder(&enc);
     if (rc) return rc;
     const int Mp = p->rows_pad;
+    ECORD_RET_IF(Mp % (2 * BM) != 0, ECORD_E_SIZE);                   // CTA pairs: 256-row tiles
     const int np = split ? 2 : 1;                                      // planes (hi [, lo]) the activation maps cover
     const __nv_bfloat16 *wh = reinterpret_cast<const __nv_bfloat16 *>(w->gru_w_bf16);
-    const __nv_bfloat16 *wu = wh + (size_t)2 * 3072 * H;
+    const __nv_bfloat16 *wum = wh + (size_t)2 * 3072 * H, *wui = wum + (size_t)2 * 3072 * 64;
     const __nv_bfloat16 *hb = reinterpret_cast<const __nv_bfloat16 *>(p->hidden_bf16);
-    CUtensorMap mU, mWu, mA0, mA1, mB;
-    const bool pair = use_pair(Mp);
-    ECORD_RET_IF(split && !pair, ECORD_E_UNSUPPORTED);
     const uint32_t bc = split ? 32 : 64;                               // k-chunk width (tc2_bk)
-    if ((rc = make_map(enc, &mU, p->u_bf16, (uint64_t)np * Mp, 64, BM, bc))) return rc;
-    if ((rc = make_map(enc, &mWu, wu, 2 * 4096, 64, pair ? 128 : 256, bc))) return rc;
-    if ((rc = make_map(enc, &mA0, hb, (uint64_t)np * Mp, H, BM, bc))) return rc;
-    if ((rc = make_map(enc, &mA1, hb + (size_t)np * Mp * H, (uint64_t)np * Mp, H, BM, bc))) return rc;
-    if ((rc = make_map(enc, &mB, wh, 2 * 3072, H, pair ? 96 : 192, bc))) return rc;
+    const GruSched sc = gru_schedule((H / 64) * (Mp / (2 * BM)));
+    TcMaps m;
+    if ((rc = make_map(enc, &m.u, p->u_bf16, (uint64_t)np * Mp, 64, BM, bc))) return rc;
+    if ((rc = make_map(enc, &m.a0, hb, (uint64_t)np * Mp, H, BM, bc))) return rc;
+    if ((rc = make_map(enc, &m.a1, hb + (size_t)np * Mp * H, (uint64_t)np * Mp, H, BM, bc))) return rc;
+    for (int i = 0; i < 2; ++i) {                                      // box heights: this CTA's half of the tile's rows
+        const int kw = i == 0 ? 4 : sc.kn;
+        if ((rc = make_map(enc, &m.b[i], wh, 2 * 3072, H, 24 * kw, bc))) return rc;
+        if ((rc = make_map(enc, &m.wum[i], wum, 2 * 3072, 64, 24 * kw, bc))) return rc;
+        if ((rc = make_map(enc, &m.wui[i], wui, 2 * 1024, 64, 8 * kw, bc))) return rc;
+    }
     TcParams prm{};
     prm.hidden = p->hidden; prm.hidden_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->hidden_bf16);
     prm.th_bf16 = reinterpret_cast<__nv_bfloat16 *>(p->th_bf16);
     prm.bih = w->gru_bih; prm.bhh = w->gru_bhh;
     prm.rows = p->rows; prm.rows_pad = Mp; prm.step_base = step_base; prm.step_off = step_off;
+    prm.sched_full = sc.full; prm.sched_kn = sc.kn; prm.sched_narrow = sc.narrow;
     { static const int dbg = [] { const char *e = getenv("ECORD_TC_DEBUG"); return e ? atoi(e) : 0; }(); prm.debug = dbg; }
     ECORD_RET_IF(prm.debug & 4, ECORD_E_UNSUPPORTED);      // the no-TMA diagnostic no longer terminates (it hung the GPU when tried)
-    if (pair) {
-        const int nblk2 = H / 64, tiles2 = nblk2 * (Mp / (2 * BM));
-        int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        { const char *e = getenv("ECORD_TC_CLUSTERS"); if (e && atoi(e) > 0 && atoi(e) < clusters) clusters = atoi(e); }   // diagnostics
-        if (split)
-            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 3>), dim3(2 * clusters), dim3(kThreads2), (size_t)tc2_smem_bytes<0, 3>(), st, mU, mWu, mA0, mA1, mB,
-                             prm, tiles2, nblk2);
-        else
-            ECORD_PDL_LAUNCH((k_gemm_tc2<0, 1>), dim3(2 * clusters), dim3(kThreads2), (size_t)tc2_smem_bytes<0, 1>(), st, mU, mWu, mA0, mA1, mB,
-                             prm, tiles2, nblk2);
-        return 0;
-    }
-    const int nblk = H / 64, num_tiles = nblk * (Mp / BM);
-    ECORD_PDL_LAUNCH(k_gemm_tc<0>, dim3(num_tiles < kNumSMs ? num_tiles : kNumSMs), dim3(kThreads), (size_t)tc_smem_bytes<0>(), st,
-                     mU, mWu, mA0, mA1, mB, prm, num_tiles, nblk);
+    int clusters = sc.clusters;
+    { const char *e = getenv("ECORD_TC_CLUSTERS"); if (e && atoi(e) > 0 && atoi(e) < clusters && sc.kn == 4 && sc.full == 0) clusters = atoi(e); }   // diagnostics
+    if (split)
+        ECORD_PDL_LAUNCH((k_gemm_tc2<0, 3>), dim3(2 * clusters), dim3(kThreads2), (size_t)tc2_smem_bytes<0, 3>(), st, m, prm, 0, 0);
+    else
+        ECORD_PDL_LAUNCH((k_gemm_tc2<0, 1>), dim3(2 * clusters), dim3(kThreads2), (size_t)tc2_smem_bytes<0, 1>(), st, m, prm, 0, 0);
     return 0;
 }
 
@@ -920,29 +790,24 @@ int launch_proj1_tc(const ecord_weights *w, const ecord_policy *p, int split, cu
     int rc = get_encoder(&enc);
     if (rc) return rc;
     const int Mp = p->rows_pad;
-    CUtensorMap mA, mB;
-    const bool pair = use_pair(Mp);
-    ECORD_RET_IF(split && !pair, ECORD_E_UNSUPPORTED);
-    if ((rc = make_map(enc, &mA, p->th_bf16, (uint64_t)(split ? 2 : 1) * Mp, H, BM, split ? 32 : 64))) return rc;
-    if ((rc = make_map(enc, &mB, w->p1_w_bf16, 2 * 512, H, pair ? 88 : 176, split ? 32 : 64))) return rc;
+    ECORD_RET_IF(Mp % (2 * BM) != 0, ECORD_E_SIZE);
+    TcMaps m;
+    if ((rc = make_map(enc, &m.a0, p->th_bf16, (uint64_t)(split ? 2 : 1) * Mp, H, BM, split ? 32 : 64))) return rc;
+    if ((rc = make_map(enc, &m.b[0], w->p1_w_bf16, 2 * 512, H, 88, split ? 32 : 64))) return rc;
+    m.u = m.a1 = m.a0;                                     // (unused by the projection; valid descriptors all the same)
+    m.b[1] = m.wum[0] = m.wum[1] = m.wui[0] = m.wui[1] = m.b[0];
     TcParams prm{};
     prm.p1_b = w->p1_b; prm.y1 = p->y1; prm.rows = p->rows; prm.rows_pad = Mp;
-    if (pair) {
-        const int nblk2 = 3, tiles2 = nblk2 * (Mp / (2 * BM));
-        const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
-        const dim3 grid(2 * clusters), block(kThreads2);
+    const int nblk2 = 3, tiles2 = nblk2 * (Mp / (2 * BM));
+    const int clusters = tiles2 < kNumSMs / 2 ? tiles2 : kNumSMs / 2;
+    const dim3 grid(2 * clusters), block(kThreads2);
 #define ECORD_PROJ_LAUNCH(MODE, NS) \
-        ECORD_PDL_LAUNCH((k_gemm_tc2<MODE, NS>), grid, block, (size_t)tc2_smem_bytes<MODE, NS>(), st, mA, mB, mA, mA, mB, prm, tiles2, nblk2)
-        if (tiles2 <= clusters) {        // one tile per CTA pair: deep pipeline, staging on top of the stages
-            if (split) ECORD_PROJ_LAUNCH(2, 3); else ECORD_PROJ_LAUNCH(2, 1);
-        } else {
-            if (split) ECORD_PROJ_LAUNCH(1, 3); else ECORD_PROJ_LAUNCH(1, 1);
-        }
-#undef ECORD_PROJ_LAUNCH
-        return 0;
+    ECORD_PDL_LAUNCH((k_gemm_tc2<MODE, NS>), grid, block, (size_t)tc2_smem_bytes<MODE, NS>(), st, m, prm, tiles2, nblk2)
+    if (tiles2 <= clusters) {        // one tile per CTA pair: deep pipeline, staging on top of the stages
+        if (split) ECORD_PROJ_LAUNCH(2, 3); else ECORD_PROJ_LAUNCH(2, 1);
+    } else {
+        if (split) ECORD_PROJ_LAUNCH(1, 3); else ECORD_PROJ_LAUNCH(1, 1);
     }
-    const int nblk = 3, num_tiles = nblk * (Mp / BM);
-    ECORD_PDL_LAUNCH(k_gemm_tc<1>, dim3(num_tiles < kNumSMs ? num_tiles : kNumSMs), dim3(kThreads), (size_t)tc_smem_bytes<1>(), st,
-                     mA, mB, mA, mA, mB, prm, num_tiles, nblk);
+#undef ECORD_PROJ_LAUNCH
     return 0;
 }

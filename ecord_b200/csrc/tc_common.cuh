@@ -101,6 +101,7 @@ struct TcParams {
     const int32_t *step_base;     // device step counter (or NULL)
     int step_off;
     int debug;                    // diagnostics (ECORD_TC_DEBUG): 1 = no MMA issue, 2 = no epilogue math, 4 = no TMA
+    int sched_full, sched_kn, sched_narrow;      // GRU tile schedule (gemm_tc.cu: tc2_tile)
 };
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,

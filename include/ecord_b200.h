@@ -120,9 +120,10 @@ typedef struct ecord_weights {
     const float *v1_w, *v1_b, *v2_w, *v2_b;        /* [32,32],[32],[1,32],[1] */
     const float *q1_w, *q1_b, *qln_w, *qln_b, *q2_w, *q2_b; /* [64,64],[64],[64],[64],[1,64],[1] */
     /* derived by ecord_pack_weights() into caller-allocated buffers */
-    void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [16][192][1024] (rows r|z|hn of each 64-unit block; tile
-                            order of the tcgen05 GRU kernel) as a hi plane (bf16(w)) and a lo plane (bf16(w - hi)), followed by
-                            the Wu pack [16][256][64] (rows r|z|0|in), hi plane and lo plane */
+    void  *gru_w_bf16;   /* bf16, ECORD_GRU_PACK_ELEMS elements: Wh pack [64][48][1024] (rows r16|z16|hn16 of each 16-unit
+                            sub-block: a GRU tile of 16, 32 or 64 units is a contiguous row range) as a hi plane (bf16(w)) and a
+                            lo plane (bf16(w - hi)); then the Wu_main pack [64][48][64] (rows r16|z16|0), hi plane | lo plane;
+                            then Wu_in [1024][64] (W_in), hi plane | lo plane */
     void  *p1_w_bf16;    /* bf16, ECORD_P1_PACK_ELEMS elements: proj_rnn_to_gnn.1 weight [512][1024] hi plane | lo plane, followed
                             by proj_rnn_to_gnn.4 weight [32][512] hi plane | lo plane */
     float *q_tc;         /* f32 [ECORD_QTC_FLOATS] operands of the tensor-core Q kernel (ECORD_Q_TC), or NULL:

@@ -394,9 +394,10 @@ def test_epsilon_greedy_is_distributionally_right(gemm):
 
 
 def test_gemm_variants_agree_in_subprocesses():
-    """The CTA-pair (cta_group::2) tcgen05 kernels, the single-CTA ones (ECORD_GEMM_PAIR=0) and plain launches
-    (ECORD_PDL=0, no programmatic dependent launch) compute the same rollout: the switches are read once per process,
-    so each variant runs in its own interpreter and prints a digest of hidden state, scores and actions."""
+    """The GRU kernel with its leftover tiles cut to 64, 32 or 16 hidden units (ECORD_GRU_NARROW = 4 | 2 | 1 sub-blocks; the
+    default picks the width per launch) and plain launches (ECORD_PDL=0, no programmatic dependent launch) compute the same
+    rollout bit for bit, in both tensor-core modes: the switches are read once per process, so each variant runs in its own
+    interpreter and prints a digest of hidden state, scores and actions."""
     import subprocess
     import sys
     code = r'''
@@ -411,7 +412,7 @@ graphs = synthetic_set("er", 150, 3, p=0.1)
 w = DeviceWeights(random_state_dicts(5, perturb_norms=True))
 dg = DeviceGraph(GraphBatcher()(graphs).tg)
 T = 70
-st = RolloutState(dg, w, T, gemm="bf16", max_steps=40)
+st = RolloutState(dg, w, T, gemm=sys.argv[1], max_steps=40)
 st.gnn_embed(); st.env_init(np.random.RandomState(2).randint(0, 2, (dg.N, T)).astype(np.int8))
 st.run(37); torch.cuda.synchronize()
 h = hashlib.sha1()
@@ -419,10 +420,12 @@ for t in (st.hidden[:, :st.M], st.score, st.action_log[:37], st.peek):
     h.update(t.cpu().numpy().tobytes())
 print("DIGEST", h.hexdigest())
 ''' % (ROOT_DIR, TESTS_DIR)
-    digests = {}
-    for name, env in (("pair+pdl", {}), ("single", {"ECORD_GEMM_PAIR": "0"}), ("no-pdl", {"ECORD_PDL": "0"})):
-        e = dict(os.environ); e.update(env)
-        out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=300)
-        assert out.returncode == 0, out.stderr[-2000:]
-        digests[name] = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0]
-    assert len(set(digests.values())) == 1, digests
+    for gemm in ("bf16x3", "bf16"):
+        digests = {}
+        for name, env in (("default", {}), ("w64", {"ECORD_GRU_NARROW": "4"}), ("w32", {"ECORD_GRU_NARROW": "2"}),
+                          ("w16", {"ECORD_GRU_NARROW": "1"}), ("no-pdl", {"ECORD_PDL": "0"})):
+            e = dict(os.environ); e.update(env)
+            out = subprocess.run([sys.executable, "-c", code, gemm], env=e, capture_output=True, text=True, timeout=300)
+            assert out.returncode == 0, out.stderr[-2000:]
+            digests[name] = [l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0]
+        assert len(set(digests.values())) == 1, (gemm, digests)

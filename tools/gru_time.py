@@ -29,4 +29,4 @@ torch.cuda.synchronize(); a.record()
 for _ in range(20): st.policy_step()
 b.record(); b.synchronize()
 print(f"{sys.argv[1:]} ECORD_TC_DEBUG={os.environ.get('ECORD_TC_DEBUG','0')} CLUSTERS={os.environ.get('ECORD_TC_CLUSTERS','-')} "
-      f"PAIR={os.environ.get('ECORD_GEMM_PAIR','1')}: {a.elapsed_time(b)/20*1e3:.1f} us per launch (mask {os.environ['ECORD_POLICY_MASK']}, warm L2)")
+      f"NARROW={os.environ.get("ECORD_GRU_NARROW","auto")}: {a.elapsed_time(b)/20*1e3:.1f} us per launch (mask {os.environ['ECORD_POLICY_MASK']}, warm L2)")
