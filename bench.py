@@ -254,9 +254,10 @@ def run_b200(args):
     dg = DeviceGraph(batch.tg, dev)
     k = args.steps_per_graph
     if K % k and K <= 2 * k:
-        # short runs (the driver's --steps 20): equal chunks instead of one full graph plus a short remainder whose cold start
-        # would be amortised over a handful of steps only
-        k = -(-K // -(-K // k))
+        # short runs (the driver's --steps 20): ONE CUDA graph of K steps, which is also what B200Solver.rollout builds for a
+        # rollout of that length, instead of a full graph plus a short remainder whose cold start (L2 flushed before every
+        # graph launch) would be amortised over a handful of steps only
+        k = K
     st = RolloutState(dg, weights, T, gemm=args.gemm, compat=True, max_steps=W + K + k, steps_per_graph=k)
     st.gnn_embed()
     st.env_init(init)
@@ -428,11 +429,17 @@ def run_b200(args):
                               "tensor_bound_units_s": tf_sus * 1e12 / F_UNIT(n), "hbm_bound_units_s": hbm * 1e9 / B_UNIT(n, avg_deg),
                               "frac_of_binding_bound": (value / world) / min(tf_sus * 1e12 / F_UNIT(n), hbm * 1e9 / B_UNIT(n, avg_deg)),
                               "note": "literal fp32-model FLOPs over the sustained bf16 peak"}
+        if gm == "bf16x3":
+            # what the tensor pipe executes in this mode: three bf16 products for every literal product of the GRU / projection /
+            # tail GEMMs (the price of fp32-grade recurrent state on bf16 tensor cores), the Q head as counted
+            f_exec = 3.0 * F_UNIT(0) + 8416.0 * n
+            roof["whole_step"]["executed"] = {"flops_per_unit": f_exec, "frac_of_tensor_peak": (value / world) * f_exec / (tf_sus * 1e12),
+                                              "note": "bf16x3 executes 3 tensor-core products per literal GEMM product"}
     st.close()
 
     # ---- e2e: the public API with host buffers (H2D of inputs, D2H of the score log inside the timed region) ----
     solver = B200Solver(gnn=sd['gnn'], rnn=sd['rnn'], gnn2rnn=sd['gnn2rnn'], node_encoder=sd['node_encoder'],
-                        device=dev, gemm=args.gemm, steps_per_graph=k)
+                        device=dev, gemm=args.gemm, steps_per_graph=args.steps_per_graph)
     Ke = K
     # warm-up call of the same shape: the solver keeps the device state of a graph batch (buffers, pinned staging, captured
     # CUDA graphs) and re-initialises it on the next call, which is the steady state of test_solver's trajectory chunks

@@ -424,7 +424,8 @@ int launch_env_step_fused(const ecord_graph *g, const ecord_env *env, const ecor
     // Large grids are launched plainly, small ones as programmatic dependents: letting 600+ small CTAs become resident
     // while the Q kernel still runs costs more than their msg_in weight staging saves (ER500, 625 CTAs: 133.3 -> 131.7 us
     // per step without the early launch), while a grid of about one CTA per SM gains (ER10000, 160 CTAs: 225.7 -> 223.5).
-    // Every other kernel of the chain gains from the early launch, 1.8 - 3.6 us each.
+    // Every other kernel of the chain gains from the early launch, 1.8 - 3.6 us each.  (1024-thread CTAs -- a quarter of the CTAs and
+    // of the weight staging, launched early -- were measured too: ER500 step 170.1 -> 172.8 us; 512 threads: no change.)
     const int ctas = ceil_div((long long)GT * 32, 256);
     static const int force = [] { const char *e = getenv("ECORD_ENV_PDL"); return e ? atoi(e) : -1; }();   // A/B: 0 plain, 1 PDL
     if (force == 0 || (force < 0 && ctas > 2 * kNumSMs))

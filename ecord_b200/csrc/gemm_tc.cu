@@ -72,7 +72,10 @@ constexpr int kStages2 = 4;      // the pair kernel's stages are 28-32 KB (half 
 // 52-55 and 72 B/clk/SM (tools/microbench/tma_ingest2d.cu, measured on the B200).  In THESE kernels a second producer changes
 // nothing (split GRU 97.2 vs 99 us): with the MMAs switched off the ring already moves 609 MB per launch in 50 us = 12.2 TB/s,
 // the L2 -> SM delivery limit of the chip, whatever the ring depth (3, 4, 5 stages: 49.7 / 50.2 / 50.0 us) -- so one it is.
-constexpr int kProducers = 1;
+#ifndef ECORD_TC_PRODUCERS
+#define ECORD_TC_PRODUCERS 1
+#endif
+constexpr int kProducers = ECORD_TC_PRODUCERS;
 constexpr int kEpiThreads = kThreads - 64;                    // 16 epilogue warps
 constexpr int kThreads2 = kThreads + 32 * (kProducers - 1);   // + the extra producer warps
 constexpr int kHsPitch = 68;     // floats per row of the fp32 epilogue staging tile (64 + 4: 16-byte aligned rows, 4-way STS.128)

@@ -173,14 +173,16 @@ class B200Solver:
         batch is rolled out again with the same shape -- test_solver's trajectory chunks (testing.py:174-189) and
         repeated validation passes -- which saves the buffer allocations and the CUDA-graph capture."""
         seed = self.seed if seed is None else seed
-        key = (id(dg), T, gemm, self.compat, tau, seed, self.steps_per_graph, epsilon)
+        # a rollout of up to two graphs' worth of steps runs as ONE CUDA graph (no remainder graph, one launch)
+        spg = S if self.steps_per_graph < S <= 2 * self.steps_per_graph else self.steps_per_graph
+        key = (id(dg), T, gemm, self.compat, tau, seed, spg, epsilon)
         for i, (k, st) in enumerate(self._state_cache):
             if k == key and st.g is dg and st.max_steps >= S:
                 self._state_cache.insert(0, self._state_cache.pop(i))
                 st.reset()
                 return st
         st = RolloutState(dg, self.weights, T, gemm=gemm, compat=self.compat, tau=tau, seed=seed, max_steps=S,
-                          log_scores=True, log_actions=True, steps_per_graph=self.steps_per_graph, dump_q=False,
+                          log_scores=True, log_actions=True, steps_per_graph=spg, dump_q=False,
                           epsilon=epsilon)
         self._state_cache.insert(0, (key, st))
         for _, old in self._state_cache[2:]:
