@@ -19,6 +19,7 @@
 
 namespace {
 constexpr int D = ECORD_DIM_GNN;   // 16
+constexpr int kYsPitch = 20;       // floats per staged y row in shared memory (k_gnn_update<true>)
 
 struct GnnSmem {
     float snd_w[D * D], snd_b[D];
@@ -117,7 +118,10 @@ __global__ void __launch_bounds__(128)
 k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const float *__restrict__ y, float *xn, double *acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GnnSmem &S = *reinterpret_cast<GnnSmem *>(smem_raw);
-    float *ys = reinterpret_cast<float *>(smem_raw + sizeof(GnnSmem));      // STAGE: [n_g][16]
+    // STAGE: [n_g][kYsPitch].  Rows of 16 floats would put every row on one of two 16-bank halves, a 16-way conflict for a
+    // warp's LDS.128 from 32 random rows (48 % of the shared-memory wavefront peak, 88 us per layer); a pitch of 20 floats
+    // walks the row starts over all eight 4-bank groups.
+    float *ys = reinterpret_cast<float *>(smem_raw + sizeof(GnnSmem));
     for (int i = threadIdx.x; i < 2 * D * 2 * D; i += blockDim.x) S.rec_w[i] = wt.gnn_rec_w[i];
     for (int i = threadIdx.x; i < 3 * D * 2 * D; i += blockDim.x) S.wih[i] = wt.gnn_wih[i];
     for (int i = threadIdx.x; i < 3 * D * D; i += blockDim.x) S.whh[i] = wt.gnn_whh[i];
@@ -131,8 +135,8 @@ k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const
         lo = g.graph_ptr[gi];
         const int n = g.graph_ptr[gi + 1] - lo;
         const float4 *src = reinterpret_cast<const float4 *>(y + (long long)lo * D);
-        float4 *dst = reinterpret_cast<float4 *>(ys);
-        for (int i = threadIdx.x; i < n * (D / 4); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < n * (D / 4); i += blockDim.x)
+            *reinterpret_cast<float4 *>(ys + (i >> 2) * kYsPitch + (i & 3) * 4) = src[i];
         const int vl = g.qtile_v0[tile] + threadIdx.x;
         live = vl < n;
         v = lo + vl;
@@ -162,10 +166,10 @@ k_gnn_update(ecord_graph g, ecord_weights wt, const float *__restrict__ x, const
             for (; k + 2 <= k1; k += 2) {               // sequential, global edge order; the next edge's indices are in flight
                 const int s0 = g.in_src[k] - lo, s1 = g.in_src[k + 1] - lo;
                 const float w0 = g.in_w[k], w1 = g.in_w[k + 1];
-                add_row(reinterpret_cast<const float4 *>(ys + s0 * D), w0);
-                add_row(reinterpret_cast<const float4 *>(ys + s1 * D), w1);
+                add_row(reinterpret_cast<const float4 *>(ys + s0 * kYsPitch), w0);
+                add_row(reinterpret_cast<const float4 *>(ys + s1 * kYsPitch), w1);
             }
-            if (k < k1) add_row(reinterpret_cast<const float4 *>(ys + (g.in_src[k] - lo) * D), g.in_w[k]);
+            if (k < k1) add_row(reinterpret_cast<const float4 *>(ys + (g.in_src[k] - lo) * kYsPitch), g.in_w[k]);
         } else {
             int k = k0;
             for (; k + 4 <= k1; k += 4) {               // four edges' row loads in flight, sums in edge order
@@ -317,16 +321,16 @@ extern "C" int ecord_gnn_embed(const ecord_graph *g, const ecord_weights *w, flo
     ECORD_LAUNCH_CHECK();
     // shared-memory staging of a graph's y rows: needs the vertex tiling and rows that fit beside a few co-resident CTAs
     static const int smem_cap = [] {
-        cudaFuncSetAttribute(k_gnn_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GnnSmem) + 64 * 1024);
-        return 64 * 1024;
+        cudaFuncSetAttribute(k_gnn_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GnnSmem) + 96 * 1024);
+        return 96 * 1024;
     }();
     static_assert(ECORD_QTILE == 128, "k_gnn_update<true>: one thread per vertex of a tile");
-    const bool stage = g->num_qtiles > 0 && g->qtile_graph && g->qtile_v0 && (size_t)g->n_max * D * sizeof(float) <= (size_t)smem_cap;
+    const bool stage = g->num_qtiles > 0 && g->qtile_graph && g->qtile_v0 && (size_t)g->n_max * kYsPitch * sizeof(float) <= (size_t)smem_cap;
     float *cur = x, *nxt = xn;
     for (int l = 0; l < 4; ++l) {   // num_layers is hard-coded to 4 by experiments/configs.py:99
         k_gnn_ln_send<<<nb, TB, 0, st>>>(N, cur, acc + 2 * l, w->gnn_snd_w, w->gnn_snd_b, y);
         ECORD_LAUNCH_CHECK();
-        if (stage) k_gnn_update<true><<<g->num_qtiles, TB, sizeof(GnnSmem) + (size_t)g->n_max * D * sizeof(float), st>>>(*g, *w, cur, y, nxt, acc + 2 * (l + 1));
+        if (stage) k_gnn_update<true><<<g->num_qtiles, TB, sizeof(GnnSmem) + (size_t)g->n_max * kYsPitch * sizeof(float), st>>>(*g, *w, cur, y, nxt, acc + 2 * (l + 1));
         else k_gnn_update<false><<<nb, TB, sizeof(GnnSmem), st>>>(*g, *w, cur, y, nxt, acc + 2 * (l + 1));
         ECORD_LAUNCH_CHECK();
         float *t = cur; cur = nxt; nxt = t;

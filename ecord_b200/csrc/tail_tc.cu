@@ -246,6 +246,11 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
     __syncthreads();          // (the MMAs have completed: the A-operand tile is free for the reduction below)
 
     // ---------------- phase 3b: 512 / R threads per row ----------------
+    // The 32 value-head units and 64 Q channels of a row are cut into SIXTEEN groups (2 units + 4 channels each) whatever R is:
+    // a thread takes one group (R = 32) or two (R = 64), every group's 22 partial sums go to shared memory and the row's first
+    // thread adds the sixteen partials in group order.  The association of every sum is therefore the same for both R, i.e. a
+    // row's result does not depend on how many rows the launch has -- which is what lets a trajectory or graph shard of a
+    // rollout reproduce the single-GPU run bit for bit (R follows the batch size, see launch_tail_tc).
     {
         const int nparts = kTtThreads / R;                    // 16 or 8
         const int rloc = tid % R, part = tid / R;             // part is warp-uniform (R is a multiple of 32)
@@ -255,24 +260,6 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
 #pragma unroll
         for (int o = 0; o < ND; ++o) { P[o] = Z.Ps[rloc][o]; Tp[o] = Z.Ts[rloc][o]; }
         const float meanA = Z.meanA[rloc];
-        float acc[22];                                        // Wg^T a' (16) | Cc^T a' (3) | |a'|^2 | LA | v   (partial sums)
-#pragma unroll
-        for (int i = 0; i < 22; ++i) acc[i] = 0.0f;
-        // state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 -- this part's value-head units
-        const int nv = ND / nparts;
-        for (int jj = 0; jj < nv; ++jj) {
-            const int j = part * nv + jj;
-            const float4 *vr = reinterpret_cast<const float4 *>(&S.v1[j * ND]);
-            float h0 = w.v1_b[j], h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
-#pragma unroll
-            for (int o4 = 0; o4 < ND / 4; ++o4) {
-                const float4 v4 = vr[o4];
-                h0 = fmaf(v4.x, Tp[4 * o4], h0); h1 = fmaf(v4.y, Tp[4 * o4 + 1], h1);
-                h2 = fmaf(v4.z, Tp[4 * o4 + 2], h2); h3 = fmaf(v4.w, Tp[4 * o4 + 3], h3);
-            }
-            acc[21] = fmaf(w.v2_w[j], lrelu((h0 + h1) + (h2 + h3)), acc[21]);
-        }
-        // this part's Q channels: a_c, then everything that is linear in it
         float *Ao = p.A + (long long)m * QC;
         float *Aco = p.Ac ? p.Ac + (long long)m * QC : nullptr;
         // the qa rows of the CTA are assembled in shared memory (behind the partial sums in the free A-operand tile) and leave as
@@ -280,49 +267,69 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         constexpr int kQsPitch = ECORD_QA_STRIDE + 1;
         uint32_t *qs_base = reinterpret_cast<uint32_t *>(S.act) + 24576;              // 96 KB into the 128 KB tile
         uint32_t *qw = p.qa ? qs_base + rloc * kQsPitch : nullptr;
-        const int nc = QC / nparts;
-        for (int cc_ = 0; cc_ < nc; ++cc_) {
-            const int c = part * nc + cc_;
-            const float4 *qr = reinterpret_cast<const float4 *>(&S.q1[c * ND]);
-            float a0 = w.q1_b[c], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        float *red = reinterpret_cast<float *>(S.act);                                // [22][16 groups][64 rows]: 88 KB
+        float acc[22];                                        // Wg^T a' (16) | Cc^T a' (3) | |a'|^2 | LA | v   (partial sums)
+        const int ngrp = 16 / nparts;                         // groups per thread: 1 or 2
+        for (int gq = 0; gq < ngrp; ++gq) {
+            const int grp = part * ngrp + gq;
 #pragma unroll
-            for (int o4 = 0; o4 < ND / 4; ++o4) {
-                const float4 q4 = qr[o4];
-                a0 = fmaf(q4.x, P[4 * o4], a0); a1 = fmaf(q4.y, P[4 * o4 + 1], a1);
-                a2 = fmaf(q4.z, P[4 * o4 + 2], a2); a3 = fmaf(q4.w, P[4 * o4 + 3], a3);
-            }
-            const float a = (a0 + a1) + (a2 + a3);
-            const float ac = a - meanA;
-            acc[20] = fmaf(w.q2_w[c] * w.qln_w[c], ac, acc[20]);
-            if (live) {
-                if (!qw) Ao[c] = a;               // A itself is read by the exact Q kernel only
-                if (Aco) Aco[c] = ac;
-            }
-            if (qw) {
-                const float4 cc4 = *reinterpret_cast<const float4 *>(&S.cc[c * 4]);
-                const float ap = ac + cc4.w;
-                qw[c] = split_h2(w.qln_w[c] * ap);
+            for (int i = 0; i < 22; ++i) acc[i] = 0.0f;
+            // state value: v = W_v2 LReLU(W_v1 tanh(P) + b_v1) + b_v2 -- this group's value-head units
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = grp * 2 + jj;
+                const float4 *vr = reinterpret_cast<const float4 *>(&S.v1[j * ND]);
+                float h0 = w.v1_b[j], h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 g4 = *reinterpret_cast<const float4 *>(&S.wg[c * 16 + 4 * k4]);
-                    acc[4 * k4] = fmaf(g4.x, ap, acc[4 * k4]); acc[4 * k4 + 1] = fmaf(g4.y, ap, acc[4 * k4 + 1]);
-                    acc[4 * k4 + 2] = fmaf(g4.z, ap, acc[4 * k4 + 2]); acc[4 * k4 + 3] = fmaf(g4.w, ap, acc[4 * k4 + 3]);
+                for (int o4 = 0; o4 < ND / 4; ++o4) {
+                    const float4 v4 = vr[o4];
+                    h0 = fmaf(v4.x, Tp[4 * o4], h0); h1 = fmaf(v4.y, Tp[4 * o4 + 1], h1);
+                    h2 = fmaf(v4.z, Tp[4 * o4 + 2], h2); h3 = fmaf(v4.w, Tp[4 * o4 + 3], h3);
                 }
-                acc[16] = fmaf(cc4.x, ap, acc[16]); acc[17] = fmaf(cc4.y, ap, acc[17]); acc[18] = fmaf(cc4.z, ap, acc[18]);
-                acc[19] = fmaf(ap, ap, acc[19]);
+                acc[21] = fmaf(w.v2_w[j], lrelu((h0 + h1) + (h2 + h3)), acc[21]);
             }
-        }
-        // combine the parts of each row: red[i][part][row] (conflict-free), summed by part 0
-        float *red = reinterpret_cast<float *>(S.act);
-        if (part) {
+            // this group's Q channels: a_c, then everything that is linear in it
+            for (int cc_ = 0; cc_ < 4; ++cc_) {
+                const int c = grp * 4 + cc_;
+                const float4 *qr = reinterpret_cast<const float4 *>(&S.q1[c * ND]);
+                float a0 = w.q1_b[c], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 22; ++i) red[(i * 15 + part - 1) * 64 + rloc] = acc[i];
+                for (int o4 = 0; o4 < ND / 4; ++o4) {
+                    const float4 q4 = qr[o4];
+                    a0 = fmaf(q4.x, P[4 * o4], a0); a1 = fmaf(q4.y, P[4 * o4 + 1], a1);
+                    a2 = fmaf(q4.z, P[4 * o4 + 2], a2); a3 = fmaf(q4.w, P[4 * o4 + 3], a3);
+                }
+                const float a = (a0 + a1) + (a2 + a3);
+                const float ac = a - meanA;
+                acc[20] = fmaf(w.q2_w[c] * w.qln_w[c], ac, acc[20]);
+                if (live) {
+                    if (!qw) Ao[c] = a;               // A itself is read by the exact Q kernel only
+                    if (Aco) Aco[c] = ac;
+                }
+                if (qw) {
+                    const float4 cc4 = *reinterpret_cast<const float4 *>(&S.cc[c * 4]);
+                    const float ap = ac + cc4.w;
+                    qw[c] = split_h2(w.qln_w[c] * ap);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const float4 g4 = *reinterpret_cast<const float4 *>(&S.wg[c * 16 + 4 * k4]);
+                        acc[4 * k4] = fmaf(g4.x, ap, acc[4 * k4]); acc[4 * k4 + 1] = fmaf(g4.y, ap, acc[4 * k4 + 1]);
+                        acc[4 * k4 + 2] = fmaf(g4.z, ap, acc[4 * k4 + 2]); acc[4 * k4 + 3] = fmaf(g4.w, ap, acc[4 * k4 + 3]);
+                    }
+                    acc[16] = fmaf(cc4.x, ap, acc[16]); acc[17] = fmaf(cc4.y, ap, acc[17]); acc[18] = fmaf(cc4.z, ap, acc[18]);
+                    acc[19] = fmaf(ap, ap, acc[19]);
+                }
+            }
+            // publish the group's partial sums: red[i][group][row] (conflict-free)
+#pragma unroll
+            for (int i = 0; i < 22; ++i) red[(i * 16 + grp) * 64 + rloc] = acc[i];
         }
         __syncthreads();
         if (part == 0 && live) {
-            for (int q = 0; q < nparts - 1; ++q) {
 #pragma unroll
-                for (int i = 0; i < 22; ++i) acc[i] += red[(i * 15 + q) * 64 + rloc];
+            for (int i = 0; i < 22; ++i) acc[i] = red[(i * 16) * 64 + rloc];
+            for (int q = 1; q < 16; ++q) {
+#pragma unroll
+                for (int i = 0; i < 22; ++i) acc[i] += red[(i * 16 + q) * 64 + rloc];
             }
             const float vv = acc[21] + w.v2_b[0];
             p.v[m] = vv;

@@ -173,9 +173,10 @@ class B200Solver:
         batch is rolled out again with the same shape -- test_solver's trajectory chunks (testing.py:174-189) and
         repeated validation passes -- which saves the buffer allocations and the CUDA-graph capture."""
         seed = self.seed if seed is None else seed
-        # a rollout of up to two graphs' worth of steps runs as ONE CUDA graph (no remainder graph, one launch)
+        # a state created for a rollout of up to two graphs' worth of steps runs it as ONE CUDA graph (no remainder graph, one
+        # launch); a cached state is reused with whatever graph length it was built for
         spg = S if self.steps_per_graph < S <= 2 * self.steps_per_graph else self.steps_per_graph
-        key = (id(dg), T, gemm, self.compat, tau, seed, spg, epsilon)
+        key = (id(dg), T, gemm, self.compat, tau, seed, self.steps_per_graph, epsilon)
         for i, (k, st) in enumerate(self._state_cache):
             if k == key and st.g is dg and st.max_steps >= S:
                 self._state_cache.insert(0, self._state_cache.pop(i))

@@ -595,3 +595,21 @@ def test_graph_sharding_reproduces_the_full_batch_rollout(gemm, compat, ragged):
                 assert torch.equal(log['best_state'][k, :ns[g]], full['best_state'][g, :ns[g]]), (world, rank, g)
             seen += own
         assert seen == list(range(len(ns)))
+
+
+@pytest.mark.parametrize("gemm", ["bf16x3", "bf16"])
+def test_trajectory_shards_reproduce_the_full_batch_rollout(gemm):
+    """SURVEY.md 8e, trajectory axis: a shard of the trajectories (B200Solver.rollout(traj_slice=...), what every rank of
+    dist.rollout_sharded runs) gives the single-GPU rollout's scores bit for bit -- a row's arithmetic may not depend on how many
+    rows the launch has.  The full batch has 5000 rows (64-row CTAs in the policy tail, 64-unit GRU tiles), the shards 600-700
+    (32-row CTAs, narrower GRU tiles): the case that differed before the tail's sums were given one association for both."""
+    sd = random_state_dicts(9, perturb_norms=True)
+    graphs = synthetic_set("er", 40, 100, seed0=3, p=0.15, signed=True)
+    batch = GraphBatcher()(graphs)
+    T, S = 50, 60
+    init = np.random.RandomState(5).randint(0, 2, (batch.tg.num_nodes, T), dtype=np.int8)
+    solver = _solver(sd, gemm=gemm)
+    full = torch.stack(solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init)['scores'], -1)
+    for lo, hi in ((0, 6), (6, 13), (43, 50)):
+        part = solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init, traj_slice=(lo, hi))
+        assert torch.equal(torch.stack(part['scores'], -1), full[:, lo:hi]), (lo, hi)
