@@ -238,6 +238,11 @@ lo, hi = shard_bounds(T, 2, rank)
 best, by_all = reduce_best(full[:, lo:hi].contiguous(), T)
 assert torch.equal(by_all, full), (rank, by_all)
 assert torch.equal(best, full.max(-1).values)
+T2 = 8                                               # equal split: the fast path (no padding)
+full2 = torch.arange(G * T2, dtype=torch.float32).view(G, T2) * (1 - 2 * (torch.arange(G).view(G, 1) % 2))
+lo, hi = shard_bounds(T2, 2, rank)
+best2, by_all2 = reduce_best(full2[:, lo:hi].contiguous(), T2)
+assert torch.equal(by_all2, full2) and torch.equal(best2, full2.max(-1).values)
 from ecord_b200.dist import gather_graph_shards
 glo, ghi = shard_bounds(G, 2, rank)                  # graph sharding: 3 + 2 graphs
 assert torch.equal(gather_graph_shards(full[glo:ghi].contiguous(), G), full)
