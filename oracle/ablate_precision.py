@@ -116,6 +116,8 @@ class AblatedModel(orc.ModelOracle):
 def load_set(name, count):
     if name == "er500":
         return synthetic_set("er", 500, count, p=0.15, signed=True)
+    if name in ("er2000", "er2000s"):      # BASELINE config 4's family: G(2000, avg degree 10), unit ("s": +-1) weights
+        return synthetic_set("er", 2000, count, avg_degree=10, signed=name.endswith("s"))
     import pickle
     f = {"er200": "testing/ER_200spin_p15_50graphs.pkl", "ba500": "testing/BA_500spin_m4_50graphs.pkl",
          "er40": "validation/ER_40spin_p15_100graphs.pkl", "er100": "testing/ER_100spin_p15_50graphs.pkl"}[name]
@@ -146,20 +148,32 @@ VARIANTS = {
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "er200"
     count = int(sys.argv[2]) if len(sys.argv) > 2 else 10
-    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
-    T = 50
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 and sys.argv[3] else None
+    num_steps = int(sys.argv[4]) if len(sys.argv) > 4 else -4          # default: the full 4 |V| steps
+    T = int(sys.argv[5]) if len(sys.argv) > 5 else 50
     torch.set_num_threads(os.cpu_count())
     graphs = load_set(name, count)
     ob = orc.build_batch(graphs)
     init = np.random.RandomState(7).randint(0, 2, (ob.N, T)).astype(np.int8)
     sd = random_state_dicts(0)
     base = None
-    print(f"{name}: {count} graphs x {T} trajectories, {4 * int(ob.num_nodes_list.max())} steps, random-init weights seed 0")
+    print(f"{name}: {count} graphs x {T} trajectories, {num_steps if num_steps > 0 else 4 * int(ob.num_nodes_list.max())} steps, random-init weights seed 0")
     for i, (vn, kw) in enumerate(VARIANTS.items()):
         if only and i and str(i) not in only:
             continue
         t0 = time.time()
-        log = orc.rollout(AblatedModel(sd, **kw), ob, T, -4, init, tau=0.0)
+        log = orc.rollout(AblatedModel(sd, **kw), ob, T, num_steps, init, tau=0.0, record=(i == 0))
+        if i == 0 and 'q' in log:        # how close the reference's own top two Q-values are, relative to the unit's Q spread
+            gaps = []
+            for q in log['q']:
+                for g in range(ob.G):
+                    qq = q[int(ob.ptr[g]):int(ob.ptr[g + 1])]
+                    top = qq.topk(2, 0).values
+                    gaps.append(((top[0] - top[1]) / (qq.max(0).values - qq.min(0).values)).flatten())
+            gaps = torch.cat(gaps)
+            print("    top-2 gap of the reference's Q-values / Q spread of the unit, over all units and steps: "
+                  + "  ".join(f"P(< {t:g}) = {(gaps < t).float().mean().item():.3f}" for t in (1e-6, 1e-5, 1e-4, 1e-3))
+                  + f"  exact ties {(gaps == 0).float().mean().item():.3f}", flush=True)
         s = torch.stack(log['scores'], -1)                 # [G,T,S]
         by_t = s.max(-1).values
         smax = by_t.max(-1).values

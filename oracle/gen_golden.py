@@ -294,13 +294,29 @@ def _to_nx(g):
 def gen_fullsize(which=("er200", "er500", "ba500")):
     """BASELINE configs 2-3 at the real rollout length, through the reference's own test_solver."""
     from ecord_b200.graphs import synthetic_set
-    wseed, sseed, T, KEEP_T = 0, 4242, 50, 8
+    wseed, sseed, KEEP_T = 0, 4242, 8
     sd = random_state_dicts(wseed, perturb_norms=False)
     for name in which:
+        T, num_steps = 50, -4
         if name == "er200":
             graphs, _ = load("testing/ER_200spin_p15_50graphs"); graphs = graphs[:10]; out_name = "config2_er200.npz"
         elif name == "ba500":
             graphs, _ = load("testing/BA_500spin_m4_50graphs"); graphs = graphs[:10]; out_name = "config3_ba500.npz"
+        elif name == "er2000":
+            # BASELINE config 4's graph family (graphs/generated: G(n, avg degree 10), unit weights) at n = 2000: 16 vertex tiles per
+            # graph, so the arg-max of a unit spans 16 CTAs of the Q kernel.  2 graphs x 32 trajectories x 1500 steps (the full
+            # 4 |V| = 8000 steps x 128 trajectories would take the CPU reference half an hour per graph)
+            graphs = [_to_nx(g) for g in synthetic_set("er", 2000, 2, avg_degree=10, signed=False)]; out_name = "config4_er2000.npz"
+            T, num_steps = 32, 1500
+        elif name == "er2000s":
+            # the same family with +-1 weights.  With UNIT weights the t=0 GNN is degenerate -- every vertex starts from the same
+            # feature and a mean over identical neighbour messages is that message, so all vertices share one embedding up to
+            # rounding -- and 96 % of the reference's arg-max decisions are ties within 1e-6 of the Q spread (26 % exact): no
+            # implementation with another summation order follows its trajectories (oracle/ablate_precision.py er2000: an fp64
+            # evaluation leaves them after 1.8 steps).  Signed weights break the symmetry, so this fixture can be held to the
+            # trajectory bar of configs 2-3 at n = 2000.
+            graphs = [_to_nx(g) for g in synthetic_set("er", 2000, 2, avg_degree=10, signed=True)]; out_name = "config4_er2000_signed.npz"
+            T, num_steps = 32, 1500
         else:
             graphs = [_to_nx(g) for g in synthetic_set("er", 500, 5, p=0.15, signed=True)]; out_name = "config2_er500.npz"
         solver, gb = make_solver(sd)
@@ -314,7 +330,7 @@ def gen_fullsize(which=("er200", "er500", "ba500")):
             return ret
 
         actor.action_select = wrapped
-        cfg = TestGraphsConfig(graphs=graphs, opt_scores=None, num_steps=-4, tradj_per_graph=T, tau=0, max_time=None,
+        cfg = TestGraphsConfig(graphs=graphs, opt_scores=None, num_steps=num_steps, tradj_per_graph=T, tau=0, max_time=None,
                                graphs_bsz=len(graphs), tradj_bsz=T)
         np.random.seed(sseed)
         import time
