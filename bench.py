@@ -399,7 +399,8 @@ def run_b200(args):
                               {"flops_per_unit": 2 * 1088 * 3072, "units_per_launch": M, "tensor_products_per_literal_flop": int(ns)},
                               f"k_gemm_tc2<0, {ns}>",
                               "literal fp32-model FLOPs; bf16x3 issues 3 MMAs per literal product (hi.hi + lo.hi + hi.lo), so the tensor pipe "
-                              "does 3x this work" if ns == "3" else None))
+                              "does 3x this work" if ns == "3" else None,
+                              extra={"executed_frac_of_peak": int(ns) * 2.0 * M * 1088 * 3072 / (tms["gru"] * 1e-3) / 1e12 / tf_burst}))
             ents.append(entry(f"k_gemm_tc2<1|2,{ns}> (projection 1024->512)", "tensor", tms["proj"], 2.0 * M * 1024 * 512,
                               {"flops_per_unit": 2 * 1024 * 512, "units_per_launch": M}, f"k_gemm_tc2<2, {ns}>"))
             ents.append(entry("k_tail_tc (LN512, 512->32 on tcgen05, LN32, value head, Q operands)", "tensor", tms["tail"],
