@@ -42,6 +42,7 @@
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 constexpr int Q = ECORD_DIM_Q;        // 64
@@ -392,6 +393,8 @@ int qtc_init_attrs() {
 
 // trajectory split that minimises (waves of CTAs) x (set-up + trajectories per CTA)
 static int qtc_t_chunk(int tiles, int T) {
+    static const int forced = [] { const char *e = getenv("ECORD_QTC_CHUNK"); return e ? atoi(e) : 0; }();      // A/B tests
+    if (forced > 0) return forced < T ? (forced < kTcMaxT ? forced : kTcMaxT) : (T < kTcMaxT ? T : kTcMaxT);
     const int slots = kCtasPerSM * kNumSMs, setup = 6;
     long long best_cost = -1;
     int best = 1;
