@@ -317,6 +317,10 @@ def gen_fullsize(which=("er200", "er500", "ba500")):
             # trajectory bar of configs 2-3 at n = 2000.
             graphs = [_to_nx(g) for g in synthetic_set("er", 2000, 2, avg_degree=10, signed=True)]; out_name = "config4_er2000_signed.npz"
             T, num_steps = 32, 1500
+        elif name == "er10000s":
+            # the largest size of config 4 (79 vertex tiles per graph), +-1 weights (see er2000s): 1 graph x 16 trajectories x 400 steps
+            graphs = [_to_nx(g) for g in synthetic_set("er", 10000, 1, avg_degree=10, signed=True)]; out_name = "config4_er10000_signed.npz"
+            T, num_steps = 16, 400
         else:
             graphs = [_to_nx(g) for g in synthetic_set("er", 500, 5, p=0.15, signed=True)]; out_name = "config2_er500.npz"
         solver, gb = make_solver(sd)

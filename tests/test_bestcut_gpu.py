@@ -2,7 +2,8 @@
 reference (oracle/gen_golden.py full -> tests/golden/config2_er200.npz, config2_er500.npz, config3_ba500.npz):
 4*|V| greedy steps, 50 trajectories, all graphs of a fixture in one rollout batch, random-init canonical network.
 config4_er2000_signed.npz pins BASELINE config 4's graph family at n = 2000 (16 vertex tiles per graph: a unit's arg-max spans
-16 CTAs of the Q kernel): 2 graphs x 32 trajectories x 1500 steps of the unmodified reference, +-1 weights.  config4_er2000.npz is
+16 CTAs of the Q kernel): 2 graphs x 32 trajectories x 1500 steps of the unmodified reference, +-1 weights;
+config4_er10000_signed.npz the family's largest size (n = 10000, 79 tiles: 1 graph x 16 trajectories x 400 steps).  config4_er2000.npz is
 the same with the family's own UNIT weights, where the reference's trajectories cannot be followed by any other implementation
 (see test_config4_unit_weights_*): it is held to what CAN be pinned there.
 
@@ -27,7 +28,7 @@ from util import load_gold, unpack_graphs
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = ["config2_er200.npz", "config2_er500.npz", "config3_ba500.npz", "config4_er2000_signed.npz"]
+FIXTURES = ["config2_er200.npz", "config2_er500.npz", "config3_ba500.npz", "config4_er2000_signed.npz", "config4_er10000_signed.npz"]
 
 
 def _run(fixture, gemm):
