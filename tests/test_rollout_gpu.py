@@ -601,15 +601,16 @@ def test_graph_sharding_reproduces_the_full_batch_rollout(gemm, compat, ragged):
 def test_trajectory_shards_reproduce_the_full_batch_rollout(gemm):
     """SURVEY.md 8e, trajectory axis: a shard of the trajectories (B200Solver.rollout(traj_slice=...), what every rank of
     dist.rollout_sharded runs) gives the single-GPU rollout's scores bit for bit -- a row's arithmetic may not depend on how many
-    rows the launch has.  The full batch has 5000 rows (64-row CTAs in the policy tail, 64-unit GRU tiles), the shards 600-700
-    (32-row CTAs, narrower GRU tiles): the case that differed before the tail's sums were given one association for both."""
+    rows the launch has.  The full batch has 7000 rows (64-row CTAs in the policy tail, several 64-unit GRU tiles and several
+    projection tiles per CTA pair: the multi-tile projection kernel), the shards 600-700 (32-row CTAs, narrower GRU tiles, the
+    one-tile projection kernel): the case that differed before the tail's sums were given one association for both."""
     sd = random_state_dicts(9, perturb_norms=True)
     graphs = synthetic_set("er", 40, 100, seed0=3, p=0.15, signed=True)
     batch = GraphBatcher()(graphs)
-    T, S = 50, 60
+    T, S = 70, 60
     init = np.random.RandomState(5).randint(0, 2, (batch.tg.num_nodes, T), dtype=np.int8)
     solver = _solver(sd, gemm=gemm)
     full = torch.stack(solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init)['scores'], -1)
-    for lo, hi in ((0, 6), (6, 13), (43, 50)):
+    for lo, hi in ((0, 6), (30, 37), (63, 70)):
         part = solver.rollout(batch, num_tradj=T, num_steps=S, tau=0, use_epsilon=False, init_state=init, traj_slice=(lo, hi))
         assert torch.equal(torch.stack(part['scores'], -1), full[:, lo:hi]), (lo, hi)
