@@ -28,18 +28,30 @@ def main(path):
     raw = list(csv.reader(io.StringIO(run(["-i", path, "--page", "raw", "--csv"]))))
     hdr, units = raw[0], raw[1]
     print(f"# {path}")
+    tables = None
     for n, row in enumerate(raw[2:], 1):
         d = dict(zip(hdr, row))
         print(f"\n## launch {n}: {d.get('Kernel Name', '?')[:100]}")
         for h, u in zip(hdr, units):
             if any(h.startswith(k.strip()) and (k.endswith(' ') and h == k.strip() or not k.endswith(' ')) for k in KEYS):
                 print(f"{h:90s} {d[h]:>16s} {u}")
-        src = list(csv.reader(io.StringIO(run(["-i", path, "--page", "source", "--csv", "--kernel-id", f":::{n}"]))))
-        if len(src) < 3:
+        if tables is None:           # the source page of the whole report, split into one table per launch ("Kernel Name" rows)
+            tables = []
+            for r in csv.reader(io.StringIO(run(["-i", path, "--page", "source", "--csv"]))):
+                if r and r[0] == "Kernel Name":
+                    tables.append([r[1] if len(r) > 1 else "", []])
+                elif tables:
+                    tables[-1][1].append(r)
+        # the source page holds `per` tables per launch in launch order (with --import-source: the SASS view, then the CUDA-C view)
+        per = max(1, len(tables) // max(1, len(raw) - 2))
+        pick = tables[(n - 1) * per] if (n - 1) * per < len(tables) else None
+        if pick is None or len(pick[1]) < 2:
             continue
-        sh = src[1]
+        sh = pick[1][0]
         ix = {h: i for i, h in enumerate(sh)}
-        data = src[2:]
+        data = [r for r in pick[1][1:] if len(r) == len(sh)]
+        if '# Samples' not in ix or not data:
+            continue
         tot = sum(int(r[ix['# Samples']]) for r in data) or 1
         print(f"-- top stall sites ({tot} samples, {sum(int(r[ix['Instructions Executed']]) for r in data)} warp instructions)")
         for r in sorted(data, key=lambda r: -int(r[ix['# Samples']]))[:12]:
