@@ -410,9 +410,9 @@ k_gemm_tc2(const __grid_constant__ TcMaps maps, TcParams prm, int num_tiles, int
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int jl = part * 16 + i;
-                            const float r = sigmoidf_acc(ar[i] + bias_s[ab][0][jl]);
-                            const float z = sigmoidf_acc(az[i] + bias_s[ab][1][jl]);
-                            const float n = tanhf(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
+                            const float r = gate_sigmoid(ar[i] + bias_s[ab][0][jl]);
+                            const float z = gate_sigmoid(az[i] + bias_s[ab][1][jl]);
+                            const float n = gate_tanh(fmaf(ahn[i] + bias_s[ab][2][jl], r, ain[i] + bias_s[ab][3][jl]));
                             hv[i] = fmaf(hv[i] - n, z, n);
                         }
 #pragma unroll
@@ -453,7 +453,7 @@ k_gemm_tc2(const __grid_constant__ TcMaps maps, TcParams prm, int num_tiles, int
                         const int r = 8 * ew + 2 * i + (lane >> 4), c4 = lane & 15;
                         if (m0 + r < prm.rows && 4 * c4 < tw && !(prm.debug & 128)) {
                             const float4 hv4 = *reinterpret_cast<const float4 *>(&Hs[r][4 * c4]);
-                            const float4 tv4 = make_float4(tanhf(hv4.x), tanhf(hv4.y), tanhf(hv4.z), tanhf(hv4.w));   // projection input
+                            const float4 tv4 = make_float4(gate_tanh(hv4.x), gate_tanh(hv4.y), gate_tanh(hv4.z), gate_tanh(hv4.w));   // projection input
                             const size_t o = (size_t)(m0 + r) * H + unit0 + 4 * c4;
                             *reinterpret_cast<float4 *>(hnew + nxt_off * H + o) = hv4;
                             uint2 hi, lo;

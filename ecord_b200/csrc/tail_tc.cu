@@ -232,7 +232,7 @@ k_tail_tc(const __grid_constant__ CUtensorMap mapW2, ecord_weights w, ecord_poli
         for (int o = 0; o < ND; ++o) {
             P[o] = lrelu(fmaf(P[o] * rstd, w.ln2_w[o], w.ln2_b[o]));
             Z.Ps[tid][o] = P[o];
-            Z.Ts[tid][o] = NS == 3 ? tanhf(P[o]) : tanh_fast(P[o]);   // MUFU.TANH on the bf16-tolerance path only
+            Z.Ts[tid][o] = NS == 3 ? gate_tanh(P[o]) : tanh_fast(P[o]);   // MUFU.TANH on the bf16-tolerance path only
             sa = fmaf(S.colsum[o], P[o], sa);
         }
         // mean over the 64 channels of A = Wq[:, :32] P + b_q, without forming A

@@ -88,6 +88,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+// Gate functions of the split (bf16x3) kernels' epilogues (GRU cell, tanh(h') for the projection, tanh(P) in the tail): exp through MUFU.EX2 (2 ulp) and an approximate reciprocal -- fp32-grade (~3e-7
+// absolute on sigmoid / tanh) at a third of the instructions of expf / tanhf.  A/B against the library functions
+// (-DECORD_GATES_LIBM) on the reference fixtures of tests/test_bestcut_gpu.py: best cut and per-trajectory best unchanged, whole
+// trajectories identical 0.975 / 0.950 / 0.900 / 0.31 / 0.63 against 0.975 / 0.950 / 0.912 / 0.31 / 0.50 (ER200 / ER500 / BA500 /
+// ER2000 / ER10000): differences of single trajectories either way, the size of fp32 rounding; GRU kernel 79.6 -> 75.2 us at ER500.
+// (MUFU.TANH, 2^-11, is NOT fp32-grade: it costs a fifth of the trajectories, oracle/ablate_precision.py.)
+#ifndef ECORD_GATES_LIBM
+__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) {
+    const float e = __expf(-2.0f * fabsf(x));                   // in (0, 1]
+    return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+}
+#else
+__device__ __forceinline__ float gate_sigmoid(float x) { return sigmoidf_acc(x); }
+__device__ __forceinline__ float gate_tanh(float x) { return tanhf(x); }
+#endif
+
 struct TcParams {
     // GRU
     const float *hidden;          // [2][Mp][1024] fp32
