@@ -262,3 +262,16 @@ def test_trajectory_sharding_reduce_over_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_double_q_construction_fails_the_way_validate_py_expects():
+    """experiments/validate.py:187-200 first tries DQNSolver(use_double_q_networks=True, ...) and falls back to the single-Q
+    actor when that raises: the engine's constructor must raise (before touching CUDA), not silently run one network."""
+    from ecord_b200.solver import B200Solver
+    sd = random_state_dicts(0) if "random_state_dicts" in globals() else None
+    if sd is None:
+        from ecord_b200.network import random_state_dicts as rsd
+        sd = rsd(0)
+    for kw in (dict(use_double_q_networks=True), dict(use_ecodqn=True)):
+        with pytest.raises(NotImplementedError):
+            B200Solver(gnn=sd['gnn'], rnn=sd['rnn'], gnn2rnn=sd['gnn2rnn'], node_encoder=sd['node_encoder'], **kw)
