@@ -1,4 +1,4 @@
-// tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (gemm_tc.cu, gemm_tc2.cu): mbarrier, TMA,
+// tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (gemm_tc.cu, tail_tc.cu, qtc.cu): mbarrier, TMA,
 // UMMA descriptors, tcgen05.mma / commit / ld, and the host-side tensor-map encoder.
 #pragma once
 #include "common.cuh"
@@ -11,7 +11,6 @@ constexpr int H = ECORD_DIM_H;
 constexpr int BM = 128;          // rows per tile (UMMA_M)
 constexpr int BK = 64;           // bf16 elements per k-chunk = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kThreads = 576;    // 18 warps: TMA, MMA, 16 epilogue (four per TMEM lane quarter)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,7 +116,8 @@ struct TcParams {
     int rows, rows_pad;
     const int32_t *step_base;     // device step counter (or NULL)
     int step_off;
-    int debug;                    // diagnostics (ECORD_TC_DEBUG): 1 = no MMA issue, 2 = no epilogue math, 4 = no TMA
+    int debug;                    // diagnostics (ECORD_TC_DEBUG, bits): 1 no MMA issue, 2 no epilogue math, 4 no TMA (rejected), 8 prologue +
+                                  // teardown only, 32 hi planes only, 64 every cluster fetches tile (0, 0), 128 no epilogue global traffic
     int sched_full, sched_kn, sched_narrow;      // GRU tile schedule (gemm_tc.cu: tc2_tile)
 };
 
