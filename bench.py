@@ -196,11 +196,11 @@ def run_reference(args):
         return
     graphs, n, G, T, desc = make_graphs(args.workload)
     gs = max(1, min(G, args.cpu_graphs))
-    # warm-up on the default sample; then bound the sample so that K timed steps end within ~2 minutes
+    # warm-up on a small sample; then the WHOLE workload (all G graphs in one rollout batch, the b200 arm's config) if K timed
+    # steps of it end within ~2 minutes at the measured pace, else the largest sample that does
     rate_w, dt_w, _ = cpu_rollout_rate(graphs[:gs], T, max(args.warmup, 1))
-    est = dt_w / max(args.warmup, 1) * args.steps
-    if est > 120.0:
-        gs = max(1, int(gs * 120.0 / est))
+    est_full = dt_w / max(args.warmup, 1) * args.steps * (G / gs)
+    gs = G if est_full <= 120.0 else max(1, int(G * 120.0 / est_full))
     sample = graphs[:gs]
     rate, dt, have_ref = cpu_rollout_rate(sample, T, args.steps)
     cores = os.cpu_count()
