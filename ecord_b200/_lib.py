@@ -91,6 +91,7 @@ SYMBOLS = {
     "ecord_version": (_i32, []),
     "ecord_error_string": (C.c_char_p, [_i32]),
     "ecord_abi_sizeof": (_i64, [_i32]),
+    "ecord_gru_tile_schedule": (_i32, [_i32, _vp, _i32, _vp]),
     "ecord_step_cy": (_i32, [_vp] * 11 + [_i32] * 5),
     "ecord_step_cy_device": (_i32, [_vp] * 11 + [_i32] * 6 + [_vp]),
     "ecord_step_cy_ctx_create": (_i32, [_i32] * 5 + [_vp] * 3 + [_P(_vp)]),

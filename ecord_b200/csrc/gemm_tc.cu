@@ -152,26 +152,32 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {      //
 // tile i of cluster `cluster_id`.  PROJ: pair tiles cluster_id + i * num_clusters of 256 rows x TILE_N columns.  GRU: first
 // prm.sched_full rounds of 64-unit tiles, then the leftover 64-unit tiles cut into prm.sched_kn-sub-block ones
 // (prm.sched_narrow of them), both dealt round-robin; nb = first 16-unit sub-block, k = sub-blocks (4, 2 or 1).
+// GRU tile i of cluster `cluster_id`: first `full` rounds of 64-unit tiles, then the leftover 64-unit tiles cut into kn-sub-block
+// ones (`narrow` of them), both dealt round-robin; nb = first 16-unit sub-block, k = sub-blocks (4, 2 or 1).  Host + device: the
+// same code enumerates the tiles for ecord_gru_tile_schedule(), which tests/ check for exact coverage at any batch size.
+__host__ __device__ __forceinline__ bool gru_tile(int i, int cluster_id, int num_clusters, int full, int kn, int narrow,
+                                                  int &m0_pair, int &nb, int &k) {
+    int id;
+    k = 4;
+    if (i < full) {
+        id = cluster_id + i * num_clusters;
+        nb = (id & 15) * 4;
+    } else {
+        const int j = cluster_id + (i - full) * num_clusters;
+        if (j >= narrow) return false;
+        k = kn;
+        const int per = 4 / k;
+        id = full * num_clusters + j / per;
+        nb = (id & 15) * 4 + (j % per) * k;
+    }
+    m0_pair = (id >> 4) * (2 * BM);
+    return true;
+}
+// tile i of cluster `cluster_id`.  PROJ: pair tiles cluster_id + i * num_clusters of 256 rows x TILE_N columns; GRU: gru_tile
 template <int MODE>
 __device__ __forceinline__ bool tc2_tile(int i, int cluster_id, int num_clusters, int num_tiles, int nblk, const TcParams &prm,
                                          int &m0_pair, int &nb, int &k) {
-    if (MODE == 0) {
-        int id;
-        k = 4;
-        if (i < prm.sched_full) {
-            id = cluster_id + i * num_clusters;
-            nb = (id & 15) * 4;
-        } else {
-            const int j = cluster_id + (i - prm.sched_full) * num_clusters;
-            if (j >= prm.sched_narrow) return false;
-            k = prm.sched_kn;
-            const int per = 4 / k;
-            id = prm.sched_full * num_clusters + j / per;
-            nb = (id & 15) * 4 + (j % per) * k;
-        }
-        m0_pair = (id >> 4) * (2 * BM);
-        return true;
-    }
+    if (MODE == 0) return gru_tile(i, cluster_id, num_clusters, prm.sched_full, prm.sched_kn, prm.sched_narrow, m0_pair, nb, k);
     const int tile = cluster_id + i * num_clusters;
     if (tile >= num_tiles) return false;
     m0_pair = (tile / nblk) * (2 * BM);
@@ -749,6 +755,23 @@ static GruSched gru_schedule(int tiles64) {
 }
 
 // split != 0: ECORD_GEMM_BF16X3 (bf16 hi / lo operands, three products; CTA-pair kernels only)
+// Diagnostics / tests: the tile schedule the GRU kernel would use for a batch of `rows_pad` rows (a multiple of 256), as
+// (first row, first hidden unit, units) triples in out[3 * i], cluster by cluster.  Returns the number of tiles, or a negative
+// error; *num_clusters receives the CTA pairs of the launch.  No GPU needed.
+extern "C" int ecord_gru_tile_schedule(int32_t rows_pad, int32_t *out, int32_t max_tiles, int32_t *num_clusters) {
+    if (rows_pad <= 0 || rows_pad % (2 * BM) != 0 || !out || max_tiles < 0) return ECORD_E_SIZE;
+    const GruSched sc = gru_schedule((H / 64) * (rows_pad / (2 * BM)));
+    if (num_clusters) *num_clusters = sc.clusters;
+    int n = 0;
+    for (int c = 0; c < sc.clusters; ++c) {
+        int m0, nb, k;
+        for (int i = 0; gru_tile(i, c, sc.clusters, sc.full, sc.kn, sc.narrow, m0, nb, k); ++i, ++n) {
+            if (n < max_tiles) { out[3 * n] = m0; out[3 * n + 1] = nb * 16; out[3 * n + 2] = k * 16; }
+        }
+    }
+    return n;
+}
+
 int launch_gru_tc_ex(const ecord_weights *w, const ecord_policy *p, const int32_t *step_base, int step_off, int split, cudaStream_t st) {
     PFN_encodeTiled enc;
     int rc = get_encoder(&enc);

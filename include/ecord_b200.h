@@ -205,6 +205,11 @@ const char *ecord_error_string(int code);
 /* sizeof() of the structs above as compiled, so bindings can assert their mirror is in sync:
  * which = 0 graph, 1 env, 2 weights, 3 policy, 4 rollout_desc */
 int64_t     ecord_abi_sizeof(int which);
+/* Diagnostics (no GPU needed): the tile schedule of the tcgen05 GRU kernel (the a6 update, models/rnn_decoder.py:369-381) for a
+ * batch of rows_pad rows (a multiple of 256): out[3 i .. 3 i + 2] = (first row, first hidden unit, hidden units) of tile i, cluster
+ * by cluster; *num_clusters (may be NULL) = CTA pairs of the launch.  Returns the number of tiles (which may exceed max_tiles;
+ * only the first max_tiles are written), or ECORD_E_SIZE (negative).  tests/ check that the tiles cover [rows_pad] x [1024] exactly once. */
+int         ecord_gru_tile_schedule(int32_t rows_pad, int32_t *out, int32_t max_tiles, int32_t *num_clusters);
 
 /* ---- B3: the reference's native seam.  Same arguments, meaning and in-place semantics as
  *      step_cy() (_tradjectory_step_cy.pyx:152-171) called from Tradjectories.step()

@@ -86,3 +86,24 @@ def test_sass_is_blackwell_native():
                      "UBLKCP"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_gru_tile_schedule_covers_every_batch_size_exactly_once(lib):
+    """The tcgen05 GRU kernel's tiles (64-unit tiles in full rounds over the CTA pairs, the leftover ones cut to 32 or 16 units;
+    the enumeration is the kernel's own host + device function) must cover [rows_pad] x [1024 hidden units] exactly once for
+    every batch size, use at most 74 CTA pairs and give every pair at most one tile more than any other per width class."""
+    import numpy as np
+    for rt in list(range(1, 41)) + [74, 75, 100, 157, 200]:
+        rows_pad = 256 * rt
+        cap = 16 * rt * 4 + 8
+        out = np.zeros(3 * cap, np.int32)
+        ncl = C.c_int32(0)
+        n = lib.ecord_gru_tile_schedule(rows_pad, out.ctypes.data_as(C.c_void_p), cap, C.byref(ncl))
+        assert 0 < n <= cap and 1 <= ncl.value <= 74, (rt, n, ncl.value)
+        t = out[:3 * n].reshape(n, 3)
+        cover = np.zeros((rt, 64), np.int32)                       # (row tile, 16-unit sub-block)
+        for m0, u0, w in t:
+            assert m0 % 256 == 0 and 0 <= m0 < rows_pad and w in (16, 32, 64) and u0 % w == 0 and u0 + w <= 1024, (rt, m0, u0, w)
+            cover[m0 // 256, u0 // 16:(u0 + w) // 16] += 1
+        assert (cover == 1).all(), rt
+    assert lib.ecord_gru_tile_schedule(100, None, 0, None) < 0
