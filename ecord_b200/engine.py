@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import GEMM_BF16, GEMM_BF16X3, GEMM_FP32, Q_EXACT, Q_FAST, Q_TC, check, ptr
 from .network import check_state_dicts
 
-# "bf16x3" (the default): tcgen05 GEMMs on bf16 hi/lo operand pairs, three products, exact gate functions -- fp32-grade
+# "bf16x3" (the default): tcgen05 GEMMs on bf16 hi/lo operand pairs, three products, fp32-grade gate functions -- fp32-grade
 # recurrent state on the tensor cores; "bf16": single bf16 products + MUFU.TANH (fast, 2e-2 tolerance); "fp32": CUDA-core SGEMM
 _GEMM_MODES = {"fp32": GEMM_FP32, "bf16": GEMM_BF16, "bf16x3": GEMM_BF16X3}
 _Q_MODES = {"exact": Q_EXACT, "fast": Q_FAST, "tc": Q_TC}
