@@ -9,7 +9,7 @@ the same with the family's own UNIT weights, where the reference's trajectories 
 
 Bar (north_star): the greedy rollout reproduces the reference's best cut on >= 99 % of the instances -- with 5-10
 instances per fixture that means on every one of them.  It holds for the two fp32-grade modes: "fp32" (CUDA-core
-SGEMM) and "bf16x3" (the default: tcgen05 GEMMs on bf16 hi / lo operand pairs, exact gate functions).  The opt-in
+SGEMM) and "bf16x3" (the default: tcgen05 GEMMs on bf16 hi / lo operand pairs, fp32-grade gate functions).  The opt-in
 "bf16" fast mode (single bf16 products, MUFU.TANH) is held to a statistical bar only and its agreement is printed.
 
 Beyond the best cut the tests compare what the fixtures hold per trajectory: the best score of every one of the 50

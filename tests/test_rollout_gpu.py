@@ -132,7 +132,7 @@ def test_config1_best_cut_parity():
 @pytest.mark.parametrize("gemm,bar", [("bf16x3", 0.99), ("bf16", 0.97)])
 def test_config1_best_cut_tensor_core_modes(gemm, bar):
     """The same config through the tensor-core paths (tcgen05 GRU / projection / tail, fp16-split tensor-core Q).
-    "bf16x3" (the default and the benchmarked mode: bf16 hi / lo operand pairs, exact gate functions) is held to the
+    "bf16x3" (the default and the benchmarked mode: bf16 hi / lo operand pairs, fp32-grade gate functions) is held to the
     north_star bar of 99 %.  The opt-in fast mode "bf16" rounds the recurrent update to bf16, which can change a near-tie
     arg-max: 97 % (measured 99-100 %).  Both: per-graph mean-over-trajectories within 1 %."""
     from ecord_b200.testing import TestGraphsConfig, test_solver
